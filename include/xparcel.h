@@ -1,0 +1,200 @@
+/*
+ * xparcel.h -- C ABI of libxparcel.so: B200-native column parcel lifting
+ * (LCL -> parcel profile -> LCL insertion -> LFC/EL -> CAPE/CIN for surface-based,
+ * mixed-layer and most-unstable parcels).
+ *
+ * The reference (traupach/xarray_parcel) is pure Python and has no FFI: its boundary for
+ * this path is the function surface of modules/parcel_functions.py ("PF").  Each entry
+ * point below names the PF function(s) it replaces (file:line); the Python binding a
+ * maintainer would add is shown in INTEGRATION.md and implemented in
+ * xarray_parcel_b200/_lib.py.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  The caller owns every buffer.  No exceptions cross
+ *    the ABI: every function returns an xp_status; xp_last_error() gives the message.
+ *  - Column data are LEVEL-MAJOR: element (level k, column i) of an array is at
+ *    base[k * level_stride + i]; consecutive columns are contiguous so every level read
+ *    by a warp is one coalesced line.  Level 0 is the surface; pressure decreases with k.
+ *    A (time, level, y, x) C-ordered model field is already level-major per time step.
+ *  - Units: hPa and K (PF docstrings, README.md:9).  NaN marks missing data.
+ *  - dtype: inputs are float32 or float64; outputs have the dtype of the inputs.
+ *    Decision-critical arithmetic is float64 inside the kernels either way.
+ *  - mem = XP_MEM_DEVICE: pointers are device pointers on the context's device and the
+ *    call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default).
+ *    mem = XP_MEM_HOST: pointers are host pointers; the library stages column blocks
+ *    through pinned buffers (H2D, kernel, D2H overlapped) and returns when outputs are
+ *    complete.
+ *  - Reference `assert`s that depend on data (PF:131 'Vertical pressures are not unique',
+ *    PF:1149 'Top temperature is NaN.') are reported through xp_take_flags().
+ */
+#ifndef XPARCEL_H
+#define XPARCEL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XP_VERSION_MAJOR 0
+#define XP_VERSION_MINOR 1
+
+typedef struct xp_context xp_context; /* one per (process, device): tables + staging buffers */
+
+typedef enum {
+    XP_OK = 0,
+    XP_ERR_INVALID_ARGUMENT = 1,
+    XP_ERR_CUDA = 2,
+    XP_ERR_TABLES_NOT_LOADED = 3, /* PF:56-61 'Call load_moist_adiabat_lookups first.' */
+    XP_ERR_NO_DEVICE = 4
+} xp_status;
+
+typedef enum { XP_F32 = 0, XP_F64 = 1 } xp_dtype;
+typedef enum { XP_MEM_DEVICE = 0, XP_MEM_HOST = 1 } xp_memspace;
+
+/* Which parcel is lifted (PF:1477 / PF:1651 / PF:1557 / PF:1394 with explicit parcel). */
+typedef enum {
+    XP_PARCEL_SURFACE = 0,
+    XP_PARCEL_MIXED_LAYER = 1,
+    XP_PARCEL_MOST_UNSTABLE = 2,
+    XP_PARCEL_EXPLICIT = 3
+} xp_parcel_kind;
+
+/* Data-dependent reference assertions, OR-ed over all columns of all calls since the last
+ * xp_take_flags(). */
+#define XP_FLAG_TOP_TEMPERATURE_NAN 1u     /* PF:1149 */
+#define XP_FLAG_PRESSURES_NOT_UNIQUE 2u    /* PF:131  */
+
+/* Environment columns: pressure/temperature/dewpoint [n_levels][n_columns]. */
+typedef struct {
+    const void *pressure;
+    const void *temperature;
+    const void *dewpoint;
+    int64_t n_columns;
+    int32_t n_levels;
+    int32_t dtype;                 /* xp_dtype */
+    int64_t level_stride;          /* elements between levels of temperature and dewpoint */
+    int64_t pressure_level_stride; /* elements between levels of pressure */
+    int32_t pressure_is_1d;        /* 1: pressure is one shared axis [n_levels] (ERA5-style
+                                      pressure levels); element k at pressure[k*pressure_level_stride] */
+    int32_t mem;                   /* xp_memspace, applies to inputs AND outputs of the call */
+} xp_columns;
+
+/* Function kwargs of the reference that select behaviour (PF:1394-1397, PF:1291-1293). */
+typedef struct {
+    int32_t virtual_temperature_correction; /* default 1 (PF:1396) */
+    int32_t lcl_interp_log;                 /* 1 = 'log' (default, PF:1396), 0 = 'linear' */
+    int32_t pos_cape_neg_cin;               /* default 1 (PF:1293) */
+    int32_t post_zero_cin;                  /* default 0 (PF:1293) */
+    int32_t metpy_compat;                   /* 141 = MetPy 1.4.1 formulas (default), 162 = 1.6.2 */
+    int32_t reserved;
+    double mixed_layer_depth;               /* hPa, default 100 (PF:1652) */
+    double most_unstable_depth;             /* hPa, default 300 (PF:1558) */
+} xp_options;
+
+/* Outputs for one parcel kind.  Every pointer is optional (NULL = not written).
+ * Scalars are [n_columns]; profile arrays are [n_levels + 1][n_columns] with
+ * profile_level_stride elements between levels, NaN-padded at the top. */
+typedef struct {
+    void *cape, *cin;                                                /* PF:1291-1392, J/kg */
+    void *lcl_pressure, *lcl_temperature, *lcl_virtual_temperature;  /* PF:609-682 */
+    void *lfc_pressure, *lfc_temperature, *el_pressure, *el_temperature; /* PF:1066-1198 */
+    void *parcel_pressure, *parcel_temperature, *parcel_dewpoint;    /* the lifted parcel
+                                         (PF:229-289 mixed_parcel / PF:102-135 most_unstable_parcel) */
+    int32_t *level_shift; /* number of input levels removed below the lifted column (PF:1551-1553
+                             MU: index of the MU level; PF:1636-1638 ML: levels in the mixed layer);
+                             n_levels for a column with no valid parcel */
+    void *profile_pressure, *profile_temperature, *profile_virtual_temperature;      /* PF:806-931 */
+    void *profile_environment_temperature, *profile_environment_virtual_temperature;
+    void *profile_environment_dewpoint;
+    int64_t profile_level_stride;
+} xp_parcel_out;
+
+/* Explicit parcel for XP_PARCEL_EXPLICIT (PF:1394 cape_cin's parcel_* arguments): [n_columns]. */
+typedef struct {
+    const void *pressure, *temperature, *dewpoint;
+} xp_parcel_in;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+const char *xp_version(void);
+xp_status xp_create(int device, xp_context **out_ctx);
+void xp_destroy(xp_context *ctx);
+const char *xp_last_error(const xp_context *ctx); /* ctx may be NULL: last error of xp_create */
+xp_status xp_take_flags(xp_context *ctx, void *stream, uint32_t *out_flags); /* syncs `stream` */
+void xp_default_options(xp_options *opts);
+
+/* ---- moist-adiabat lookup tables: PF:39-61, 318-356, 447-523 --------------------------
+ * index grid uint16 [XP_TABLE_NP (descending pressure 1100..2.5)][XP_TABLE_NT (173..315.98)],
+ * 0 = no adiabat; curves float32 [XP_TABLE_NADIABATS][XP_TABLE_NP] on ASCENDING pressure
+ * (PF:54 sortby('pressure')). */
+#define XP_TABLE_NP 2196
+#define XP_TABLE_NT 7150
+#define XP_TABLE_NADIABATS 14300
+xp_status xp_tables_build(xp_context *ctx, void *stream);   /* replaces moist_adiabat_lookup PF:447-523 */
+xp_status xp_tables_set(xp_context *ctx, const uint16_t *index_grid_host, const float *curves_host);
+xp_status xp_tables_get(xp_context *ctx, uint16_t *index_grid_host, float *curves_host);
+int xp_tables_loaded(const xp_context *ctx);                 /* lookup_tables_loaded PF:56-61 */
+
+/* ---- the fused hot path ----------------------------------------------------------------
+ * xp_cape_cin: one parcel kind.  Replaces surface_based_cape_cin (PF:1477-1514),
+ * mixed_layer_cape_cin (PF:1651-1697) incl. mix_layer/mixed_parcel/mixed_layer/get_layer,
+ * most_unstable_cape_cin (PF:1557-1602) incl. from_most_unstable_parcel/most_unstable_parcel/
+ * bound_pressure/shift_out_nans, and cape_cin (PF:1394-1475) for an explicit parcel; inside:
+ * lcl, parcel_profile(_with_lcl), moist_lapse, add_lcl_to_profile/insert_level,
+ * linear/log_interp, find_intersections, lfc_el, trap_around_zeros, trapz, cape_cin_base.
+ * `explicit_parcel` is used only for XP_PARCEL_EXPLICIT. */
+xp_status xp_cape_cin(xp_context *ctx, const xp_columns *cols, int32_t kind,
+                      const xp_parcel_in *explicit_parcel, const xp_options *opts,
+                      const xp_parcel_out *out, void *stream);
+
+/* xp_suite: surface-based + mixed-layer + most-unstable in ONE pass over the columns
+ * (the benchmark metric).  out[0]=SB, out[1]=ML, out[2]=MU; an entry may be NULL. */
+xp_status xp_suite(xp_context *ctx, const xp_columns *cols, const xp_options *opts,
+                   const xp_parcel_out *out_sb, const xp_parcel_out *out_ml,
+                   const xp_parcel_out *out_mu, void *stream);
+
+/* ---- individually exposed steps (device memory only) ------------------------------------ */
+/* lcl PF:609-682: [n] parcels -> lcl pressure/temperature/virtual temperature. */
+xp_status xp_lcl(xp_context *ctx, const void *parcel_pressure, const void *parcel_temperature,
+                 const void *parcel_dewpoint, int64_t n, int32_t dtype, const xp_options *opts,
+                 void *lcl_pressure, void *lcl_temperature, void *lcl_virtual_temperature,
+                 void *stream);
+/* moist_lapse PF:525-607: parcel temperature at pressure[k][i] on the adiabat through
+ * (parcel_pressure[i], parcel_temperature[i]). */
+xp_status xp_moist_lapse(xp_context *ctx, const void *pressure, int64_t level_stride,
+                         int32_t n_levels, int64_t n_columns, int32_t dtype,
+                         const void *parcel_temperature, const void *parcel_pressure,
+                         void *out_temperature, int64_t out_level_stride, void *stream);
+/* parcel_profile PF:712-780 (no LCL level): temperature and virtual temperature of the lifted
+ * parcel on the input levels. */
+xp_status xp_parcel_profile(xp_context *ctx, const void *pressure, int64_t level_stride,
+                            int32_t n_levels, int64_t n_columns, int32_t dtype,
+                            const xp_parcel_in *parcel, const xp_options *opts,
+                            void *out_temperature, void *out_virtual_temperature,
+                            int64_t out_level_stride, void *lcl_pressure, void *lcl_temperature,
+                            void *lcl_virtual_temperature, void *stream);
+/* lfc_el PF:1066-1198 on caller-supplied parcel/environment temperature arrays [m][n]. */
+xp_status xp_lfc_el(xp_context *ctx, const void *pressure, const void *parcel_temperature,
+                    const void *temperature, int64_t level_stride, int32_t n_levels,
+                    int64_t n_columns, int32_t dtype, const void *lcl_pressure,
+                    const void *lcl_temperature, void *lfc_pressure, void *lfc_temperature,
+                    void *el_pressure, void *el_temperature, void *stream);
+/* cape_cin_base PF:1291-1392 (+ trap_around_zeros PF:1200-1289, trapz PF:164-206). */
+xp_status xp_cape_cin_base(xp_context *ctx, const void *pressure, const void *temperature,
+                           const void *parcel_temperature, int64_t level_stride,
+                           int32_t n_levels, int64_t n_columns, int32_t dtype,
+                           const void *lfc_pressure, const void *el_pressure,
+                           const xp_options *opts, void *cape, void *cin, void *stream);
+
+/* ---- instrumentation -------------------------------------------------------------------- */
+/* Number of kernels this library has launched on ctx since creation. */
+uint64_t xp_launch_count(const xp_context *ctx);
+/* Device time (ms) of the most recent xp_cape_cin/xp_suite kernel launch with
+ * mem = XP_MEM_DEVICE, measured with CUDA events on the launch stream; syncs the stream. */
+xp_status xp_last_kernel_ms(xp_context *ctx, float *out_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XPARCEL_H */

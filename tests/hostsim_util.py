@@ -1,0 +1,81 @@
+"""Build and call tests/hostsim (TEST-ONLY host compile of the per-column kernel code)."""
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "hostsim", "hostsim.cpp")
+BUILD = os.path.join(HERE, "hostsim", "_build")
+LIB = os.path.join(BUILD, "libhostsim.so")
+CSRC = os.path.join(os.path.dirname(HERE), "xarray_parcel_b200", "csrc")
+
+SCALARS = ["cape", "cin", "lcl_pressure", "lcl_temperature", "lcl_virtual_temperature",
+           "lfc_pressure", "lfc_temperature", "el_pressure", "el_temperature",
+           "parcel_pressure", "parcel_temperature", "parcel_dewpoint"]
+PROFILE = ["pressure", "temperature", "virtual_temperature", "environment_temperature",
+           "environment_virtual_temperature", "environment_dewpoint"]
+KINDS = {"sb": 0, "ml": 1, "mu": 2, "explicit": 3}
+
+
+def build():
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("xp_math.cuh", "xp_column.cuh", "xp_parcels.cuh")]
+    if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
+        return LIB
+    os.makedirs(BUILD, exist_ok=True)
+    # -ffp-contract=off: keep host arithmetic un-fused, like NumPy's
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++", SRC,
+           "-o", LIB]
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.hostsim_cape_cin.restype = None
+    return _lib
+
+
+def cape_cin(p, t, td, tables, kind="sb", explicit=None, vtc=True, lcl_interp="log",
+             pos_cape_neg_cin=True, post_zero_cin=False, metpy_compat=141, ml_depth=100.0,
+             mu_depth=300.0, profile=False):
+    """Run the host-compiled kernel code on [L, N] float64 arrays.  Returns dict of [N] arrays
+    (+ 'profile' dict of [L+1, N] arrays, 'level_shift', 'flags')."""
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    td = np.ascontiguousarray(td, dtype=np.float64)
+    L, N = t.shape
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    p1d = int(p.ndim == 1)
+    out = np.empty((12, N))
+    shift = np.empty(N, dtype=np.int32)
+    prof = np.empty((6, L + 1, N)) if profile else None
+    flags = ctypes.c_uint32(0)
+    iopts = (ctypes.c_int * 5)(int(vtc), int(lcl_interp == "log"), int(pos_cape_neg_cin),
+                               int(post_zero_cin), int(metpy_compat))
+    ex = None
+    if explicit is not None:
+        ex = np.ascontiguousarray(np.stack([np.broadcast_to(np.asarray(e, dtype=np.float64), (N,))
+                                            for e in explicit]))
+    idx = np.ascontiguousarray(tables.index_grid, dtype=np.uint16)
+    cur = np.ascontiguousarray(tables.curves_asc, dtype=np.float32)
+
+    def ptr(a):
+        return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+    lib().hostsim_cape_cin(ptr(p), ptr(t), ptr(td), ctypes.c_int64(N), ctypes.c_int(L),
+                           ctypes.c_int(p1d), ctypes.c_int(KINDS[kind]), ptr(ex), iopts,
+                           ctypes.c_double(ml_depth), ctypes.c_double(mu_depth), ptr(idx), ptr(cur),
+                           ptr(out), ptr(shift), ptr(prof), ctypes.byref(flags))
+    res = {k: out[i] for i, k in enumerate(SCALARS)}
+    res["level_shift"] = shift
+    res["flags"] = flags.value
+    if profile:
+        res["profile"] = {k: prof[i] for i, k in enumerate(PROFILE)}
+    return res

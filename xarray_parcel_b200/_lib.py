@@ -1,0 +1,381 @@
+"""ctypes binding of libxparcel.so (the C ABI declared in include/xparcel.h).
+
+This is the binding a maintainer of the reference would add.  PyTorch is
+used only for device/pinned memory and streams; no torch type crosses the ABI -- only raw
+pointers, sizes and a cudaStream_t.
+"""
+
+import ctypes
+import os
+import threading
+
+import torch
+
+from . import _build
+
+c_void_p, c_int32, c_int64, c_double = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+
+XP_OK = 0
+XP_F32, XP_F64 = 0, 1
+XP_MEM_DEVICE, XP_MEM_HOST = 0, 1
+KIND = {"sb": 0, "ml": 1, "mu": 2, "explicit": 3}
+FLAG_TOP_TEMPERATURE_NAN = 1
+FLAG_PRESSURES_NOT_UNIQUE = 2
+TABLE_NP, TABLE_NT, TABLE_NADIABATS = 2196, 7150, 14300
+
+SCALAR_FIELDS = ["cape", "cin", "lcl_pressure", "lcl_temperature", "lcl_virtual_temperature",
+                 "lfc_pressure", "lfc_temperature", "el_pressure", "el_temperature",
+                 "parcel_pressure", "parcel_temperature", "parcel_dewpoint"]
+PROFILE_FIELDS = ["profile_pressure", "profile_temperature", "profile_virtual_temperature",
+                  "profile_environment_temperature", "profile_environment_virtual_temperature",
+                  "profile_environment_dewpoint"]
+
+
+class XpColumns(ctypes.Structure):
+    _fields_ = [("pressure", c_void_p), ("temperature", c_void_p), ("dewpoint", c_void_p),
+                ("n_columns", c_int64), ("n_levels", c_int32), ("dtype", c_int32),
+                ("level_stride", c_int64), ("pressure_level_stride", c_int64),
+                ("pressure_is_1d", c_int32), ("mem", c_int32)]
+
+
+class XpOptions(ctypes.Structure):
+    _fields_ = [("virtual_temperature_correction", c_int32), ("lcl_interp_log", c_int32),
+                ("pos_cape_neg_cin", c_int32), ("post_zero_cin", c_int32),
+                ("metpy_compat", c_int32), ("reserved", c_int32),
+                ("mixed_layer_depth", c_double), ("most_unstable_depth", c_double)]
+
+
+class XpParcelOut(ctypes.Structure):
+    _fields_ = ([(f, c_void_p) for f in SCALAR_FIELDS] + [("level_shift", c_void_p)] +
+                [(f, c_void_p) for f in PROFILE_FIELDS] + [("profile_level_stride", c_int64)])
+
+
+class XpParcelIn(ctypes.Structure):
+    _fields_ = [("pressure", c_void_p), ("temperature", c_void_p), ("dewpoint", c_void_p)]
+
+
+EXPORTS = ["xp_version", "xp_create", "xp_destroy", "xp_last_error", "xp_take_flags",
+           "xp_default_options", "xp_tables_build", "xp_tables_set", "xp_tables_get",
+           "xp_tables_loaded", "xp_cape_cin", "xp_suite", "xp_lcl", "xp_moist_lapse",
+           "xp_parcel_profile", "xp_lfc_el", "xp_cape_cin_base", "xp_launch_count",
+           "xp_last_kernel_ms"]
+
+
+class XparcelError(RuntimeError):
+    pass
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """dlopen xarray_parcel_b200/libxparcel.so.  There is no fallback: a missing library is an
+    error (build it with ``python -m xarray_parcel_b200._build`` / ``__graft_entry__.build()``)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        if not os.path.exists(path):
+            raise XparcelError(f"{path} is missing: build the CUDA library first "
+                               "(python -m xarray_parcel_b200._build); there is no CPU fallback")
+        lib = ctypes.CDLL(path)
+        lib.xp_version.restype = ctypes.c_char_p
+        lib.xp_last_error.restype = ctypes.c_char_p
+        lib.xp_last_error.argtypes = [c_void_p]
+        lib.xp_create.argtypes = [ctypes.c_int, ctypes.POINTER(c_void_p)]
+        lib.xp_destroy.argtypes = [c_void_p]
+        lib.xp_destroy.restype = None
+        lib.xp_take_flags.argtypes = [c_void_p, c_void_p, ctypes.POINTER(ctypes.c_uint32)]
+        lib.xp_default_options.argtypes = [ctypes.POINTER(XpOptions)]
+        lib.xp_default_options.restype = None
+        lib.xp_tables_build.argtypes = [c_void_p, c_void_p]
+        lib.xp_tables_set.argtypes = [c_void_p, c_void_p, c_void_p]
+        lib.xp_tables_get.argtypes = [c_void_p, c_void_p, c_void_p]
+        lib.xp_tables_loaded.argtypes = [c_void_p]
+        lib.xp_cape_cin.argtypes = [c_void_p, ctypes.POINTER(XpColumns), c_int32,
+                                    ctypes.POINTER(XpParcelIn), ctypes.POINTER(XpOptions),
+                                    ctypes.POINTER(XpParcelOut), c_void_p]
+        lib.xp_suite.argtypes = [c_void_p, ctypes.POINTER(XpColumns), ctypes.POINTER(XpOptions),
+                                 ctypes.POINTER(XpParcelOut), ctypes.POINTER(XpParcelOut),
+                                 ctypes.POINTER(XpParcelOut), c_void_p]
+        lib.xp_lcl.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                               ctypes.POINTER(XpOptions), c_void_p, c_void_p, c_void_p, c_void_p]
+        lib.xp_moist_lapse.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int32,
+                                       c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
+        lib.xp_parcel_profile.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int32,
+                                          ctypes.POINTER(XpParcelIn), ctypes.POINTER(XpOptions),
+                                          c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                          c_void_p]
+        lib.xp_lfc_el.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64,
+                                  c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p]
+        lib.xp_cape_cin_base.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                         c_int64, c_int32, c_void_p, c_void_p,
+                                         ctypes.POINTER(XpOptions), c_void_p, c_void_p, c_void_p]
+        lib.xp_launch_count.argtypes = [c_void_p]
+        lib.xp_launch_count.restype = ctypes.c_uint64
+        lib.xp_last_kernel_ms.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_float)]
+        _lib = lib
+        return lib
+
+
+def make_options(virtual_temperature_correction=True, lcl_interp="log", pos_cape_neg_cin=True,
+                 post_zero_cin=False, metpy_compat="1.4.1", mixed_layer_depth=100.0,
+                 most_unstable_depth=300.0):
+    assert lcl_interp in ["linear", "log"], "interpolator must be linear or log"   # PF:878
+    compat = {"1.4.1": 141, "1.6.2": 162, 141: 141, 162: 162}[metpy_compat]
+    return XpOptions(int(bool(virtual_temperature_correction)), int(lcl_interp == "log"),
+                     int(bool(pos_cape_neg_cin)), int(bool(post_zero_cin)), compat, 0,
+                     float(mixed_layer_depth), float(most_unstable_depth))
+
+
+def _dtype_code(t):
+    if t.dtype == torch.float32:
+        return XP_F32
+    if t.dtype == torch.float64:
+        return XP_F64
+    raise TypeError(f"unsupported dtype {t.dtype}: float32 or float64 required")
+
+
+class Context:
+    """One xp_context (tables + staging) on one CUDA device."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise XparcelError("no CUDA device available: xarray_parcel_b200 has no CPU fallback")
+        self.device = int(device)
+        h = c_void_p()
+        st = self.lib.xp_create(self.device, ctypes.byref(h))
+        if st != XP_OK:
+            raise XparcelError(f"xp_create failed ({st}): {self.lib.xp_last_error(None).decode()}")
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.xp_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st, what):
+        if st != XP_OK:
+            msg = self.lib.xp_last_error(self.handle).decode()
+            if st == 3:
+                raise AssertionError(msg)          # PF:60-61
+            raise XparcelError(f"{what} failed ({st}): {msg}")
+
+    def _stream(self):
+        return c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- tables -------------------------------------------------------------------------
+    def tables_loaded(self):
+        return bool(self.lib.xp_tables_loaded(self.handle))
+
+    def tables_build(self):
+        self._check(self.lib.xp_tables_build(self.handle, self._stream()), "xp_tables_build")
+
+    def tables_set(self, index_grid, curves):
+        import numpy as np
+        idx = np.ascontiguousarray(index_grid, dtype=np.uint16)
+        cur = np.ascontiguousarray(curves, dtype=np.float32)
+        assert idx.shape == (TABLE_NP, TABLE_NT) and cur.shape == (TABLE_NADIABATS, TABLE_NP)
+        self._check(self.lib.xp_tables_set(self.handle, idx.ctypes.data, cur.ctypes.data), "xp_tables_set")
+
+    def tables_get(self):
+        import numpy as np
+        idx = np.empty((TABLE_NP, TABLE_NT), dtype=np.uint16)
+        cur = np.empty((TABLE_NADIABATS, TABLE_NP), dtype=np.float32)
+        self._check(self.lib.xp_tables_get(self.handle, idx.ctypes.data, cur.ctypes.data), "xp_tables_get")
+        return idx, cur
+
+    def take_flags(self):
+        f = ctypes.c_uint32(0)
+        self._check(self.lib.xp_take_flags(self.handle, self._stream(), ctypes.byref(f)), "xp_take_flags")
+        return f.value
+
+    def launch_count(self):
+        return int(self.lib.xp_launch_count(self.handle))
+
+    def last_kernel_ms(self):
+        ms = ctypes.c_float(0)
+        self._check(self.lib.xp_last_kernel_ms(self.handle, ctypes.byref(ms)), "xp_last_kernel_ms")
+        return ms.value
+
+    # ---- fused path -----------------------------------------------------------------------
+    def _columns(self, p, t, td):
+        if t.dim() != 2 or td.shape != t.shape:
+            raise ValueError("temperature/dewpoint must be [n_levels, n_columns]")
+        L, N = t.shape
+        if t.dtype != td.dtype or t.dtype != p.dtype:
+            raise TypeError("pressure, temperature and dewpoint must share a dtype")
+        if t.device != td.device or t.device != p.device:
+            raise ValueError("pressure, temperature and dewpoint must be on one device")
+        if N > 1 and (t.stride(1) != 1 or td.stride(1) != 1):
+            raise ValueError("columns must be contiguous (level-major layout)")
+        if t.stride(0) != td.stride(0):
+            raise ValueError("temperature and dewpoint must share their level stride")
+        p1d = p.dim() == 1
+        if p1d:
+            if p.shape[0] != L:
+                raise ValueError("1-D pressure must have n_levels entries")
+            pls = p.stride(0) if L > 1 else 1
+        else:
+            if p.shape != t.shape or (N > 1 and p.stride(1) != 1):
+                raise ValueError("pressure must be [n_levels] or level-major [n_levels, n_columns]")
+            pls = p.stride(0) if L > 1 else N
+        mem = XP_MEM_DEVICE if t.is_cuda else XP_MEM_HOST
+        if t.is_cuda and t.device.index != self.device:
+            raise ValueError(f"tensors are on {t.device}, context is on cuda:{self.device}")
+        ls = t.stride(0) if L > 1 else N
+        return XpColumns(p.data_ptr(), t.data_ptr(), td.data_ptr(), N, L, _dtype_code(t),
+                         max(ls, N), max(pls, 1 if p1d else N), int(p1d), mem), L, N
+
+    def _alloc_out(self, like, N, L, profile, pin):
+        """Output block for one parcel kind: scalars [12, N], shift [N], optional profile [6, L+1, N]."""
+        kw = dict(dtype=like.dtype, device=like.device)
+        pin = pin and not like.is_cuda
+        scal = torch.empty((len(SCALAR_FIELDS), N), pin_memory=pin, **kw)
+        shift = torch.empty((N,), dtype=torch.int32, device=like.device, pin_memory=pin)
+        prof = torch.empty((len(PROFILE_FIELDS), L + 1, N), pin_memory=pin, **kw) if profile else None
+        po = XpParcelOut()
+        for i, f in enumerate(SCALAR_FIELDS):
+            setattr(po, f, scal[i].data_ptr())
+        po.level_shift = shift.data_ptr()
+        if prof is not None:
+            for i, f in enumerate(PROFILE_FIELDS):
+                setattr(po, f, prof[i].data_ptr())
+        po.profile_level_stride = N
+        return po, scal, shift, prof
+
+    def cape_cin(self, p, t, td, kinds=("sb",), options=None, profile=False, explicit=None,
+                 pin_outputs=False):
+        """Run the fused kernel for the requested parcel kinds on level-major torch tensors.
+
+        CUDA tensors: asynchronous on the current stream.  CPU tensors: staged through the
+        device by the library (host path of the C ABI).  Returns {kind: {field: tensor}}.
+        """
+        opts = options if options is not None else make_options()
+        cols, L, N = self._columns(p, t, td)
+        kinds = tuple(kinds)
+        outs, keep = {}, {}
+        for k in kinds:
+            outs[k] = self._alloc_out(t, N, L, profile, pin_outputs)
+        if set(kinds) <= {"sb", "ml", "mu"} and len(kinds) > 1:
+            ptrs = [ctypes.byref(outs[k][0]) if k in outs else None for k in ("sb", "ml", "mu")]
+            st = self.lib.xp_suite(self.handle, ctypes.byref(cols), ctypes.byref(opts), ptrs[0], ptrs[1],
+                                   ptrs[2], self._stream())
+            self._check(st, "xp_suite")
+        else:
+            for k in kinds:
+                pin = None
+                if k == "explicit":
+                    ep, et, etd = [e.contiguous() for e in explicit]
+                    keep[k] = (ep, et, etd)
+                    pin = ctypes.byref(XpParcelIn(ep.data_ptr(), et.data_ptr(), etd.data_ptr()))
+                st = self.lib.xp_cape_cin(self.handle, ctypes.byref(cols), KIND[k], pin,
+                                          ctypes.byref(opts), ctypes.byref(outs[k][0]), self._stream())
+                self._check(st, "xp_cape_cin")
+        res = {}
+        for k in kinds:
+            _, scal, shift, prof = outs[k]
+            d = {f: scal[i] for i, f in enumerate(SCALAR_FIELDS)}
+            d["level_shift"] = shift
+            if prof is not None:
+                for i, f in enumerate(PROFILE_FIELDS):
+                    d[f] = prof[i]
+            res[k] = d
+        return res
+
+    # ---- individually exposed steps (device tensors) ---------------------------------------
+    def lcl(self, p, t, td, options=None):
+        opts = options if options is not None else make_options()
+        p, t, td = [x.contiguous() for x in torch.broadcast_tensors(p, t, td)]
+        out = torch.empty((3,) + tuple(p.shape), dtype=p.dtype, device=p.device)
+        st = self.lib.xp_lcl(self.handle, p.data_ptr(), t.data_ptr(), td.data_ptr(), p.numel(),
+                             _dtype_code(p), ctypes.byref(opts), out[0].data_ptr(), out[1].data_ptr(),
+                             out[2].data_ptr(), self._stream())
+        self._check(st, "xp_lcl")
+        return out[0], out[1], out[2]
+
+    def moist_lapse(self, pressure, parcel_temperature, parcel_pressure):
+        pressure = pressure.contiguous()
+        L, N = pressure.shape
+        pt = parcel_temperature.expand(N).contiguous()
+        pp = parcel_pressure.expand(N).contiguous()
+        out = torch.empty_like(pressure)
+        st = self.lib.xp_moist_lapse(self.handle, pressure.data_ptr(), N, L, N, _dtype_code(pressure),
+                                     pt.data_ptr(), pp.data_ptr(), out.data_ptr(), N, self._stream())
+        self._check(st, "xp_moist_lapse")
+        return out
+
+    def parcel_profile(self, pressure, parcel_pressure, parcel_temperature, parcel_dewpoint,
+                       options=None):
+        opts = options if options is not None else make_options()
+        pressure = pressure.contiguous()
+        L, N = pressure.shape
+        pp = parcel_pressure.expand(N).contiguous()
+        pt = parcel_temperature.expand(N).contiguous()
+        pd = parcel_dewpoint.expand(N).contiguous()
+        out = torch.empty((2, L, N), dtype=pressure.dtype, device=pressure.device)
+        lcl = torch.empty((3, N), dtype=pressure.dtype, device=pressure.device)
+        pin = XpParcelIn(pp.data_ptr(), pt.data_ptr(), pd.data_ptr())
+        st = self.lib.xp_parcel_profile(self.handle, pressure.data_ptr(), N, L, N, _dtype_code(pressure),
+                                        ctypes.byref(pin), ctypes.byref(opts), out[0].data_ptr(),
+                                        out[1].data_ptr(), N, lcl[0].data_ptr(), lcl[1].data_ptr(),
+                                        lcl[2].data_ptr(), self._stream())
+        self._check(st, "xp_parcel_profile")
+        return {"temperature": out[0], "virtual_temperature": out[1], "lcl_pressure": lcl[0],
+                "lcl_temperature": lcl[1], "lcl_virtual_temperature": lcl[2]}
+
+    def lfc_el(self, pressure, parcel_temperature, temperature, lcl_pressure, lcl_temperature):
+        pressure, parcel_temperature, temperature = [x.contiguous() for x in
+                                                     (pressure, parcel_temperature, temperature)]
+        L, N = pressure.shape
+        lp = lcl_pressure.expand(N).contiguous()
+        lt = lcl_temperature.expand(N).contiguous()
+        out = torch.empty((4, N), dtype=pressure.dtype, device=pressure.device)
+        st = self.lib.xp_lfc_el(self.handle, pressure.data_ptr(), parcel_temperature.data_ptr(),
+                                temperature.data_ptr(), N, L, N, _dtype_code(pressure), lp.data_ptr(),
+                                lt.data_ptr(), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                out[3].data_ptr(), self._stream())
+        self._check(st, "xp_lfc_el")
+        return {"lfc_pressure": out[0], "lfc_temperature": out[1], "el_pressure": out[2],
+                "el_temperature": out[3]}
+
+    def cape_cin_base(self, pressure, temperature, lfc_pressure, el_pressure, parcel_temperature,
+                      options=None):
+        opts = options if options is not None else make_options()
+        pressure, temperature, parcel_temperature = [x.contiguous() for x in
+                                                     (pressure, temperature, parcel_temperature)]
+        L, N = pressure.shape
+        lf = lfc_pressure.expand(N).contiguous()
+        el = el_pressure.expand(N).contiguous()
+        out = torch.empty((2, N), dtype=pressure.dtype, device=pressure.device)
+        st = self.lib.xp_cape_cin_base(self.handle, pressure.data_ptr(), temperature.data_ptr(),
+                                       parcel_temperature.data_ptr(), N, L, N, _dtype_code(pressure),
+                                       lf.data_ptr(), el.data_ptr(), ctypes.byref(opts),
+                                       out[0].data_ptr(), out[1].data_ptr(), self._stream())
+        self._check(st, "xp_cape_cin_base")
+        return {"cape": out[0], "cin": out[1]}
+
+
+_contexts = {}
+_ctx_lock = threading.Lock()
+
+
+def get_context(device=None):
+    """Process-wide context per device (the reference keeps its tables in module globals, PF:18-21)."""
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    device = int(device)
+    with _ctx_lock:
+        if device not in _contexts:
+            _contexts[device] = Context(device)
+        return _contexts[device]

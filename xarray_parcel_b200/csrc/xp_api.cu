@@ -1,0 +1,576 @@
+// xp_api.cu -- the C ABI of libxparcel.so (see include/xparcel.h).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/xparcel.h"
+#include "xp_kernels.cuh"
+
+using namespace xp;
+
+namespace {
+std::string g_create_error;
+}
+
+struct xp_context {
+    int device = 0;
+    uint16_t *d_index = nullptr;
+    float *d_curves = nullptr;
+    bool tables = false;
+    uint32_t *d_flags = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    // host-staging pipeline (mem = XP_MEM_HOST)
+    static constexpr int kSlots = 3;
+    cudaStream_t slot_stream[kSlots] = {nullptr, nullptr, nullptr};
+    void *slot_buf[kSlots] = {nullptr, nullptr, nullptr};
+    size_t slot_bytes = 0;
+    std::mutex mu;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+            cudaSetDevice(dev);
+            changed = true;
+        }
+    }
+    ~DeviceGuard() {
+        if (changed) cudaSetDevice(prev);
+    }
+};
+
+xp_status fail(xp_context *ctx, xp_status st, const std::string &msg) {
+    if (ctx) ctx->err = msg;
+    else g_create_error = msg;
+    return st;
+}
+
+xp_status check_cuda(xp_context *ctx, cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return XP_OK;
+    return fail(ctx, XP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define XP_CUDA(ctx, call)                                            \
+    do {                                                              \
+        xp_status _st = check_cuda((ctx), (call), #call);             \
+        if (_st != XP_OK) return _st;                                 \
+    } while (0)
+
+Opts to_opts(const xp_options *o) {
+    xp_options d;
+    xp_default_options(&d);
+    if (o) d = *o;
+    Opts r;
+    r.vtc = d.virtual_temperature_correction != 0;
+    r.log_interp = d.lcl_interp_log != 0;
+    r.pos_neg = d.pos_cape_neg_cin != 0;
+    r.post_zero = d.post_zero_cin != 0;
+    r.compat = d.metpy_compat == 162 ? 162 : 141;
+    r.ml_depth = d.mixed_layer_depth;
+    r.mu_depth = d.most_unstable_depth;
+    return r;
+}
+
+template <typename T>
+OutArg<T> to_out(const xp_parcel_out *o) {
+    OutArg<T> r;
+    std::memset(&r, 0, sizeof(r));
+    if (!o) return r;
+    r.enabled = 1;
+    r.cape = (T *)o->cape; r.cin = (T *)o->cin;
+    r.lcl_p = (T *)o->lcl_pressure; r.lcl_t = (T *)o->lcl_temperature;
+    r.lcl_tv = (T *)o->lcl_virtual_temperature;
+    r.lfc_p = (T *)o->lfc_pressure; r.lfc_t = (T *)o->lfc_temperature;
+    r.el_p = (T *)o->el_pressure; r.el_t = (T *)o->el_temperature;
+    r.par_p = (T *)o->parcel_pressure; r.par_t = (T *)o->parcel_temperature;
+    r.par_td = (T *)o->parcel_dewpoint;
+    r.shift = o->level_shift;
+    r.prof_p = (T *)o->profile_pressure; r.prof_t = (T *)o->profile_temperature;
+    r.prof_tv = (T *)o->profile_virtual_temperature;
+    r.prof_et = (T *)o->profile_environment_temperature;
+    r.prof_etv = (T *)o->profile_environment_virtual_temperature;
+    r.prof_etd = (T *)o->profile_environment_dewpoint;
+    r.prof_ls = o->profile_level_stride;
+    return r;
+}
+
+template <typename T>
+ColsArg<T> to_cols(const xp_columns *c) {
+    ColsArg<T> r;
+    r.p = (const T *)c->pressure; r.t = (const T *)c->temperature; r.td = (const T *)c->dewpoint;
+    r.n = c->n_columns; r.L = c->n_levels;
+    r.ls = c->level_stride; r.pls = c->pressure_level_stride; r.p1d = c->pressure_is_1d != 0;
+    return r;
+}
+
+xp_status validate_cols(xp_context *ctx, const xp_columns *c) {
+    if (!c) return fail(ctx, XP_ERR_INVALID_ARGUMENT, "columns is NULL");
+    if (!c->pressure || !c->temperature || !c->dewpoint)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "pressure/temperature/dewpoint must not be NULL");
+    if (c->n_levels < 1 || c->n_columns < 0)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "n_levels must be >= 1 and n_columns >= 0");
+    if (c->dtype != XP_F32 && c->dtype != XP_F64)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "dtype must be XP_F32 or XP_F64");
+    if (c->level_stride < c->n_columns)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "level_stride must be >= n_columns");
+    if (!c->pressure_is_1d && c->pressure_level_stride < c->n_columns)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "pressure_level_stride must be >= n_columns");
+    if (c->mem != XP_MEM_DEVICE && c->mem != XP_MEM_HOST)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "mem must be XP_MEM_DEVICE or XP_MEM_HOST");
+    return XP_OK;
+}
+
+// Launch the fused kernel on device-resident columns.
+template <typename T>
+xp_status run_device(xp_context *ctx, const xp_columns *cols, int kind_mask,
+                     const xp_parcel_out *const outs[4], const xp_parcel_in *ex, const Opts &o,
+                     cudaStream_t stream, bool time_it) {
+    OutArg<T> oa[4];
+    for (int i = 0; i < 4; ++i) oa[i] = to_out<T>(((kind_mask >> i) & 1) ? outs[i] : nullptr);
+    ParcelArg<T> pa = {nullptr, nullptr, nullptr};
+    if (kind_mask & kEX) {
+        if (!ex || !ex->pressure || !ex->temperature || !ex->dewpoint)
+            return fail(ctx, XP_ERR_INVALID_ARGUMENT, "explicit parcel arrays are required");
+        pa.p = (const T *)ex->pressure; pa.t = (const T *)ex->temperature; pa.td = (const T *)ex->dewpoint;
+    }
+    Tables tb = {ctx->d_index, ctx->d_curves};
+    if (time_it) cudaEventRecord(ctx->ev0, stream);
+    launch_cape_cin<T>(to_cols<T>(cols), tb, o, kind_mask, oa, pa, ctx->d_flags, stream);
+    if (time_it) { cudaEventRecord(ctx->ev1, stream); ctx->ev_valid = true; }
+    ctx->launches += (cols->n_columns > 0) ? 1 : 0;
+    return check_cuda(ctx, cudaGetLastError(), "cape_cin kernel launch");
+}
+
+size_t elt_size(int dtype) { return dtype == XP_F64 ? 8 : 4; }
+
+// Host-resident columns: stream column blocks through the device (H2D, kernel, D2H on
+// kSlots streams so copies of one block overlap the kernel of another).
+xp_status run_host(xp_context *ctx, const xp_columns *cols, int kind_mask,
+                   const xp_parcel_out *const outs[4], const xp_parcel_in *ex, const Opts &o) {
+    const size_t es = elt_size(cols->dtype);
+    const int L = cols->n_levels;
+    const int64_t N = cols->n_columns;
+    if (N == 0) return XP_OK;
+    // per-column device bytes: inputs + every requested output
+    size_t per_col = (size_t)(cols->pressure_is_1d ? 2 : 3) * L * es;
+    int n_scalar[4] = {0, 0, 0, 0}, n_prof[4] = {0, 0, 0, 0};
+    for (int k = 0; k < 4; ++k) {
+        if (!((kind_mask >> k) & 1) || !outs[k]) continue;
+        const xp_parcel_out *q = outs[k];
+        void *sc[] = {q->cape, q->cin, q->lcl_pressure, q->lcl_temperature, q->lcl_virtual_temperature,
+                      q->lfc_pressure, q->lfc_temperature, q->el_pressure, q->el_temperature,
+                      q->parcel_pressure, q->parcel_temperature, q->parcel_dewpoint};
+        for (void *p : sc) n_scalar[k] += p ? 1 : 0;
+        void *pr[] = {q->profile_pressure, q->profile_temperature, q->profile_virtual_temperature,
+                      q->profile_environment_temperature, q->profile_environment_virtual_temperature,
+                      q->profile_environment_dewpoint};
+        for (void *p : pr) n_prof[k] += p ? 1 : 0;
+        per_col += (size_t)n_scalar[k] * es + (q->level_shift ? 4 : 0) + (size_t)n_prof[k] * (L + 1) * es;
+    }
+    if (kind_mask & kEX) per_col += 3 * es;
+    // block size: ~256 MB per slot, multiple of 1024 columns
+    int64_t C = (int64_t)((size_t)256 << 20) / (int64_t)per_col;
+    C = std::max<int64_t>(1024, (C / 1024) * 1024);
+    C = std::min<int64_t>(C, ((N + 1023) / 1024) * 1024);
+    const size_t need = (size_t)C * per_col + 4096;
+    if (need > ctx->slot_bytes) {
+        for (int s = 0; s < xp_context::kSlots; ++s) {
+            if (ctx->slot_buf[s]) { cudaFree(ctx->slot_buf[s]); ctx->slot_buf[s] = nullptr; }
+        }
+        ctx->slot_bytes = 0;
+        for (int s = 0; s < xp_context::kSlots; ++s) XP_CUDA(ctx, cudaMalloc(&ctx->slot_buf[s], need));
+        ctx->slot_bytes = need;
+    }
+    for (int s = 0; s < xp_context::kSlots; ++s)
+        if (!ctx->slot_stream[s]) XP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->slot_stream[s], cudaStreamNonBlocking));
+
+    const char *hp = (const char *)cols->pressure, *ht = (const char *)cols->temperature,
+               *htd = (const char *)cols->dewpoint;
+    int slot = 0;
+    for (int64_t c0 = 0; c0 < N; c0 += C, slot = (slot + 1) % xp_context::kSlots) {
+        const int64_t n = std::min<int64_t>(C, N - c0);
+        cudaStream_t st = ctx->slot_stream[slot];
+        char *base = (char *)ctx->slot_buf[slot];
+        size_t off = 0;
+        auto carve = [&](size_t bytes) { char *p = base + off; off += (bytes + 255) & ~(size_t)255; return p; };
+        // the slot's previous block must be fully drained (its D2H copies are on the same stream,
+        // so stream order already guarantees it)
+        xp_columns dc = *cols;
+        dc.mem = XP_MEM_DEVICE;
+        dc.n_columns = n;
+        dc.level_stride = n;
+        char *dT = carve((size_t)L * n * es), *dTd = carve((size_t)L * n * es), *dP;
+        XP_CUDA(ctx, cudaMemcpy2DAsync(dT, n * es, ht + c0 * es, cols->level_stride * es, n * es, L,
+                                       cudaMemcpyHostToDevice, st));
+        XP_CUDA(ctx, cudaMemcpy2DAsync(dTd, n * es, htd + c0 * es, cols->level_stride * es, n * es, L,
+                                       cudaMemcpyHostToDevice, st));
+        if (cols->pressure_is_1d) {
+            dP = carve((size_t)L * es);
+            XP_CUDA(ctx, cudaMemcpy2DAsync(dP, es, hp, cols->pressure_level_stride * es, es, L,
+                                           cudaMemcpyHostToDevice, st));
+            dc.pressure_level_stride = 1;
+        } else {
+            dP = carve((size_t)L * n * es);
+            XP_CUDA(ctx, cudaMemcpy2DAsync(dP, n * es, hp + c0 * es, cols->pressure_level_stride * es,
+                                           n * es, L, cudaMemcpyHostToDevice, st));
+            dc.pressure_level_stride = n;
+        }
+        dc.pressure = dP; dc.temperature = dT; dc.dewpoint = dTd;
+        xp_parcel_in dex = {nullptr, nullptr, nullptr};
+        if (kind_mask & kEX) {
+            if (!ex || !ex->pressure || !ex->temperature || !ex->dewpoint)
+                return fail(ctx, XP_ERR_INVALID_ARGUMENT, "explicit parcel arrays are required");
+            const void *src[3] = {ex->pressure, ex->temperature, ex->dewpoint};
+            const void **dst[3] = {&dex.pressure, &dex.temperature, &dex.dewpoint};
+            for (int i = 0; i < 3; ++i) {
+                char *d = carve((size_t)n * es);
+                XP_CUDA(ctx, cudaMemcpyAsync(d, (const char *)src[i] + c0 * es, n * es, cudaMemcpyHostToDevice, st));
+                *dst[i] = d;
+            }
+        }
+        // device-side outputs mirror the host layout per block
+        xp_parcel_out dout[4];
+        const xp_parcel_out *douts[4] = {nullptr, nullptr, nullptr, nullptr};
+        struct Copy { char *d; char *h; size_t width; size_t hpitch; int rows; };
+        std::vector<Copy> copies;
+        for (int k = 0; k < 4; ++k) {
+            if (!((kind_mask >> k) & 1) || !outs[k]) continue;
+            const xp_parcel_out *q = outs[k];
+            xp_parcel_out &d = dout[k];
+            std::memset(&d, 0, sizeof(d));
+            void *const hs[] = {q->cape, q->cin, q->lcl_pressure, q->lcl_temperature,
+                                q->lcl_virtual_temperature, q->lfc_pressure, q->lfc_temperature,
+                                q->el_pressure, q->el_temperature, q->parcel_pressure,
+                                q->parcel_temperature, q->parcel_dewpoint};
+            void **ds[] = {&d.cape, &d.cin, &d.lcl_pressure, &d.lcl_temperature,
+                           &d.lcl_virtual_temperature, &d.lfc_pressure, &d.lfc_temperature,
+                           &d.el_pressure, &d.el_temperature, &d.parcel_pressure,
+                           &d.parcel_temperature, &d.parcel_dewpoint};
+            for (int i = 0; i < 12; ++i) {
+                if (!hs[i]) continue;
+                char *p = carve((size_t)n * es);
+                *ds[i] = p;
+                copies.push_back({p, (char *)hs[i] + c0 * es, (size_t)n * es, 0, 1});
+            }
+            if (q->level_shift) {
+                char *p = carve((size_t)n * 4);
+                d.level_shift = (int32_t *)p;
+                copies.push_back({p, (char *)q->level_shift + c0 * 4, (size_t)n * 4, 0, 1});
+            }
+            void *const hpv[] = {q->profile_pressure, q->profile_temperature,
+                                 q->profile_virtual_temperature, q->profile_environment_temperature,
+                                 q->profile_environment_virtual_temperature,
+                                 q->profile_environment_dewpoint};
+            void **dpv[] = {&d.profile_pressure, &d.profile_temperature,
+                            &d.profile_virtual_temperature, &d.profile_environment_temperature,
+                            &d.profile_environment_virtual_temperature,
+                            &d.profile_environment_dewpoint};
+            d.profile_level_stride = n;
+            for (int i = 0; i < 6; ++i) {
+                if (!hpv[i]) continue;
+                char *p = carve((size_t)(L + 1) * n * es);
+                *dpv[i] = p;
+                copies.push_back({p, (char *)hpv[i] + c0 * es, (size_t)n * es,
+                                  (size_t)q->profile_level_stride * es, L + 1});
+            }
+            douts[k] = &d;
+        }
+        xp_status stt = (cols->dtype == XP_F32)
+                            ? run_device<float>(ctx, &dc, kind_mask, douts, &dex, o, st, false)
+                            : run_device<double>(ctx, &dc, kind_mask, douts, &dex, o, st, false);
+        if (stt != XP_OK) return stt;
+        for (const Copy &c : copies) {
+            if (c.rows == 1)
+                XP_CUDA(ctx, cudaMemcpyAsync(c.h, c.d, c.width, cudaMemcpyDeviceToHost, st));
+            else
+                XP_CUDA(ctx, cudaMemcpy2DAsync(c.h, c.hpitch, c.d, c.width, c.width, c.rows,
+                                               cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (int s = 0; s < xp_context::kSlots; ++s) XP_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
+    return XP_OK;
+}
+
+xp_status run_any(xp_context *ctx, const xp_columns *cols, int kind_mask,
+                  const xp_parcel_out *const outs[4], const xp_parcel_in *ex, const xp_options *opts,
+                  void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    xp_status st = validate_cols(ctx, cols);
+    if (st != XP_OK) return st;
+    if (!ctx->tables)
+        return fail(ctx, XP_ERR_TABLES_NOT_LOADED, "Call load_moist_adiabat_lookups first.");
+    DeviceGuard guard(ctx->device);
+    const Opts o = to_opts(opts);
+    if (cols->mem == XP_MEM_HOST) return run_host(ctx, cols, kind_mask, outs, ex, o);
+    if (cols->dtype == XP_F32)
+        return run_device<float>(ctx, cols, kind_mask, outs, ex, o, (cudaStream_t)stream, true);
+    return run_device<double>(ctx, cols, kind_mask, outs, ex, o, (cudaStream_t)stream, true);
+}
+
+}  // namespace
+
+// ================================================================================ C ABI
+extern "C" {
+
+const char *xp_version(void) { return "xparcel-b200 0.1 (sm_100a)"; }
+
+void xp_default_options(xp_options *o) {
+    if (!o) return;
+    o->virtual_temperature_correction = 1;
+    o->lcl_interp_log = 1;
+    o->pos_cape_neg_cin = 1;
+    o->post_zero_cin = 0;
+    o->metpy_compat = 141;
+    o->reserved = 0;
+    o->mixed_layer_depth = 100.0;
+    o->most_unstable_depth = 300.0;
+}
+
+xp_status xp_create(int device, xp_context **out_ctx) {
+    if (!out_ctx) return fail(nullptr, XP_ERR_INVALID_ARGUMENT, "out_ctx is NULL");
+    *out_ctx = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, XP_ERR_NO_DEVICE,
+                    std::string("no CUDA device: ") + (e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)));
+    if (device < 0 || device >= count)
+        return fail(nullptr, XP_ERR_INVALID_ARGUMENT, "device index out of range");
+    xp_context *ctx = new xp_context();
+    ctx->device = device;
+    DeviceGuard guard(device);
+    if ((e = cudaMalloc(&ctx->d_flags, sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMemset(ctx->d_flags, 0, sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
+        g_create_error = std::string("xp_create: ") + cudaGetErrorString(e);
+        delete ctx;
+        return XP_ERR_CUDA;
+    }
+    *out_ctx = ctx;
+    return XP_OK;
+}
+
+void xp_destroy(xp_context *ctx) {
+    if (!ctx) return;
+    {
+        DeviceGuard guard(ctx->device);
+        cudaFree(ctx->d_index);
+        cudaFree(ctx->d_curves);
+        cudaFree(ctx->d_flags);
+        for (int s = 0; s < xp_context::kSlots; ++s) {
+            if (ctx->slot_buf[s]) cudaFree(ctx->slot_buf[s]);
+            if (ctx->slot_stream[s]) cudaStreamDestroy(ctx->slot_stream[s]);
+        }
+        if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+        if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    }
+    delete ctx;
+}
+
+const char *xp_last_error(const xp_context *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+xp_status xp_take_flags(xp_context *ctx, void *stream, uint32_t *out_flags) {
+    if (!ctx || !out_flags) return XP_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    XP_CUDA(ctx, cudaMemcpyAsync(out_flags, ctx->d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    XP_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(uint32_t), st));
+    XP_CUDA(ctx, cudaStreamSynchronize(st));
+    return XP_OK;
+}
+
+static xp_status ensure_table_memory(xp_context *ctx) {
+    if (!ctx->d_index) XP_CUDA(ctx, cudaMalloc(&ctx->d_index, (size_t)kNP * kNT * sizeof(uint16_t)));
+    if (!ctx->d_curves) XP_CUDA(ctx, cudaMalloc(&ctx->d_curves, (size_t)kNAdiabats * kNP * sizeof(float)));
+    return XP_OK;
+}
+
+xp_status xp_tables_build(xp_context *ctx, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    xp_status st = ensure_table_memory(ctx);
+    if (st != XP_OK) return st;
+    uint32_t *scratch = nullptr;
+    XP_CUDA(ctx, cudaMalloc(&scratch, (size_t)kNP * kNT * sizeof(uint32_t)));
+    launch_build_tables(ctx->d_index, ctx->d_curves, scratch, (cudaStream_t)stream);
+    ctx->launches += 2;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(scratch);
+    XP_CUDA(ctx, e);
+    ctx->tables = true;
+    return XP_OK;
+}
+
+xp_status xp_tables_set(xp_context *ctx, const uint16_t *index_grid_host, const float *curves_host) {
+    if (!ctx || !index_grid_host || !curves_host) return XP_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    xp_status st = ensure_table_memory(ctx);
+    if (st != XP_OK) return st;
+    XP_CUDA(ctx, cudaMemcpy(ctx->d_index, index_grid_host, (size_t)kNP * kNT * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    XP_CUDA(ctx, cudaMemcpy(ctx->d_curves, curves_host, (size_t)kNAdiabats * kNP * sizeof(float), cudaMemcpyHostToDevice));
+    ctx->tables = true;
+    return XP_OK;
+}
+
+xp_status xp_tables_get(xp_context *ctx, uint16_t *index_grid_host, float *curves_host) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (!ctx->tables) return fail(ctx, XP_ERR_TABLES_NOT_LOADED, "Call load_moist_adiabat_lookups first.");
+    DeviceGuard guard(ctx->device);
+    if (index_grid_host)
+        XP_CUDA(ctx, cudaMemcpy(index_grid_host, ctx->d_index, (size_t)kNP * kNT * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    if (curves_host)
+        XP_CUDA(ctx, cudaMemcpy(curves_host, ctx->d_curves, (size_t)kNAdiabats * kNP * sizeof(float), cudaMemcpyDeviceToHost));
+    return XP_OK;
+}
+
+int xp_tables_loaded(const xp_context *ctx) { return ctx && ctx->tables ? 1 : 0; }
+
+xp_status xp_cape_cin(xp_context *ctx, const xp_columns *cols, int32_t kind,
+                      const xp_parcel_in *explicit_parcel, const xp_options *opts,
+                      const xp_parcel_out *out, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (kind < 0 || kind > 3) return fail(ctx, XP_ERR_INVALID_ARGUMENT, "unknown parcel kind");
+    if (!out) return fail(ctx, XP_ERR_INVALID_ARGUMENT, "out is NULL");
+    const xp_parcel_out *outs[4] = {nullptr, nullptr, nullptr, nullptr};
+    outs[kind] = out;
+    return run_any(ctx, cols, 1 << kind, outs, explicit_parcel, opts, stream);
+}
+
+xp_status xp_suite(xp_context *ctx, const xp_columns *cols, const xp_options *opts,
+                   const xp_parcel_out *out_sb, const xp_parcel_out *out_ml,
+                   const xp_parcel_out *out_mu, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    const xp_parcel_out *outs[4] = {out_sb, out_ml, out_mu, nullptr};
+    int mask = (out_sb ? kSB : 0) | (out_ml ? kML : 0) | (out_mu ? kMU : 0);
+    if (!mask) return fail(ctx, XP_ERR_INVALID_ARGUMENT, "no outputs requested");
+    return run_any(ctx, cols, mask, outs, nullptr, opts, stream);
+}
+
+#define XP_DISPATCH(dtype, CALL_F32, CALL_F64)                                  \
+    do {                                                                        \
+        if ((dtype) == XP_F32) { CALL_F32; }                                    \
+        else if ((dtype) == XP_F64) { CALL_F64; }                               \
+        else return fail(ctx, XP_ERR_INVALID_ARGUMENT, "dtype must be XP_F32 or XP_F64"); \
+    } while (0)
+
+xp_status xp_lcl(xp_context *ctx, const void *p, const void *t, const void *td, int64_t n,
+                 int32_t dtype, const xp_options *opts, void *lcl_p, void *lcl_t, void *lcl_tv,
+                 void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (!p || !t || !td || n < 0) return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad lcl arguments");
+    DeviceGuard guard(ctx->device);
+    const Opts o = to_opts(opts);
+    cudaStream_t st = (cudaStream_t)stream;
+    XP_DISPATCH(dtype,
+                launch_lcl<float>((const float *)p, (const float *)t, (const float *)td, n, o, (float *)lcl_p, (float *)lcl_t, (float *)lcl_tv, st),
+                launch_lcl<double>((const double *)p, (const double *)t, (const double *)td, n, o, (double *)lcl_p, (double *)lcl_t, (double *)lcl_tv, st));
+    ctx->launches += n > 0;
+    return check_cuda(ctx, cudaGetLastError(), "lcl kernel launch");
+}
+
+xp_status xp_moist_lapse(xp_context *ctx, const void *pressure, int64_t level_stride,
+                         int32_t n_levels, int64_t n_columns, int32_t dtype,
+                         const void *parcel_temperature, const void *parcel_pressure,
+                         void *out_temperature, int64_t out_level_stride, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (!ctx->tables) return fail(ctx, XP_ERR_TABLES_NOT_LOADED, "Call load_moist_adiabat_lookups first.");
+    if (!pressure || !parcel_temperature || !parcel_pressure || !out_temperature)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad moist_lapse arguments");
+    DeviceGuard guard(ctx->device);
+    Tables tb = {ctx->d_index, ctx->d_curves};
+    cudaStream_t st = (cudaStream_t)stream;
+    XP_DISPATCH(dtype,
+                launch_moist_lapse<float>((const float *)pressure, level_stride, n_levels, n_columns, tb, (const float *)parcel_temperature, (const float *)parcel_pressure, (float *)out_temperature, out_level_stride, st),
+                launch_moist_lapse<double>((const double *)pressure, level_stride, n_levels, n_columns, tb, (const double *)parcel_temperature, (const double *)parcel_pressure, (double *)out_temperature, out_level_stride, st));
+    ctx->launches += n_columns > 0;
+    return check_cuda(ctx, cudaGetLastError(), "moist_lapse kernel launch");
+}
+
+xp_status xp_parcel_profile(xp_context *ctx, const void *pressure, int64_t level_stride,
+                            int32_t n_levels, int64_t n_columns, int32_t dtype,
+                            const xp_parcel_in *parcel, const xp_options *opts,
+                            void *out_temperature, void *out_virtual_temperature,
+                            int64_t out_level_stride, void *lcl_pressure, void *lcl_temperature,
+                            void *lcl_virtual_temperature, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (!ctx->tables) return fail(ctx, XP_ERR_TABLES_NOT_LOADED, "Call load_moist_adiabat_lookups first.");
+    if (!pressure || !parcel || !parcel->pressure || !parcel->temperature || !parcel->dewpoint)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad parcel_profile arguments");
+    DeviceGuard guard(ctx->device);
+    Tables tb = {ctx->d_index, ctx->d_curves};
+    const Opts o = to_opts(opts);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == XP_F32) {
+        ParcelArg<float> pa = {(const float *)parcel->pressure, (const float *)parcel->temperature, (const float *)parcel->dewpoint};
+        launch_parcel_profile<float>((const float *)pressure, level_stride, n_levels, n_columns, tb, o, pa, (float *)out_temperature, (float *)out_virtual_temperature, out_level_stride, (float *)lcl_pressure, (float *)lcl_temperature, (float *)lcl_virtual_temperature, st);
+    } else if (dtype == XP_F64) {
+        ParcelArg<double> pa = {(const double *)parcel->pressure, (const double *)parcel->temperature, (const double *)parcel->dewpoint};
+        launch_parcel_profile<double>((const double *)pressure, level_stride, n_levels, n_columns, tb, o, pa, (double *)out_temperature, (double *)out_virtual_temperature, out_level_stride, (double *)lcl_pressure, (double *)lcl_temperature, (double *)lcl_virtual_temperature, st);
+    } else {
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "dtype must be XP_F32 or XP_F64");
+    }
+    ctx->launches += n_columns > 0;
+    return check_cuda(ctx, cudaGetLastError(), "parcel_profile kernel launch");
+}
+
+xp_status xp_lfc_el(xp_context *ctx, const void *pressure, const void *parcel_temperature,
+                    const void *temperature, int64_t level_stride, int32_t n_levels,
+                    int64_t n_columns, int32_t dtype, const void *lcl_pressure,
+                    const void *lcl_temperature, void *lfc_pressure, void *lfc_temperature,
+                    void *el_pressure, void *el_temperature, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (!pressure || !parcel_temperature || !temperature || !lcl_pressure || !lcl_temperature)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad lfc_el arguments");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    XP_DISPATCH(dtype,
+                launch_lfc_el<float>((const float *)pressure, (const float *)parcel_temperature, (const float *)temperature, level_stride, n_levels, n_columns, (const float *)lcl_pressure, (const float *)lcl_temperature, (float *)lfc_pressure, (float *)lfc_temperature, (float *)el_pressure, (float *)el_temperature, ctx->d_flags, st),
+                launch_lfc_el<double>((const double *)pressure, (const double *)parcel_temperature, (const double *)temperature, level_stride, n_levels, n_columns, (const double *)lcl_pressure, (const double *)lcl_temperature, (double *)lfc_pressure, (double *)lfc_temperature, (double *)el_pressure, (double *)el_temperature, ctx->d_flags, st));
+    ctx->launches += n_columns > 0;
+    return check_cuda(ctx, cudaGetLastError(), "lfc_el kernel launch");
+}
+
+xp_status xp_cape_cin_base(xp_context *ctx, const void *pressure, const void *temperature,
+                           const void *parcel_temperature, int64_t level_stride,
+                           int32_t n_levels, int64_t n_columns, int32_t dtype,
+                           const void *lfc_pressure, const void *el_pressure,
+                           const xp_options *opts, void *cape, void *cin, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (!pressure || !temperature || !parcel_temperature || !lfc_pressure || !el_pressure)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad cape_cin_base arguments");
+    DeviceGuard guard(ctx->device);
+    const Opts o = to_opts(opts);
+    cudaStream_t st = (cudaStream_t)stream;
+    XP_DISPATCH(dtype,
+                launch_cape_cin_base<float>((const float *)pressure, (const float *)temperature, (const float *)parcel_temperature, level_stride, n_levels, n_columns, (const float *)lfc_pressure, (const float *)el_pressure, o, (float *)cape, (float *)cin, st),
+                launch_cape_cin_base<double>((const double *)pressure, (const double *)temperature, (const double *)parcel_temperature, level_stride, n_levels, n_columns, (const double *)lfc_pressure, (const double *)el_pressure, o, (double *)cape, (double *)cin, st));
+    ctx->launches += n_columns > 0;
+    return check_cuda(ctx, cudaGetLastError(), "cape_cin_base kernel launch");
+}
+
+uint64_t xp_launch_count(const xp_context *ctx) { return ctx ? ctx->launches : 0; }
+
+xp_status xp_last_kernel_ms(xp_context *ctx, float *out_ms) {
+    if (!ctx || !out_ms) return XP_ERR_INVALID_ARGUMENT;
+    if (!ctx->ev_valid) return fail(ctx, XP_ERR_INVALID_ARGUMENT, "no timed launch yet");
+    DeviceGuard guard(ctx->device);
+    XP_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    XP_CUDA(ctx, cudaEventElapsedTime(out_ms, ctx->ev0, ctx->ev1));
+    return XP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+// xp_kernels.cuh -- kernel argument structs and launch prototypes shared by the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "xp_column.cuh"
+
+namespace xp {
+
+// Environment columns in device memory (level-major).
+template <typename T>
+struct ColsArg {
+    const T *p, *t, *td;
+    int64_t n;          // columns
+    int L;              // levels
+    int64_t ls;         // level stride of t/td
+    int64_t pls;        // level stride of p
+    int p1d;            // pressure is a shared 1-D axis
+};
+
+// Outputs of one parcel kind (any pointer may be null).
+template <typename T>
+struct OutArg {
+    T *cape, *cin, *lcl_p, *lcl_t, *lcl_tv, *lfc_p, *lfc_t, *el_p, *el_t;
+    T *par_p, *par_t, *par_td;
+    int32_t *shift;
+    T *prof_p, *prof_t, *prof_tv, *prof_et, *prof_etv, *prof_etd;
+    int64_t prof_ls;
+    int enabled;
+};
+
+template <typename T>
+struct ParcelArg {
+    const T *p, *t, *td;     // explicit parcel [n]
+};
+
+enum KindBits { kSB = 1, kML = 2, kMU = 4, kEX = 8 };
+
+template <typename T>
+void launch_cape_cin(const ColsArg<T> &cols, const Tables &tb, const Opts &o, int kind_mask,
+                     const OutArg<T> *outs /*[4]: SB, ML, MU, EX*/, const ParcelArg<T> &ex,
+                     uint32_t *flags, cudaStream_t stream);
+
+template <typename T>
+void launch_lcl(const T *p, const T *t, const T *td, int64_t n, const Opts &o, T *lcl_p, T *lcl_t,
+                T *lcl_tv, cudaStream_t stream);
+
+template <typename T>
+void launch_moist_lapse(const T *pressure, int64_t ls, int L, int64_t n, const Tables &tb,
+                        const T *parcel_t, const T *parcel_p, T *out, int64_t out_ls,
+                        cudaStream_t stream);
+
+template <typename T>
+void launch_parcel_profile(const T *pressure, int64_t ls, int L, int64_t n, const Tables &tb,
+                           const Opts &o, const ParcelArg<T> &parcel, T *out_t, T *out_tv,
+                           int64_t out_ls, T *lcl_p, T *lcl_t, T *lcl_tv, cudaStream_t stream);
+
+template <typename T>
+void launch_lfc_el(const T *pressure, const T *parcel_t, const T *env_t, int64_t ls, int L,
+                   int64_t n, const T *lcl_p, const T *lcl_t, T *lfc_p, T *lfc_t, T *el_p, T *el_t,
+                   uint32_t *flags, cudaStream_t stream);
+
+template <typename T>
+void launch_cape_cin_base(const T *pressure, const T *env_t, const T *parcel_t, int64_t ls, int L,
+                          int64_t n, const T *lfc_p, const T *el_p, const Opts &o, T *cape, T *cin,
+                          cudaStream_t stream);
+
+// Table builder (xp_tables.cu): fills index_grid (uint16 [kNP][kNT]) and curves (float
+// [kNAdiabats][kNP] ascending pressure).  `scratch_u32` must hold kNP*kNT uint32.
+void launch_build_tables(uint16_t *index_grid, float *curves, uint32_t *scratch_u32,
+                         cudaStream_t stream);
+
+}  // namespace xp

@@ -1,0 +1,603 @@
+"""Drop-in host layer for the parcel path of ``modules/parcel_functions.py`` ("PF").
+
+Same function names, argument meaning, defaults, returned variable names/attrs and
+``AssertionError`` messages as the reference, for the hot path named in BASELINE.json.  The
+work is done by hand-written sm_100a kernels behind the C ABI of ``libxparcel.so``
+(include/xparcel.h); this module only unwraps arrays into level-major buffers and wraps
+the results.  There is no CPU implementation here: without the CUDA library or a GPU every
+compute call raises.
+
+Accepted inputs
+  * ``xarray.DataArray`` (when xarray is installed): ``vert_dim`` names the vertical
+    dimension; results are ``xarray.Dataset``/``DataArray`` with the same dims/coords.
+  * ``numpy.ndarray`` / ``torch.Tensor``: ``vert_axis`` (default 0) is the vertical axis;
+    results come back in a ``Dataset`` (a dict with attribute access) of the same array
+    type.  CUDA tensors are used in place (zero copy); host arrays go through the
+    library's pinned staging pipeline.
+
+Units: hPa and K (README.md:9).  Level 0 is the surface; pressure must decrease with level.
+"""
+
+import numpy as np
+import torch
+
+from . import _lib
+
+try:  # optional: the reference's container types
+    import xarray as _xr
+except Exception:  # pragma: no cover - xarray is absent in the build image
+    _xr = None
+
+__all__ = ["load_moist_adiabat_lookups", "lookup_tables_loaded", "moist_adiabat_tables", "lcl",
+           "dry_lapse", "moist_lapse", "mixing_ratio", "virtual_temperature", "parcel_profile",
+           "parcel_profile_with_lcl", "lfc_el", "cape_cin_base", "cape_cin",
+           "surface_based_cape_cin", "mixed_layer_cape_cin", "most_unstable_cape_cin",
+           "mixed_parcel", "most_unstable_parcel", "mix_layer", "from_most_unstable_parcel",
+           "parcel_suite", "Dataset"]
+
+KAPPA = 0.28571428571428564       # metpy.constants.kappa (PF:313)
+
+# variable metadata of the reference (PF:669-677, 769-770, 849-852, 1188-1196, 1366-1385)
+_ATTRS = {
+    "lcl_pressure": {"long_name": "Lifting condensation level pressure", "units": "hPa"},
+    "lcl_temperature": {"long_name": "Lifting condensation level temperature", "units": "K"},
+    "lcl_virtual_temperature": {"long_name": "Lifting condensation level virtual temperature",
+                                "units": "K"},
+    "lfc_pressure": {"long_name": "Level of free convection pressure", "units": "hPa"},
+    "lfc_temperature": {"long_name": "Level of free convection temperature", "units": "K"},
+    "el_pressure": {"long_name": "Equilibrium level pressure", "units": "hPa"},
+    "el_temperature": {"long_name": "Equilibrium level temperature", "units": "K"},
+    "cape": {"long_name": "Convective available potential energy", "units": "J kg$^{-1}$"},
+    "cin": {"long_name": "Convective inhibition", "units": "J kg$^{-1}$"},
+    "pressure": {"long_name": "Pressure at LCL"},                       # PF:890 (sic)
+    "temperature": {"long_name": "Temperature at LCL", "units": "K"},   # PF:889 (sic)
+    "virtual_temperature": {"long_name": "Virtual temperature", "units": "K"},
+    "environment_temperature": {"long_name": "Environment temperature", "units": "K"},
+    "environment_dewpoint": {"long_name": "Environment dewpoint", "units": "K"},
+    "environment_virtual_temperature": {"long_name": "Virtual temperature", "units": "K"},
+}
+
+
+class Dataset(dict):
+    """Minimal stand-in for ``xarray.Dataset`` when inputs are plain arrays: a dict of arrays
+    with attribute access, ``attrs`` and per-variable ``var_attrs``."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.attrs = {}
+        self.var_attrs = {}
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError as e:
+            raise AttributeError(name) from e
+
+    def rename(self, mapping):
+        out = Dataset((mapping.get(k, k), v) for k, v in self.items())
+        out.attrs = dict(self.attrs)
+        out.var_attrs = {mapping.get(k, k): v for k, v in self.var_attrs.items()}
+        return out
+
+
+# ----------------------------------------------------------------------------- table state
+def load_moist_adiabat_lookups(device=None, tables=None, **kwargs):
+    """PF:39-54.  Build the two moist-adiabat lookup tables on the GPU (PF:447-523 takes ~100 s
+    of SciPy solves; the CUDA builder a few ms), or install caller-provided ones
+    (``tables=(index_grid uint16 [2196, 7150], curves float32 [14300, 2196])``)."""
+    ctx = _lib.get_context(device)
+    if tables is not None:
+        ctx.tables_set(tables[0], tables[1])
+    else:
+        ctx.tables_build()
+    return ctx
+
+
+def lookup_tables_loaded(device=None):
+    """PF:56-61."""
+    assert _lib.get_context(device).tables_loaded(), "Call load_moist_adiabat_lookups first."
+
+
+def moist_adiabat_tables(regenerate=False, cache=True, device=None, **kwargs):
+    """PF:318-356: returns (index_grid, curves) as NumPy arrays (uint16 [2196, 7150] on descending
+    pressure x temperature, float32 [14300, 2196] on ascending pressure)."""
+    ctx = _lib.get_context(device)
+    if regenerate or not ctx.tables_loaded():
+        ctx.tables_build()
+    return ctx.tables_get()
+
+
+# ----------------------------------------------------------------------------- (un)wrapping
+class _Layout:
+    """How an input field maps to level-major [L, N] blocks and how results map back."""
+
+    def __init__(self, template, vert_dim, vert_axis):
+        self.is_xr = _xr is not None and isinstance(template, _xr.DataArray)
+        self.template = template
+        if self.is_xr:
+            self.vert_dim = vert_dim
+            self.vert_axis = template.dims.index(vert_dim) if vert_dim in template.dims else None
+            arr = template.data
+        else:
+            self.vert_dim = vert_dim
+            self.vert_axis = vert_axis
+            arr = template
+        self.is_torch = isinstance(arr, torch.Tensor)
+        self.shape = tuple(arr.shape)
+        va = self.vert_axis
+        self.L = self.shape[va] if va is not None else 1
+        self.col_shape = tuple(s for i, s in enumerate(self.shape) if i != va)
+
+    def to_block(self, x, device, dtype):
+        """Any input -> torch tensor [L, N] (or [L] for a 1-D pressure axis), level-major."""
+        if self.is_xr and _xr is not None and isinstance(x, _xr.DataArray):
+            if x.dims != self.template.dims:
+                if set(x.dims) == {self.vert_dim}:
+                    x = x.data
+                    t = torch.as_tensor(np.asarray(x)) if not isinstance(x, torch.Tensor) else x
+                    return t.to(dtype)
+                x = x.broadcast_like(self.template).transpose(*self.template.dims)
+            x = x.data
+        if not isinstance(x, torch.Tensor):
+            x = np.asarray(x)
+            if x.dtype not in (np.float32, np.float64):
+                x = x.astype(np.float64)
+            x = torch.from_numpy(np.ascontiguousarray(x)) if x.ndim else torch.tensor(float(x))
+        if x.dtype != dtype:
+            x = x.to(dtype)
+        if x.dim() == 1 and len(self.shape) > 1 and x.shape[0] == self.L:
+            return x                                          # shared 1-D vertical axis
+        if tuple(x.shape) != self.shape:
+            x = x.expand(self.shape)
+        va = self.vert_axis
+        if va != 0:
+            x = x.movedim(va, 0)
+        x = x.reshape(self.L, -1)
+        if x.shape[1] > 1 and x.stride(1) != 1:
+            x = x.contiguous()
+        if x.shape[0] > 1 and x.stride(0) < x.shape[1]:
+            x = x.contiguous()
+        return x
+
+    def scalar_to_block(self, x, dtype):
+        """Per-column quantity (no vertical dim) -> torch [N]."""
+        if self.is_xr and _xr is not None and isinstance(x, _xr.DataArray):
+            dims = tuple(d for d in self.template.dims if d != self.vert_dim)
+            if x.dims != dims:
+                x = x.broadcast_like(self.template.isel({self.vert_dim: 0}, drop=True)).transpose(*dims)
+            x = x.data
+        if not isinstance(x, torch.Tensor):
+            x = torch.as_tensor(np.asarray(x, dtype=np.float64))
+        x = x.to(dtype)
+        n = int(np.prod(self.col_shape)) if self.col_shape else 1
+        if x.numel() == 1:
+            return x.reshape(1).expand(n)
+        return x.expand(self.col_shape).reshape(n)
+
+    def _finish(self, t):
+        if self.is_torch:
+            return t
+        return t.cpu().numpy() if t.is_cuda else t.numpy()
+
+    def wrap_scalar(self, t, name):
+        t = self._finish(t.reshape(self.col_shape))
+        if self.is_xr:
+            dims = tuple(d for d in self.template.dims if d != self.vert_dim)
+            coords = {k: v for k, v in self.template.coords.items()
+                      if self.vert_dim not in v.dims}
+            return _xr.DataArray(t, dims=dims, coords=coords, name=name, attrs=dict(_ATTRS.get(name, {})))
+        return t
+
+    def wrap_profile(self, t, name, n_levels):
+        """[n_levels, N] -> original dim order with the vertical axis re-labelled 0..n-1
+        offset by the template's first label (PF:968-970)."""
+        va = self.vert_axis if self.vert_axis is not None else 0
+        t = t[:n_levels].reshape((n_levels,) + self.col_shape)
+        if va != 0:
+            t = t.movedim(0, va)
+        t = self._finish(t)
+        if self.is_xr:
+            first = self.template[self.vert_dim].values[0] if self.vert_dim in self.template.coords else 0
+            coords = {k: v for k, v in self.template.coords.items() if self.vert_dim not in v.dims}
+            coords[self.vert_dim] = np.arange(n_levels) + first
+            return _xr.DataArray(t, dims=self.template.dims, coords=coords, name=name,
+                                 attrs=dict(_ATTRS.get(name, {})))
+        return t
+
+    def dataset(self, variables):
+        if self.is_xr:
+            return _xr.Dataset(variables)
+        ds = Dataset(variables)
+        ds.var_attrs = {k: dict(_ATTRS.get(k, {})) for k in variables}
+        return ds
+
+
+def _prepare(pressure, temperature, dewpoint, vert_dim, vert_axis, device):
+    lay = _Layout(temperature, vert_dim, vert_axis)
+    raw = temperature.data if lay.is_xr else temperature
+    if isinstance(raw, torch.Tensor):
+        dtype = raw.dtype if raw.dtype in (torch.float32, torch.float64) else torch.float64
+        dev = raw.device
+    else:
+        raw = np.asarray(raw)
+        dtype = torch.float32 if raw.dtype == np.float32 else torch.float64
+        dev = torch.device("cpu")
+    t = lay.to_block(temperature, dev, dtype)
+    td = lay.to_block(dewpoint, dev, dtype)
+    p = lay.to_block(pressure, dev, dtype)
+    if t.stride(0) != td.stride(0):
+        td = td.contiguous()
+        t = t.contiguous()
+    ctx = _lib.get_context(device if device is not None else (dev.index if dev.type == "cuda" else None))
+    return lay, ctx, p.to(dev), t, td
+
+
+def _options(kwargs):
+    known = ("virtual_temperature_correction", "lcl_interp", "pos_cape_neg_cin", "post_zero_cin",
+             "metpy_compat")
+    return {k: kwargs[k] for k in known if k in kwargs}
+
+
+def _check_flags(ctx):
+    flags = ctx.take_flags()
+    assert not (flags & _lib.FLAG_PRESSURES_NOT_UNIQUE), "Vertical pressures are not unique"   # PF:131
+    assert not (flags & _lib.FLAG_TOP_TEMPERATURE_NAN), "Top temperature is NaN."              # PF:1149
+
+
+_PROFILE_VARS = [("pressure", "profile_pressure"), ("temperature", "profile_temperature"),
+                 ("virtual_temperature", "profile_virtual_temperature"),
+                 ("environment_temperature", "profile_environment_temperature"),
+                 ("environment_virtual_temperature", "profile_environment_virtual_temperature"),
+                 ("environment_dewpoint", "profile_environment_dewpoint")]
+_SCALAR_VARS = ["lcl_pressure", "lcl_temperature", "lcl_virtual_temperature", "lfc_pressure",
+                "lfc_temperature", "el_pressure", "el_temperature"]
+
+
+def _profile_levels(kind, res, L):
+    """Vertical length of the returned profile: the reference trims levels that are NaN in
+    every column with dropna(how='all') before lifting (PF:1552, PF:1637)."""
+    if kind in ("sb", "explicit"):
+        return L + 1
+    shift = res["level_shift"]
+    min_shift = int(shift.min().item()) if shift.numel() else 0
+    min_shift = min(min_shift, L - 1) if kind == "mu" else min(min_shift, L)
+    return (L - min_shift) + (1 if kind == "ml" else 0) + 1
+
+
+def _run(kind, pressure, temperature, dewpoint, vert_dim, vert_axis, device, profile, explicit=None,
+         depth=None, **kwargs):
+    lay, ctx, p, t, td = _prepare(pressure, temperature, dewpoint, vert_dim, vert_axis, device)
+    okw = _options(kwargs)
+    if depth is not None:
+        okw["mixed_layer_depth" if kind == "ml" else "most_unstable_depth"] = depth
+    opts = _lib.make_options(**okw)
+    ex = None
+    if explicit is not None:
+        ex = [lay.scalar_to_block(e, t.dtype).to(t.device) for e in explicit]
+    res = ctx.cape_cin(p, t, td, kinds=(kind,), options=opts, profile=profile, explicit=ex)[kind]
+    _check_flags(ctx)
+    cc = lay.dataset({"cape": lay.wrap_scalar(res["cape"], "cape"),
+                      "cin": lay.wrap_scalar(res["cin"], "cin")})
+    vtc = okw.get("virtual_temperature_correction", True)
+    cc.attrs["correction"] = ("Virtual temperature correction used in CAPE/CIN calculations." if vtc else
+                              "Virtual temperature correction not used in CAPE/CIN calculations.")
+    pv = {}
+    if profile:
+        n_lev = _profile_levels(kind, res, lay.L)
+        for name, key in _PROFILE_VARS:
+            pv[name] = lay.wrap_profile(res[key], name, n_lev)
+    for name in _SCALAR_VARS:
+        pv[name] = lay.wrap_scalar(res[name], name)
+    prof = lay.dataset(pv)
+    parcel = lay.dataset({"pressure": lay.wrap_scalar(res["parcel_pressure"], "pressure"),
+                          "temperature": lay.wrap_scalar(res["parcel_temperature"], "temperature"),
+                          "dewpoint": lay.wrap_scalar(res["parcel_dewpoint"], "dewpoint")})
+    return cc, prof, parcel, lay, res
+
+
+def _describe(cc, cape_desc, cin_desc, prefix):
+    if isinstance(cc, Dataset):
+        cc.var_attrs.setdefault("cape", {})["description"] = cape_desc
+        cc.var_attrs.setdefault("cin", {})["description"] = cin_desc
+    else:
+        cc["cape"].attrs["description"] = cape_desc
+        cc["cin"].attrs["description"] = cin_desc
+    if prefix is not None:
+        cc = cc.rename({"cape": prefix + "_cape", "cin": prefix + "_cin"})
+    return cc
+
+
+# ----------------------------------------------------------------------------- public API
+def cape_cin(pressure, temperature, dewpoint, parcel_temperature, parcel_pressure, parcel_dewpoint,
+             vert_dim="model_level_number", virtual_temperature_correction=True, lcl_interp="log",
+             vert_axis=0, device=None, profile=True, **kwargs):
+    """PF:1394-1475.  Returns (Dataset{cape, cin}, profile Dataset incl. LCL/LFC/EL)."""
+    cc, prof, _, _, _ = _run("explicit", pressure, temperature, dewpoint, vert_dim, vert_axis, device,
+                             profile, explicit=(parcel_pressure, parcel_temperature, parcel_dewpoint),
+                             virtual_temperature_correction=virtual_temperature_correction,
+                             lcl_interp=lcl_interp, **kwargs)
+    return cc, prof
+
+
+def surface_based_cape_cin(pressure, temperature, dewpoint, vert_dim="model_level_number", prefix=None,
+                           vert_axis=0, device=None, profile=True, **kwargs):
+    """PF:1477-1514."""
+    cc, prof, _, _, _ = _run("sb", pressure, temperature, dewpoint, vert_dim, vert_axis, device,
+                             profile, **kwargs)
+    cc = _describe(cc, "CAPE for surface-based parcel.", "CIN for surface-based parcel.", prefix)
+    return cc, prof
+
+
+def mixed_layer_cape_cin(pressure, temperature, dewpoint, vert_dim="model_level_number", depth=100,
+                         prefix=None, vert_axis=0, device=None, profile=True, **kwargs):
+    """PF:1651-1697.  Returns (cape_cin, profile, mixed parcel)."""
+    cc, prof, mp, _, _ = _run("ml", pressure, temperature, dewpoint, vert_dim, vert_axis, device,
+                              profile, depth=depth, **kwargs)
+    desc = f"fully-mixed lowest {depth} hPa parcel"
+    cc = _describe(cc, f"CAPE for {desc}.", f"CIN for {desc}", prefix)
+    return cc, prof, mp
+
+
+def most_unstable_cape_cin(pressure, temperature, dewpoint, vert_dim="model_level_number", depth=300,
+                           prefix=None, vert_axis=0, device=None, profile=True, **kwargs):
+    """PF:1557-1602.  Returns (cape_cin, profile, unstable_layer)."""
+    cc, prof, ul, _, _ = _run("mu", pressure, temperature, dewpoint, vert_dim, vert_axis, device,
+                              profile, depth=depth, **kwargs)
+    desc = f"most-unstable parcel in lowest {depth} hPa."
+    cc = _describe(cc, f"CAPE for {desc}", f"CIN for {desc}", prefix)
+    return cc, prof, ul
+
+
+def parcel_profile_with_lcl(pressure, temperature, dewpoint, parcel_pressure, parcel_temperature,
+                            parcel_dewpoint, vert_dim="model_level_number", lcl_interp="log",
+                            vert_axis=0, device=None, **kwargs):
+    """PF:806-856."""
+    _, prof, _, _, _ = _run("explicit", pressure, temperature, dewpoint, vert_dim, vert_axis, device,
+                            True, explicit=(parcel_pressure, parcel_temperature, parcel_dewpoint),
+                            lcl_interp=lcl_interp, **kwargs)
+    for k in ("lfc_pressure", "lfc_temperature", "el_pressure", "el_temperature"):
+        if isinstance(prof, Dataset):
+            prof.pop(k, None)
+        else:
+            prof = prof.drop_vars(k)
+    return prof
+
+
+def mixed_parcel(pressure, temperature, dewpoint, depth=100, vert_dim="model_level_number",
+                 vert_axis=0, device=None, **kwargs):
+    """PF:229-289: Dataset{pressure, temperature, dewpoint} of the fully mixed lowest ``depth`` hPa."""
+    _, _, mp, _, _ = _run("ml", pressure, temperature, dewpoint, vert_dim, vert_axis, device, False,
+                          depth=depth, **kwargs)
+    return mp
+
+
+def most_unstable_parcel(dat=None, depth=300, vert_dim="model_level_number", pressure=None,
+                         temperature=None, dewpoint=None, vert_axis=0, device=None, **kwargs):
+    """PF:102-135.  ``dat`` is a Dataset/dict with pressure, temperature and dewpoint."""
+    if dat is not None:
+        pressure, temperature, dewpoint = dat["pressure"], dat["temperature"], dat["dewpoint"]
+    _, _, ul, _, _ = _run("mu", pressure, temperature, dewpoint, vert_dim, vert_axis, device, False,
+                          depth=depth, **kwargs)
+    return ul
+
+
+def _lifted_columns(kind, pressure, temperature, dewpoint, vert_dim, depth, vert_axis, device, **kwargs):
+    """The lifted column of mix_layer (PF:1604-1649) / from_most_unstable_parcel (PF:1517-1555) is
+    the environment part of the profile without its LCL level; the host removes that level."""
+    cc, prof, parcel, lay, res = _run(kind, pressure, temperature, dewpoint, vert_dim, vert_axis, device,
+                                      True, depth=depth, **kwargs)
+    L = lay.L
+    n_lev = _profile_levels(kind, res, L)
+    P = res["profile_pressure"][:n_lev]
+    lcl_p = res["lcl_pressure"]
+    # index of the inserted LCL level: number of levels with p >= lcl_p (PF:965)
+    pos = ((P >= lcl_p[None, :]).sum(dim=0) - 1).clamp(min=0)
+    # the inserted level is the LAST level with p >= lcl among equal pressures
+    n = n_lev - 1
+    idx = torch.arange(n, device=P.device)[:, None]
+    src = idx + (idx >= pos[None, :]).to(idx.dtype)
+    bad = torch.isnan(lcl_p)
+    src = torch.where(bad[None, :], idx.expand(-1, P.shape[1]), src)
+    out = {}
+    for name, key in (("pressure", "profile_pressure"), ("temperature", "profile_environment_temperature"),
+                      ("dewpoint", "profile_environment_dewpoint")):
+        out[name] = lay.wrap_profile(torch.gather(res[key][:n_lev], 0, src), name, n)
+    return out["pressure"], out["temperature"], out["dewpoint"], parcel
+
+
+def mix_layer(pressure, temperature, dewpoint, vert_dim="model_level_number", depth=100, load=True,
+              vert_axis=0, device=None, **kwargs):
+    """PF:1604-1649: (pressure, temperature, dewpoint) with the mixed parcel as the bottom level and
+    the mixed layer removed, plus the mixed parcel.  Columns whose parcel is NaN come back as NaN."""
+    return _lifted_columns("ml", pressure, temperature, dewpoint, vert_dim, depth, vert_axis, device,
+                           **kwargs)
+
+
+def from_most_unstable_parcel(pressure, temperature, dewpoint, vert_dim="model_level_number", depth=300,
+                              vert_axis=0, device=None, **kwargs):
+    """PF:1517-1555."""
+    return _lifted_columns("mu", pressure, temperature, dewpoint, vert_dim, depth, vert_axis, device,
+                           **kwargs)
+
+
+def parcel_suite(pressure, temperature, dewpoint, vert_dim="model_level_number", vert_axis=0,
+                 device=None, mixed_layer_depth=100, most_unstable_depth=300, **kwargs):
+    """Surface-based + mixed-layer + most-unstable CAPE/CIN/LCL/LFC/EL in ONE pass over the columns
+    (the hot-path part of parcel_test.py:416-547 ``conv_properties_xarray``; no profile output).
+    Returns a Dataset with the reference's prefixed names: surface_*, mixed_100_*, max_*."""
+    lay, ctx, p, t, td = _prepare(pressure, temperature, dewpoint, vert_dim, vert_axis, device)
+    opts = _lib.make_options(mixed_layer_depth=mixed_layer_depth, most_unstable_depth=most_unstable_depth,
+                             **_options(kwargs))
+    res = ctx.cape_cin(p, t, td, kinds=("sb", "ml", "mu"), options=opts, profile=False)
+    _check_flags(ctx)
+    out = {}
+    prefixes = {"sb": "surface", "ml": f"mixed_{int(mixed_layer_depth)}", "mu": "max"}
+    for kind, pre in prefixes.items():
+        for name in ["cape", "cin"] + _SCALAR_VARS:
+            out[f"{pre}_{name}"] = lay.wrap_scalar(res[kind][name], name)
+        if kind != "sb":
+            for name in ("pressure", "temperature", "dewpoint"):
+                out[f"{pre}_parcel_{name}"] = lay.wrap_scalar(res[kind]["parcel_" + name], name)
+    return lay.dataset(out)
+
+
+# ---- individually exposed steps ---------------------------------------------------------------
+def _to_dev(x, like=None, dtype=None):
+    if _xr is not None and isinstance(x, _xr.DataArray):
+        x = x.data
+    if not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(np.asarray(x, dtype=np.float64 if dtype is None else None))
+    if dtype is not None:
+        x = x.to(dtype)
+    elif x.dtype not in (torch.float32, torch.float64):
+        x = x.to(torch.float64)
+    if not x.is_cuda:
+        x = x.cuda()
+    return x
+
+
+def _back(t, template):
+    raw = template.data if (_xr is not None and isinstance(template, _xr.DataArray)) else template
+    if isinstance(raw, torch.Tensor):
+        return t if raw.is_cuda else t.cpu()
+    return t.cpu().numpy()
+
+
+def lcl(parcel_pressure, parcel_temperature, parcel_dewpoint, device=None, **kwargs):
+    """PF:609-682.  Returns Dataset{lcl_pressure, lcl_temperature, lcl_virtual_temperature}."""
+    ctx = _lib.get_context(device)
+    pt = _to_dev(parcel_temperature)
+    pp = _to_dev(parcel_pressure, dtype=pt.dtype)
+    pd = _to_dev(parcel_dewpoint, dtype=pt.dtype)
+    a, b, c = ctx.lcl(pp, pt, pd, _lib.make_options(**_options(kwargs)))
+    ds = Dataset({"lcl_pressure": _back(a, parcel_temperature), "lcl_temperature": _back(b, parcel_temperature),
+                  "lcl_virtual_temperature": _back(c, parcel_temperature)})
+    ds.var_attrs = {k: dict(_ATTRS[k]) for k in ds}
+    return ds
+
+
+def dry_lapse(pressure, parcel_temperature, parcel_pressure=None, vert_dim="model_level_number",
+              vert_axis=0):
+    """PF:291-316: T0 * (p / p0) ** kappa (elementwise; stays on the caller's array library)."""
+    if parcel_pressure is None:
+        if _xr is not None and isinstance(pressure, _xr.DataArray):
+            parcel_pressure = pressure.max(vert_dim)
+        elif isinstance(pressure, torch.Tensor):
+            parcel_pressure = pressure.amax(dim=vert_axis, keepdim=True)
+        else:
+            parcel_pressure = np.max(pressure, axis=vert_axis, keepdims=True)
+    return parcel_temperature * (pressure / parcel_pressure) ** KAPPA
+
+
+def virtual_temperature(temperature, mixing_ratio, epsilon=0.608):
+    """PF:782-804."""
+    return temperature * (1 + epsilon * mixing_ratio)
+
+
+def mixing_ratio(temperature, dewpoint, pressure, metpy_compat="1.4.1"):
+    """PF:684-710 (elementwise; Bolton saturation vapour pressure as in MetPy <= 1.6)."""
+    lib = torch if isinstance(temperature, torch.Tensor) else np
+
+    def es(t):
+        return 6.112 * lib.exp(17.67 * (t - 273.15) / (t - 29.65))
+
+    eps = 0.6219569100577033
+    es_t = es(temperature)
+    rh = es(dewpoint) / es_t
+    ws = eps * es_t / (pressure - es_t)
+    if str(metpy_compat) in ("1.6.2", "162"):
+        return eps * ws * rh / (eps + ws * (1.0 - rh))
+    return rh * ws
+
+
+def moist_lapse(pressure, parcel_temperature, parcel_pressure=None, vert_dim="model_level_number",
+                persist=True, vert_axis=0, device=None):
+    """PF:525-607: lookup-table moist adiabat.  ``pressure`` is [L, ...] (vertical axis first for
+    plain arrays)."""
+    ctx = _lib.get_context(device)
+    lookup_tables_loaded(device)
+    lay = _Layout(pressure, vert_dim, vert_axis)
+    raw = pressure.data if lay.is_xr else pressure
+    dtype = raw.dtype if isinstance(raw, torch.Tensor) else (torch.float32 if np.asarray(raw).dtype == np.float32 else torch.float64)
+    p = lay.to_block(pressure, None, dtype).cuda()
+    if p.dim() == 1:
+        p = p[:, None]
+    if parcel_pressure is None:
+        parcel_pressure = p[0]
+        pp = parcel_pressure
+    else:
+        pp = lay.scalar_to_block(parcel_pressure, dtype).cuda()
+    pt = lay.scalar_to_block(parcel_temperature, dtype).cuda()
+    out = ctx.moist_lapse(p.contiguous(), pt, pp)
+    return lay.wrap_profile(out if isinstance(raw, torch.Tensor) and raw.is_cuda else out.cpu(),
+                            "temperature", lay.L)
+
+
+def parcel_profile(pressure, parcel_pressure, parcel_temperature, parcel_dewpoint,
+                   vert_dim="model_level_number", vert_axis=0, device=None, **kwargs):
+    """PF:712-780: parcel temperature / virtual temperature on the input levels + the LCL."""
+    ctx = _lib.get_context(device)
+    lookup_tables_loaded(device)
+    lay = _Layout(pressure, vert_dim, vert_axis)
+    raw = pressure.data if lay.is_xr else pressure
+    dtype = raw.dtype if isinstance(raw, torch.Tensor) else (torch.float32 if np.asarray(raw).dtype == np.float32 else torch.float64)
+    on_gpu = isinstance(raw, torch.Tensor) and raw.is_cuda
+    p = lay.to_block(pressure, None, dtype).cuda()
+    if p.dim() == 1:
+        p = p[:, None]
+    pp = lay.scalar_to_block(parcel_pressure, dtype).cuda()
+    pt = lay.scalar_to_block(parcel_temperature, dtype).cuda()
+    pd = lay.scalar_to_block(parcel_dewpoint, dtype).cuda()
+    r = ctx.parcel_profile(p.contiguous(), pp, pt, pd, _lib.make_options(**_options(kwargs)))
+    fix = (lambda x: x) if on_gpu else (lambda x: x.cpu())
+    out = {"pressure": lay.wrap_profile(fix(p.contiguous()), "pressure", lay.L),
+           "temperature": lay.wrap_profile(fix(r["temperature"]), "temperature", lay.L),
+           "virtual_temperature": lay.wrap_profile(fix(r["virtual_temperature"]), "virtual_temperature", lay.L)}
+    for k in ("lcl_pressure", "lcl_temperature", "lcl_virtual_temperature"):
+        out[k] = lay.wrap_scalar(fix(r[k]), k)
+    return lay.dataset(out)
+
+
+def lfc_el(pressure, parcel_temperature, temperature, lcl_pressure, lcl_temperature,
+           vert_dim="model_level_number", vert_axis=0, device=None):
+    """PF:1066-1198 on caller-supplied parcel and environment temperature profiles."""
+    ctx = _lib.get_context(device)
+    lay = _Layout(temperature, vert_dim, vert_axis)
+    raw = temperature.data if lay.is_xr else temperature
+    dtype = raw.dtype if isinstance(raw, torch.Tensor) else (torch.float32 if np.asarray(raw).dtype == np.float32 else torch.float64)
+    on_gpu = isinstance(raw, torch.Tensor) and raw.is_cuda
+    blocks = []
+    for x in (pressure, parcel_temperature, temperature):
+        b = lay.to_block(x, None, dtype).cuda()
+        if b.dim() == 1:
+            b = b[:, None].expand(lay.L, int(np.prod(lay.col_shape)) if lay.col_shape else 1)
+        blocks.append(b.contiguous())
+    lp = lay.scalar_to_block(lcl_pressure, dtype).cuda()
+    lt = lay.scalar_to_block(lcl_temperature, dtype).cuda()
+    r = ctx.lfc_el(blocks[0], blocks[1], blocks[2], lp, lt)
+    _check_flags(ctx)
+    fix = (lambda x: x) if on_gpu else (lambda x: x.cpu())
+    return lay.dataset({k: lay.wrap_scalar(fix(v), k) for k, v in r.items()})
+
+
+def cape_cin_base(pressure, temperature, lfc_pressure, el_pressure, parcel_temperature,
+                  vert_dim="model_level_number", pos_cape_neg_cin=True, post_zero_cin=False,
+                  vert_axis=0, device=None, **kwargs):
+    """PF:1291-1392 (extra kwargs are swallowed like the reference's ``**kwargs``, PF:1293)."""
+    ctx = _lib.get_context(device)
+    lay = _Layout(temperature, vert_dim, vert_axis)
+    raw = temperature.data if lay.is_xr else temperature
+    dtype = raw.dtype if isinstance(raw, torch.Tensor) else (torch.float32 if np.asarray(raw).dtype == np.float32 else torch.float64)
+    on_gpu = isinstance(raw, torch.Tensor) and raw.is_cuda
+    blocks = []
+    for x in (pressure, temperature, parcel_temperature):
+        b = lay.to_block(x, None, dtype).cuda()
+        if b.dim() == 1:
+            b = b[:, None].expand(lay.L, int(np.prod(lay.col_shape)) if lay.col_shape else 1)
+        blocks.append(b.contiguous())
+    lf = lay.scalar_to_block(lfc_pressure, dtype).cuda()
+    el = lay.scalar_to_block(el_pressure, dtype).cuda()
+    opts = _lib.make_options(pos_cape_neg_cin=pos_cape_neg_cin, post_zero_cin=post_zero_cin)
+    r = ctx.cape_cin_base(blocks[0], blocks[1], lf, el, blocks[2], opts)
+    fix = (lambda x: x) if on_gpu else (lambda x: x.cpu())
+    return lay.dataset({k: lay.wrap_scalar(fix(v), k) for k, v in r.items()})
