@@ -1,0 +1,469 @@
+"""GPU parity tests: the sm_100a kernels, called through the C ABI (libxparcel.so via
+xarray_parcel_b200._lib), against the CPU oracle on the same seeded inputs and the same
+lookup tables.
+
+Tolerances (BASELINE.json north_star): level indices / bracketing bit-exact, NaN patterns
+identical, LCL pressure/temperature within 1e-3 relative, CAPE/CIN within 0.1 % or 1 J/kg.
+The kernels compute in float64, so the observed differences are far smaller; the tighter
+bounds asserted here (1e-9 for float64 I/O, float32 rounding for float32 I/O) are what keeps
+regressions visible.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import parcel as op
+from oracle import tables as otab
+from xarray_parcel_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ["cape", "cin", "lcl_pressure", "lcl_temperature", "lcl_virtual_temperature",
+          "lfc_pressure", "lfc_temperature", "el_pressure", "el_temperature"]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    c = _lib.get_context(0)
+    c.tables_build()
+    return c
+
+
+@pytest.fixture(scope="module")
+def gpu_tables(ctx):
+    """The GPU-built tables wrapped for the oracle: both sides consume the same arrays."""
+    idx, cur = ctx.tables_get()
+    pl, tl = otab.default_grids()
+    return otab.AdiabatTables(pl, tl, idx, cur)
+
+
+def _np64(*a):
+    return [x.double().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x, np.float64) for x in a]
+
+
+def _check(res, ora, prefix, rtol, what="", knife=None):
+    """north_star tolerances for every column + the tighter regression bound ``rtol``.
+
+    ``knife``: mask of knife-edge columns -- parcels saturated to the last bit (T == Td), where
+    the reference's own result hinges on whether ``dewpoint(vapor_pressure(p, w))`` round-trips to
+    T exactly and on the sign of 1e-14 K differences in a zero-width interval at the duplicated LCL
+    pressure (PF:1019-1050), i.e. on libm rounding.  Those columns must still meet the
+    north_star tolerances; up to 2 % of them may miss the tighter ``rtol``."""
+    for f in FIELDS:
+        a = res[f].double().cpu().numpy()
+        b = ora[prefix + f]
+        nan_mis = np.flatnonzero(np.isnan(a) != np.isnan(b))
+        assert nan_mis.size == 0, f"{what}{prefix}{f}: NaN pattern differs in columns {nan_mis[:8]}"
+        ok = ~np.isnan(b)
+        if not ok.any():
+            continue
+        diff = np.where(ok, np.abs(a - b), 0.0)
+        if f in ("cape", "cin"):
+            bad = np.flatnonzero((diff > 1.0) & (diff > 1e-3 * np.abs(b)))
+            msg = "outside 0.1%/1 J/kg"
+        else:
+            bad = np.flatnonzero(diff > 1e-3 * np.abs(b))
+            msg = "outside 1e-3 relative"
+        assert bad.size == 0, (f"{what}{prefix}{f} {msg} in {bad.size} columns, e.g. "
+                               f"{[(int(i), float(a[i]), float(b[i])) for i in bad[:4]]}")
+        err = diff / np.maximum(np.abs(np.where(ok, b, 1.0)), 1.0)
+        if knife is not None and knife.any():
+            over = (err >= rtol) & knife
+            assert over.sum() <= max(1, int(0.02 * knife.sum())), f"{what}{prefix}{f}: {over.sum()} knife-edge columns off"
+            err = np.where(knife, 0.0, err)
+        i = int(np.argmax(err))
+        assert err[i] < rtol, f"{what}{prefix}{f}: max rel err {err[i]:.3e} >= {rtol} (column {i}: {a[i]} vs {b[i]})"
+
+
+def _oracle_suite(p, t, td, tables, **kw):
+    p, t, td = _np64(p, t, td)
+    if p.ndim == 1:
+        p = np.broadcast_to(p[:, None], t.shape)
+    compat = kw.pop("metpy_compat", "1.4.1")
+    opts = op.Options(op.MoistLapseLUT(tables), lcl_mode="converged", metpy_compat=compat)
+    return op.suite(p, t, td, opts, **kw)
+
+
+# --------------------------------------------------------------------------- tables
+def test_tables_match_oracle_generator(ctx):
+    """xp_tables_build (CUDA RK4 + atomicMax marking) vs oracle/tables.py (NumPy RK4 + the
+    reference's two marking passes, PF:447-523).  Curves agree to float32 rounding; index-grid
+    cells may differ only where a temperature sits within rounding of a 0.01 K cell edge."""
+    idx, cur = ctx.tables_get()
+    tb = otab.load_tables()
+    assert idx.shape == tb.index_grid.shape and cur.shape == tb.curves_asc.shape
+    dcur = np.abs(cur.astype(np.float64) - tb.curves_asc.astype(np.float64))
+    assert dcur.max() < 6.2e-5, dcur.max()          # 2 float32 ulp at ~300 K
+    assert (dcur > 0).mean() < 0.02
+    assert np.array_equal(idx == 0, tb.index_grid == 0) or ((idx == 0) != (tb.index_grid == 0)).mean() < 1e-5
+    mism = (idx != tb.index_grid)
+    assert mism.mean() < 1e-4, f"index grid mismatch fraction {mism.mean():.2e}"
+    # where they differ it is by neighbouring adiabats only
+    if mism.any():
+        d = np.abs(idx[mism].astype(np.int64) - tb.index_grid[mism].astype(np.int64))
+        assert np.percentile(d, 99) <= 3
+
+
+def test_tables_set_get_roundtrip(ctx):
+    idx, cur = ctx.tables_get()
+    c2 = _lib.Context(0)
+    try:
+        assert not c2.tables_loaded()
+        with pytest.raises(AssertionError, match="load_moist_adiabat_lookups"):
+            p, t, td = synth.model_level_columns(64, 20, seed=1, device="cuda")
+            c2.cape_cin(p, t, td)
+        c2.tables_set(idx, cur)
+        assert c2.tables_loaded()
+        i2, c2c = c2.tables_get()
+        assert np.array_equal(i2, idx) and np.array_equal(c2c, cur)
+    finally:
+        c2.close()
+
+
+# --------------------------------------------------------------------------- the fused suite
+OPTION_SETS = [
+    dict(virtual_temperature_correction=True, lcl_interp="log", pos_cape_neg_cin=True),
+    dict(virtual_temperature_correction=False, lcl_interp="linear", pos_cape_neg_cin=True),
+    dict(virtual_temperature_correction=True, lcl_interp="linear", pos_cape_neg_cin=False,
+         metpy_compat="1.6.2"),
+    dict(virtual_temperature_correction=False, lcl_interp="log", pos_cape_neg_cin=False,
+         post_zero_cin=True),
+]
+
+
+@pytest.mark.parametrize("o", OPTION_SETS, ids=["default", "metpy-mode", "compat162", "novtc-postzero"])
+@pytest.mark.parametrize("shape", ["model70", "era5"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+def test_suite_matches_oracle(ctx, gpu_tables, o, shape, dtype):
+    if shape == "model70":
+        p, t, td = synth.model_level_columns(6000, 70, seed=11)
+    else:
+        p, t, td = synth.era5_columns(6000, seed=12, nan_columns=0.02)
+    p, t, td = p.to(dtype), t.to(dtype), td.to(dtype)
+    ora = _oracle_suite(p, t, td, gpu_tables, **dict(o))
+    opts = _lib.make_options(**o)
+    res = ctx.cape_cin(p.cuda(), t.cuda(), td.cuda(), kinds=("sb", "ml", "mu"), options=opts)
+    assert ctx.take_flags() == 0
+    rtol = 1e-9 if dtype == torch.float64 else 3e-7
+    for kind in ("sb", "ml", "mu"):
+        _check(res[kind], ora, kind + "_", rtol, what=f"{shape}/{dtype}: ")
+        if kind != "sb":
+            for f in ("pressure", "temperature", "dewpoint"):
+                a = res[kind]["parcel_" + f].double().cpu().numpy()
+                b = ora[f"{kind}_parcel_{f}"]
+                assert np.array_equal(np.isnan(a), np.isnan(b))
+                ok = ~np.isnan(b)
+                assert np.allclose(a[ok], b[ok], rtol=rtol, atol=0)
+
+
+def test_single_kind_calls_equal_suite(ctx):
+    """xp_cape_cin per kind == xp_suite (bit-exact)."""
+    p, t, td = synth.model_level_columns(5000, 70, seed=21, device="cuda")
+    both = ctx.cape_cin(p, t, td, kinds=("sb", "ml", "mu"))
+    for kind in ("sb", "ml", "mu"):
+        one = ctx.cape_cin(p, t, td, kinds=(kind,))[kind]
+        for f in _lib.SCALAR_FIELDS:
+            assert torch.equal(one[f].view(torch.int32), both[kind][f].view(torch.int32)), (kind, f)
+        assert torch.equal(one["level_shift"], both[kind]["level_shift"])
+
+
+@pytest.mark.parametrize("kind", ["sb", "ml", "mu"])
+def test_profile_rows_match_oracle(ctx, gpu_tables, kind):
+    """parcel_profile_with_lcl output (PF:806-931): every row of the (L+1)-level profile, and the
+    level shift (index of the first lifted level) bit-exact."""
+    p, t, td = synth.model_level_columns(3000, 50, seed=5)
+    p, t, td = p.double(), t.double(), td.double()
+    opts = op.Options(op.MoistLapseLUT(gpu_tables), lcl_mode="converged")
+    fn = {"sb": op.surface_based_cape_cin, "ml": op.mixed_layer_cape_cin,
+          "mu": op.most_unstable_cape_cin}[kind]
+    prof = fn(*_np64(p, t, td), opts)[1]
+    res = ctx.cape_cin(p.cuda(), t.cuda(), td.cuda(), kinds=(kind,), profile=True)[kind]
+    n = prof["pressure"].shape[0]
+    names = ["pressure", "temperature", "virtual_temperature", "environment_temperature",
+             "environment_virtual_temperature", "environment_dewpoint"]
+    for k in names:
+        a = res["profile_" + k].cpu().numpy()
+        b = prof[k]
+        assert np.array_equal(np.isnan(a[:n]), np.isnan(b)), f"{k}: NaN pattern differs"
+        ok = ~np.isnan(b)
+        assert np.allclose(a[:n][ok], b[ok], rtol=1e-10, atol=0), k
+        assert np.isnan(a[n:]).all()
+    # bracketing: the LCL row index (count of levels with p >= lcl_p) is identical
+    a = res["profile_pressure"].cpu().numpy()[:n]
+    lcl = res["lcl_pressure"].cpu().numpy()
+    with np.errstate(invalid="ignore"):
+        pos_gpu = (a >= lcl[None, :]).sum(0)
+        pos_ora = (prof["pressure"] >= prof["lcl_pressure"][None, :]).sum(0)
+    assert np.array_equal(pos_gpu, pos_ora)
+
+
+def test_level_shift_bit_exact(ctx, gpu_tables):
+    """MU level index and number of mixed-layer levels (integer outputs) against the oracle."""
+    p, t, td = synth.model_level_columns(8000, 70, seed=31)
+    P, T, D = _np64(p, t, td)
+    res = ctx.cape_cin(p.cuda(), t.cuda(), td.cuda(), kinds=("ml", "mu"))
+    mu = op.most_unstable_parcel({"pressure": P, "temperature": T, "dewpoint": D}, depth=300)
+    with np.errstate(invalid="ignore"):
+        k_mu = np.where(np.isnan(mu["pressure"]), P.shape[0], (P > mu["pressure"][None, :]).sum(0))
+        k_ml = np.where(np.isnan(P[0]), P.shape[0], (P >= (np.nanmax(P, axis=0) - 100.0)[None, :]).sum(0))
+    assert np.array_equal(res["mu"]["level_shift"].cpu().numpy(), k_mu)
+    assert np.array_equal(res["ml"]["level_shift"].cpu().numpy(), k_ml)
+
+
+def test_explicit_parcel_matches_oracle(ctx, gpu_tables):
+    p, t, td = synth.model_level_columns(2000, 40, seed=9)
+    p, t, td = p.double(), t.double(), td.double()
+    pp, pt, pd_ = p[3].clone(), t[3] + 1.0, td[3].clone()
+    opts = op.Options(op.MoistLapseLUT(gpu_tables), lcl_mode="converged")
+    cc, prof = op.cape_cin(*_np64(p, t, td), *_np64(pt, pp, pd_), opts)
+    ora = {"x_" + k: v for k, v in {**cc, **prof}.items() if v.ndim == 1}
+    res = ctx.cape_cin(p.cuda(), t.cuda(), td.cuda(), kinds=("explicit",),
+                       explicit=(pp.cuda(), pt.cuda(), pd_.cuda()))["explicit"]
+    _check(res, ora, "x_", 1e-9)
+
+
+def test_reference_soundings_on_gpu(ctx, gpu_tables, soundings):
+    """Every sounding of the reference's unit tests (tests/golden/ut_soundings.json), lookup-table
+    mode, all three parcels, float64, against the oracle; plus the reference's own loose
+    statement about its table (SB CAPE of UT:940-951 within ~1-2 % of the exact-ODE pin)."""
+    names = [n for n, s in soundings.items()
+             if all(k in s for k in ("levels", "temperatures", "dewpoints")) and s["levels"].size > 3]
+    L = max(soundings[n]["levels"].size for n in names)
+
+    def pad(a):
+        return np.concatenate([a, np.full(L - a.size, np.nan)])
+
+    P = np.stack([pad(soundings[n]["levels"]) for n in names], axis=1)
+    T = np.stack([pad(soundings[n]["temperatures"]) for n in names], axis=1)
+    D = np.stack([pad(soundings[n]["dewpoints"]) for n in names], axis=1)
+    ora = _oracle_suite(P, T, D, gpu_tables)
+    dev = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (P, T, D)]
+    res = ctx.cape_cin(*dev, kinds=("sb", "ml", "mu"))
+    for kind in ("sb", "ml", "mu"):
+        _check(res[kind], ora, kind + "_", 1e-9, what="UT soundings: ")
+    i = names.index("test_surface_based_cape_cin")
+    cape = float(res["sb"]["cape"][i]); cin = float(res["sb"]["cin"][i])
+    assert abs(cape - 230.1982) / 230.1982 < 0.02 and abs(cin + 58.0673) < 1.0
+
+
+# --------------------------------------------------------------------------- edge cases
+def test_edge_cases(ctx, gpu_tables):
+    """All-NaN columns, NaN parcel, saturated surface (LCL == surface), one-level and two-level
+    columns, zero columns."""
+    p, t, td = synth.model_level_columns(512, 30, seed=3, saturated=0.5, allnan_columns=0.1,
+                                         nan_columns=0.3, nan_levels=0.3)
+    p, t, td = p.double(), t.double(), td.double()
+    t[0, 5] = float("nan")               # NaN surface parcel
+    td[0, 6] = float("nan")
+    ora = _oracle_suite(p, t, td, gpu_tables)
+    res = ctx.cape_cin(p.cuda(), t.cuda(), td.cuda(), kinds=("sb", "ml", "mu"))
+    for kind in ("sb", "ml", "mu"):
+        pt, pd_ = (ora[f"{kind}_parcel_temperature"], ora[f"{kind}_parcel_dewpoint"]) if kind != "sb" \
+            else (t[0].numpy(), td[0].numpy())
+        _check(res[kind], ora, kind + "_", 1e-9, what="edge: ", knife=(pt == pd_))
+    # short columns
+    for L in (1, 2, 3):
+        ps, ts, tds = p[:L].contiguous(), t[:L].contiguous(), td[:L].contiguous()
+        ora = _oracle_suite(ps, ts, tds, gpu_tables)
+        res = ctx.cape_cin(ps.cuda(), ts.cuda(), tds.cuda(), kinds=("sb", "ml", "mu"))
+        for kind in ("sb", "ml", "mu"):
+            _check(res[kind], ora, kind + "_", 1e-9, what=f"L={L}: ")
+    # empty input
+    e = torch.empty((30, 0), dtype=torch.float64, device="cuda")
+    res = ctx.cape_cin(e, e, e, kinds=("sb",))
+    assert res["sb"]["cape"].numel() == 0
+
+
+def test_strided_and_1d_pressure(ctx):
+    """A column block that is a slice of a wider array (level_stride > n_columns) and a shared
+    1-D pressure axis give the same bits as contiguous / broadcast inputs."""
+    p1, t, td = synth.era5_columns(4096, seed=4, device="cuda")
+    full = ctx.cape_cin(p1, t, td, kinds=("sb", "ml", "mu"))
+    pb = p1[:, None].expand(-1, 4096).contiguous()
+    bro = ctx.cape_cin(pb, t, td, kinds=("sb", "ml", "mu"))
+    sl = ctx.cape_cin(p1, t[:, 1024:3072], td[:, 1024:3072], kinds=("sb", "ml", "mu"))
+    for kind in ("sb", "ml", "mu"):
+        for f in FIELDS:
+            assert torch.equal(full[kind][f].view(torch.int32), bro[kind][f].view(torch.int32)), (kind, f)
+            assert torch.equal(full[kind][f][1024:3072].view(torch.int32), sl[kind][f].view(torch.int32)), (kind, f)
+
+
+def test_host_memory_path_equals_device_path(ctx):
+    """mem = XP_MEM_HOST (pinned staging pipeline inside the library) == device path, bit-exact,
+    including profile outputs and a block size that does not divide the column count."""
+    p, t, td = synth.model_level_columns(70001, 37, seed=8)
+    dev = ctx.cape_cin(p.cuda(), t.cuda(), td.cuda(), kinds=("sb", "ml", "mu"), profile=True)
+    host = ctx.cape_cin(p, t, td, kinds=("sb", "ml", "mu"), profile=True)
+    for kind in ("sb", "ml", "mu"):
+        for f in _lib.SCALAR_FIELDS + _lib.PROFILE_FIELDS:
+            a, b = dev[kind][f].cpu(), host[kind][f]
+            assert not b.is_cuda
+            assert torch.equal(a.view(torch.int32), b.view(torch.int32)), (kind, f)
+        assert torch.equal(dev[kind]["level_shift"].cpu(), host[kind]["level_shift"])
+
+
+# --------------------------------------------------------------------------- individual steps
+def test_lcl_kernel(ctx):
+    rng = np.random.default_rng(0)
+    n = 20000
+    p = rng.uniform(500, 1050, n); t = rng.uniform(230, 315, n); td = t - rng.uniform(0, 30, n)
+    td[:100] = t[:100]                   # saturated: LCL snaps to the parcel pressure
+    p[100:110] = np.nan
+    o = op.lcl(p, t, td, op.Options(None, lcl_mode="converged"))
+    a, b, c = ctx.lcl(*[torch.from_numpy(x).cuda() for x in (p, t, td)])
+    for got, key in ((a, "lcl_pressure"), (b, "lcl_temperature"), (c, "lcl_virtual_temperature")):
+        g = got.cpu().numpy()
+        assert np.array_equal(np.isnan(g), np.isnan(o[key]))
+        ok = ~np.isnan(g)
+        assert np.allclose(g[ok], o[key][ok], rtol=1e-11, atol=0), key
+    assert np.array_equal(a.cpu().numpy()[:100], p[:100])
+    # UT:247-256 pin: 864.806 hPa / 17.676 degC at 2 decimals
+    a, b, _ = ctx.lcl(torch.tensor([1000.], dtype=torch.float64).cuda(),
+                      torch.tensor([30. + 273.15], dtype=torch.float64).cuda(),
+                      torch.tensor([20. + 273.15], dtype=torch.float64).cuda())
+    assert abs(float(a) - 864.806) < 5e-3 and abs(float(b) - 273.15 - 17.676) < 5e-3
+
+
+def test_moist_lapse_and_parcel_profile_kernels(ctx, gpu_tables):
+    p, t, td = synth.model_level_columns(3000, 60, seed=13, nan_columns=0, allnan_columns=0)
+    P, T, D = _np64(p, t, td)
+    lut = op.MoistLapseLUT(gpu_tables)
+    t0 = T[0]; p0 = P[0]
+    ref = lut(P, t0, p0)
+    got = ctx.moist_lapse(torch.from_numpy(P).cuda(), torch.from_numpy(t0).cuda(), torch.from_numpy(p0).cuda())
+    g = got.cpu().numpy()
+    assert np.array_equal(np.isnan(g), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert np.allclose(g[ok], ref[ok], rtol=1e-12, atol=0)
+    # UT:166-188 at the reference's LUT tolerance (2 decimals, UT:106-112)
+    lv = np.array([1000., 800., 600., 500., 400.])[:, None]     # UT:166-170
+    got = ctx.moist_lapse(torch.from_numpy(lv).cuda(), torch.tensor([293.], dtype=torch.float64).cuda(),
+                          torch.tensor([1000.], dtype=torch.float64).cuda()).cpu().numpy()[:, 0]
+    assert np.allclose(got, [293, 284.64, 272.81, 264.42, 252.91], atol=0.05)
+    # parcel_profile PF:712-780
+    opts = op.Options(lut, lcl_mode="converged")
+    ref = op.parcel_profile(P, P[0], T[0], D[0], opts)
+    r = ctx.parcel_profile(torch.from_numpy(P).cuda(), torch.from_numpy(P[0].copy()).cuda(),
+                           torch.from_numpy(T[0].copy()).cuda(), torch.from_numpy(D[0].copy()).cuda())
+    for k in ("temperature", "virtual_temperature", "lcl_pressure", "lcl_temperature"):
+        g = r[k].cpu().numpy()
+        assert np.array_equal(np.isnan(g), np.isnan(ref[k])), k
+        ok = ~np.isnan(ref[k])
+        assert np.allclose(g[ok], ref[k][ok], rtol=1e-11, atol=0), k
+
+
+def test_lfc_el_and_cape_cin_base_kernels(ctx, gpu_tables):
+    """lfc_el (PF:1066-1198) and cape_cin_base (PF:1291-1392) on caller-supplied curves."""
+    p, t, td = synth.model_level_columns(3000, 60, seed=17)
+    P, T, D = _np64(p, t, td)
+    opts = op.Options(op.MoistLapseLUT(gpu_tables), lcl_mode="converged")
+    prof = op.parcel_profile_with_lcl(P, T, D, P[0], T[0], D[0], opts)
+    ref = op.lfc_el(prof["pressure"], prof["virtual_temperature"], prof["environment_virtual_temperature"],
+                    prof["lcl_pressure"], prof["lcl_virtual_temperature"])
+    dv = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    got = ctx.lfc_el(dv(prof["pressure"]), dv(prof["virtual_temperature"]),
+                     dv(prof["environment_virtual_temperature"]), dv(prof["lcl_pressure"]),
+                     dv(prof["lcl_virtual_temperature"]))
+    ctx.take_flags()
+    for k, v in ref.items():
+        g = got[k].cpu().numpy()
+        assert np.array_equal(np.isnan(g), np.isnan(v)), k
+        ok = ~np.isnan(v)
+        assert np.allclose(g[ok], v[ok], rtol=1e-10, atol=0), k
+    cc = op.cape_cin_base(prof["pressure"], prof["environment_virtual_temperature"], ref["lfc_pressure"],
+                          ref["el_pressure"], prof["virtual_temperature"])
+    got = ctx.cape_cin_base(dv(prof["pressure"]), dv(prof["environment_virtual_temperature"]),
+                            dv(ref["lfc_pressure"]), dv(ref["el_pressure"]), dv(prof["virtual_temperature"]))
+    for k in ("cape", "cin"):
+        assert np.allclose(got[k].cpu().numpy(), cc[k], rtol=1e-9, atol=1e-9), k
+    # arbitrary (non-crossing) LFC/EL: the literal per-area inclusion tests
+    lfc = np.full(P.shape[1], 850.0); el = np.full(P.shape[1], 300.0)
+    cc = op.cape_cin_base(prof["pressure"], prof["environment_virtual_temperature"], lfc, el,
+                          prof["virtual_temperature"], pos_cape_neg_cin=False)
+    got = ctx.cape_cin_base(dv(prof["pressure"]), dv(prof["environment_virtual_temperature"]), dv(lfc),
+                            dv(el), dv(prof["virtual_temperature"]),
+                            options=_lib.make_options(pos_cape_neg_cin=False))
+    for k in ("cape", "cin"):
+        assert np.allclose(got[k].cpu().numpy(), cc[k], rtol=1e-9, atol=1e-9), k
+
+
+# --------------------------------------------------------------------------- full-size properties
+def test_full_size_properties(ctx, gpu_tables):
+    """BASELINE config sizes (1 M x 70 model levels; 1440x721 x 37 ERA5 hour): properties that do
+    not need the oracle at full size -- determinism, column-permutation equivariance, block-split
+    invariance, sign constraints, ordering LCL >= LFC -- plus an oracle check on a random
+    sample of the same columns."""
+    for shape in ("model70", "era5"):
+        if shape == "model70":
+            p, t, td = synth.model_level_columns(1_000_000, 70, seed=101, device="cuda")
+        else:
+            p, t, td = synth.era5_columns(1440 * 721, seed=102, device="cuda")
+        r1 = ctx.cape_cin(p, t, td, kinds=("sb", "ml", "mu"))
+        r2 = ctx.cape_cin(p, t, td, kinds=("sb", "ml", "mu"))
+        N = t.shape[1]
+        perm = torch.randperm(N, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+        pp = p if p.dim() == 1 else p[:, perm].contiguous()
+        r3 = ctx.cape_cin(pp, t[:, perm].contiguous(), td[:, perm].contiguous(), kinds=("sb", "ml", "mu"))
+        h = N // 2 + 13
+        pa = p if p.dim() == 1 else p[:, :h]
+        r4 = ctx.cape_cin(pa, t[:, :h], td[:, :h], kinds=("sb", "ml", "mu"))
+        for kind in ("sb", "ml", "mu"):
+            for f in FIELDS:
+                a = r1[kind][f]
+                assert torch.equal(a.view(torch.int32), r2[kind][f].view(torch.int32)), "not deterministic"
+                assert torch.equal(a[perm].view(torch.int32), r3[kind][f].view(torch.int32)), "not column-local"
+                assert torch.equal(a[:h].view(torch.int32), r4[kind][f].view(torch.int32)), "not split-invariant"
+            cape, cin = r1[kind]["cape"], r1[kind]["cin"]
+            assert bool((cape >= 0).all()) and bool((cin <= 0).all())
+            assert not bool(torch.isnan(cape).any()) and not bool(torch.isnan(cin).any())
+            lcl, lfc, el = r1[kind]["lcl_pressure"], r1[kind]["lfc_pressure"], r1[kind]["el_pressure"]
+            ok = ~torch.isnan(lfc)
+            assert bool((lfc[ok] <= lcl[ok]).all())
+            assert float((cape > 0).float().mean()) > 0.05           # the workload is not degenerate
+        # oracle on a sample of the same columns
+        sel = torch.randperm(N, device="cuda", generator=torch.Generator(device="cuda").manual_seed(9))[:3000]
+        ps = p if p.dim() == 1 else p[:, sel]
+        ora = _oracle_suite(ps, t[:, sel], td[:, sel], gpu_tables)
+        for kind in ("sb", "ml", "mu"):
+            sub = {f: r1[kind][f][sel] for f in FIELDS}
+            _check(sub, ora, kind + "_", 3e-7, what=f"{shape} sample: ")
+
+
+# --------------------------------------------------------------------------- drop-in API
+def test_parcel_functions_api_numpy(ctx, gpu_tables):
+    """The reference-facing Python surface (same names / kwargs / returned variable names) on
+    NumPy inputs; vertical axis not first; host arrays in -> host arrays out."""
+    import xarray_parcel_b200.parcel_functions as parcel
+    parcel.load_moist_adiabat_lookups()
+    parcel.lookup_tables_loaded()
+    p, t, td = synth.model_level_columns(30 * 40, 45, seed=23)
+    P, T, D = [x.numpy().reshape(45, 30, 40).transpose(1, 0, 2).copy() for x in (p, t, td)]   # [y, level, x]
+    cc, prof = parcel.surface_based_cape_cin(P, T, D, vert_axis=1, prefix="surface")
+    assert set(cc) == {"surface_cape", "surface_cin"} and cc["surface_cape"].shape == (30, 40)
+    assert prof["pressure"].shape == (30, 46, 40)
+    for k in ("lcl_pressure", "lfc_pressure", "el_pressure", "temperature", "environment_virtual_temperature"):
+        assert k in prof
+    ora = _oracle_suite(p, t, td, gpu_tables)
+    assert np.allclose(cc["surface_cape"].reshape(-1), ora["sb_cape"], rtol=3e-6, atol=1e-3)
+    cc, prof, mp = parcel.mixed_layer_cape_cin(P, T, D, vert_axis=1, depth=100, prefix="mixed_100")
+    assert np.allclose(cc["mixed_100_cin"].reshape(-1), ora["ml_cin"], rtol=3e-6, atol=1e-3)
+    assert set(mp) == {"pressure", "temperature", "dewpoint"}
+    cc, prof, ul = parcel.most_unstable_cape_cin(P, T, D, vert_axis=1, depth=300, prefix="max")
+    assert np.allclose(cc["max_cape"].reshape(-1), ora["mu_cape"], rtol=3e-6, atol=1e-3)
+    ok = ~np.isnan(ora["mu_parcel_pressure"])
+    assert np.allclose(ul["pressure"].reshape(-1)[ok], ora["mu_parcel_pressure"][ok], rtol=1e-6)
+    ds = parcel.parcel_suite(P, T, D, vert_axis=1)
+    assert np.allclose(ds["max_cape"].reshape(-1), ora["mu_cape"], rtol=3e-6, atol=1e-3)
+    assert np.allclose(ds["mixed_100_cape"].reshape(-1), ora["ml_cape"], rtol=3e-6, atol=1e-3)
+    with pytest.raises(AssertionError, match="interpolator must be linear or log"):
+        parcel.surface_based_cape_cin(P, T, D, vert_axis=1, lcl_interp="cubic")
+
+
+def test_launch_count_and_timer(ctx):
+    p, t, td = synth.model_level_columns(4096, 37, seed=2, device="cuda")
+    n0 = ctx.launch_count()
+    ctx.cape_cin(p, t, td, kinds=("sb", "ml", "mu"))
+    assert ctx.launch_count() == n0 + 1          # the suite is ONE fused launch
+    assert ctx.last_kernel_ms() > 0

@@ -11,6 +11,9 @@ SOURCES = ["xp_api.cu", "xp_kernels.cu", "xp_tables.cu"]
 HEADERS = ["xp_math.cuh", "xp_column.cuh", "xp_parcels.cuh", "xp_kernels.cuh",
            os.path.join("..", "..", "include", "xparcel.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              # no FMA contraction: the float64 path must round like the reference's NumPy arithmetic
+              # (knife-edge cases such as zero-width intervals at a duplicated LCL pressure, PF:1046-1050)
+              "-fmad=false",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 
 

@@ -237,25 +237,48 @@ class Context:
         return XpColumns(p.data_ptr(), t.data_ptr(), td.data_ptr(), N, L, _dtype_code(t),
                          max(ls, N), max(pls, 1 if p1d else N), int(p1d), mem), L, N
 
-    def _alloc_out(self, like, N, L, profile, pin):
-        """Output block for one parcel kind: scalars [12, N], shift [N], optional profile [6, L+1, N]."""
+    def _alloc_out(self, like, N, L, profile, pin, fields=None, shift=True):
+        """Output block for one parcel kind: scalars [n_fields, N], shift [N], optional profile
+        [6, L+1, N].  ``fields`` restricts the scalar outputs (NULL pointers are not written)."""
         kw = dict(dtype=like.dtype, device=like.device)
         pin = pin and not like.is_cuda
-        scal = torch.empty((len(SCALAR_FIELDS), N), pin_memory=pin, **kw)
-        shift = torch.empty((N,), dtype=torch.int32, device=like.device, pin_memory=pin)
+        names = list(SCALAR_FIELDS) if fields is None else [f for f in SCALAR_FIELDS if f in fields]
+        scal = torch.empty((len(names), N), pin_memory=pin, **kw)
+        sh = torch.empty((N,), dtype=torch.int32, device=like.device, pin_memory=pin) if shift else None
         prof = torch.empty((len(PROFILE_FIELDS), L + 1, N), pin_memory=pin, **kw) if profile else None
         po = XpParcelOut()
-        for i, f in enumerate(SCALAR_FIELDS):
+        for i, f in enumerate(names):
             setattr(po, f, scal[i].data_ptr())
-        po.level_shift = shift.data_ptr()
+        if sh is not None:
+            po.level_shift = sh.data_ptr()
         if prof is not None:
             for i, f in enumerate(PROFILE_FIELDS):
                 setattr(po, f, prof[i].data_ptr())
         po.profile_level_stride = N
-        return po, scal, shift, prof
+        return po, scal, sh, prof, names
+
+    def alloc_outputs(self, like, kinds=("sb",), profile=False, pin_outputs=False, fields=None,
+                      shift=True):
+        """Reusable output blocks for ``cape_cin(..., out=...)`` (``like``: the temperature block
+        [L, N]).  ``fields`` may be a list (all kinds) or {kind: list}."""
+        L, N = like.shape
+        outs = {}
+        for k in kinds:
+            f = fields.get(k) if isinstance(fields, dict) else fields
+            outs[k] = self._alloc_out(like, N, L, profile, pin_outputs, f, shift)
+        return outs
+
+    def output_bytes(self, outs):
+        """Bytes the library writes into an ``alloc_outputs`` block set."""
+        n = 0
+        for po, scal, sh, prof, _ in outs.values():
+            n += scal.numel() * scal.element_size()
+            n += sh.numel() * 4 if sh is not None else 0
+            n += prof.numel() * prof.element_size() if prof is not None else 0
+        return n
 
     def cape_cin(self, p, t, td, kinds=("sb",), options=None, profile=False, explicit=None,
-                 pin_outputs=False):
+                 pin_outputs=False, out=None):
         """Run the fused kernel for the requested parcel kinds on level-major torch tensors.
 
         CUDA tensors: asynchronous on the current stream.  CPU tensors: staged through the
@@ -264,11 +287,10 @@ class Context:
         opts = options if options is not None else make_options()
         cols, L, N = self._columns(p, t, td)
         kinds = tuple(kinds)
-        outs, keep = {}, {}
-        for k in kinds:
-            outs[k] = self._alloc_out(t, N, L, profile, pin_outputs)
+        keep = {}
+        outs = out if out is not None else self.alloc_outputs(t, kinds, profile, pin_outputs)
         if set(kinds) <= {"sb", "ml", "mu"} and len(kinds) > 1:
-            ptrs = [ctypes.byref(outs[k][0]) if k in outs else None for k in ("sb", "ml", "mu")]
+            ptrs = [ctypes.byref(outs[k][0]) if k in kinds else None for k in ("sb", "ml", "mu")]
             st = self.lib.xp_suite(self.handle, ctypes.byref(cols), ctypes.byref(opts), ptrs[0], ptrs[1],
                                    ptrs[2], self._stream())
             self._check(st, "xp_suite")
@@ -284,9 +306,10 @@ class Context:
                 self._check(st, "xp_cape_cin")
         res = {}
         for k in kinds:
-            _, scal, shift, prof = outs[k]
-            d = {f: scal[i] for i, f in enumerate(SCALAR_FIELDS)}
-            d["level_shift"] = shift
+            _, scal, shift, prof, names = outs[k]
+            d = {f: scal[i] for i, f in enumerate(names)}
+            if shift is not None:
+                d["level_shift"] = shift
             if prof is not None:
                 for i, f in enumerate(PROFILE_FIELDS):
                     d[f] = prof[i]
