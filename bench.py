@@ -309,6 +309,7 @@ def run_b200(args):
     total_ms = max_over_ranks(total_ms)
     value = spec["N"] * world * args.steps / (total_ms * 1e-3)
     flags = ctx.take_flags()
+    n_exact = ctx.last_exact_count()
 
     # ---- end to end through the C ABI with host buffers --------------------------------------
     e2e_steps = args.e2e_steps or min(args.steps, 10)
@@ -364,12 +365,15 @@ def run_b200(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "xp::cape_cin_kernel<float>", "kernel_ms": kernel_ms,
+                         "kernel": ("xp::suite_fast_kernel + prep/coef + suite_list_kernel (exact fix-up)"
+                                    if n_exact >= 0 else "xp::cape_cin_kernel<float>"),
+                         "kernel_ms": kernel_ms,
                          "kernel_ms_min": per_ms[0], "algorithmic_bytes_per_launch": b_in + b_out,
                          "bytes_per_column": (b_in + b_out) / spec["N"]},
             "cpu_baseline": cpu,
             "clocks": clocks,
             "reference_assert_flags": flags,
+            "exact_path_columns": n_exact,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

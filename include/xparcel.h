@@ -88,7 +88,8 @@ typedef struct {
     int32_t pos_cape_neg_cin;               /* default 1 (PF:1293) */
     int32_t post_zero_cin;                  /* default 0 (PF:1293) */
     int32_t metpy_compat;                   /* 141 = MetPy 1.4.1 formulas (default), 162 = 1.6.2 */
-    int32_t reserved;
+    int32_t exact_only;                     /* default 0; 1 = always run the float64 exact kernel (no
+                                               float32 fast path; see DESIGN.md "fast path") */
     double mixed_layer_depth;               /* hPa, default 100 (PF:1652) */
     double most_unstable_depth;             /* hPa, default 300 (PF:1558) */
 } xp_options;
@@ -190,6 +191,10 @@ xp_status xp_cape_cin_base(xp_context *ctx, const void *pressure, const void *te
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* Number of kernels this library has launched on ctx since creation. */
 uint64_t xp_launch_count(const xp_context *ctx);
+/* Columns of the most recent xp_cape_cin/xp_suite call that took the float32 fast path and were
+ * recomputed by the float64 exact kernel because a decision was within the float32 error margin
+ * (-1 if that call did not use the fast path).  Synchronises the call's stream. */
+xp_status xp_last_exact_count(xp_context *ctx, int64_t *out_count);
 /* Device time (ms) of the most recent xp_cape_cin/xp_suite kernel launch with
  * mem = XP_MEM_DEVICE, measured with CUDA events on the launch stream; syncs the stream. */
 xp_status xp_last_kernel_ms(xp_context *ctx, float *out_ms);

@@ -7,7 +7,9 @@
 // the product path (libxparcel.so) has no host implementation.
 #include <cstdint>
 
-#include "../../xarray_parcel_b200/csrc/xp_parcels.cuh"
+#include <vector>
+
+#include "../../xarray_parcel_b200/csrc/xp_fast.cuh"
 
 namespace {
 
@@ -58,4 +60,49 @@ extern "C" void hostsim_cape_cin(const double *p, const double *t, const double 
         if (shift) shift[c] = sh;
     }
     if (flags) *flags = fl;
+}
+
+// The float32 fast path of the suite (xp_fast.cuh) on a shared pressure axis.
+// out: [3 kinds][12 fields][n] float32, shift [3][n], redo [n] (mask of kinds the fast path hands to
+// the exact kernel).  Returns Prep.ok.
+namespace {
+struct HostRdF {
+    const float *t, *td;
+    int64_t ls;
+    float T(int k) const { return t[(int64_t)k * ls]; }
+    float Td(int k) const { return td[(int64_t)k * ls]; }
+};
+struct HostCoef {
+    const xp::fast::Coef *base;
+    xp::fast::Coef at(int k, int m) const { return base[k * xp::fast::kNI + m]; }
+};
+}  // namespace
+
+extern "C" int hostsim_fast_suite(const float *p, const float *t, const float *td, int64_t n, int L,
+                                  const int *iopts, double ml_depth, double mu_depth,
+                                  const uint16_t *index_grid, const float *curves, float *out,
+                                  int32_t *shift, uint32_t *redo) {
+    xp::Tables tb = {index_grid, curves};
+    xp::Opts o;
+    o.vtc = iopts[0]; o.log_interp = iopts[1]; o.pos_neg = iopts[2]; o.post_zero = iopts[3];
+    o.compat = iopts[4]; o.exact_only = 0; o.ml_depth = ml_depth; o.mu_depth = mu_depth;
+    static xp::fast::Prep pr;
+    xp::fast::compute_prep(p, 1, L, o, pr);
+    if (!pr.ok) return 0;
+    std::vector<xp::fast::Coef> coef((size_t)L * xp::fast::kNI);
+    for (int k = 0; k < pr.n_table; ++k)
+        for (int m = 0; m < xp::fast::kNI; ++m) coef[(size_t)k * xp::fast::kNI + m] = xp::fast::compute_coef(pr, curves, k, m);
+    HostCoef cf = {coef.data()};
+    for (int64_t c = 0; c < n; ++c) {
+        HostRdF rd = {t + c, td + c, n};
+        xp::fast::FResult r[3];
+        redo[c] = xp::fast::suite_column(rd, cf, pr, tb, o, 7u, r);
+        for (int q = 0; q < 3; ++q) {
+            const float vals[12] = {r[q].cape, r[q].cin, r[q].lcl_p, r[q].lcl_t, r[q].lcl_tv, r[q].lfc_p,
+                                    r[q].lfc_t, r[q].el_p, r[q].el_t, r[q].par_p, r[q].par_t, r[q].par_td};
+            for (int f = 0; f < 12; ++f) out[((int64_t)q * 12 + f) * n + c] = vals[f];
+            shift[(int64_t)q * n + c] = r[q].shift;
+        }
+    }
+    return 1;
 }

@@ -1,0 +1,99 @@
+"""CPU check of the float32 FAST PATH logic (xarray_parcel_b200/csrc/xp_fast.cuh compiled for the
+host by tests/hostsim, test-only) against the whole-array oracle.
+
+The fast path may hand any column to the float64 exact kernel (`redo` mask).  For every column it
+keeps it must (a) reproduce the oracle's NaN pattern of LFC/EL exactly (i.e. the same crossings
+were found), (b) reproduce the integer outputs exactly, (c) meet the north_star tolerances with a
+large margin.  The fraction it hands over must stay small.
+"""
+
+import numpy as np
+import pytest
+
+import hostsim_util as hs
+from oracle import parcel as op
+from xarray_parcel_b200 import synth
+
+FIELDS = ["cape", "cin", "lcl_pressure", "lcl_temperature", "lcl_virtual_temperature",
+          "lfc_pressure", "lfc_temperature", "el_pressure", "el_temperature"]
+# (relative, absolute) regression bounds of the float32 path -- far inside the north_star tolerances
+BOUND = {"cape": (2e-5, 0.05), "cin": (2e-5, 0.05), "lcl_pressure": (3e-7, 0), "lcl_temperature": (3e-7, 0),
+         "lcl_virtual_temperature": (6e-7, 0), "lfc_pressure": (4e-4, 0), "lfc_temperature": (1e-4, 0),
+         "el_pressure": (4e-4, 0), "el_temperature": (1e-4, 0)}
+
+OPTION_SETS = [
+    dict(vtc=True, lcl_interp="log", pos_cape_neg_cin=True, compat="1.4.1"),
+    dict(vtc=False, lcl_interp="linear", pos_cape_neg_cin=True, compat="1.4.1"),
+    dict(vtc=True, lcl_interp="linear", pos_cape_neg_cin=False, compat="1.6.2"),
+    dict(vtc=False, lcl_interp="log", pos_cape_neg_cin=False, compat="1.4.1"),
+]
+
+
+def check_fast(res, redo, ora, max_redo):
+    n = redo.size
+    for q, kind in enumerate(("sb", "ml", "mu")):
+        keep = ((redo >> q) & 1) == 0
+        assert 1.0 - keep.mean() <= max_redo, f"{kind}: {1 - keep.mean():.4f} of the columns handed to the exact path"
+        for f in FIELDS:
+            a = res[kind][f].astype(np.float64)
+            b = ora[f"{kind}_{f}"]
+            mis = np.flatnonzero((np.isnan(a) != np.isnan(b)) & keep)
+            assert mis.size == 0, f"{kind}_{f}: NaN pattern differs in kept columns {mis[:8]}"
+            ok = keep & ~np.isnan(b)
+            diff = np.abs(a - b)
+            rel, ab = BOUND[f]
+            bad = np.flatnonzero(ok & (diff > rel * np.abs(b) + ab))
+            assert bad.size == 0, (f"{kind}_{f}: {bad.size}/{n} kept columns outside the float32 bound, e.g. "
+                                   f"{[(int(i), float(a[i]), float(b[i])) for i in bad[:4]]}")
+        if kind != "sb":
+            for f in ("pressure", "temperature", "dewpoint"):
+                a = res[kind]["parcel_" + f].astype(np.float64)
+                b = ora[f"{kind}_parcel_{f}"]
+                ok = keep & ~np.isnan(b)
+                assert np.allclose(a[ok], b[ok], rtol=2e-7, atol=0), (kind, f)
+
+
+@pytest.mark.parametrize("o", OPTION_SETS, ids=lambda o: f"vtc{int(o['vtc'])}-{o['lcl_interp']}-pn{int(o['pos_cape_neg_cin'])}-{o['compat']}")
+def test_fast_suite_matches_oracle_era5(oracle_tables, o):
+    p, t, td = synth.era5_columns(6000, seed=12, nan_columns=0.01)
+    P = np.broadcast_to(p.numpy().astype(np.float64)[:, None], t.shape)
+    T, D = t.numpy().astype(np.float64), td.numpy().astype(np.float64)
+    opts = op.Options(op.MoistLapseLUT(oracle_tables), lcl_mode="converged", metpy_compat=o["compat"])
+    ora = op.suite(P, T, D, opts, virtual_temperature_correction=o["vtc"], lcl_interp=o["lcl_interp"],
+                   pos_cape_neg_cin=o["pos_cape_neg_cin"])
+    out = hs.fast_suite(p.numpy(), t.numpy(), td.numpy(), oracle_tables, vtc=o["vtc"], lcl_interp=o["lcl_interp"],
+                        pos_cape_neg_cin=o["pos_cape_neg_cin"], metpy_compat=141 if o["compat"] == "1.4.1" else 162)
+    assert out is not None
+    res, redo = out
+    check_fast(res, redo, ora, max_redo=0.04)
+    # integer outputs: most-unstable level index, number of mixed-layer levels
+    mu = op.most_unstable_parcel({"pressure": P, "temperature": T, "dewpoint": D}, depth=300)
+    with np.errstate(invalid="ignore"):
+        k_mu = (P > mu["pressure"][None, :]).sum(0)
+    keep = ((redo >> 2) & 1) == 0
+    assert np.array_equal(res["mu"]["level_shift"][keep], k_mu[keep])
+    assert (res["ml"]["level_shift"] == 5).all()        # 1000, 975, 950, 925, 900 hPa
+
+
+def test_fast_suite_other_axes(oracle_tables):
+    """A shared axis that is not ERA5's: uneven levels, mixed-layer top between levels, depth options."""
+    rng = np.random.default_rng(3)
+    p = np.sort(np.concatenate([[1013.0], rng.uniform(120, 1010, 30), [80.0, 40.0, 12.0, 4.0, 1.5]]))[::-1]
+    p = p.astype(np.float32)
+    N = 3000
+    z = 7.5 * np.log(1013.0 / p.astype(np.float64))[:, None]
+    t0 = rng.uniform(275, 305, N); lapse = rng.uniform(5.5, 9.0, N)
+    T = np.maximum(t0[None, :] - lapse[None, :] * z, rng.uniform(200, 220, N)[None, :]).astype(np.float32)
+    D = (T - (rng.uniform(1, 15, N)[None, :] + 1.5 * z)).astype(np.float32)
+    P = np.broadcast_to(p.astype(np.float64)[:, None], T.shape)
+    opts = op.Options(op.MoistLapseLUT(oracle_tables), lcl_mode="converged")
+    ora = op.suite(P, T.astype(np.float64), D.astype(np.float64), opts, ml_depth=75.0, mu_depth=250.0)
+    res, redo = hs.fast_suite(p, T, D, oracle_tables, ml_depth=75.0, mu_depth=250.0)
+    check_fast(res, redo, ora, max_redo=0.04)
+
+
+def test_fast_path_refuses_bad_axes(oracle_tables):
+    t = np.full((5, 4), 280.0, dtype=np.float32)
+    for p in ([1000, 900, 900, 700, 500], [900, 1000, 800, 700, 600], [1200, 1000, 800, 700, 600],
+              [1000, np.nan, 800, 700, 600]):
+        assert hs.fast_suite(np.array(p, dtype=np.float32), t, t - 5, oracle_tables) is None

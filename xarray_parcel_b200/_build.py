@@ -7,14 +7,17 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libxparcel.so")
-SOURCES = ["xp_api.cu", "xp_kernels.cu", "xp_tables.cu"]
-HEADERS = ["xp_math.cuh", "xp_column.cuh", "xp_parcels.cuh", "xp_kernels.cuh",
+SOURCES = ["xp_api.cu", "xp_kernels.cu", "xp_tables.cu", "xp_fast.cu"]
+HEADERS = ["xp_math.cuh", "xp_column.cuh", "xp_parcels.cuh", "xp_kernels.cuh", "xp_fast.cuh",
            os.path.join("..", "..", "include", "xparcel.h")]
-NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              # no FMA contraction: the float64 path must round like the reference's NumPy arithmetic
-              # (knife-edge cases such as zero-width intervals at a duplicated LCL pressure, PF:1046-1050)
-              "-fmad=false",
-              "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
+NVCC_COMMON = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+               "-Xcompiler", "-fPIC"]
+# The float64 exact path must round like the reference's NumPy arithmetic (knife-edge cases such as
+# zero-width intervals at a duplicated LCL pressure, PF:1046-1050): no FMA contraction there.  The
+# float32 fast path (xp_fast.cu) takes no decision inside its error margin, so it may contract.
+PER_FILE_FLAGS = {"xp_fast.cu": [], "xp_api.cu": ["-fmad=false"], "xp_kernels.cu": ["-fmad=false"],
+                  "xp_tables.cu": ["-fmad=false"]}
+LINK_FLAGS = ["-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
 
 
 def find_nvcc():
@@ -36,15 +39,31 @@ def build(force=False, verbose=False):
     """Compile the CUDA sources into xarray_parcel_b200/libxparcel.so.  Returns the path."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+    nvcc = find_nvcc()
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", f".{os.getpid()}.o"))
+        cmd = [nvcc] + NVCC_COMMON + PER_FILE_FLAGS.get(src, []) + (["-Xptxas", "-v"] if verbose else [])
+        cmd += ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    objs, log = [], ""
+    for src, obj, pr in procs:
+        out, err = pr.communicate()
+        log += out + err
+        if pr.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + out + err)
+        objs.append(obj)
     tmp = LIB_PATH + f".tmp{os.getpid()}"
-    cmd += ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    res = subprocess.run([nvcc] + LINK_FLAGS + ["-o", tmp] + objs, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     os.replace(tmp, LIB_PATH)
+    for o in objs:
+        os.remove(o)
     if verbose:
-        print(res.stderr)
+        print(log)
     return LIB_PATH
 
 

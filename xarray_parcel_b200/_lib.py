@@ -41,7 +41,7 @@ class XpColumns(ctypes.Structure):
 class XpOptions(ctypes.Structure):
     _fields_ = [("virtual_temperature_correction", c_int32), ("lcl_interp_log", c_int32),
                 ("pos_cape_neg_cin", c_int32), ("post_zero_cin", c_int32),
-                ("metpy_compat", c_int32), ("reserved", c_int32),
+                ("metpy_compat", c_int32), ("exact_only", c_int32),
                 ("mixed_layer_depth", c_double), ("most_unstable_depth", c_double)]
 
 
@@ -58,7 +58,7 @@ EXPORTS = ["xp_version", "xp_create", "xp_destroy", "xp_last_error", "xp_take_fl
            "xp_default_options", "xp_tables_build", "xp_tables_set", "xp_tables_get",
            "xp_tables_loaded", "xp_cape_cin", "xp_suite", "xp_lcl", "xp_moist_lapse",
            "xp_parcel_profile", "xp_lfc_el", "xp_cape_cin_base", "xp_launch_count",
-           "xp_last_kernel_ms"]
+           "xp_last_kernel_ms", "xp_last_exact_count"]
 
 
 class XparcelError(RuntimeError):
@@ -117,17 +117,18 @@ def load_library():
         lib.xp_launch_count.argtypes = [c_void_p]
         lib.xp_launch_count.restype = ctypes.c_uint64
         lib.xp_last_kernel_ms.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_float)]
+        lib.xp_last_exact_count.argtypes = [c_void_p, ctypes.POINTER(c_int64)]
         _lib = lib
         return lib
 
 
 def make_options(virtual_temperature_correction=True, lcl_interp="log", pos_cape_neg_cin=True,
                  post_zero_cin=False, metpy_compat="1.4.1", mixed_layer_depth=100.0,
-                 most_unstable_depth=300.0):
+                 most_unstable_depth=300.0, exact_only=False):
     assert lcl_interp in ["linear", "log"], "interpolator must be linear or log"   # PF:878
     compat = {"1.4.1": 141, "1.6.2": 162, 141: 141, 162: 162}[metpy_compat]
     return XpOptions(int(bool(virtual_temperature_correction)), int(lcl_interp == "log"),
-                     int(bool(pos_cape_neg_cin)), int(bool(post_zero_cin)), compat, 0,
+                     int(bool(pos_cape_neg_cin)), int(bool(post_zero_cin)), compat, int(bool(exact_only)),
                      float(mixed_layer_depth), float(most_unstable_depth))
 
 
@@ -202,6 +203,13 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.xp_launch_count(self.handle))
+
+    def last_exact_count(self):
+        """Columns of the last call that the float32 fast path handed to the exact kernel (-1: the
+        call did not use the fast path)."""
+        n = c_int64(0)
+        self._check(self.lib.xp_last_exact_count(self.handle, ctypes.byref(n)), "xp_last_exact_count")
+        return n.value
 
     def last_kernel_ms(self):
         ms = ctypes.c_float(0)

@@ -4,8 +4,10 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/xparcel.h"
@@ -32,6 +34,12 @@ struct xp_context {
     cudaStream_t slot_stream[kSlots] = {nullptr, nullptr, nullptr};
     void *slot_buf[kSlots] = {nullptr, nullptr, nullptr};
     size_t slot_bytes = 0;
+    // fast-path scratch (prep, coefficient table, uncertain-column list), one per stream in use
+    struct Scratch { void *ptr = nullptr; size_t bytes = 0; };
+    std::map<cudaStream_t, Scratch> scratch;
+    cudaStream_t last_fast_stream = nullptr;
+    bool last_was_fast = false;
+    int sm_count = 148;
     std::mutex mu;
 };
 
@@ -80,6 +88,7 @@ Opts to_opts(const xp_options *o) {
     r.compat = d.metpy_compat == 162 ? 162 : 141;
     r.ml_depth = d.mixed_layer_depth;
     r.mu_depth = d.most_unstable_depth;
+    r.exact_only = d.exact_only != 0;
     return r;
 }
 
@@ -146,6 +155,27 @@ xp_status run_device(xp_context *ctx, const xp_columns *cols, int kind_mask,
         pa.p = (const T *)ex->pressure; pa.t = (const T *)ex->temperature; pa.td = (const T *)ex->dewpoint;
     }
     Tables tb = {ctx->d_index, ctx->d_curves};
+    ctx->last_was_fast = false;
+    if constexpr (std::is_same<T, float>::value) {
+        const ColsArg<float> ca = to_cols<float>(cols);
+        if (!o.exact_only && cols->n_columns > 0 && fast_eligible(ca, kind_mask, oa)) {
+            xp_context::Scratch &sc = ctx->scratch[stream];
+            const size_t need = fast_scratch_bytes(cols->n_columns);
+            if (sc.bytes < need) {
+                if (sc.ptr) { cudaStreamSynchronize(stream); cudaFree(sc.ptr); sc.ptr = nullptr; sc.bytes = 0; }
+                XP_CUDA(ctx, cudaMalloc(&sc.ptr, need));
+                sc.bytes = need;
+            }
+            if (time_it) cudaEventRecord(ctx->ev0, stream);
+            const int nl = launch_suite_fast(ca, tb, o, kind_mask, oa, sc.ptr, ctx->d_flags, ctx->sm_count, stream);
+            if (nl < 0) return check_cuda(ctx, cudaGetLastError(), "fast suite shared-memory attribute");
+            ctx->launches += nl;
+            if (time_it) { cudaEventRecord(ctx->ev1, stream); ctx->ev_valid = true; }
+            ctx->last_was_fast = true;
+            ctx->last_fast_stream = stream;
+            return check_cuda(ctx, cudaGetLastError(), "fast suite launch");
+        }
+    }
     if (time_it) cudaEventRecord(ctx->ev0, stream);
     launch_cape_cin<T>(to_cols<T>(cols), tb, o, kind_mask, oa, pa, ctx->d_flags, stream);
     if (time_it) { cudaEventRecord(ctx->ev1, stream); ctx->ev_valid = true; }
@@ -334,7 +364,7 @@ void xp_default_options(xp_options *o) {
     o->pos_cape_neg_cin = 1;
     o->post_zero_cin = 0;
     o->metpy_compat = 141;
-    o->reserved = 0;
+    o->exact_only = 0;
     o->mixed_layer_depth = 100.0;
     o->most_unstable_depth = 300.0;
 }
@@ -352,6 +382,7 @@ xp_status xp_create(int device, xp_context **out_ctx) {
     xp_context *ctx = new xp_context();
     ctx->device = device;
     DeviceGuard guard(device);
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if ((e = cudaMalloc(&ctx->d_flags, sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMemset(ctx->d_flags, 0, sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
@@ -374,6 +405,7 @@ void xp_destroy(xp_context *ctx) {
             if (ctx->slot_buf[s]) cudaFree(ctx->slot_buf[s]);
             if (ctx->slot_stream[s]) cudaStreamDestroy(ctx->slot_stream[s]);
         }
+        for (auto &kv : ctx->scratch) cudaFree(kv.second.ptr);
         if (ctx->ev0) cudaEventDestroy(ctx->ev0);
         if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     }
@@ -563,6 +595,17 @@ xp_status xp_cape_cin_base(xp_context *ctx, const void *pressure, const void *te
 }
 
 uint64_t xp_launch_count(const xp_context *ctx) { return ctx ? ctx->launches : 0; }
+
+xp_status xp_last_exact_count(xp_context *ctx, int64_t *out_count) {
+    if (!ctx || !out_count) return XP_ERR_INVALID_ARGUMENT;
+    *out_count = -1;
+    if (!ctx->last_was_fast) return XP_OK;
+    DeviceGuard guard(ctx->device);
+    auto it = ctx->scratch.find(ctx->last_fast_stream);
+    if (it == ctx->scratch.end() || !it->second.ptr) return XP_OK;
+    *out_count = (int64_t)fast_last_list_count(it->second.ptr, ctx->last_fast_stream);
+    return check_cuda(ctx, cudaGetLastError(), "xp_last_exact_count");
+}
 
 xp_status xp_last_kernel_ms(xp_context *ctx, float *out_ms) {
     if (!ctx || !out_ms) return XP_ERR_INVALID_ARGUMENT;

@@ -27,6 +27,7 @@ struct Tables {
 
 struct Opts {
     int vtc, log_interp, pos_neg, post_zero, compat;
+    int exact_only;      // 1: never take the float32 fast path
     double ml_depth, mu_depth;
 };
 

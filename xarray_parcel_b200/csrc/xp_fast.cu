@@ -1,0 +1,272 @@
+// xp_fast.cu -- sm_100a kernels of the float32 fast path (see xp_fast.cuh) and of the exact-path
+// fix-up over the compact list of columns whose decisions were uncertain in float32.
+#include "xp_fast.cuh"
+#include "xp_kernels.cuh"
+
+namespace xp {
+
+using fast::Coef;
+using fast::Prep;
+
+namespace {
+
+// ---- prep kernels: axis constants (one thread) and the cubic coefficient table -----------------------
+__global__ void fast_prep_kernel(const float *__restrict__ p, int64_t pls, int L, Opts o, Prep *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    fast::compute_prep(p, pls, L, o, *out);
+}
+
+__global__ void fast_coef_kernel(const Prep *__restrict__ prep, const float *__restrict__ curves, Coef *__restrict__ coef) {
+    const int k = blockIdx.x, m = threadIdx.x;
+    if (!prep->ok || k >= prep->n_table || m >= fast::kNI) return;
+    coef[(size_t)k * fast::kNI + m] = fast::compute_coef(*prep, curves, k, m);
+}
+
+// ---- the fast suite kernel ---------------------------------------------------------------------------------------
+struct FastParams {
+    const float *t, *td;
+    int64_t n, ls;
+    const Prep *prep;
+    const Coef *coef;
+    Tables tb;
+    Opts o;
+    unsigned kinds;
+    OutArg<float> outs[3];
+    uint32_t *list;          // [n] entries: column | redo-mask << 29
+    uint32_t *list_count;
+};
+
+struct GlobalRd {
+    const float *t, *td;
+    int64_t ls;
+    __device__ __forceinline__ float T(int k) const { return __ldg(t + (int64_t)k * ls); }
+    __device__ __forceinline__ float Td(int k) const { return __ldg(td + (int64_t)k * ls); }
+};
+
+struct SmemCoef {
+    const Coef *base;
+    __device__ __forceinline__ Coef at(int k, int m) const {
+        const float4 v = *reinterpret_cast<const float4 *>(base + k * fast::kNI + m);
+        return Coef{v.x, v.y, v.z, v.w};
+    }
+};
+
+__device__ __forceinline__ void store_fast(const OutArg<float> &o, int64_t col, const fast::FResult &r) {
+    if (o.cape) o.cape[col] = r.cape;
+    if (o.cin) o.cin[col] = r.cin;
+    if (o.lcl_p) o.lcl_p[col] = r.lcl_p;
+    if (o.lcl_t) o.lcl_t[col] = r.lcl_t;
+    if (o.lcl_tv) o.lcl_tv[col] = r.lcl_tv;
+    if (o.lfc_p) o.lfc_p[col] = r.lfc_p;
+    if (o.lfc_t) o.lfc_t[col] = r.lfc_t;
+    if (o.el_p) o.el_p[col] = r.el_p;
+    if (o.el_t) o.el_t[col] = r.el_t;
+    if (o.par_p) o.par_p[col] = r.par_p;
+    if (o.par_t) o.par_t[col] = r.par_t;
+    if (o.par_td) o.par_td[col] = r.par_td;
+    if (o.shift) o.shift[col] = r.shift;
+}
+
+constexpr int kFastThreads = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(kFastThreads, 1) suite_fast_kernel(const __grid_constant__ FastParams prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+    Prep *s_prep = reinterpret_cast<Prep *>(smem_raw);
+    constexpr size_t kPrepBytes = (sizeof(Prep) + 127) & ~(size_t)127;
+    Coef *s_coef = reinterpret_cast<Coef *>(smem_raw + kPrepBytes);
+
+    // Prep (a few KB): plain cooperative copy
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(prm.prep);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s_prep);
+        for (int i = threadIdx.x; i < (int)(sizeof(Prep) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const Prep &pr = *s_prep;
+    if (!pr.ok) {
+        // the axis does not qualify: every column goes to the exact path
+        for (int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; col < prm.n;
+             col += (int64_t)gridDim.x * blockDim.x) {
+            const uint32_t slot = atomicAdd(prm.list_count, 1u);
+            prm.list[slot] = (uint32_t)col | (prm.kinds << 29);
+        }
+        return;
+    }
+    // the adiabat table: one bulk asynchronous copy (TMA) per level row into shared memory
+    const uint32_t row_bytes = fast::kNI * sizeof(Coef);
+    if (threadIdx.x == 0) {
+        const uint32_t total = row_bytes * (uint32_t)pr.n_table;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(total) : "memory");
+        for (int k = 0; k < pr.n_table; ++k) {
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    smem_u32(s_coef + (size_t)k * fast::kNI)),
+                "l"(prm.coef + (size_t)k * fast::kNI), "r"(row_bytes), "r"(smem_u32(&mbar))
+                : "memory");
+        }
+    }
+    {   // everyone waits for the table (phase 0)
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0u) : "memory");
+        }
+    }
+    const SmemCoef cf{s_coef};
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < prm.n; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t col = base + threadIdx.x;
+        if (col >= prm.n) continue;
+        const GlobalRd rd{prm.t + col, prm.td + col, prm.ls};
+        fast::FResult res[3];
+        const unsigned redo = fast::suite_column(rd, cf, pr, prm.tb, prm.o, prm.kinds, res);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if ((prm.kinds >> q) & 1u) store_fast(prm.outs[q], col, res[q]);
+        if (redo) {
+            const uint32_t slot = atomicAdd(prm.list_count, 1u);
+            prm.list[slot] = (uint32_t)col | (redo << 29);
+        }
+    }
+}
+
+// ---- exact fix-up over the list ------------------------------------------------------------------------------------------
+struct NoProf {
+    __device__ __forceinline__ void put(int, const ProfileRow &) const {}
+};
+
+struct ListParams {
+    ColsArg<float> cols;
+    Tables tb;
+    Opts o;
+    OutArg<float> outs[3];
+    const uint32_t *list;
+    const uint32_t *list_count;
+    uint32_t *flags;
+};
+
+struct ExactRd {
+    const float *p, *t, *td;
+    int64_t ls, pls;
+    int L;
+    __device__ __forceinline__ double P(int k) const { return (double)__ldg(p + (int64_t)k * pls); }
+    __device__ __forceinline__ double Tk(int k) const { return (double)__ldg(t + (int64_t)k * ls); }
+    __device__ __forceinline__ double Td(int k) const { return (double)__ldg(td + (int64_t)k * ls); }
+};
+
+// One thread per (list entry, parcel kind) item.
+__global__ void __launch_bounds__(128) suite_list_kernel(const __grid_constant__ ListParams prm) {
+    const uint32_t count = *prm.list_count;
+    if (count == 0) return;
+    // kind-major item order keeps the parcel kind uniform inside a warp
+    for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < (uint64_t)count * 3u;
+         it += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t e = prm.list[it % count];
+        const int kind = (int)(it / count);
+        if (!((e >> (29 + kind)) & 1u)) continue;
+        const int64_t col = (int64_t)(e & 0x1fffffffu);
+        ExactRd rd;
+        rd.p = prm.cols.p1d ? prm.cols.p : prm.cols.p + col;
+        rd.t = prm.cols.t + col; rd.td = prm.cols.td + col;
+        rd.ls = prm.cols.ls; rd.pls = prm.cols.pls; rd.L = prm.cols.L;
+        ParcelResult r;
+        double p0, t0, td0;
+        int shift;
+        NoProf np;
+        run_column(rd, kind, prm.tb, prm.o, qnan(), qnan(), qnan(), r, p0, t0, td0, shift, np);
+        const OutArg<float> &o = prm.outs[kind];
+        if (o.cape) o.cape[col] = (float)r.cape;
+        if (o.cin) o.cin[col] = (float)r.cin;
+        if (o.lcl_p) o.lcl_p[col] = (float)r.lcl_p;
+        if (o.lcl_t) o.lcl_t[col] = (float)r.lcl_t;
+        if (o.lcl_tv) o.lcl_tv[col] = (float)r.lcl_tv;
+        if (o.lfc_p) o.lfc_p[col] = (float)r.lfc_p;
+        if (o.lfc_t) o.lfc_t[col] = (float)r.lfc_t;
+        if (o.el_p) o.el_p[col] = (float)r.el_p;
+        if (o.el_t) o.el_t[col] = (float)r.el_t;
+        if (o.par_p) o.par_p[col] = (float)p0;
+        if (o.par_t) o.par_t[col] = (float)t0;
+        if (o.par_td) o.par_td[col] = (float)td0;
+        if (o.shift) o.shift[col] = shift;
+        if (r.flags && prm.flags) atomicOr(prm.flags, r.flags);
+    }
+}
+
+}  // namespace
+
+size_t fast_scratch_bytes(int64_t n) {
+    // Prep | coef table | list counter | list
+    return ((sizeof(Prep) + 255) & ~(size_t)255) + (size_t)fast::kMaxLevels * fast::kNI * sizeof(Coef) + 256 +
+           (size_t)n * sizeof(uint32_t);
+}
+
+bool fast_eligible(const ColsArg<float> &cols, int kind_mask, const OutArg<float> *outs) {
+    if (!cols.p1d || cols.L < 3 || cols.L > fast::kMaxLevels || cols.n >= (int64_t)1 << 29) return false;
+    if (kind_mask & ~(kSB | kML | kMU)) return false;
+    for (int q = 0; q < 3; ++q) {
+        if (!((kind_mask >> q) & 1)) continue;
+        const OutArg<float> &o = outs[q];
+        if (o.prof_p || o.prof_t || o.prof_tv || o.prof_et || o.prof_etv || o.prof_etd) return false;
+    }
+    return true;
+}
+
+int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &o, int kind_mask,
+                      const OutArg<float> *outs, void *scratch, uint32_t *flags, int sm_count,
+                      cudaStream_t stream) {
+    if (cols.n <= 0) return 0;
+    unsigned char *base = static_cast<unsigned char *>(scratch);
+    Prep *prep = reinterpret_cast<Prep *>(base);
+    size_t off = (sizeof(Prep) + 255) & ~(size_t)255;
+    Coef *coef = reinterpret_cast<Coef *>(base + off);
+    off += (size_t)fast::kMaxLevels * fast::kNI * sizeof(Coef);
+    uint32_t *count = reinterpret_cast<uint32_t *>(base + off);
+    off += 256;
+    uint32_t *list = reinterpret_cast<uint32_t *>(base + off);
+
+    cudaMemsetAsync(count, 0, sizeof(uint32_t), stream);
+    fast_prep_kernel<<<1, 32, 0, stream>>>(cols.p, cols.pls, cols.L, o, prep);
+    fast_coef_kernel<<<cols.L, fast::kNI, 0, stream>>>(prep, tb.curves, coef);
+
+    FastParams fp;
+    fp.t = cols.t; fp.td = cols.td; fp.n = cols.n; fp.ls = cols.ls;
+    fp.prep = prep; fp.coef = coef; fp.tb = tb; fp.o = o; fp.kinds = (unsigned)kind_mask;
+    for (int q = 0; q < 3; ++q) fp.outs[q] = outs[q];
+    fp.list = list; fp.list_count = count;
+    const size_t smem = ((sizeof(Prep) + 127) & ~(size_t)127) + (size_t)cols.L * fast::kNI * sizeof(Coef);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        if (cudaFuncSetAttribute(suite_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return -1;
+        smem_set = smem;
+    }
+    const int64_t tiles = (cols.n + kFastThreads - 1) / kFastThreads;
+    const int grid = (int)(tiles < sm_count ? tiles : sm_count);
+    suite_fast_kernel<<<grid, kFastThreads, smem, stream>>>(fp);
+
+    ListParams lp;
+    lp.cols = cols; lp.tb = tb; lp.o = o;
+    for (int q = 0; q < 3; ++q) lp.outs[q] = outs[q];
+    lp.list = list; lp.list_count = count; lp.flags = flags;
+    suite_list_kernel<<<sm_count * 8, 128, 0, stream>>>(lp);
+    return 4;
+}
+
+// number of list entries of the last fast launch (debug/metrics; synchronous copy)
+uint32_t fast_last_list_count(void *scratch, cudaStream_t stream) {
+    unsigned char *base = static_cast<unsigned char *>(scratch);
+    size_t off = ((sizeof(Prep) + 255) & ~(size_t)255) + (size_t)fast::kMaxLevels * fast::kNI * sizeof(Coef);
+    uint32_t v = 0;
+    cudaMemcpyAsync(&v, base + off, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+    return v;
+}
+
+}  // namespace xp

@@ -65,6 +65,16 @@ void launch_cape_cin_base(const T *pressure, const T *env_t, const T *parcel_t, 
                           int64_t n, const T *lfc_p, const T *el_p, const Opts &o, T *cape, T *cin,
                           cudaStream_t stream);
 
+// Float32 fast path of the suite on a shared pressure axis (xp_fast.cu / xp_fast.cuh): prep +
+// coefficient + fast kernel + exact fix-up over the uncertain-column list, all on `stream`.
+// `scratch` must hold fast_scratch_bytes(n) bytes and must not be shared by launches in flight.
+bool fast_eligible(const ColsArg<float> &cols, int kind_mask, const OutArg<float> *outs);
+size_t fast_scratch_bytes(int64_t n);
+int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &o, int kind_mask,
+                      const OutArg<float> *outs, void *scratch, uint32_t *flags, int sm_count,
+                      cudaStream_t stream);
+uint32_t fast_last_list_count(void *scratch, cudaStream_t stream);
+
 // Table builder (xp_tables.cu): fills index_grid (uint16 [kNP][kNT]) and curves (float
 // [kNAdiabats][kNP] ascending pressure).  `scratch_u32` must hold kNP*kNT uint32.
 void launch_build_tables(uint16_t *index_grid, float *curves, uint32_t *scratch_u32,
