@@ -71,10 +71,19 @@ struct HostRdF {
     int64_t ls;
     float T(int k) const { return t[(int64_t)k * ls]; }
     float Td(int k) const { return td[(int64_t)k * ls]; }
+    const float *tptr(int k) const { return t + (int64_t)k * ls; }
+    const float *tdptr(int k) const { return td + (int64_t)k * ls; }
+    int64_t stride() const { return ls; }
+    static float ld(const float *p) { return *p; }
+};
+struct HostCoefRow {
+    const xp::fast::Coef *row;
+    void advance() { row += xp::fast::kNI; }
+    xp::fast::Coef at(int m) const { return row[m]; }
 };
 struct HostCoef {
     const xp::fast::Coef *base;
-    xp::fast::Coef at(int k, int m) const { return base[k * xp::fast::kNI + m]; }
+    HostCoefRow row(int k) const { return HostCoefRow{base + k * xp::fast::kNI}; }
 };
 }  // namespace
 
@@ -96,7 +105,8 @@ extern "C" int hostsim_fast_suite(const float *p, const float *t, const float *t
     for (int64_t c = 0; c < n; ++c) {
         HostRdF rd = {t + c, td + c, n};
         xp::fast::FResult r[3];
-        redo[c] = xp::fast::suite_column(rd, cf, pr, tb, o, 7u, r);
+        redo[c] = (o.vtc && o.compat == 141) ? xp::fast::suite_column<7u, 1>(rd, cf, pr, tb, o, r)
+                                              : xp::fast::suite_column<7u, 0>(rd, cf, pr, tb, o, r);
         for (int q = 0; q < 3; ++q) {
             const float vals[12] = {r[q].cape, r[q].cin, r[q].lcl_p, r[q].lcl_t, r[q].lcl_tv, r[q].lfc_p,
                                     r[q].lfc_t, r[q].el_p, r[q].el_t, r[q].par_p, r[q].par_t, r[q].par_td};

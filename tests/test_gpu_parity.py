@@ -319,7 +319,9 @@ def test_edge_cases(ctx, gpu_tables):
         ora = _oracle_suite(ps, ts, tds, gpu_tables)
         res = ctx.cape_cin(ps.cuda(), ts.cuda(), tds.cuda(), kinds=("sb", "ml", "mu"))
         for kind in ("sb", "ml", "mu"):
-            _check(res[kind], ora, kind + "_", 1e-9, what=f"L={L}: ")
+            pt, pd_ = (ora[f"{kind}_parcel_temperature"], ora[f"{kind}_parcel_dewpoint"]) if kind != "sb" \
+                else (t[0].numpy(), td[0].numpy())
+            _check(res[kind], ora, kind + "_", 1e-9, what=f"L={L}: ", knife=(pt == pd_))
     # empty input
     e = torch.empty((30, 0), dtype=torch.float64, device="cuda")
     res = ctx.cape_cin(e, e, e, kinds=("sb",))

@@ -41,14 +41,23 @@ struct GlobalRd {
     int64_t ls;
     __device__ __forceinline__ float T(int k) const { return __ldg(t + (int64_t)k * ls); }
     __device__ __forceinline__ float Td(int k) const { return __ldg(td + (int64_t)k * ls); }
+    __device__ __forceinline__ const float *tptr(int k) const { return t + (int64_t)k * ls; }
+    __device__ __forceinline__ const float *tdptr(int k) const { return td + (int64_t)k * ls; }
+    __device__ __forceinline__ int64_t stride() const { return ls; }
+    static __device__ __forceinline__ float ld(const float *p) { return __ldg(p); }
 };
 
-struct SmemCoef {
-    const Coef *base;
-    __device__ __forceinline__ Coef at(int k, int m) const {
-        const float4 v = *reinterpret_cast<const float4 *>(base + k * fast::kNI + m);
+struct SmemCoefRow {
+    const Coef *row;
+    __device__ __forceinline__ void advance() { row += fast::kNI; }
+    __device__ __forceinline__ Coef at(int m) const {
+        const float4 v = *reinterpret_cast<const float4 *>(row + m);
         return Coef{v.x, v.y, v.z, v.w};
     }
+};
+struct SmemCoef {
+    const Coef *base;
+    __device__ __forceinline__ SmemCoefRow row(int k) const { return SmemCoefRow{base + k * fast::kNI}; }
 };
 
 __device__ __forceinline__ void store_fast(const OutArg<float> &o, int64_t col, const fast::FResult &r) {
@@ -71,6 +80,7 @@ constexpr int kFastThreads = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+template <unsigned KINDS, int MODE>
 __global__ void __launch_bounds__(kFastThreads, 1) suite_fast_kernel(const __grid_constant__ FastParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
@@ -126,10 +136,10 @@ __global__ void __launch_bounds__(kFastThreads, 1) suite_fast_kernel(const __gri
         if (col >= prm.n) continue;
         const GlobalRd rd{prm.t + col, prm.td + col, prm.ls};
         fast::FResult res[3];
-        const unsigned redo = fast::suite_column(rd, cf, pr, prm.tb, prm.o, prm.kinds, res);
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-            if ((prm.kinds >> q) & 1u) store_fast(prm.outs[q], col, res[q]);
+        const unsigned redo = fast::suite_column<KINDS, MODE>(rd, cf, pr, prm.tb, prm.o, res);
+        if (KINDS & 1u) store_fast(prm.outs[0], col, res[0]);
+        if (KINDS & 2u) store_fast(prm.outs[1], col, res[1]);
+        if (KINDS & 4u) store_fast(prm.outs[2], col, res[2]);
         if (redo) {
             const uint32_t slot = atomicAdd(prm.list_count, 1u);
             prm.list[slot] = (uint32_t)col | (redo << 29);
@@ -241,15 +251,30 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
     for (int q = 0; q < 3; ++q) fp.outs[q] = outs[q];
     fp.list = list; fp.list_count = count;
     const size_t smem = ((sizeof(Prep) + 127) & ~(size_t)127) + (size_t)cols.L * fast::kNI * sizeof(Coef);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        if (cudaFuncSetAttribute(suite_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return -1;
-        smem_set = smem;
-    }
     const int64_t tiles = (cols.n + kFastThreads - 1) / kFastThreads;
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
-    suite_fast_kernel<<<grid, kFastThreads, smem, stream>>>(fp);
+    static size_t smem_set[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
+    const int mode = (o.vtc && o.compat == 141) ? 1 : 0;
+#define XP_FAST_LAUNCH(K, M)                                                                                \
+    do {                                                                                                    \
+        if (smem > smem_set[M][K]) {                                                                        \
+            if (cudaFuncSetAttribute(suite_fast_kernel<K, M>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                     (int)smem) != cudaSuccess)                                             \
+                return -1;                                                                                  \
+            smem_set[M][K] = smem;                                                                          \
+        }                                                                                                   \
+        suite_fast_kernel<K, M><<<grid, kFastThreads, smem, stream>>>(fp);                                  \
+    } while (0)
+#define XP_FAST_CASE(K)                                                 \
+    case K:                                                             \
+        if (mode) XP_FAST_LAUNCH(K, 1); else XP_FAST_LAUNCH(K, 0);      \
+        break;
+    switch (kind_mask & 7) {
+        XP_FAST_CASE(1) XP_FAST_CASE(2) XP_FAST_CASE(3) XP_FAST_CASE(4) XP_FAST_CASE(5) XP_FAST_CASE(6) XP_FAST_CASE(7)
+        default: return -1;
+    }
+#undef XP_FAST_LAUNCH
+#undef XP_FAST_CASE
 
     ListParams lp;
     lp.cols = cols; lp.tb = tb; lp.o = o;

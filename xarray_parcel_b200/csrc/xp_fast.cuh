@@ -207,61 +207,38 @@ XP_HD void lcl_fast(double p0, double t, double td, double &lcl_p, double &lcl_t
     lcl_p = p0 * qd;
 }
 
-// ---- sweep state of one parcel (float32 version of Sweep in xp_column.cuh) -------------------------
-struct FSweep {
-    float xprev, dprev, aprev;          // ln p, parcel - environment, parcel curve at the previous row
-    float pos, tot;                     // running sums of positive areas and of all areas (ln p units)
+// ---- one parcel: constants + sweep state, all in registers ------------------------------------------------
+//
+// Row schedule.  The profile of a parcel is: start row (parcel == environment), the levels below
+// the LCL, the inserted LCL row (PF:858-931), the levels above it.  The sweep runs over ITERATIONS
+// it = 1 .. n_table shared by the three parcels: at iteration `it` a parcel whose first level above
+// the LCL is `ka` processes
+//      it <  ka : level it        (dry adiabat)
+//      it == ka : the LCL row
+//      it >  ka : level it - 1    (moist adiabat; the parcel "lags" one level behind)
+// so every lane executes the same instruction stream whatever its LCL height, the environment of
+// level it / it-1 is shared by the parcels, and "above the LCL" is simply `it > ka`.
+struct FParcel {
+    // constants
+    float c_dryv;               // dry-adiabat curve value = c_dryv * p^kappa (virtual temperature folded in)
+    float f;                    // position inside the cubic interval of the adiabat
+    int m;                      // cubic interval
+    int ka;                     // first level above the LCL = iteration of the LCL row
+    int kfirst;                 // first iteration at which this parcel processes a row
+    float x_lcl, a_lcl, b_lcl;  // the inserted LCL row
+    float lcl_p, lcl_t, lcl_tv;
+    bool bad;                   // must go to the exact path
+    // sweep state (float32 version of Sweep in xp_column.cuh)
+    float xprev, dprev, aprev;  // ln p, parcel - environment, parcel curve at the previous row
+    float pos, tot;             // running sums of the positive areas and of all areas (ln p units)
     float lcl_pos, lcl_tot;
     float lfc_pos, lfc_tot, lfc_x, lfc_t;
     float el_pos, el_tot, el_x, el_t;
-    int row;                            // index of the next row
-    int lfc_row, el_row;                // upper row of the interval holding the LFC / EL crossing (-1: none)
-    bool after_lcl, any_inc, pos_parcel, el_above, unc;
-
-    XP_HD void init(float x0, float a0) {
-        xprev = x0; dprev = 0.0f; aprev = a0;      // first row: parcel == environment (PF:1117-1120)
-        pos = tot = lcl_pos = lcl_tot = 0.0f;
-        lfc_pos = lfc_tot = lfc_x = lfc_t = 0.0f;
-        el_pos = el_tot = el_x = el_t = 0.0f;
-        row = 1; lfc_row = el_row = -1;
-        after_lcl = any_inc = pos_parcel = el_above = unc = false;
-    }
-
-    // Next row at ln p = x with parcel curve a and environment curve b (find_intersections
-    // PF:992-1064 + trap_around_zeros PF:1200-1289 + trapz PF:164-206 for the interval below it).
-    XP_HD void step(float x, float a, float b, bool is_lcl) {
-        const float d = a - b;
-        const float dx = xprev - x;
-        const bool cross = dprev * d < 0.0f;
-        const float frac = cross ? dprev * f_rcp(dprev - d) : 1.0f;    // zero at xprev - frac dx
-        const float h = 0.5f * dx;
-        const float a_lo = h * dprev * frac;
-        const float a_hi = h * d * (cross ? 1.0f - frac : 1.0f);
-        pos += fmaxf(a_lo, 0.0f); tot += a_lo;
-        if (cross) {
-            unc = unc || (fabsf(dprev - d) < kCrossSlope * dx);
-            const float ix = f_fma(-frac, dx, xprev);
-            const float iy = f_fma(frac, a - aprev, aprev);
-            if (d > 0.0f) {                                            // increasing (PF:1058)
-                any_inc = true;
-                if (after_lcl && lfc_row < 0) {                        // max-pressure one above the LCL (PF:1127-1132)
-                    lfc_row = row; lfc_pos = pos; lfc_tot = tot; lfc_x = ix; lfc_t = iy;
-                }
-            } else {                                                   // decreasing: min pressure wins (PF:1136)
-                el_row = row; el_pos = pos; el_tot = tot; el_x = ix; el_t = iy; el_above = after_lcl;
-            }
-        }
-        pos += fmaxf(a_hi, 0.0f); tot += a_hi;
-        if (is_lcl) { lcl_pos = pos; lcl_tot = tot; after_lcl = true; }
-        else if (after_lcl && d > 0.0f) pos_parcel = true;             // PF:1166-1169
-        unc = unc || !(fabsf(d) >= kDecisionEps);                      // also catches NaN
-        xprev = x; dprev = d; aprev = a; ++row;
-    }
-};
-
-struct FResult {
-    float cape, cin, lcl_p, lcl_t, lcl_tv, lfc_p, lfc_t, el_p, el_t, par_p, par_t, par_td;
-    int shift;
+    int lfc_it, el_it;          // iteration of the upper row of the interval with the LFC / EL crossing (0: none)
+    int n_inc;                  // increasing crossings seen (PF:1161)
+    float min_abs_d;            // min |parcel - environment| over the rows    -> decision margin
+    float min_slope;            // min over crossings of |d0 - d1| - kCrossSlope dx -> crossing placement margin
+    float max_d_above;          // max (parcel - environment) over rows above the LCL (PF:1166-1169)
 };
 
 XP_HD float f_qnan() {
@@ -272,26 +249,78 @@ XP_HD float f_qnan() {
 #endif
 }
 
+XP_HD void sweep_init(FParcel &c, float x0, float a0) {
+    c.xprev = x0; c.dprev = 0.0f; c.aprev = a0;        // start row: parcel == environment (PF:1117-1120)
+    c.pos = c.tot = c.lcl_pos = c.lcl_tot = 0.0f;
+    c.lfc_pos = c.lfc_tot = c.lfc_x = c.lfc_t = 0.0f;
+    c.el_pos = c.el_tot = c.el_x = c.el_t = 0.0f;
+    c.lfc_it = c.el_it = 0; c.n_inc = 0;
+    c.min_abs_d = 1e30f; c.min_slope = 1e30f; c.max_d_above = -1e30f;
+}
+
+// One row (ln p = x, parcel curve a, environment curve b): find_intersections PF:992-1064 +
+// trap_around_zeros PF:1200-1289 + trapz PF:164-206 for the interval below it.  Branch-free.
+XP_HD void sweep_step(FParcel &c, int it, float x, float a, float b, bool is_lcl, bool above) {
+    const float d = a - b;
+    const float dx = c.xprev - x;
+    const float den = c.dprev - d;
+    const bool cross = c.dprev * d < 0.0f;
+    const float fr = c.dprev * f_rcp(den);
+    const float frac = cross ? fr : 1.0f;                        // zero at xprev - frac dx
+    const float g = cross ? 1.0f - fr : 1.0f;
+    const float h = 0.5f * dx;
+    const float a_lo = h * c.dprev * frac;
+    const float a_hi = h * d * g;
+    c.pos += fmaxf(a_lo, 0.0f); c.tot += a_lo;
+    const float ix = f_fma(-frac, dx, c.xprev);
+    const float iy = f_fma(frac, a - c.aprev, c.aprev);
+    const bool inc = cross && d > 0.0f;                          // PF:1058
+    const bool dec = cross && !(d > 0.0f);                       // PF:1060
+    c.n_inc += inc ? 1 : 0;
+    // LFC: max-pressure increasing crossing above the LCL (PF:1127-1132) = the first one met
+    const bool take_lfc = inc && above && c.lfc_it == 0;
+    c.lfc_it = take_lfc ? it : c.lfc_it;
+    c.lfc_pos = take_lfc ? c.pos : c.lfc_pos; c.lfc_tot = take_lfc ? c.tot : c.lfc_tot;
+    c.lfc_x = take_lfc ? ix : c.lfc_x; c.lfc_t = take_lfc ? iy : c.lfc_t;
+    // EL: min-pressure decreasing crossing (PF:1136) = the last one met
+    c.el_it = dec ? it : c.el_it;
+    c.el_pos = dec ? c.pos : c.el_pos; c.el_tot = dec ? c.tot : c.el_tot;
+    c.el_x = dec ? ix : c.el_x; c.el_t = dec ? iy : c.el_t;
+    c.pos += fmaxf(a_hi, 0.0f); c.tot += a_hi;
+    c.lcl_pos = is_lcl ? c.pos : c.lcl_pos; c.lcl_tot = is_lcl ? c.tot : c.lcl_tot;
+    c.max_d_above = fmaxf(c.max_d_above, above ? d : -1e30f);
+    c.min_abs_d = fminf(c.min_abs_d, fabsf(d));
+    c.min_slope = fminf(c.min_slope, cross ? f_fma(-kCrossSlope, dx, fabsf(den)) : 1e30f);
+    c.xprev = x; c.dprev = d; c.aprev = a;
+}
+
+struct FResult {
+    float cape, cin, lcl_p, lcl_t, lcl_tv, lfc_p, lfc_t, el_p, el_t, par_p, par_t, par_td;
+    int shift;
+};
+
 // Sweep.finish of xp_column.cuh (lfc_el PF:1140-1185, cape_cin_base PF:1329-1388) on the float32 state.
-XP_HD void finish(const FSweep &s, float lcl_p, float lcl_targ, const Opts &o, FResult &r) {
+XP_HD void sweep_finish(const FParcel &s, const Opts &o, FResult &r) {
+    const float lcl_targ = o.vtc ? s.lcl_tv : s.lcl_t;
     const bool top_colder = s.dprev <= 0.0f;                            // PF:1151
-    const bool el_exists = top_colder && s.el_row >= 0 && s.el_above;   // PF:1152-1153
-    const bool lfc_missing = !s.any_inc;                                // PF:1161
-    const bool lfc_found = s.lfc_row >= 0;
-    const bool replace = (s.pos_parcel && lfc_missing) || (!lfc_missing && !lfc_found && el_exists);
+    const bool el_exists = top_colder && s.el_it > s.ka;                // PF:1152-1153 (EL above the LCL)
+    const bool lfc_missing = s.n_inc == 0;                              // PF:1161
+    const bool lfc_found = s.lfc_it != 0;
+    const bool pos_parcel = s.max_d_above > 0.0f;
+    const bool replace = (pos_parcel && lfc_missing) || (!lfc_missing && !lfc_found && el_exists);
     const bool have_lfc = lfc_found || replace;
     float l_pos = s.lfc_pos, l_tot = s.lfc_tot;
     r.lfc_p = lfc_found ? f_ex2(s.lfc_x * kLog2e) : f_qnan();
     r.lfc_t = lfc_found ? s.lfc_t : f_qnan();
-    if (replace) { r.lfc_p = lcl_p; r.lfc_t = lcl_targ; l_pos = s.lcl_pos; l_tot = s.lcl_tot; }
+    if (replace) { r.lfc_p = s.lcl_p; r.lfc_t = lcl_targ; l_pos = s.lcl_pos; l_tot = s.lcl_tot; }
     r.el_p = el_exists ? f_ex2(s.el_x * kLog2e) : f_qnan();
     r.el_t = el_exists ? s.el_t : f_qnan();
     float cape = 0.0f, cin = 0.0f;
     if (have_lfc) {
         const float e_pos = el_exists ? s.el_pos : s.pos;
         const float e_tot = el_exists ? s.el_tot : s.tot;
-        // EL below the LFC (PF:1352-1353 leaves no level between them): compare by interval index
-        const bool el_below_lfc = el_exists && lfc_found && !replace && s.el_row < s.lfc_row;
+        // EL below the LFC (PF:1352-1353 leaves no level between them): compare by interval
+        const bool el_below_lfc = el_exists && lfc_found && !replace && s.el_it < s.lfc_it;
         if (o.pos_neg) {
             cin = l_tot - l_pos;
             cape = el_below_lfc ? 0.0f : (e_pos - l_pos);
@@ -303,26 +332,15 @@ XP_HD void finish(const FSweep &s, float lcl_p, float lcl_targ, const Opts &o, F
     cape *= (float)kRd; cin *= (float)kRd;
     if (o.post_zero && !(cin <= 0.0f)) cin = 0.0f;
     r.cape = cape; r.cin = cin;
+    r.lcl_p = s.lcl_p; r.lcl_t = s.lcl_t; r.lcl_tv = s.lcl_tv;
 }
 
-// One parcel: everything that is constant along the column.
-struct FParcel {
-    float c_dry, w_parcel;      // dry adiabat T = c_dry * p^kappa (PF:291-316); parcel mixing ratio (PF:748)
-    float f;                    // position inside the cubic interval
-    int m;                      // cubic interval of the adiabat
-    int ka;                     // first level above the LCL (p < lcl_p)
-    int kfirst;                 // first level of the lifted column that is swept (after the start row)
-    float x_lcl, a_lcl, b_lcl;  // the inserted LCL row (PF:858-931)
-    float lcl_p, lcl_t, lcl_tv;
-    bool bad;                   // this parcel must go to the exact path
-};
-
-// Set up one parcel after its (p0, T0, Td0) are known.  `kstart` is the level of the start row (the
-// parcel level; for the mixed layer the start row is the prepended parcel itself and the column
-// continues at `knext`).  Td/T of the bracketing levels come through `rd`.
+// Set up one parcel once its (p0, T0, Td0) are known.  `kstart` is the level of the start row (the
+// parcel level; for the mixed layer the start row is the prepended parcel at p[0]) and the lifted
+// column continues at level `knext`.  T/Td of the levels bracketing the LCL come through `rd`.
 template <class Rd>
 XP_HD void setup_parcel(const Rd &rd, const Prep &pr, const Tables &tb, const Opts &o, double p0, double t0,
-                        double td0, int kstart, int knext, bool start_is_virtual, FParcel &pc) {
+                        double td0, int kstart, int knext, FParcel &pc) {
     pc.bad = false;
     pc.kfirst = knext;
     // saturated / supersaturated / NaN parcels: the LCL snaps to the parcel level (np.isclose in
@@ -340,8 +358,10 @@ XP_HD void setup_parcel(const Rd &rd, const Prep &pr, const Tables &tb, const Op
     pc.lcl_p = lpf; pc.lcl_t = ltf;
     const float es_l = f_es(ltf);
     pc.lcl_tv = f_tv(ltf, f_mixing_ratio(es_l, es_l, lpf, o.compat));           // PF:653-657
-    pc.w_parcel = f_mixing_ratio(f_es(t0f), f_es(td0f), p0f, o.compat);         // PF:748
-    pc.c_dry = t0f * f_rcp(pr.pk[kstart]);                                      // p0 == p[kstart]
+    const float w_parcel = f_mixing_ratio(f_es(t0f), f_es(td0f), p0f, o.compat);   // PF:748
+    const float c_dry = t0f * f_rcp(pr.pk[kstart]);                             // p0 == p[kstart]; PF:291-316
+    pc.c_dryv = o.vtc ? c_dry * f_fma(0.608f, w_parcel, 1.0f) : c_dry;          // PF:767, 773, 775
+    sweep_init(pc, pr.lnp[kstart], o.vtc ? f_tv(t0f, w_parcel) : t0f);
     // LCL position among the levels of the lifted column (insert_level PF:965-966): exact in float64
     int ka = knext;
     while (ka < pr.L && pr.p64[ka] >= lp) ++ka;
@@ -350,15 +370,15 @@ XP_HD void setup_parcel(const Rd &rd, const Prep &pr, const Tables &tb, const Op
     // p >= lcl_p (the start row when the LCL is below the first swept level), "after" = level ka.
     const int kb = ka - 1;
     const bool before_is_start = (ka == knext);
+    pc.x_lcl = pr.lnp[kstart]; pc.a_lcl = pc.b_lcl = 0.0f;
     if (ka >= pr.n_table || (!before_is_start && pr.p64[kb] == lp) || (before_is_start && p0 == lp)) {
         pc.bad = true;      // LCL above the table top / exactly on a level: exact path
-        pc.ka = pr.L; pc.x_lcl = pr.lnp[pr.L - 1]; pc.a_lcl = pc.b_lcl = 0.0f;
+        pc.ka = pr.n_table;
         return;
     }
     float tb_, tdb, xb;
     if (before_is_start) { tb_ = t0f; tdb = td0f; xb = o.log_interp ? pr.lnp[kstart] : pr.p[kstart]; }
     else { tb_ = rd.T(kb); tdb = rd.Td(kb); xb = o.log_interp ? pr.lnp[kb] : pr.p[kb]; }
-    if (start_is_virtual && before_is_start) xb = o.log_interp ? pr.lnp[0] : pr.p[0];
     const float ta = rd.T(ka), tda = rd.Td(ka);
     const float xa = o.log_interp ? pr.lnp[ka] : pr.p[ka];
     const float x_l = kLn2 * f_lg2(lpf);
@@ -372,28 +392,50 @@ XP_HD void setup_parcel(const Rd &rd, const Prep &pr, const Tables &tb, const Op
     if (!(te == te) || !(tde == tde)) pc.bad = true;
 }
 
-// The whole suite for one column.  Rd: float T(k), Td(k).  Cf: Coef at(k, m) from shared memory.
-// Returns the mask of parcel kinds (bit 0 SB, 1 ML, 2 MU) that must be recomputed by the exact path.
-template <class Rd, class Cf>
+// One parcel, one iteration of the shared sweep (see the row schedule above FParcel).
+// `cprev` = coefficient row of level it-1; *_cur / *_prv = level it / it-1.
+template <class CoefRow>
+XP_HD void parcel_iteration(FParcel &c, int it, bool last, const CoefRow &cprev, float pk_cur, float p_prv,
+                            float x_cur, float x_prv, float b_cur, float b_prv, bool vtc) {
+    const bool above = it > c.ka;          // the row is above the LCL (and lags one level)
+    const bool is_lcl = it == c.ka;
+    if (it < c.kfirst || (last && !above)) return;
+    // moist adiabat at level it-1 (PF:585-592) and its saturation mixing ratio (PF:760)
+    const Coef cc = cprev.at(c.m);
+    const float tm = f_fma(f_fma(f_fma(cc.c3, c.f, cc.c2), c.f, cc.c1), c.f, cc.c0);
+    const float es = f_es(tm);
+    const float a_m = vtc ? f_tv(tm, kEpsF * es * f_rcp(p_prv - es)) : tm;
+    const float a_d = c.c_dryv * pk_cur;                                        // PF:742
+    const float a = is_lcl ? c.a_lcl : (above ? a_m : a_d);
+    const float b = is_lcl ? c.b_lcl : (above ? b_prv : b_cur);
+    const float x = is_lcl ? c.x_lcl : (above ? x_prv : x_cur);
+    sweep_step(c, it, x, a, b, is_lcl, above);
+}
+
+// The whole suite for one column.  Rd: float T(k), Td(k).  Cf: row(k) -> object with Coef at(m).
+// KINDS: bit 0 SB, 1 ML, 2 MU.  MODE 1: the reference's default options (virtual temperature
+// correction, MetPy 1.4.1 formulas) folded in at compile time; MODE 0: options read at run time.
+// Returns the mask of kinds that the exact path must recompute.
+template <unsigned KINDS, int MODE, class Rd, class Cf>
 XP_HD unsigned suite_column(const Rd &rd, const Cf &cf, const Prep &pr, const Tables &tb, const Opts &o,
-                            unsigned kinds, FResult res[3]) {
+                            FResult res[3]) {
     unsigned redo = 0;
-    bool nan_seen = false;
+    float nanacc = 0.0f;                   // becomes NaN if any T/Td read is NaN or infinite
     // ---- pre-pass over the lowest levels: mixed-layer means (float64) and most-unstable argmax ----
     double sum_th = 0.0, sum_w = 0.0;
     float best = -1e30f, second = -1e30f, mu_t = 0.0f, mu_td = 0.0f;
     int k_mu = 0;
-    const int n_pre = max((kinds & 4u) ? pr.K_mu : 0, (kinds & 2u) ? pr.n_ml_w : 0);
+    const int n_pre = max((KINDS & 4u) ? pr.K_mu : 0, (KINDS & 2u) ? pr.n_ml_w : 0);
     for (int k = 0; k < n_pre; ++k) {
         const float t = rd.T(k), td = rd.Td(k);
-        nan_seen = nan_seen || !(t == t) || !(td == td);
-        if ((kinds & 2u) && k < pr.n_ml_w) {
+        nanacc = f_fma(t, 0.0f, f_fma(td, 0.0f, nanacc));
+        if ((KINDS & 2u) && k < pr.n_ml_w) {
             // mixed_parcel PF:253-258: theta and saturation mixing ratio of the dewpoint, float64
             const double e = sat_vapor_pressure((double)td);
             sum_th += pr.mlw[k] * ((double)t * pr.thfac[k]);
             sum_w += pr.mlw[k] * (kEps * e / (pr.p64[k] - e));
         }
-        if ((kinds & 4u) && k < pr.K_mu) {
+        if ((KINDS & 4u) && k < pr.K_mu) {
             // ln(theta_e), Bolton (1980) eq. 39 as in metpy.calc.equivalent_potential_temperature (PF:123)
             const float p = pr.p[k];
             const float e = f_es(td);
@@ -406,69 +448,73 @@ XP_HD unsigned suite_column(const Rd &rd, const Cf &cf, const Prep &pr, const Ta
             v = f_fma((float)kKappa * kLn2, f_lg2(1000.0f * ipe), v);               // + kappa ln(1000/(p-e))
             v = f_fma(0.28f * r * kLn2, l2t - f_lg2(t_l), v);                       // + 0.28 r ln(T/t_l)
             v = f_fma(r * f_fma(0.448f, r, 1.0f), f_fma(3036.0f, it_l, -1.78f), v);
+            nanacc = f_fma(v, 0.0f, nanacc);
             if (v > best) { second = best; best = v; k_mu = k; mu_t = t; mu_td = td; }   // ties: larger p (PF:128)
             else if (v > second) second = v;
-            if (!(v == v)) nan_seen = true;
         }
     }
     // ---- parcels --------------------------------------------------------------------------------
-    FParcel pc[3];
-    FSweep sw[3];
+    FParcel sb, ml, mu;
     const float t_sfc = rd.T(0), td_sfc = rd.Td(0);
-    nan_seen = nan_seen || !(t_sfc == t_sfc) || !(td_sfc == td_sfc);
-    if (kinds & 1u) {
-        setup_parcel(rd, pr, tb, o, pr.p0, (double)t_sfc, (double)td_sfc, 0, 1, false, pc[0]);
+    nanacc = f_fma(t_sfc, 0.0f, f_fma(td_sfc, 0.0f, nanacc));
+    if (KINDS & 1u) {
+        setup_parcel(rd, pr, tb, o, pr.p0, (double)t_sfc, (double)td_sfc, 0, 1, sb);
         res[0].par_p = pr.p[0]; res[0].par_t = t_sfc; res[0].par_td = td_sfc; res[0].shift = 0;
-        sw[0].init(pr.lnp[0], o.vtc ? f_tv(t_sfc, pc[0].w_parcel) : t_sfc);
     }
-    if (kinds & 2u) {
+    if (KINDS & 2u) {
         const double mp_t = sum_th * pr.exner0;                                  // PF:268-269
         const double mp_td = dewpoint_from_e(vapor_pressure(pr.p0, sum_w));      // PF:275-282
-        setup_parcel(rd, pr, tb, o, pr.p0, mp_t, mp_td, 0, pr.K_ml, true, pc[1]);
+        setup_parcel(rd, pr, tb, o, pr.p0, mp_t, mp_td, 0, pr.K_ml, ml);
         res[1].par_p = pr.p[0]; res[1].par_t = (float)mp_t; res[1].par_td = (float)mp_td; res[1].shift = pr.K_ml;
-        sw[1].init(pr.lnp[0], o.vtc ? f_tv((float)mp_t, pc[1].w_parcel) : (float)mp_t);
     }
-    if (kinds & 4u) {
+    if (KINDS & 4u) {
         if (!(best - second >= kThetaEMargin)) redo |= 4u;                       // argmax within float32 error
-        setup_parcel(rd, pr, tb, o, pr.p64[k_mu], (double)mu_t, (double)mu_td, k_mu, k_mu + 1, false, pc[2]);
+        setup_parcel(rd, pr, tb, o, pr.p64[k_mu], (double)mu_t, (double)mu_td, k_mu, k_mu + 1, mu);
         res[2].par_p = pr.p[k_mu]; res[2].par_t = mu_t; res[2].par_td = mu_td; res[2].shift = k_mu;
-        sw[2].init(pr.lnp[k_mu], o.vtc ? f_tv(mu_t, pc[2].w_parcel) : mu_t);
     }
-    // ---- the sweep over the levels -------------------------------------------------------------------
-    for (int k = 1; k < pr.n_table; ++k) {
-        const float t = rd.T(k), td = rd.Td(k);
-        nan_seen = nan_seen || !(t == t) || !(td == td);
-        const float p = pr.p[k], x = pr.lnp[k];
-        const float es_t = f_es(t), es_td = f_es(td);
-        const float b = o.vtc ? f_tv(t, f_mixing_ratio(es_t, es_td, p, o.compat)) : t;      // PF:839-843
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            if (!((kinds >> q) & 1u) || k < pc[q].kfirst) continue;
-            const FParcel &c = pc[q];
-            if (k == c.ka) sw[q].step(c.x_lcl, c.a_lcl, c.b_lcl, true);          // the inserted LCL row
-            float tp, w;
-            if (k < c.ka) { tp = c.c_dry * pr.pk[k]; w = c.w_parcel; }           // PF:742, 767, 773
-            else {
-                const Coef cc = cf.at(k, c.m);
-                tp = f_fma(f_fma(f_fma(cc.c3, c.f, cc.c2), c.f, cc.c1), c.f, cc.c0);        // PF:585-592
-                const float es = f_es(tp);
-                w = kEpsF * es * f_rcp(p - es);                                  // PF:760
+    // ---- the sweep --------------------------------------------------------------------------------------
+    const int nt = pr.n_table;
+    const bool vtc = (MODE == 1) ? true : (o.vtc != 0);
+    const int compat = (MODE == 1) ? 141 : o.compat;
+    const float *lp_p = pr.p + 1, *lp_x = pr.lnp + 1, *lp_k = pr.pk + 1;      // level `it` of the axis constants
+    float b_prv = 0.0f, x_prv = pr.lnp[0], p_prv = pr.p[0];
+    const float *tp = rd.tptr(1), *tdp = rd.tdptr(1);
+    const int64_t ls = rd.stride();
+    float t_nxt = Rd::ld(tp), td_nxt = Rd::ld(tdp);
+    auto crow = cf.row(0);
+    for (int it = 1; it <= nt; ++it) {
+        const bool last = (it == nt);
+        const float t = t_nxt, td = td_nxt;
+        tp += ls; tdp += ls;
+        if (it + 1 < nt) { t_nxt = Rd::ld(tp); td_nxt = Rd::ld(tdp); }          // prefetch the next level
+        float b_cur = 0.0f, x_cur = x_prv, pk_cur = 0.0f, p_cur = p_prv;
+        if (!last) {
+            nanacc = f_fma(t, 0.0f, f_fma(td, 0.0f, nanacc));
+            p_cur = *lp_p++; x_cur = *lp_x++; pk_cur = *lp_k++;
+            if (vtc) {
+                const float es_t = f_es(t), es_td = f_es(td);
+                b_cur = f_tv(t, f_mixing_ratio(es_t, es_td, p_cur, compat));    // PF:839-843
+            } else {
+                b_cur = t;
             }
-            const float a = o.vtc ? f_tv(tp, w) : tp;
-            sw[q].step(x, a, b, false);
         }
+        if (KINDS & 1u) parcel_iteration(sb, it, last, crow, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
+        if (KINDS & 2u) parcel_iteration(ml, it, last, crow, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
+        if (KINDS & 4u) parcel_iteration(mu, it, last, crow, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
+        b_prv = b_cur; x_prv = x_cur; p_prv = p_cur;
+        crow.advance();
     }
     // ---- results ---------------------------------------------------------------------------------------
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        if (!((kinds >> q) & 1u)) continue;
-        const FParcel &c = pc[q];
-        FResult &r = res[q];
-        r.lcl_p = c.lcl_p; r.lcl_t = c.lcl_t; r.lcl_tv = c.lcl_tv;
-        finish(sw[q], c.lcl_p, o.vtc ? c.lcl_tv : c.lcl_t, o, r);
-        if (c.bad || sw[q].unc || nan_seen || c.ka >= pr.n_table) redo |= (1u << q);
-    }
-    return redo & kinds;
+    const bool nan_seen = !(nanacc == 0.0f);
+    auto wrap = [&](const FParcel &c, FResult &r, unsigned bit) {
+        sweep_finish(c, o, r);
+        const bool unc = !(c.min_abs_d >= kDecisionEps) || !(c.min_slope >= 0.0f);
+        if (c.bad || unc || nan_seen) redo |= bit;
+    };
+    if (KINDS & 1u) wrap(sb, res[0], 1u);
+    if (KINDS & 2u) wrap(ml, res[1], 2u);
+    if (KINDS & 4u) wrap(mu, res[2], 4u);
+    return redo;
 }
 
 }  // namespace fast
