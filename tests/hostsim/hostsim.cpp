@@ -105,7 +105,7 @@ extern "C" int hostsim_fast_suite(const float *p, const float *t, const float *t
     for (int64_t c = 0; c < n; ++c) {
         HostRdF rd = {t + c, td + c, n};
         xp::fast::FResult r[3];
-        redo[c] = (o.vtc && o.compat == 141) ? xp::fast::suite_column<7u, 1>(rd, cf, pr, tb, o, r)
+        redo[c] = (o.vtc && o.compat == 141 && o.pos_neg) ? xp::fast::suite_column<7u, 1>(rd, cf, pr, tb, o, r)
                                               : xp::fast::suite_column<7u, 0>(rd, cf, pr, tb, o, r);
         for (int q = 0; q < 3; ++q) {
             const float vals[12] = {r[q].cape, r[q].cin, r[q].lcl_p, r[q].lcl_t, r[q].lcl_tv, r[q].lfc_p,

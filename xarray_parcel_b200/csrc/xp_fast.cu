@@ -1,5 +1,7 @@
 // xp_fast.cu -- sm_100a kernels of the float32 fast path (see xp_fast.cuh) and of the exact-path
 // fix-up over the compact list of columns whose decisions were uncertain in float32.
+#include <cstdlib>
+
 #include "xp_fast.cuh"
 #include "xp_kernels.cuh"
 
@@ -80,8 +82,8 @@ constexpr int kFastThreads = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <unsigned KINDS, int MODE>
-__global__ void __launch_bounds__(kFastThreads, 1) suite_fast_kernel(const __grid_constant__ FastParams prm) {
+template <unsigned KINDS, int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) suite_fast_kernel(const __grid_constant__ FastParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
     Prep *s_prep = reinterpret_cast<Prep *>(smem_raw);
@@ -251,23 +253,31 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
     for (int q = 0; q < 3; ++q) fp.outs[q] = outs[q];
     fp.list = list; fp.list_count = count;
     const size_t smem = ((sizeof(Prep) + 127) & ~(size_t)127) + (size_t)cols.L * fast::kNI * sizeof(Coef);
-    const int64_t tiles = (cols.n + kFastThreads - 1) / kFastThreads;
+    // threads per CTA (one CTA per SM): 512 x 128 registers by default; XP_FAST_THREADS=640 trades
+    // registers (102) for 20 resident warps (tuning knob, read once)
+    static int threads = 0;
+    if (!threads) {
+        const char *e = getenv("XP_FAST_THREADS");
+        threads = (e && atoi(e) == 640) ? 640 : kFastThreads;
+    }
+    const int64_t tiles = (cols.n + threads - 1) / threads;
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
-    static size_t smem_set[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
-    const int mode = (o.vtc && o.compat == 141) ? 1 : 0;
-#define XP_FAST_LAUNCH(K, M)                                                                                \
-    do {                                                                                                    \
-        if (smem > smem_set[M][K]) {                                                                        \
-            if (cudaFuncSetAttribute(suite_fast_kernel<K, M>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                     (int)smem) != cudaSuccess)                                             \
-                return -1;                                                                                  \
-            smem_set[M][K] = smem;                                                                          \
-        }                                                                                                   \
-        suite_fast_kernel<K, M><<<grid, kFastThreads, smem, stream>>>(fp);                                  \
+    static size_t smem_set[2][2][8] = {};
+    const int mode = (o.vtc && o.compat == 141 && o.pos_neg) ? 1 : 0;
+#define XP_FAST_LAUNCH(K, M, T)                                                                                \
+    do {                                                                                                       \
+        if (smem > smem_set[T == 640][M][K]) {                                                                 \
+            if (cudaFuncSetAttribute(suite_fast_kernel<K, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                     (int)smem) != cudaSuccess)                                                \
+                return -1;                                                                                     \
+            smem_set[T == 640][M][K] = smem;                                                                   \
+        }                                                                                                      \
+        suite_fast_kernel<K, M, T><<<grid, T, smem, stream>>>(fp);                                             \
     } while (0)
-#define XP_FAST_CASE(K)                                                 \
-    case K:                                                             \
-        if (mode) XP_FAST_LAUNCH(K, 1); else XP_FAST_LAUNCH(K, 0);      \
+#define XP_FAST_CASE(K)                                                                   \
+    case K:                                                                               \
+        if (threads == 640) { if (mode) XP_FAST_LAUNCH(K, 1, 640); else XP_FAST_LAUNCH(K, 0, 640); } \
+        else { if (mode) XP_FAST_LAUNCH(K, 1, 512); else XP_FAST_LAUNCH(K, 0, 512); }     \
         break;
     switch (kind_mask & 7) {
         XP_FAST_CASE(1) XP_FAST_CASE(2) XP_FAST_CASE(3) XP_FAST_CASE(4) XP_FAST_CASE(5) XP_FAST_CASE(6) XP_FAST_CASE(7)

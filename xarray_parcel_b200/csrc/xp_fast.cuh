@@ -31,7 +31,11 @@ constexpr float kDecisionEps = 6e-4f;       // K: |parcel - environment| below t
 constexpr float kThetaEMargin = 4e-6f;      // ln(theta_e) gap below this is a most-unstable tie
 constexpr float kCrossSlope = 0.5f;         // K per unit ln p: a crossing with |d0 - d1| < kCrossSlope * dx is too
                                             // shallow to place within 1e-3 relative in pressure in float32
-constexpr double kSaturationMargin = 2e-3;  // K: T - Td below this -> exact path (LCL snap, PF:644 isclose)
+constexpr double kSaturationMargin = 2e-3;
+// margins for a parcel that is itself only float32-accurate (`approx`; currently unused: all parcels are
+// exact float32 data or float64 means): |dT_lcl| < 4e-5 K, |dp_lcl| < 5e-4 hPa
+constexpr float kApproxCellEdge = 4e-3f;    // cell units: 8e-5 K of 0.02 K, 2e-3 hPa of 0.5 hPa
+constexpr double kApproxLclP = 2e-3;        // hPa  // K: T - Td below this -> exact path (LCL snap, PF:644 isclose)
 
 struct Coef { float c0, c1, c2, c3; };      // T(f) = c0 + f (c1 + f (c2 + f c3)), f in [0, 1)
 
@@ -207,6 +211,20 @@ XP_HD void lcl_fast(double p0, double t, double td, double &lcl_p, double &lcl_t
     lcl_p = p0 * qd;
 }
 
+// ---- table cell of the LCL (PF:554-557 .sel(method='nearest')) --------------------------------------------
+// Nearest 0.5 hPa x 0.02 K cell, ties to the larger node, clamped -- as adiabat_lookup() in
+// xp_column.cuh but with the node values taken as exact multiples (they are the doubles nearest to
+// them, so the two differ only for an LCL within 3e-14 of a cell edge).  `edge` returns the distance
+// (in cell units, 0..0.5) of the LCL from the nearest cell edge, so that callers whose LCL is only
+// approximately known can hand edge cases to the exact path.
+XP_HD int adiabat_cell(const Tables &tb, double p, double t, float &edge) {
+    const double xs = (p - 2.5) * 2.0, ts = (t - 173.0) * 50.0;
+    const double fp = floor(xs + 0.5), ft = floor(ts + 0.5);
+    const int ip = min(max((int)fp, 0), kNP - 1), it = min(max((int)ft, 0), kNT - 1);
+    edge = (float)fmin(0.5 - fabs(xs - fp), 0.5 - fabs(ts - ft));
+    return (int)XP_LDG(tb.index_grid + (size_t)(kNP - 1 - ip) * kNT + it);
+}
+
 // ---- one parcel: constants + sweep state, all in registers ------------------------------------------------
 //
 // Row schedule.  The profile of a parcel is: start row (parcel == environment), the levels below
@@ -260,6 +278,7 @@ XP_HD void sweep_init(FParcel &c, float x0, float a0) {
 
 // One row (ln p = x, parcel curve a, environment curve b): find_intersections PF:992-1064 +
 // trap_around_zeros PF:1200-1289 + trapz PF:164-206 for the interval below it.  Branch-free.
+template <int MODE>
 XP_HD void sweep_step(FParcel &c, int it, float x, float a, float b, bool is_lcl, bool above) {
     const float d = a - b;
     const float dx = c.xprev - x;
@@ -284,7 +303,8 @@ XP_HD void sweep_step(FParcel &c, int it, float x, float a, float b, bool is_lcl
     c.lfc_x = take_lfc ? ix : c.lfc_x; c.lfc_t = take_lfc ? iy : c.lfc_t;
     // EL: min-pressure decreasing crossing (PF:1136) = the last one met
     c.el_it = dec ? it : c.el_it;
-    c.el_pos = dec ? c.pos : c.el_pos; c.el_tot = dec ? c.tot : c.el_tot;
+    c.el_pos = dec ? c.pos : c.el_pos;
+    if (MODE != 1) c.el_tot = dec ? c.tot : c.el_tot;         // only needed without pos_cape_neg_cin
     c.el_x = dec ? ix : c.el_x; c.el_t = dec ? iy : c.el_t;
     c.pos += fmaxf(a_hi, 0.0f); c.tot += a_hi;
     c.lcl_pos = is_lcl ? c.pos : c.lcl_pos; c.lcl_tot = is_lcl ? c.tot : c.lcl_tot;
@@ -300,6 +320,7 @@ struct FResult {
 };
 
 // Sweep.finish of xp_column.cuh (lfc_el PF:1140-1185, cape_cin_base PF:1329-1388) on the float32 state.
+template <int MODE>
 XP_HD void sweep_finish(const FParcel &s, const Opts &o, FResult &r) {
     const float lcl_targ = o.vtc ? s.lcl_tv : s.lcl_t;
     const bool top_colder = s.dprev <= 0.0f;                            // PF:1151
@@ -321,7 +342,7 @@ XP_HD void sweep_finish(const FParcel &s, const Opts &o, FResult &r) {
         const float e_tot = el_exists ? s.el_tot : s.tot;
         // EL below the LFC (PF:1352-1353 leaves no level between them): compare by interval
         const bool el_below_lfc = el_exists && lfc_found && !replace && s.el_it < s.lfc_it;
-        if (o.pos_neg) {
+        if (MODE == 1 || o.pos_neg) {
             cin = l_tot - l_pos;
             cape = el_below_lfc ? 0.0f : (e_pos - l_pos);
         } else {
@@ -338,9 +359,11 @@ XP_HD void sweep_finish(const FParcel &s, const Opts &o, FResult &r) {
 // Set up one parcel once its (p0, T0, Td0) are known.  `kstart` is the level of the start row (the
 // parcel level; for the mixed layer the start row is the prepended parcel at p[0]) and the lifted
 // column continues at level `knext`.  T/Td of the levels bracketing the LCL come through `rd`.
+// `approx`: the parcel itself carries float32-level errors (mixed-layer means of float32 mixing
+// ratios): LCL decisions closer than kApproxCellEdge / kApproxLclP to an edge go to the exact path.
 template <class Rd>
 XP_HD void setup_parcel(const Rd &rd, const Prep &pr, const Tables &tb, const Opts &o, double p0, double t0,
-                        double td0, int kstart, int knext, FParcel &pc) {
+                        double td0, int kstart, int knext, bool approx, FParcel &pc) {
     pc.bad = false;
     pc.kfirst = knext;
     // saturated / supersaturated / NaN parcels: the LCL snaps to the parcel level (np.isclose in
@@ -348,7 +371,9 @@ XP_HD void setup_parcel(const Rd &rd, const Prep &pr, const Tables &tb, const Op
     if (!(t0 - td0 >= kSaturationMargin) || !(p0 > 0.0)) { pc.bad = true; t0 = 280.0; td0 = 270.0; p0 = 1000.0; }
     double lp, lt;
     lcl_fast(p0, t0, td0, lp, lt);
-    const int adiabat = adiabat_lookup(tb, lp, lt);                    // PF:554-557, exact cell
+    float edge;
+    const int adiabat = adiabat_cell(tb, lp, lt, edge);                // PF:554-557
+    if (approx && edge < kApproxCellEdge) pc.bad = true;
     const int a0 = adiabat - 1;
     pc.m = a0 / kNodeStride;
     if (adiabat <= 0 || pc.m < kFirstInterval || pc.m > kLastInterval) { pc.bad = true; pc.m = kFirstInterval; }
@@ -366,6 +391,8 @@ XP_HD void setup_parcel(const Rd &rd, const Prep &pr, const Tables &tb, const Op
     int ka = knext;
     while (ka < pr.L && pr.p64[ka] >= lp) ++ka;
     pc.ka = ka;
+    if (approx && ((ka < pr.L && fabs(pr.p64[ka] - lp) < kApproxLclP) ||
+                   (ka > knext && fabs(pr.p64[ka - 1] - lp) < kApproxLclP))) pc.bad = true;
     // bracketing levels for the environment at the LCL (PF:1774-1806): "before" = last level with
     // p >= lcl_p (the start row when the LCL is below the first swept level), "after" = level ka.
     const int kb = ka - 1;
@@ -394,7 +421,7 @@ XP_HD void setup_parcel(const Rd &rd, const Prep &pr, const Tables &tb, const Op
 
 // One parcel, one iteration of the shared sweep (see the row schedule above FParcel).
 // `cprev` = coefficient row of level it-1; *_cur / *_prv = level it / it-1.
-template <class CoefRow>
+template <int MODE, class CoefRow>
 XP_HD void parcel_iteration(FParcel &c, int it, bool last, const CoefRow &cprev, float pk_cur, float p_prv,
                             float x_cur, float x_prv, float b_cur, float b_prv, bool vtc) {
     const bool above = it > c.ka;          // the row is above the LCL (and lags one level)
@@ -409,12 +436,12 @@ XP_HD void parcel_iteration(FParcel &c, int it, bool last, const CoefRow &cprev,
     const float a = is_lcl ? c.a_lcl : (above ? a_m : a_d);
     const float b = is_lcl ? c.b_lcl : (above ? b_prv : b_cur);
     const float x = is_lcl ? c.x_lcl : (above ? x_prv : x_cur);
-    sweep_step(c, it, x, a, b, is_lcl, above);
+    sweep_step<MODE>(c, it, x, a, b, is_lcl, above);
 }
 
 // The whole suite for one column.  Rd: float T(k), Td(k).  Cf: row(k) -> object with Coef at(m).
 // KINDS: bit 0 SB, 1 ML, 2 MU.  MODE 1: the reference's default options (virtual temperature
-// correction, MetPy 1.4.1 formulas) folded in at compile time; MODE 0: options read at run time.
+// correction, MetPy 1.4.1 formulas, pos_cape_neg_cin) folded in at compile time; MODE 0: run time.
 // Returns the mask of kinds that the exact path must recompute.
 template <unsigned KINDS, int MODE, class Rd, class Cf>
 XP_HD unsigned suite_column(const Rd &rd, const Cf &cf, const Prep &pr, const Tables &tb, const Opts &o,
@@ -429,18 +456,20 @@ XP_HD unsigned suite_column(const Rd &rd, const Cf &cf, const Prep &pr, const Ta
     for (int k = 0; k < n_pre; ++k) {
         const float t = rd.T(k), td = rd.Td(k);
         nanacc = f_fma(t, 0.0f, f_fma(td, 0.0f, nanacc));
+        const float p = pr.p[k];
+        const float e = f_es(td);
+        const float ipe = f_rcp(p - e);
+        const float r = kEpsF * e * ipe;                 // saturation mixing ratio of the dewpoint (PF:258)
         if ((KINDS & 2u) && k < pr.n_ml_w) {
-            // mixed_parcel PF:253-258: theta and saturation mixing ratio of the dewpoint, float64
-            const double e = sat_vapor_pressure((double)td);
+            // mixed_parcel PF:253-258: theta and saturation mixing ratio of the dewpoint in float64, so
+            // that the table cell of this parcel's LCL is the reference's (a float32 mixing ratio would
+            // put ~1.7 % of the mixed-layer parcels within its error of a cell edge)
+            const double e64 = sat_vapor_pressure((double)td);
             sum_th += pr.mlw[k] * ((double)t * pr.thfac[k]);
-            sum_w += pr.mlw[k] * (kEps * e / (pr.p64[k] - e));
+            sum_w += pr.mlw[k] * (kEps * e64 / (pr.p64[k] - e64));
         }
         if ((KINDS & 4u) && k < pr.K_mu) {
             // ln(theta_e), Bolton (1980) eq. 39 as in metpy.calc.equivalent_potential_temperature (PF:123)
-            const float p = pr.p[k];
-            const float e = f_es(td);
-            const float ipe = f_rcp(p - e);
-            const float r = kEpsF * e * ipe;
             const float l2t = f_lg2(t), l2td = f_lg2(td);
             const float t_l = 56.0f + f_rcp(f_rcp(td - 56.0f) + (l2t - l2td) * (kLn2 / 800.0f));
             const float it_l = f_rcp(t_l);
@@ -458,18 +487,18 @@ XP_HD unsigned suite_column(const Rd &rd, const Cf &cf, const Prep &pr, const Ta
     const float t_sfc = rd.T(0), td_sfc = rd.Td(0);
     nanacc = f_fma(t_sfc, 0.0f, f_fma(td_sfc, 0.0f, nanacc));
     if (KINDS & 1u) {
-        setup_parcel(rd, pr, tb, o, pr.p0, (double)t_sfc, (double)td_sfc, 0, 1, sb);
+        setup_parcel(rd, pr, tb, o, pr.p0, (double)t_sfc, (double)td_sfc, 0, 1, false, sb);
         res[0].par_p = pr.p[0]; res[0].par_t = t_sfc; res[0].par_td = td_sfc; res[0].shift = 0;
     }
     if (KINDS & 2u) {
         const double mp_t = sum_th * pr.exner0;                                  // PF:268-269
         const double mp_td = dewpoint_from_e(vapor_pressure(pr.p0, sum_w));      // PF:275-282
-        setup_parcel(rd, pr, tb, o, pr.p0, mp_t, mp_td, 0, pr.K_ml, ml);
+        setup_parcel(rd, pr, tb, o, pr.p0, mp_t, mp_td, 0, pr.K_ml, false, ml);
         res[1].par_p = pr.p[0]; res[1].par_t = (float)mp_t; res[1].par_td = (float)mp_td; res[1].shift = pr.K_ml;
     }
     if (KINDS & 4u) {
         if (!(best - second >= kThetaEMargin)) redo |= 4u;                       // argmax within float32 error
-        setup_parcel(rd, pr, tb, o, pr.p64[k_mu], (double)mu_t, (double)mu_td, k_mu, k_mu + 1, mu);
+        setup_parcel(rd, pr, tb, o, pr.p64[k_mu], (double)mu_t, (double)mu_td, k_mu, k_mu + 1, false, mu);
         res[2].par_p = pr.p[k_mu]; res[2].par_t = mu_t; res[2].par_td = mu_td; res[2].shift = k_mu;
     }
     // ---- the sweep --------------------------------------------------------------------------------------
@@ -498,16 +527,16 @@ XP_HD unsigned suite_column(const Rd &rd, const Cf &cf, const Prep &pr, const Ta
                 b_cur = t;
             }
         }
-        if (KINDS & 1u) parcel_iteration(sb, it, last, crow, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
-        if (KINDS & 2u) parcel_iteration(ml, it, last, crow, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
-        if (KINDS & 4u) parcel_iteration(mu, it, last, crow, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
+        if (KINDS & 1u) parcel_iteration<MODE>(sb, it, last, crow, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
+        if (KINDS & 2u) parcel_iteration<MODE>(ml, it, last, crow, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
+        if (KINDS & 4u) parcel_iteration<MODE>(mu, it, last, crow, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
         b_prv = b_cur; x_prv = x_cur; p_prv = p_cur;
         crow.advance();
     }
     // ---- results ---------------------------------------------------------------------------------------
     const bool nan_seen = !(nanacc == 0.0f);
     auto wrap = [&](const FParcel &c, FResult &r, unsigned bit) {
-        sweep_finish(c, o, r);
+        sweep_finish<MODE>(c, o, r);
         const bool unc = !(c.min_abs_d >= kDecisionEps) || !(c.min_slope >= 0.0f);
         if (c.bad || unc || nan_seen) redo |= bit;
     };
