@@ -9,7 +9,7 @@
 
 #include <vector>
 
-#include "../../xarray_parcel_b200/csrc/xp_fast.cuh"
+#include "../../xarray_parcel_b200/csrc/xp_fast_pcol.cuh"
 
 namespace {
 
@@ -107,6 +107,46 @@ extern "C" int hostsim_fast_suite(const float *p, const float *t, const float *t
         xp::fast::FResult r[3];
         redo[c] = (o.vtc && o.compat == 141 && o.pos_neg) ? xp::fast::suite_column<7u, 1>(rd, cf, pr, tb, o, r)
                                               : xp::fast::suite_column<7u, 0>(rd, cf, pr, tb, o, r);
+        for (int q = 0; q < 3; ++q) {
+            const float vals[12] = {r[q].cape, r[q].cin, r[q].lcl_p, r[q].lcl_t, r[q].lcl_tv, r[q].lfc_p,
+                                    r[q].lfc_t, r[q].el_p, r[q].el_t, r[q].par_p, r[q].par_t, r[q].par_td};
+            for (int f = 0; f < 12; ++f) out[((int64_t)q * 12 + f) * n + c] = vals[f];
+            shift[(int64_t)q * n + c] = r[q].shift;
+        }
+    }
+    return 1;
+}
+
+// The float32 fast path for per-column pressure (xp_fast_pcol.cuh).  Same outputs as hostsim_fast_suite.
+namespace {
+struct HostRdP {
+    const float *p, *t, *td;
+    int64_t ls;
+    float P(int k) const { return p[(int64_t)k * ls]; }
+    float T(int k) const { return t[(int64_t)k * ls]; }
+    float Td(int k) const { return td[(int64_t)k * ls]; }
+    const float *pptr(int k) const { return p + (int64_t)k * ls; }
+    const float *tptr(int k) const { return t + (int64_t)k * ls; }
+    const float *tdptr(int k) const { return td + (int64_t)k * ls; }
+    int64_t stride() const { return ls; }
+    int64_t pstride() const { return ls; }
+    static float ld(const float *q) { return *q; }
+};
+}  // namespace
+
+extern "C" int hostsim_fast_suite_pcol(const float *p, const float *t, const float *td, int64_t n, int L,
+                                       const int *iopts, double ml_depth, double mu_depth,
+                                       const uint16_t *index_grid, const float *curves, float *out,
+                                       int32_t *shift, uint32_t *redo) {
+    xp::Tables tb = {index_grid, curves};
+    xp::Opts o;
+    o.vtc = iopts[0]; o.log_interp = iopts[1]; o.pos_neg = iopts[2]; o.post_zero = iopts[3];
+    o.compat = iopts[4]; o.exact_only = 0; o.ml_depth = ml_depth; o.mu_depth = mu_depth;
+    for (int64_t c = 0; c < n; ++c) {
+        HostRdP rd = {p + c, t + c, td + c, n};
+        xp::fast::FResult r[3];
+        redo[c] = (o.vtc && o.compat == 141 && o.pos_neg) ? xp::fast::suite_column_pcol<7u, 1>(rd, L, tb, o, r)
+                                                          : xp::fast::suite_column_pcol<7u, 0>(rd, L, tb, o, r);
         for (int q = 0; q < 3; ++q) {
             const float vals[12] = {r[q].cape, r[q].cin, r[q].lcl_p, r[q].lcl_t, r[q].lcl_tv, r[q].lfc_p,
                                     r[q].lfc_t, r[q].el_p, r[q].el_t, r[q].par_p, r[q].par_t, r[q].par_td};

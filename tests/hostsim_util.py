@@ -21,7 +21,7 @@ KINDS = {"sb": 0, "ml": 1, "mu": 2, "explicit": 3}
 
 
 def build():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("xp_math.cuh", "xp_column.cuh", "xp_parcels.cuh", "xp_fast.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("xp_math.cuh", "xp_column.cuh", "xp_parcels.cuh", "xp_fast.cuh", "xp_fast_pcol.cuh")]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     os.makedirs(BUILD, exist_ok=True)
@@ -83,8 +83,8 @@ def cape_cin(p, t, td, tables, kind="sb", explicit=None, vtc=True, lcl_interp="l
 
 def fast_suite(p, t, td, tables, vtc=True, lcl_interp="log", pos_cape_neg_cin=True, post_zero_cin=False,
                metpy_compat=141, ml_depth=100.0, mu_depth=300.0):
-    """Run the host-compiled float32 fast path (xp_fast.cuh) on a shared pressure axis p [L] and
-    float32 [L, N] T/Td.  Returns ({kind: {field: float32 [N], 'level_shift'}}, redo mask [N]) or None
+    """Run the host-compiled float32 fast path on a shared pressure axis p [L] (xp_fast.cuh) or
+    per-column pressure p [L, N] (xp_fast_pcol.cuh) and float32 [L, N] T/Td.  Returns ({kind: {field: float32 [N], 'level_shift'}}, redo mask [N]) or None
     if the axis does not qualify."""
     t = np.ascontiguousarray(t, dtype=np.float32)
     td = np.ascontiguousarray(td, dtype=np.float32)
@@ -102,8 +102,9 @@ def fast_suite(p, t, td, tables, vtc=True, lcl_interp="log", pos_cape_neg_cin=Tr
         return a.ctypes.data_as(ctypes.c_void_p)
 
     l = lib()
-    l.hostsim_fast_suite.restype = ctypes.c_int
-    ok = l.hostsim_fast_suite(ptr(p), ptr(t), ptr(td), ctypes.c_int64(N), ctypes.c_int(L), iopts,
+    fn = l.hostsim_fast_suite if p.ndim == 1 else l.hostsim_fast_suite_pcol
+    fn.restype = ctypes.c_int
+    ok = fn(ptr(p), ptr(t), ptr(td), ctypes.c_int64(N), ctypes.c_int(L), iopts,
                               ctypes.c_double(ml_depth), ctypes.c_double(mu_depth), ptr(idx), ptr(cur),
                               ptr(out), ptr(shift), ptr(redo))
     if not ok:

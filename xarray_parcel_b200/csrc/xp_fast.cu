@@ -3,6 +3,7 @@
 #include <cstdlib>
 
 #include "xp_fast.cuh"
+#include "xp_fast_pcol.cuh"
 #include "xp_kernels.cuh"
 
 namespace xp {
@@ -14,8 +15,9 @@ namespace {
 
 // ---- prep kernels: axis constants (one thread) and the cubic coefficient table -----------------------
 __global__ void fast_prep_kernel(const float *__restrict__ p, int64_t pls, int L, Opts o, Prep *out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    fast::compute_prep(p, pls, L, o, *out);
+    if (threadIdx.x < L && threadIdx.x < fast::kMaxLevels) fast::compute_prep_level(p, pls, threadIdx.x, *out);
+    __syncthreads();
+    if (threadIdx.x == 0) fast::compute_prep_axis(L, o, *out);
 }
 
 __global__ void fast_coef_kernel(const Prep *__restrict__ prep, const float *__restrict__ curves, Coef *__restrict__ coef) {
@@ -34,7 +36,7 @@ struct FastParams {
     Opts o;
     unsigned kinds;
     OutArg<float> outs[3];
-    uint32_t *list;          // [n] entries: column | redo-mask << 29
+    uint32_t *list;          // [n] entries: column | redo-mask << 28 (bits 0-2 kinds, bit 3 MU == SB)
     uint32_t *list_count;
 };
 
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(THREADS, 1) suite_fast_kernel(const __grid_con
         for (int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; col < prm.n;
              col += (int64_t)gridDim.x * blockDim.x) {
             const uint32_t slot = atomicAdd(prm.list_count, 1u);
-            prm.list[slot] = (uint32_t)col | (prm.kinds << 29);
+            prm.list[slot] = (uint32_t)col | (prm.kinds << 28);
         }
         return;
     }
@@ -144,70 +146,52 @@ __global__ void __launch_bounds__(THREADS, 1) suite_fast_kernel(const __grid_con
         if (KINDS & 4u) store_fast(prm.outs[2], col, res[2]);
         if (redo) {
             const uint32_t slot = atomicAdd(prm.list_count, 1u);
-            prm.list[slot] = (uint32_t)col | (redo << 29);
+            prm.list[slot] = (uint32_t)col | (redo << 28);
         }
     }
 }
 
-// ---- exact fix-up over the list ------------------------------------------------------------------------------------------
-struct NoProf {
-    __device__ __forceinline__ void put(int, const ProfileRow &) const {}
+// ---- the fast suite kernel for per-column pressure (xp_fast_pcol.cuh) ------------------------------------------
+struct PColRd {
+    const float *p, *t, *td;
+    int64_t ls, pls;
+    __device__ __forceinline__ float P(int k) const { return __ldg(p + (int64_t)k * pls); }
+    __device__ __forceinline__ float T(int k) const { return __ldg(t + (int64_t)k * ls); }
+    __device__ __forceinline__ float Td(int k) const { return __ldg(td + (int64_t)k * ls); }
+    __device__ __forceinline__ const float *pptr(int k) const { return p + (int64_t)k * pls; }
+    __device__ __forceinline__ const float *tptr(int k) const { return t + (int64_t)k * ls; }
+    __device__ __forceinline__ const float *tdptr(int k) const { return td + (int64_t)k * ls; }
+    __device__ __forceinline__ int64_t stride() const { return ls; }
+    __device__ __forceinline__ int64_t pstride() const { return pls; }
+    static __device__ __forceinline__ float ld(const float *q) { return __ldg(q); }
 };
 
-struct ListParams {
-    ColsArg<float> cols;
+struct PColParams {
+    const float *p, *t, *td;
+    int64_t n, ls, pls;
+    int L;
     Tables tb;
     Opts o;
     OutArg<float> outs[3];
-    const uint32_t *list;
-    const uint32_t *list_count;
-    uint32_t *flags;
+    uint32_t *list;
+    uint32_t *list_count;
 };
 
-struct ExactRd {
-    const float *p, *t, *td;
-    int64_t ls, pls;
-    int L;
-    __device__ __forceinline__ double P(int k) const { return (double)__ldg(p + (int64_t)k * pls); }
-    __device__ __forceinline__ double Tk(int k) const { return (double)__ldg(t + (int64_t)k * ls); }
-    __device__ __forceinline__ double Td(int k) const { return (double)__ldg(td + (int64_t)k * ls); }
-};
+constexpr int kPColThreads = 256;
 
-// One thread per (list entry, parcel kind) item.
-__global__ void __launch_bounds__(128) suite_list_kernel(const __grid_constant__ ListParams prm) {
-    const uint32_t count = *prm.list_count;
-    if (count == 0) return;
-    // kind-major item order keeps the parcel kind uniform inside a warp
-    for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < (uint64_t)count * 3u;
-         it += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t e = prm.list[it % count];
-        const int kind = (int)(it / count);
-        if (!((e >> (29 + kind)) & 1u)) continue;
-        const int64_t col = (int64_t)(e & 0x1fffffffu);
-        ExactRd rd;
-        rd.p = prm.cols.p1d ? prm.cols.p : prm.cols.p + col;
-        rd.t = prm.cols.t + col; rd.td = prm.cols.td + col;
-        rd.ls = prm.cols.ls; rd.pls = prm.cols.pls; rd.L = prm.cols.L;
-        ParcelResult r;
-        double p0, t0, td0;
-        int shift;
-        NoProf np;
-        run_column(rd, kind, prm.tb, prm.o, qnan(), qnan(), qnan(), r, p0, t0, td0, shift, np);
-        const OutArg<float> &o = prm.outs[kind];
-        if (o.cape) o.cape[col] = (float)r.cape;
-        if (o.cin) o.cin[col] = (float)r.cin;
-        if (o.lcl_p) o.lcl_p[col] = (float)r.lcl_p;
-        if (o.lcl_t) o.lcl_t[col] = (float)r.lcl_t;
-        if (o.lcl_tv) o.lcl_tv[col] = (float)r.lcl_tv;
-        if (o.lfc_p) o.lfc_p[col] = (float)r.lfc_p;
-        if (o.lfc_t) o.lfc_t[col] = (float)r.lfc_t;
-        if (o.el_p) o.el_p[col] = (float)r.el_p;
-        if (o.el_t) o.el_t[col] = (float)r.el_t;
-        if (o.par_p) o.par_p[col] = (float)p0;
-        if (o.par_t) o.par_t[col] = (float)t0;
-        if (o.par_td) o.par_td[col] = (float)td0;
-        if (o.shift) o.shift[col] = shift;
-        if (r.flags && prm.flags) atomicOr(prm.flags, r.flags);
+template <unsigned KINDS, int MODE>
+__global__ void __launch_bounds__(kPColThreads, 2) suite_fast_pcol_kernel(const __grid_constant__ PColParams prm) {
+    const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= prm.n) return;
+    const PColRd rd{prm.p + col, prm.t + col, prm.td + col, prm.ls, prm.pls};
+    fast::FResult res[3];
+    const unsigned redo = fast::suite_column_pcol<KINDS, MODE>(rd, prm.L, prm.tb, prm.o, res);
+    if (KINDS & 1u) store_fast(prm.outs[0], col, res[0]);
+    if (KINDS & 2u) store_fast(prm.outs[1], col, res[1]);
+    if (KINDS & 4u) store_fast(prm.outs[2], col, res[2]);
+    if (redo) {
+        const uint32_t slot = atomicAdd(prm.list_count, 1u);
+        prm.list[slot] = (uint32_t)col | (redo << 28);
     }
 }
 
@@ -220,7 +204,8 @@ size_t fast_scratch_bytes(int64_t n) {
 }
 
 bool fast_eligible(const ColsArg<float> &cols, int kind_mask, const OutArg<float> *outs) {
-    if (!cols.p1d || cols.L < 3 || cols.L > fast::kMaxLevels || cols.n >= (int64_t)1 << 29) return false;
+    if (cols.L < 3 || cols.n >= (int64_t)1 << 28) return false;
+    if (cols.p1d && cols.L > fast::kMaxLevels) return false;
     if (kind_mask & ~(kSB | kML | kMU)) return false;
     for (int q = 0; q < 3; ++q) {
         if (!((kind_mask >> q) & 1)) continue;
@@ -244,7 +229,33 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
     uint32_t *list = reinterpret_cast<uint32_t *>(base + off);
 
     cudaMemsetAsync(count, 0, sizeof(uint32_t), stream);
-    fast_prep_kernel<<<1, 32, 0, stream>>>(cols.p, cols.pls, cols.L, o, prep);
+    const int mode = (o.vtc && o.compat == 141 && o.pos_neg) ? 1 : 0;
+    ListParams lp;
+    lp.cols = cols; lp.tb = tb; lp.o = o;
+    for (int q = 0; q < 3; ++q) lp.outs[q] = outs[q];
+    lp.list = list; lp.list_count = count; lp.flags = flags;
+    if (!cols.p1d) {
+        // per-column pressure: no shared-memory table, adiabats gathered from the curve table
+        PColParams pp;
+        pp.p = cols.p; pp.t = cols.t; pp.td = cols.td; pp.n = cols.n; pp.ls = cols.ls; pp.pls = cols.pls;
+        pp.L = cols.L; pp.tb = tb; pp.o = o;
+        for (int q = 0; q < 3; ++q) pp.outs[q] = outs[q];
+        pp.list = list; pp.list_count = count;
+        const unsigned g = (unsigned)((cols.n + kPColThreads - 1) / kPColThreads);
+#define XP_PCOL_CASE(K)                                                                          \
+    case K:                                                                                      \
+        if (mode) suite_fast_pcol_kernel<K, 1><<<g, kPColThreads, 0, stream>>>(pp);              \
+        else suite_fast_pcol_kernel<K, 0><<<g, kPColThreads, 0, stream>>>(pp);                   \
+        break;
+        switch (kind_mask & 7) {
+            XP_PCOL_CASE(1) XP_PCOL_CASE(2) XP_PCOL_CASE(3) XP_PCOL_CASE(4) XP_PCOL_CASE(5) XP_PCOL_CASE(6) XP_PCOL_CASE(7)
+            default: return -1;
+        }
+#undef XP_PCOL_CASE
+        launch_suite_list(lp, sm_count, stream);
+        return 2;
+    }
+    fast_prep_kernel<<<1, 64, 0, stream>>>(cols.p, cols.pls, cols.L, o, prep);
     fast_coef_kernel<<<cols.L, fast::kNI, 0, stream>>>(prep, tb.curves, coef);
 
     FastParams fp;
@@ -263,7 +274,6 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
     const int64_t tiles = (cols.n + threads - 1) / threads;
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
     static size_t smem_set[2][2][8] = {};
-    const int mode = (o.vtc && o.compat == 141 && o.pos_neg) ? 1 : 0;
 #define XP_FAST_LAUNCH(K, M, T)                                                                                \
     do {                                                                                                       \
         if (smem > smem_set[T == 640][M][K]) {                                                                 \
@@ -286,11 +296,7 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
 #undef XP_FAST_LAUNCH
 #undef XP_FAST_CASE
 
-    ListParams lp;
-    lp.cols = cols; lp.tb = tb; lp.o = o;
-    for (int q = 0; q < 3; ++q) lp.outs[q] = outs[q];
-    lp.list = list; lp.list_count = count; lp.flags = flags;
-    suite_list_kernel<<<sm_count * 8, 128, 0, stream>>>(lp);
+    launch_suite_list(lp, sm_count, stream);
     return 4;
 }
 

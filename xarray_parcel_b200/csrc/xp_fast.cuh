@@ -31,6 +31,7 @@ constexpr float kDecisionEps = 6e-4f;       // K: |parcel - environment| below t
 constexpr float kThetaEMargin = 4e-6f;      // ln(theta_e) gap below this is a most-unstable tie
 constexpr float kCrossSlope = 0.5f;         // K per unit ln p: a crossing with |d0 - d1| < kCrossSlope * dx is too
                                             // shallow to place within 1e-3 relative in pressure in float32
+constexpr unsigned kRedoMuIsSb = 8u;         // redo-mask bit (== kListMuIsSb): write the SB exact result to the MU outputs too
 constexpr double kSaturationMargin = 2e-3;
 // margins for a parcel that is itself only float32-accurate (`approx`; currently unused: all parcels are
 // exact float32 data or float64 means): |dT_lcl| < 4e-5 K, |dp_lcl| < 5e-4 hPa
@@ -57,28 +58,32 @@ struct Prep {
 };
 
 // ---- per-call constants of the shared pressure axis ----------------------------------------------------
-XP_HD void compute_prep(const float *p, int64_t pls, int L, const Opts &o, Prep &pr) {
+// Level part (independent per level; the prep kernel runs it with one thread per level).
+XP_HD void compute_prep_level(const float *p, int64_t pls, int k, Prep &pr) {
+    const double pk = (double)p[(int64_t)k * pls];
+    pr.p64[k] = pk;
+    pr.p[k] = (float)pk;
+    pr.lnp[k] = (float)log(pk);
+    pr.pk[k] = (float)pow(pk, kKappa);
+    pr.thfac[k] = 1.0 / exner(pk);                                   // PF:253 theta = T / exner(p)
+    pr.mlw[k] = 0.0;
+}
+
+// Axis part (after every level is done).
+XP_HD void compute_prep_axis(int L, const Opts &o, Prep &pr) {
     pr.L = L;
     bool ok = (L >= 3 && L <= kMaxLevels);
     if (ok) {
         for (int k = 0; k < L; ++k) {
-            const double pk = (double)p[(int64_t)k * pls];
-            pr.p64[k] = pk;
+            const double pk = pr.p64[k];
             if (!(pk > 0.0) || !isfinite(pk) || (k > 0 && !(pk < pr.p64[k - 1]))) ok = false;
         }
     }
     if (ok && !(pr.p64[0] <= 1100.0)) ok = false;
     if (!ok) { pr.ok = 0; return; }
     int n_table = 0;
-    for (int k = 0; k < L; ++k) {
-        const double pk = pr.p64[k];
-        if (pk >= 2.5) n_table = k + 1;
-        pr.p[k] = (float)pk;
-        pr.lnp[k] = (float)log(pk);
-        pr.pk[k] = (float)pow(pk, kKappa);
-        pr.thfac[k] = 1.0 / exner(pk);                                   // PF:253 theta = T / exner(p)
-        pr.mlw[k] = 0.0;
-    }
+    for (int k = 0; k < L; ++k)
+        if (pr.p64[k] >= 2.5) n_table = k + 1;
     pr.n_table = n_table;
     pr.p0 = pr.p64[0];
     pr.exner0 = exner(pr.p64[0]);
@@ -118,6 +123,11 @@ XP_HD void compute_prep(const float *p, int64_t pls, int L, const Opts &o, Prep 
     pr.K_mu = kt + 1;
     if (pr.K_mu > n_table || K_ml >= n_table || n_table < 3) ok = false;
     pr.ok = ok ? 1 : 0;
+}
+
+XP_HD void compute_prep(const float *p, int64_t pls, int L, const Opts &o, Prep &pr) {
+    for (int k = 0; k < L && k < kMaxLevels; ++k) compute_prep_level(p, pls, k, pr);
+    compute_prep_axis(L, o, pr);
 }
 
 // coef[k][m]: 4-point Lagrange cubic through adiabats (m-1, m, m+1, m+2) * 64 (0-based) evaluated at level k
@@ -543,6 +553,10 @@ XP_HD unsigned suite_column(const Rd &rd, const Cf &cf, const Prep &pr, const Ta
     if (KINDS & 1u) wrap(sb, res[0], 1u);
     if (KINDS & 2u) wrap(ml, res[1], 2u);
     if (KINDS & 4u) wrap(mu, res[2], 4u);
+    // The most-unstable parcel is (certainly) the surface parcel: its exact recomputation is the
+    // surface-based one -- tell the fix-up to do it once and write both (bit 3 replaces bit 2).
+    if ((KINDS & 5u) == 5u && (redo & 4u) && k_mu == 0 && !nan_seen && (best - second >= kThetaEMargin))
+        redo = (redo & ~4u) | 1u | kRedoMuIsSb;
     return redo;
 }
 

@@ -1,0 +1,240 @@
+// xp_fast_pcol.cuh -- float32 fast path for columns with PER-COLUMN pressure (model levels:
+// BASELINE.json configs[1], [2]; the layout of the reference's own test_data.nc).
+//
+// Same design as xp_fast.cuh (lagged-row sweep shared by the parcels, float64-polished LCL, exact
+// table cell, decisions never taken inside the float32 margin, uncertain columns handed to the
+// float64 exact kernel) with two differences forced by the per-column pressure:
+//  * ln p and p^kappa of a level are computed per thread (2 MUFU), and the mixed-layer / most-
+//    unstable layer bounds are found per column in float64;
+//  * the moist adiabat of a parcel is read straight from the float32 curve table in global memory
+//    (L2-resident), exactly as the reference evaluates it: two neighbouring 0.5 hPa nodes of adiabat
+//    i and a linear interpolation in p (PF:585-592) -- no approximation beyond float32 rounding.
+#pragma once
+#include "xp_fast.cuh"
+
+namespace xp {
+namespace fast {
+
+// np.interp(p, P_ascending, curve) in float32 (PF:585-600); p inside [2.5, 1100] is a precondition.
+XP_HD float adiabat_temperature_f32(const float *__restrict__ curve, int j, float w) {
+    const float f0 = XP_LDG(curve + j), f1 = XP_LDG(curve + j + 1);
+    return f_fma(f1 - f0, w, f0);
+}
+
+struct PColParcel : FParcel {
+    const float *curve;         // row of this parcel's adiabat in the curve table (ascending pressure)
+};
+
+// Per-parcel set-up for per-column pressure.  Rd: float P(k), T(k), Td(k).
+template <class Rd>
+XP_HD void setup_parcel_pcol(const Rd &rd, int L, const Tables &tb, const Opts &o, double p0, double t0,
+                             double td0, float x_start, int knext, PColParcel &pc) {
+    pc.bad = false;
+    pc.kfirst = knext;
+    if (!(t0 - td0 >= kSaturationMargin) || !(p0 > 0.0)) { pc.bad = true; t0 = 280.0; td0 = 270.0; p0 = 1000.0; }
+    double lp, lt;
+    lcl_fast(p0, t0, td0, lp, lt);
+    float edge;
+    const int adiabat = adiabat_cell(tb, lp, lt, edge);                // PF:554-557
+    if (adiabat <= 0) pc.bad = true;
+    pc.curve = tb.curves + (size_t)(adiabat > 0 ? adiabat - 1 : 0) * kNP;
+    pc.m = 0; pc.f = 0.0f;
+    const float p0f = (float)p0, t0f = (float)t0, td0f = (float)td0;
+    const float lpf = (float)lp, ltf = (float)lt;
+    pc.lcl_p = lpf; pc.lcl_t = ltf;
+    const float es_l = f_es(ltf);
+    pc.lcl_tv = f_tv(ltf, f_mixing_ratio(es_l, es_l, lpf, o.compat));           // PF:653-657
+    const float w_parcel = f_mixing_ratio(f_es(t0f), f_es(td0f), p0f, o.compat);   // PF:748
+    const float c_dry = t0f * f_ex2(-(float)kKappa * f_lg2(p0f));               // T0 / p0^kappa, PF:291-316
+    pc.c_dryv = o.vtc ? c_dry * f_fma(0.608f, w_parcel, 1.0f) : c_dry;
+    sweep_init(pc, x_start, o.vtc ? f_tv(t0f, w_parcel) : t0f);
+    // LCL position among the levels of the lifted column (insert_level PF:965-966): exact in float64
+    int ka = knext;
+    double pka = 0.0, pkb = p0;
+    while (ka < L) {
+        pka = (double)rd.P(ka);
+        if (!(pka >= lp)) break;
+        pkb = pka; ++ka;
+    }
+    pc.ka = ka;
+    const bool before_is_start = (ka == knext);
+    pc.x_lcl = x_start; pc.a_lcl = pc.b_lcl = 0.0f;
+    if (ka >= L || pkb == lp) { pc.bad = true; pc.ka = L; return; }            // LCL above the top / on a level
+    float tb_, tdb;
+    if (before_is_start) { tb_ = t0f; tdb = td0f; }
+    else { tb_ = rd.T(ka - 1); tdb = rd.Td(ka - 1); }
+    const float ta = rd.T(ka), tda = rd.Td(ka);
+    const float x_l = kLn2 * f_lg2(lpf);
+    float xb, xa, at;
+    if (o.log_interp) { xb = kLn2 * f_lg2((float)pkb); xa = kLn2 * f_lg2((float)pka); at = x_l; }
+    else { xb = (float)pkb; xa = (float)pka; at = lpf; }
+    const float g = (at - xb) * f_rcp(xa - xb);
+    const float te = f_fma(ta - tb_, g, tb_), tde = f_fma(tda - tdb, g, tdb);  // PF:1802
+    const float etv = f_tv(te, f_mixing_ratio(f_es(te), f_es(tde), lpf, o.compat));     // PF:916-920
+    pc.x_lcl = x_l;
+    pc.a_lcl = o.vtc ? pc.lcl_tv : ltf;
+    pc.b_lcl = o.vtc ? etv : te;
+    if (!(te == te) || !(tde == tde)) pc.bad = true;
+}
+
+// One parcel, one iteration (row schedule of xp_fast.cuh).  (j_prv, w_prv): table node and weight
+// of the pressure of level it-1.
+template <int MODE>
+XP_HD void parcel_iteration_pcol(PColParcel &c, int it, bool last, int j_prv, float w_prv, float pk_cur,
+                                 float p_prv, float x_cur, float x_prv, float b_cur, float b_prv, bool vtc) {
+    const bool above = it > c.ka;
+    const bool is_lcl = it == c.ka;
+    if (it < c.kfirst || (last && !above)) return;
+    const float tm = adiabat_temperature_f32(c.curve, j_prv, w_prv);           // PF:585-592
+    const float es = f_es(tm);
+    const float a_m = vtc ? f_tv(tm, kEpsF * es * f_rcp(p_prv - es)) : tm;      // PF:760
+    const float a_d = c.c_dryv * pk_cur;                                        // PF:742
+    const float a = is_lcl ? c.a_lcl : (above ? a_m : a_d);
+    const float b = is_lcl ? c.b_lcl : (above ? b_prv : b_cur);
+    const float x = is_lcl ? c.x_lcl : (above ? x_prv : x_cur);
+    sweep_step<MODE>(c, it, x, a, b, is_lcl, above);
+}
+
+// The suite for one column with its own pressure profile.  Returns the redo mask (see suite_column).
+template <unsigned KINDS, int MODE, class Rd>
+XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Opts &o, FResult res[3]) {
+    unsigned redo = 0;
+    float nanacc = 0.0f;
+    bool bad_axis = false;                 // pressure not finite / not strictly decreasing / outside the table
+    const float p_sfc = rd.P(0), t_sfc = rd.T(0), td_sfc = rd.Td(0);
+    nanacc = f_fma(p_sfc, 0.0f, f_fma(t_sfc, 0.0f, f_fma(td_sfc, 0.0f, nanacc)));
+    const double bottom = (double)p_sfc;                                         // PF:80 (pressure decreases upward)
+    if (!(p_sfc <= 1100.0f)) bad_axis = true;
+    // ---- pre-pass: mixed-layer means (float64) and most-unstable argmax over the lowest levels ------------
+    const double top_ml = bottom - o.ml_depth;                                   // PF:84, PF:1636
+    const double bound_mu = bottom - o.mu_depth;                                 // PF:92
+    double sum_th = 0.0, sum_w = 0.0, pp = bottom, thp = 0.0, wp = 0.0;
+    int K_ml = L;
+    bool ml_done = !(KINDS & 2u), mu_done = !(KINDS & 4u);
+    float best = -1e30f, second = -1e30f, mu_t = 0.0f, mu_td = 0.0f, mu_p = p_sfc;
+    int k_mu = 0;
+    for (int k = 0; k < L && !(ml_done && mu_done); ++k) {
+        const float pf = rd.P(k), t = rd.T(k), td = rd.Td(k);
+        nanacc = f_fma(pf, 0.0f, f_fma(t, 0.0f, f_fma(td, 0.0f, nanacc)));
+        const double p = (double)pf;
+        if (k > 0 && !(p < pp)) bad_axis = true;
+        if ((KINDS & 2u) && !ml_done) {
+            // mixed_parcel PF:229-289 on get_layer(interpolate=True) PF:63-100, trapz in p PF:186-198
+            const double e = sat_vapor_pressure((double)td);
+            const double th = (double)t * exp(-kKappa * log(p / 1000.0));        // PF:253
+            const double w = kEps * e / (p - e);                                 // PF:258
+            if (p >= top_ml) {
+                if (k > 0) {
+                    const double dx = fabs(p - pp);
+                    sum_th += dx * ((thp + th) / 2); sum_w += dx * ((wp + w) / 2);
+                }
+                thp = th; wp = w;
+            } else {
+                if (k > 0 && pp != top_ml) {                                     // layer top in ln p (PF:85-90)
+                    const double cb = log(pp), ca = log(p), at = log(top_ml);
+                    const double g = (at - cb) / (ca - cb);
+                    const double dx = fabs(top_ml - pp);
+                    sum_th += dx * ((thp + (thp + (th - thp) * g)) / 2);
+                    sum_w += dx * ((wp + (wp + (w - wp) * g)) / 2);
+                }
+                K_ml = k; ml_done = true;
+            }
+        }
+        if ((KINDS & 4u) && !mu_done) {
+            // layer of most_unstable_parcel: levels down to the one closest to bottom - depth (PF:208-227)
+            bool in_layer = true;
+            if (p < bound_mu) {
+                in_layer = (k > 0) && ((bound_mu - p) < (pp - bound_mu));
+                mu_done = true;
+            }
+            if (in_layer) {
+                const float e = f_es(td);
+                const float ipe = f_rcp(pf - e);
+                const float r = kEpsF * e * ipe;
+                const float l2t = f_lg2(t), l2td = f_lg2(td);
+                const float t_l = 56.0f + f_rcp(f_rcp(td - 56.0f) + (l2t - l2td) * (kLn2 / 800.0f));
+                const float it_l = f_rcp(t_l);
+                float v = l2t * kLn2;
+                v = f_fma((float)kKappa * kLn2, f_lg2(1000.0f * ipe), v);
+                v = f_fma(0.28f * r * kLn2, l2t - f_lg2(t_l), v);
+                v = f_fma(r * f_fma(0.448f, r, 1.0f), f_fma(3036.0f, it_l, -1.78f), v);
+                nanacc = f_fma(v, 0.0f, nanacc);
+                if (v > best) { second = best; best = v; k_mu = k; mu_t = t; mu_td = td; mu_p = pf; }
+                else if (v > second) second = v;
+            }
+        }
+        pp = p;
+    }
+    // ---- parcels ----------------------------------------------------------------------------------------
+    PColParcel sb, ml, mu;
+    const float x_sfc = kLn2 * f_lg2(p_sfc);
+    if (KINDS & 1u) {
+        setup_parcel_pcol(rd, L, tb, o, bottom, (double)t_sfc, (double)td_sfc, x_sfc, 1, sb);
+        res[0].par_p = p_sfc; res[0].par_t = t_sfc; res[0].par_td = td_sfc; res[0].shift = 0;
+    }
+    if (KINDS & 2u) {
+        const double depth = fabs(top_ml - bottom);                              // PF:158-159
+        const double mp_t = (1. / depth) * sum_th * exner(bottom);               // PF:161, 268-269
+        const double mp_td = dewpoint_from_e(vapor_pressure(bottom, (1. / depth) * sum_w));   // PF:275-282
+        if (!ml_done) redo |= 2u;              // no level above the mixed layer: exact path
+        setup_parcel_pcol(rd, L, tb, o, bottom, mp_t, mp_td, x_sfc, K_ml, ml);
+        res[1].par_p = p_sfc; res[1].par_t = (float)mp_t; res[1].par_td = (float)mp_td; res[1].shift = K_ml;
+    }
+    if (KINDS & 4u) {
+        if (!(best - second >= kThetaEMargin)) redo |= 4u;
+        setup_parcel_pcol(rd, L, tb, o, (double)mu_p, (double)mu_t, (double)mu_td, kLn2 * f_lg2(mu_p), k_mu + 1, mu);
+        res[2].par_p = mu_p; res[2].par_t = mu_t; res[2].par_td = mu_td; res[2].shift = k_mu;
+    }
+    // ---- the sweep ----------------------------------------------------------------------------------------
+    const bool vtc = (MODE == 1) ? true : (o.vtc != 0);
+    const int compat = (MODE == 1) ? 141 : o.compat;
+    float b_prv = 0.0f, x_prv = x_sfc, p_prv = p_sfc;
+    const float *ppp = rd.pptr(1), *tp = rd.tptr(1), *tdp = rd.tdptr(1);
+    const int64_t ls = rd.stride(), pls = rd.pstride();
+    float p_nxt = Rd::ld(ppp), t_nxt = Rd::ld(tp), td_nxt = Rd::ld(tdp);
+    for (int it = 1; it <= L; ++it) {
+        const bool last = (it == L);
+        const float p_cur0 = p_nxt, t = t_nxt, td = td_nxt;
+        ppp += pls; tp += ls; tdp += ls;
+        if (it + 1 < L) { p_nxt = Rd::ld(ppp); t_nxt = Rd::ld(tp); td_nxt = Rd::ld(tdp); }
+        // table node of the previous level's pressure (shared by the parcels), PF:585-592
+        const float s_prv = (p_prv - 2.5f) * 2.0f;
+        int j_prv = (int)s_prv;                                     // floor: s_prv >= 0 inside the table
+        j_prv = min(max(j_prv, 0), kNP - 2);
+        const float w_prv = s_prv - (float)j_prv;
+        float b_cur = 0.0f, x_cur = x_prv, pk_cur = 0.0f, p_cur = p_prv;
+        if (!last) {
+            nanacc = f_fma(p_cur0, 0.0f, f_fma(t, 0.0f, f_fma(td, 0.0f, nanacc)));
+            p_cur = p_cur0;
+            if (!(p_cur < p_prv) || !(p_cur >= 2.5f)) bad_axis = true;
+            const float l2p = f_lg2(p_cur);
+            x_cur = kLn2 * l2p; pk_cur = f_ex2((float)kKappa * l2p);
+            if (vtc) {
+                const float es_t = f_es(t), es_td = f_es(td);
+                b_cur = f_tv(t, f_mixing_ratio(es_t, es_td, p_cur, compat));    // PF:839-843
+            } else {
+                b_cur = t;
+            }
+        }
+        if (KINDS & 1u) parcel_iteration_pcol<MODE>(sb, it, last, j_prv, w_prv, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
+        if (KINDS & 2u) parcel_iteration_pcol<MODE>(ml, it, last, j_prv, w_prv, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
+        if (KINDS & 4u) parcel_iteration_pcol<MODE>(mu, it, last, j_prv, w_prv, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
+        b_prv = b_cur; x_prv = x_cur; p_prv = p_cur;
+    }
+    // ---- results ----------------------------------------------------------------------------------------------
+    const bool nan_seen = !(nanacc == 0.0f) || bad_axis;
+    auto wrap = [&](const PColParcel &c, FResult &r, unsigned bit) {
+        sweep_finish<MODE>(c, o, r);
+        const bool unc = !(c.min_abs_d >= kDecisionEps) || !(c.min_slope >= 0.0f);
+        if (c.bad || unc || nan_seen) redo |= bit;
+    };
+    if (KINDS & 1u) wrap(sb, res[0], 1u);
+    if (KINDS & 2u) wrap(ml, res[1], 2u);
+    if (KINDS & 4u) wrap(mu, res[2], 4u);
+    if ((KINDS & 5u) == 5u && (redo & 4u) && k_mu == 0 && !nan_seen && (best - second >= kThetaEMargin))
+        redo = (redo & ~4u) | 1u | kRedoMuIsSb;
+    return redo;
+}
+
+}  // namespace fast
+}  // namespace xp

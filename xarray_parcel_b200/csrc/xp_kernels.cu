@@ -129,6 +129,37 @@ void launch_cape_cin(const ColsArg<T> &cols, const Tables &tb, const Opts &o, in
     cape_cin_kernel<T><<<(unsigned)grid, block, 0, stream>>>(prm);
 }
 
+// ---- exact fix-up over the list of columns handed over by the float32 fast paths -----------------------------
+struct NoProf {
+    __device__ __forceinline__ void put(int, const ProfileRow &) const {}
+};
+
+// One thread per (list entry, parcel kind) item; kind-major item order keeps the kind uniform in a warp.
+__global__ void __launch_bounds__(128) suite_list_kernel(const __grid_constant__ ListParams prm) {
+    const uint32_t count = *prm.list_count;
+    if (count == 0) return;
+    for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < (uint64_t)count * 3u;
+         it += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t e = prm.list[it % count];
+        const int kind = (int)(it / count);
+        if (!((e >> (28 + kind)) & 1u)) continue;
+        const bool also_mu = kind == 0 && ((e >> 28) & kListMuIsSb);
+        const int64_t col = (int64_t)(e & 0x0fffffffu);
+        const GlobalReader<float> rd = make_reader(prm.cols, col);
+        ParcelResult r;
+        double p0, t0, td0;
+        int shift;
+        NoProf np;
+        run_column(rd, kind, prm.tb, prm.o, qnan(), qnan(), qnan(), r, p0, t0, td0, shift, np);
+        for (int w = 0; w < (also_mu ? 2 : 1); ++w) store_result(prm.outs[w == 0 ? kind : 2], col, r, p0, t0, td0, shift);
+        if (r.flags && prm.flags) atomicOr(prm.flags, r.flags);
+    }
+}
+
+void launch_suite_list(const ListParams &lp, int sm_count, cudaStream_t stream) {
+    suite_list_kernel<<<sm_count * 8, 128, 0, stream>>>(lp);
+}
+
 // ---- individually exposed steps -------------------------------------------------------------
 template <typename T>
 __global__ void lcl_kernel(const T *p, const T *t, const T *td, int64_t n, Opts o, T *lcl_p,

@@ -65,6 +65,22 @@ void launch_cape_cin_base(const T *pressure, const T *env_t, const T *parcel_t, 
                           int64_t n, const T *lfc_p, const T *el_p, const Opts &o, T *cape, T *cin,
                           cudaStream_t stream);
 
+// Exact (float64) recomputation of the columns the float32 fast paths hand over: `list` holds
+// column | mask << 28 (mask bits 0-2: SB/ML/MU to recompute, bit 3: also write the SB result to the
+// MU outputs), `list_count` the number of entries (device memory).  Lives in xp_kernels.cu because
+// that file is compiled without FMA contraction.
+struct ListParams {
+    ColsArg<float> cols;
+    Tables tb;
+    Opts o;
+    OutArg<float> outs[3];
+    const uint32_t *list;
+    const uint32_t *list_count;
+    uint32_t *flags;
+};
+constexpr unsigned kListMuIsSb = 8u;
+void launch_suite_list(const ListParams &lp, int sm_count, cudaStream_t stream);
+
 // Float32 fast path of the suite on a shared pressure axis (xp_fast.cu / xp_fast.cuh): prep +
 // coefficient + fast kernel + exact fix-up over the uncertain-column list, all on `stream`.
 // `scratch` must hold fast_scratch_bytes(n) bytes and must not be shared by launches in flight.
