@@ -188,6 +188,26 @@ xp_status xp_cape_cin_base(xp_context *ctx, const void *pressure, const void *te
                            const void *lfc_pressure, const void *el_pressure,
                            const xp_options *opts, void *cape, void *cin, void *stream);
 
+/* ---- derived convective indices (device memory only) ----------------------------------------
+ * xp_interp_levels: linear_interp / log_interp (PF:1758-1828, extrapolate=False) of n_fields <= 4
+ * fields [n_levels][n_columns] at ONE coordinate value per column (`at` [n_columns], or NULL to use
+ * `at_scalar`): bracketing levels = min{c >= at} / max{c <= at}, duplicated coordinates averaged, an
+ * exact hit returns the level value, no extrapolation (NaN).  `coords` is [n_levels][n_columns] or,
+ * with coords_is_1d, one shared axis.  log_coords = 1 interpolates in ln(coords) (log_interp).
+ * Backs lifted_index (PF:1722), deep_convective_index (PF:1830), isobar_temperature (PF:2193),
+ * lapse_rate (PF:2102) and wind_shear (PF:2216). */
+xp_status xp_interp_levels(xp_context *ctx, const void *coords, int64_t coords_level_stride,
+                           int32_t coords_is_1d, const void *const *fields, void *const *outputs,
+                           int32_t n_fields, int64_t level_stride, int32_t n_levels, int64_t n_columns,
+                           int32_t dtype, const void *at, double at_scalar, int32_t log_coords,
+                           void *stream);
+/* xp_level_crossing: lowest coordinate at which `field` crosses `level` (find_intersections PF:992-1064
+ * with log_x = False, then .min): freezing_level_height / melting_level_height (PF:2137-2191). */
+xp_status xp_level_crossing(xp_context *ctx, const void *coords, int64_t coords_level_stride,
+                            int32_t coords_is_1d, const void *field, int64_t level_stride,
+                            int32_t n_levels, int64_t n_columns, int32_t dtype, double level,
+                            void *output, void *stream);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* Number of kernels this library has launched on ctx since creation. */
 uint64_t xp_launch_count(const xp_context *ctx);

@@ -675,6 +675,50 @@ def lifted_index(profile):
     return dat["environment_temperature"] - dat["temperature"]
 
 
+# --------------------------------------------------------------------------- PF:1830-2259
+def isobar_temperature(pressure, temperature, isobar):
+    """PF:2193-2214."""
+    N = pressure.shape[1]
+    return log_interp({"t": temperature}, pressure, np.full(N, float(isobar)))["t"]
+
+
+def deep_convective_index(pressure, temperature, dewpoint, lifted_index_):
+    """PF:1830-1870."""
+    N = pressure.shape[1]
+    dat = log_interp({"temperature": temperature, "dewpoint": dewpoint}, pressure, np.full(N, 850.0))
+    return (dat["temperature"] - 273.15) + (dat["dewpoint"] - 273.15) - lifted_index_
+
+
+def lapse_rate(pressure, temperature, height, from_pressure=700, to_pressure=500):
+    """PF:2102-2135."""
+    N = pressure.shape[1]
+    lo = log_interp({"t": temperature, "h": height}, pressure, np.full(N, float(from_pressure)))
+    hi = log_interp({"t": temperature, "h": height}, pressure, np.full(N, float(to_pressure)))
+    with np.errstate(all="ignore"):
+        return (hi["t"] - lo["t"]) / (hi["h"] / 1000 - lo["h"] / 1000)
+
+
+def freezing_level_height(temperature, height, level=273.15):
+    """PF:2137-2160."""
+    inter = find_intersections(height, temperature, np.full_like(temperature, level))
+    return nanmin(inter["all_intersect_x"])
+
+
+def wet_bulb_temperature_fast(temperature, dewpoint):
+    """PF:364-387."""
+    return temperature - (1 / 3) * (temperature - dewpoint)
+
+
+def wind_shear(surface_wind_u, surface_wind_v, wind_u, wind_v, height, shear_height=6000):
+    """PF:2216-2259."""
+    N = wind_u.shape[1]
+    hi = linear_interp({"u": wind_u, "v": wind_v}, height, np.full(N, float(shear_height)))
+    su, sv = hi["u"] - surface_wind_u, hi["v"] - surface_wind_v
+    with np.errstate(invalid="ignore"):
+        return {"shear_u": su, "shear_v": sv, "shear_magnitude": np.sqrt(su ** 2 + sv ** 2),
+                "positive_shear": np.sqrt(hi["u"] ** 2 + hi["v"] ** 2) > np.sqrt(surface_wind_u ** 2 + surface_wind_v ** 2)}
+
+
 # --------------------------------------------------------------------------- suite
 def suite(pressure, temperature, dewpoint, opts, ml_depth=100, mu_depth=300, **kwargs):
     """The SB + ML + MU suite the benchmark metric is quoted on (the hot-path part of

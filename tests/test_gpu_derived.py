@@ -1,0 +1,110 @@
+"""GPU tests of the derived convective indices against the oracle: the interpolation
+and level-crossing kernels behind lifted_index, deep_convective_index, isobar_temperature, lapse_rate,
+freezing/melting_level_height and wind_shear, called through the reference-facing Python surface."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import parcel as op
+from oracle import tables as otab
+from xarray_parcel_b200 import _lib, synth
+import xarray_parcel_b200.parcel_functions as parcel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = _lib.get_context(0)
+    c.tables_build()
+    return c
+
+
+def _cols(n=4000, L=60, seed=3, **kw):
+    p, t, td = synth.model_level_columns(n, L, seed=seed, **kw)
+    P, T, D = [x.numpy().astype(np.float64) for x in (p, t, td)]
+    H = 7500.0 * np.log(P[0][None, :] / P) + 120.0             # a height field [m]
+    return P, T, D, H
+
+
+def _same(a, b, rtol=1e-12):
+    a = np.asarray(a, dtype=np.float64)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    ok = ~np.isnan(b)
+    assert np.allclose(a[ok], b[ok], rtol=rtol, atol=0)
+
+
+def test_interp_kernel_semantics(ctx):
+    """linear_interp PF:1758-1811: exact hits, duplicated coordinates (mean), NaNs, no extrapolation."""
+    c = np.array([[10., 10.], [8., 8.], [8., 6.], [4., np.nan], [2., 2.]])
+    x = np.array([[1., 1.], [3., 3.], [5., np.nan], [7., 7.], [9., 9.]])
+    for at in (8.0, 7.0, 10.0, 11.0, 1.0, 3.0):
+        ora = op.linear_interp({"x": x}, c, np.full(2, at))["x"]
+        (got,) = ctx.interp_levels(torch.from_numpy(c).cuda(), [torch.from_numpy(x).cuda()], at)
+        _same(got.cpu().numpy(), ora)
+    ora = op.log_interp({"x": x}, c, np.array([5.0, 3.0]))["x"]
+    (got,) = ctx.interp_levels(torch.from_numpy(c).cuda(), [torch.from_numpy(x).cuda()],
+                               torch.tensor([5.0, 3.0], dtype=torch.float64).cuda(), log=True)
+    _same(got.cpu().numpy(), ora)
+
+
+def test_isobar_lapse_dci_against_oracle(ctx):
+    P, T, D, H = _cols(nan_columns=0.05)
+    _same(parcel.isobar_temperature(P, T, 500), op.isobar_temperature(P, T, 500))
+    _same(parcel.lapse_rate(P, T, H), op.lapse_rate(P, T, H), rtol=1e-9)
+    li = np.linspace(-8, 6, P.shape[1])
+    got = parcel.deep_convective_index(P, T, D, li, prefix="surface")
+    _same(got["surface_dci"], op.deep_convective_index(P, T, D, li))
+    # float32 inputs and a shared pressure axis
+    p1, t, td = synth.era5_columns(3000, seed=5)
+    Pb = np.broadcast_to(p1.numpy().astype(np.float64)[:, None], t.shape)
+    got = parcel.isobar_temperature(p1.numpy(), t.numpy(), 600)
+    assert got.dtype == np.float32
+    _same(got, op.isobar_temperature(Pb, t.numpy().astype(np.float64), 600), rtol=2e-7)
+
+
+def test_freezing_and_melting_level(ctx):
+    P, T, D, H = _cols(seed=4)
+    _same(parcel.freezing_level_height(T, H), op.freezing_level_height(T, H))
+    mlh, wb = parcel.melting_level_height(P, T, D, H)
+    _same(wb, op.wet_bulb_temperature_fast(T, D))
+    _same(mlh, op.freezing_level_height(op.wet_bulb_temperature_fast(T, D), H))
+    # several crossings: the lowest one is returned (PF:2154 .min)
+    h = np.linspace(0, 5000, 11)[:, None]
+    t = (273.15 + np.array([2, 1, -1, -2, 1, 3, -1, -4, -6, -8, -9.0]))[:, None]
+    assert abs(float(parcel.freezing_level_height(t, h)[0]) - 750.0) < 1e-9
+    assert np.isnan(parcel.freezing_level_height(t + 50, h)[0])
+
+
+def test_wind_shear(ctx):
+    rng = np.random.default_rng(1)
+    N, L = 3000, 40
+    H = np.cumsum(rng.uniform(50, 600, (L, N)), axis=0)
+    U, V = rng.normal(5, 8, (L, N)), rng.normal(0, 8, (L, N))
+    su, sv = rng.normal(2, 3, N), rng.normal(0, 3, N)
+    got = parcel.wind_shear(su, sv, U, V, H, shear_height=6000)
+    ora = op.wind_shear(su, sv, U, V, H, 6000)
+    for k in ("shear_u", "shear_v", "shear_magnitude"):
+        _same(got[k], ora[k])
+    assert np.array_equal(np.asarray(got["positive_shear"]), ora["positive_shear"])
+
+
+def test_lifted_index_from_gpu_profile(ctx, soundings):
+    """lifted_index on the profile returned by mixed_layer_cape_cin (as min_conv_properties does,
+    PF:1900-1911) against the oracle, and the reference's known answer UT:1353-1386 (-7.9176350,
+    exact-ODE; the lookup table moves it by < 0.05 K)."""
+    idx, cur = ctx.tables_get()
+    pl, tl = otab.default_grids()
+    tb = otab.AdiabatTables(pl, tl, idx, cur)
+    P, T, D, _ = _cols(n=1500, L=50, seed=6, nan_columns=0, allnan_columns=0)
+    cc, prof, mp = parcel.mixed_layer_cape_cin(P, T, D, prefix="mixed_100")
+    li = parcel.lifted_index(prof, prefix="mixed_100")["mixed_100_lifted_index"]
+    opts = op.Options(op.MoistLapseLUT(tb), lcl_mode="converged")
+    _, oprof, _ = op.mixed_layer_cape_cin(P, T, D, opts)
+    _same(li, op.lifted_index(oprof), rtol=1e-9)
+    s = soundings["test_lifted_index"]
+    p, t, td = [np.asarray(s[k], dtype=np.float64)[:, None] for k in ("pressure", "temperature", "dewpoint")]
+    prof = parcel.parcel_profile(p, p[0], t[0], td[0])               # as UT:1378-1384: no LCL level
+    prof["environment_temperature"] = t
+    assert abs(float(parcel.lifted_index(prof)["lifted_index"][0]) + 7.9176350) < 0.05

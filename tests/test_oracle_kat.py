@@ -406,3 +406,25 @@ def test_columns_are_independent(soundings):
         assert_almost_equal(cc["cin"][i], c1["cin"][0], 9)
         assert_almost_equal(prof["lfc_pressure"][i], p1["lfc_pressure"][0], 9)
         assert_almost_equal(prof["el_pressure"][i], p1["el_pressure"][0], 9)
+
+
+# ---- derived indices: analytic checks of the restatements ---------------------
+def test_derived_index_restatements():
+    L, N = 30, 3
+    p = np.linspace(1000, 300, L)[:, None] * np.ones((1, N))
+    h = 7000.0 * np.log(1000.0 / p)
+    t = 290.0 - 6.5e-3 * h                                     # constant lapse rate 6.5 K/km
+    td = t - 4.0
+    assert_almost_equal(op.lapse_rate(p, t, h), -6.5 * np.ones(N), 9)
+    # 600 hPa lies between levels: log-interpolation of a field that is linear in ln p is exact
+    assert_almost_equal(op.isobar_temperature(p, t, 600.0), 290.0 - 6.5e-3 * 7000.0 * np.log(1000.0 / 600.0), 9)
+    assert_almost_equal(op.freezing_level_height(t, h), (290.0 - 273.15) / 6.5e-3 * np.ones(N), 7)   # PF:2137-2160
+    li = np.array([-3.0, 0.0, 2.0])
+    t850 = 290.0 - 6.5e-3 * 7000.0 * np.log(1000.0 / 850.0)
+    assert_almost_equal(op.deep_convective_index(p, t, td, li), (t850 - 273.15) + (t850 - 4.0 - 273.15) - li, 9)
+    u = 0.002 * h; v = -0.001 * h
+    ws = op.wind_shear(np.ones(N), np.zeros(N), u, v, h, shear_height=6000)
+    assert_almost_equal(ws["shear_u"], 12.0 - 1.0, 9)
+    assert_almost_equal(ws["shear_v"], -6.0, 9)
+    assert ws["positive_shear"].all()
+    assert_almost_equal(op.wet_bulb_temperature_fast(t, td), t - 4.0 / 3.0, 12)                     # PF:364-387

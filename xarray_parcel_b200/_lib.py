@@ -58,7 +58,8 @@ EXPORTS = ["xp_version", "xp_create", "xp_destroy", "xp_last_error", "xp_take_fl
            "xp_default_options", "xp_tables_build", "xp_tables_set", "xp_tables_get",
            "xp_tables_loaded", "xp_cape_cin", "xp_suite", "xp_lcl", "xp_moist_lapse",
            "xp_parcel_profile", "xp_lfc_el", "xp_cape_cin_base", "xp_launch_count",
-           "xp_last_kernel_ms", "xp_last_exact_count"]
+           "xp_last_kernel_ms", "xp_last_exact_count", "xp_interp_levels",
+           "xp_level_crossing"]
 
 
 class XparcelError(RuntimeError):
@@ -114,6 +115,11 @@ def load_library():
         lib.xp_cape_cin_base.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                          c_int64, c_int32, c_void_p, c_void_p,
                                          ctypes.POINTER(XpOptions), c_void_p, c_void_p, c_void_p]
+        lib.xp_interp_levels.argtypes = [c_void_p, c_void_p, c_int64, c_int32, ctypes.POINTER(c_void_p),
+                                         ctypes.POINTER(c_void_p), c_int32, c_int64, c_int32, c_int64, c_int32,
+                                         c_void_p, c_double, c_int32, c_void_p]
+        lib.xp_level_crossing.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32,
+                                          c_int64, c_int32, c_double, c_void_p, c_void_p]
         lib.xp_launch_count.argtypes = [c_void_p]
         lib.xp_launch_count.restype = ctypes.c_uint64
         lib.xp_last_kernel_ms.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_float)]
@@ -395,6 +401,44 @@ class Context:
                                        out[0].data_ptr(), out[1].data_ptr(), self._stream())
         self._check(st, "xp_cape_cin_base")
         return {"cape": out[0], "cin": out[1]}
+
+
+    # ---- derived-index helpers (device tensors) -----------------------------------------------------
+    def interp_levels(self, coords, fields, at, log=False):
+        """linear_interp / log_interp (PF:1758-1828) of up to 4 fields [L, N] at one coordinate value per
+        column.  ``coords``: [L, N] or shared [L]; ``at``: float or [N] tensor.  Returns a list of [N]."""
+        fields = [x.contiguous() for x in fields]
+        L, N = fields[0].shape
+        dt = fields[0].dtype
+        assert 1 <= len(fields) <= 4 and all(x.shape == (L, N) and x.dtype == dt for x in fields)
+        coords = coords.to(dt).contiguous()
+        c1d = coords.dim() == 1
+        outs = [torch.empty((N,), dtype=dt, device=fields[0].device) for _ in fields]
+        fp = (c_void_p * len(fields))(*[x.data_ptr() for x in fields])
+        op = (c_void_p * len(fields))(*[x.data_ptr() for x in outs])
+        if isinstance(at, torch.Tensor):
+            at_t = at.to(dt).expand(N).contiguous()
+            at_ptr, at_s = at_t.data_ptr(), 0.0
+        else:
+            at_t, at_ptr, at_s = None, None, float(at)
+        st = self.lib.xp_interp_levels(self.handle, coords.data_ptr(), 1 if c1d else N, int(c1d), fp, op,
+                                       len(fields), N, L, N, _dtype_code(fields[0]), at_ptr, at_s, int(bool(log)),
+                                       self._stream())
+        self._check(st, "xp_interp_levels")
+        return outs
+
+    def level_crossing(self, coords, field, level):
+        """Lowest coordinate at which ``field`` [L, N] crosses ``level`` (PF:992-1064 + min, PF:2153)."""
+        field = field.contiguous()
+        L, N = field.shape
+        coords = coords.to(field.dtype).contiguous()
+        c1d = coords.dim() == 1
+        out = torch.empty((N,), dtype=field.dtype, device=field.device)
+        st = self.lib.xp_level_crossing(self.handle, coords.data_ptr(), 1 if c1d else N, int(c1d),
+                                        field.data_ptr(), N, L, N, _dtype_code(field), float(level),
+                                        out.data_ptr(), self._stream())
+        self._check(st, "xp_level_crossing")
+        return out
 
 
 _contexts = {}

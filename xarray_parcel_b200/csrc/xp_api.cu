@@ -596,6 +596,43 @@ xp_status xp_cape_cin_base(xp_context *ctx, const void *pressure, const void *te
     return check_cuda(ctx, cudaGetLastError(), "cape_cin_base kernel launch");
 }
 
+xp_status xp_interp_levels(xp_context *ctx, const void *coords, int64_t coords_level_stride,
+                           int32_t coords_is_1d, const void *const *fields, void *const *outputs,
+                           int32_t n_fields, int64_t level_stride, int32_t n_levels, int64_t n_columns,
+                           int32_t dtype, const void *at, double at_scalar, int32_t log_coords,
+                           void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (n_columns == 0) return XP_OK;
+    if (!coords || !fields || !outputs || n_fields < 1 || n_fields > 4 || n_levels < 1 || n_columns < 0)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad interp_levels arguments");
+    for (int f = 0; f < n_fields; ++f)
+        if (!fields[f] || !outputs[f]) return fail(ctx, XP_ERR_INVALID_ARGUMENT, "interp_levels: NULL field/output");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    XP_DISPATCH(dtype,
+                launch_interp_levels<float>((const float *)coords, coords_level_stride, coords_is_1d, (const float *const *)fields, (float *const *)outputs, n_fields, level_stride, n_levels, n_columns, (const float *)at, at_scalar, log_coords, st),
+                launch_interp_levels<double>((const double *)coords, coords_level_stride, coords_is_1d, (const double *const *)fields, (double *const *)outputs, n_fields, level_stride, n_levels, n_columns, (const double *)at, at_scalar, log_coords, st));
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "interp_levels kernel launch");
+}
+
+xp_status xp_level_crossing(xp_context *ctx, const void *coords, int64_t coords_level_stride,
+                            int32_t coords_is_1d, const void *field, int64_t level_stride,
+                            int32_t n_levels, int64_t n_columns, int32_t dtype, double level,
+                            void *output, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (n_columns == 0) return XP_OK;
+    if (!coords || !field || !output || n_levels < 1 || n_columns < 0)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad level_crossing arguments");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    XP_DISPATCH(dtype,
+                launch_level_crossing<float>((const float *)coords, coords_level_stride, coords_is_1d, (const float *)field, level_stride, n_levels, n_columns, level, (float *)output, st),
+                launch_level_crossing<double>((const double *)coords, coords_level_stride, coords_is_1d, (const double *)field, level_stride, n_levels, n_columns, level, (double *)output, st));
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "level_crossing kernel launch");
+}
+
 uint64_t xp_launch_count(const xp_context *ctx) { return ctx ? ctx->launches : 0; }
 
 xp_status xp_last_exact_count(xp_context *ctx, int64_t *out_count) {

@@ -91,6 +91,16 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
                       cudaStream_t stream);
 uint32_t fast_last_list_count(void *scratch, cudaStream_t stream);
 
+// Derived-index helpers (xp_derived.cu): linear/log interpolation of up to 4 fields at one coordinate
+// value per column (PF:1758-1828) and the lowest crossing of a field with a constant (PF:992-1064).
+template <typename T>
+void launch_interp_levels(const T *coords, int64_t cls, int c1d, const T *const *x, T *const *out, int n_fields,
+                          int64_t ls, int L, int64_t n, const T *at, double at_scalar, int log_coords,
+                          cudaStream_t stream);
+template <typename T>
+void launch_level_crossing(const T *x, int64_t xls, int x1d, const T *a, int64_t ls, int L, int64_t n,
+                           double level, T *out, cudaStream_t stream);
+
 // Table builder (xp_tables.cu): fills index_grid (uint16 [kNP][kNT]) and curves (float
 // [kNAdiabats][kNP] ascending pressure).  `scratch_u32` must hold kNP*kNT uint32.
 void launch_build_tables(uint16_t *index_grid, float *curves, uint32_t *scratch_u32,

@@ -33,7 +33,9 @@ __all__ = ["load_moist_adiabat_lookups", "lookup_tables_loaded", "moist_adiabat_
            "parcel_profile_with_lcl", "lfc_el", "cape_cin_base", "cape_cin",
            "surface_based_cape_cin", "mixed_layer_cape_cin", "most_unstable_cape_cin",
            "mixed_parcel", "most_unstable_parcel", "mix_layer", "from_most_unstable_parcel",
-           "parcel_suite", "Dataset"]
+           "parcel_suite", "Dataset", "linear_interp", "log_interp", "lifted_index",
+           "deep_convective_index", "isobar_temperature", "lapse_rate", "freezing_level_height",
+           "melting_level_height", "wet_bulb_temperature_fast", "wind_shear"]
 
 KAPPA = 0.28571428571428564       # metpy.constants.kappa (PF:313)
 
@@ -601,3 +603,138 @@ def cape_cin_base(pressure, temperature, lfc_pressure, el_pressure, parcel_tempe
     r = ctx.cape_cin_base(blocks[0], blocks[1], lf, el, blocks[2], opts)
     fix = (lambda x: x) if on_gpu else (lambda x: x.cpu())
     return lay.dataset({k: lay.wrap_scalar(fix(v), k) for k, v in r.items()})
+
+
+# ---- derived convective indices ------------------------------------------------------
+def _blocks(lay, arrays, dtype):
+    """Inputs -> CUDA level-major blocks ([L, N]; a 1-D vertical axis stays [L])."""
+    out = []
+    for x in arrays:
+        b = lay.to_block(x, None, dtype)
+        out.append(b.cuda() if not b.is_cuda else b)
+    return out
+
+
+def _layout_of(template, vert_dim, vert_axis):
+    lay = _Layout(template, vert_dim, vert_axis)
+    raw = template.data if lay.is_xr else template
+    if isinstance(raw, torch.Tensor):
+        dtype = raw.dtype if raw.dtype in (torch.float32, torch.float64) else torch.float64
+        on_gpu = raw.is_cuda
+    else:
+        dtype = torch.float32 if np.asarray(raw).dtype == np.float32 else torch.float64
+        on_gpu = False
+    return lay, dtype, on_gpu
+
+
+def linear_interp(x, coords, at, dim="model_level_number", keep_attrs=True, extrapolate=False, vert_axis=0,
+                  device=None, log=False):
+    """PF:1758-1811 for one field ``x`` (``extrapolate=True`` is not on the parcel path and not implemented)."""
+    assert not extrapolate, "extrapolate=True is not implemented"
+    ctx = _lib.get_context(device)
+    lay, dtype, on_gpu = _layout_of(x, dim, vert_axis)
+    xb, cb = _blocks(lay, [x, coords], dtype)
+    at_v = at if np.isscalar(at) else lay.scalar_to_block(at, dtype).cuda()
+    (res,) = ctx.interp_levels(cb, [xb], at_v, log=log)
+    return lay.wrap_scalar(res if on_gpu else res.cpu(), None)
+
+
+def log_interp(x, coords, at, dim="model_level_number", vert_axis=0, device=None):
+    """PF:1813-1828."""
+    return linear_interp(x, coords, at, dim=dim, vert_axis=vert_axis, device=device, log=True)
+
+
+def lifted_index(profile, vert_dim="model_level_number", description=None, prefix=None, vert_axis=0, device=None):
+    """PF:1722-1756: environment minus parcel temperature of a parcel_profile_with_lcl() profile,
+    log-interpolated to 500 hPa."""
+    ctx = _lib.get_context(device)
+    lay, dtype, on_gpu = _layout_of(profile["temperature"], vert_dim, vert_axis)
+    tp, te, p = _blocks(lay, [profile["temperature"], profile["environment_temperature"], profile["pressure"]], dtype)
+    a, b = ctx.interp_levels(p, [tp, te], 500.0, log=True)
+    li = b - a
+    name = "lifted_index" if prefix is None else prefix + "_lifted_index"
+    ds = lay.dataset({name: lay.wrap_scalar(li if on_gpu else li.cpu(), "lifted_index")})
+    attrs = {"long_name": "Lifted index", "units": "K"}
+    if description is not None:
+        attrs["description"] = description
+    if isinstance(ds, Dataset):
+        ds.var_attrs[name] = attrs
+    else:
+        ds[name].attrs.update(attrs)
+    return ds
+
+
+def deep_convective_index(pressure, temperature, dewpoint, lifted_index, vert_dim="model_level_number",
+                          description=None, prefix=None, vert_axis=0, device=None):
+    """PF:1830-1870 (Kunz 2009): T(850 hPa) + Td(850 hPa) [C] - lifted index."""
+    ctx = _lib.get_context(device)
+    lay, dtype, on_gpu = _layout_of(temperature, vert_dim, vert_axis)
+    t, td, p = _blocks(lay, [temperature, dewpoint, pressure], dtype)
+    a, b = ctx.interp_levels(p, [t, td], 850.0, log=True)
+    li = lay.scalar_to_block(lifted_index, dtype).cuda()
+    dci = (a - 273.15) + (b - 273.15) - li
+    name = "dci" if prefix is None else prefix + "_dci"
+    ds = lay.dataset({name: lay.wrap_scalar(dci if on_gpu else dci.cpu(), "dci")})
+    attrs = {"long_name": "Deep convective index", "units": "C"}
+    if description is not None:
+        attrs["description"] = description
+    if isinstance(ds, Dataset):
+        ds.var_attrs[name] = attrs
+    else:
+        ds[name].attrs.update(attrs)
+    return ds
+
+
+def isobar_temperature(pressure, temperature, isobar, vert_dim="model_level_number", vert_axis=0, device=None):
+    """PF:2193-2214: temperature log-interpolated to ``isobar`` hPa."""
+    return log_interp(temperature, pressure, isobar, dim=vert_dim, vert_axis=vert_axis, device=device)
+
+
+def lapse_rate(pressure, temperature, height, from_pressure=700, to_pressure=500, vert_dim="model_level_number",
+               vert_axis=0, device=None):
+    """PF:2102-2135: environmental lapse rate between two pressures [K/km]."""
+    ctx = _lib.get_context(device)
+    lay, dtype, on_gpu = _layout_of(temperature, vert_dim, vert_axis)
+    t, h, p = _blocks(lay, [temperature, height, pressure], dtype)
+    ft, fh = ctx.interp_levels(p, [t, h], float(from_pressure), log=True)
+    tt, th = ctx.interp_levels(p, [t, h], float(to_pressure), log=True)
+    lapse = (tt - ft) / (th / 1000 - fh / 1000)
+    return lay.wrap_scalar(lapse if on_gpu else lapse.cpu(), None)
+
+
+def freezing_level_height(temperature, height, vert_dim="model_level_number", vert_axis=0, device=None, level=273.15):
+    """PF:2137-2160: lowest height at which the temperature crosses 273.15 K."""
+    ctx = _lib.get_context(device)
+    lay, dtype, on_gpu = _layout_of(temperature, vert_dim, vert_axis)
+    t, h = _blocks(lay, [temperature, height], dtype)
+    r = ctx.level_crossing(h, t, level)
+    return lay.wrap_scalar(r if on_gpu else r.cpu(), None)
+
+
+def wet_bulb_temperature_fast(temperature, dewpoint):
+    """PF:364-387: the "1/3 rule" (Knox et al. 2017); elementwise on the caller's array library."""
+    return temperature - (1 / 3) * (temperature - dewpoint)
+
+
+def melting_level_height(pressure, temperature, dewpoint, height, fast=True, vert_dim="model_level_number",
+                         vert_axis=0, device=None):
+    """PF:2162-2191 with fast=True (wet bulb by the 1/3 rule).  Returns (melting level height, wet bulb)."""
+    assert fast, "fast=False (Normand wet-bulb, PF:389-445) is not implemented"
+    wb = wet_bulb_temperature_fast(temperature, dewpoint)
+    return freezing_level_height(wb, height, vert_dim=vert_dim, vert_axis=vert_axis, device=device), wb
+
+
+def wind_shear(surface_wind_u, surface_wind_v, wind_u, wind_v, height, shear_height=6000,
+               vert_dim="model_level_number", vert_axis=0, device=None):
+    """PF:2216-2259: wind at ``shear_height`` (linear in height) minus the surface wind."""
+    ctx = _lib.get_context(device)
+    lay, dtype, on_gpu = _layout_of(wind_u, vert_dim, vert_axis)
+    u, v, h = _blocks(lay, [wind_u, wind_v, height], dtype)
+    hu, hv = ctx.interp_levels(h, [u, v], float(shear_height), log=False)
+    su = lay.scalar_to_block(surface_wind_u, dtype).cuda()
+    sv = lay.scalar_to_block(surface_wind_v, dtype).cuda()
+    shear_u, shear_v = hu - su, hv - sv
+    out = {"shear_u": shear_u, "shear_v": shear_v,
+           "shear_magnitude": torch.sqrt(shear_u ** 2 + shear_v ** 2),
+           "positive_shear": torch.sqrt(hu ** 2 + hv ** 2) > torch.sqrt(su ** 2 + sv ** 2)}
+    return lay.dataset({k: lay.wrap_scalar(x if on_gpu else x.cpu(), None) for k, x in out.items()})
