@@ -719,6 +719,44 @@ def wind_shear(surface_wind_u, surface_wind_v, wind_u, wind_v, height, shear_hei
                 "positive_shear": np.sqrt(hi["u"] ** 2 + hi["v"] ** 2) > np.sqrt(surface_wind_u ** 2 + surface_wind_v ** 2)}
 
 
+def conv_properties(dat, opts, min_set=False):
+    """PF:1951-2100 (min_set: PF:1872-1949 min_conv_properties).  ``dat``: dict of [L,N] arrays pressure,
+    temperature, specific_humidity, height_asl, wind_u, wind_v, wind_height_above_surface and [N] arrays
+    surface_wind_u, surface_wind_v.  Returns a flat dict of [N] arrays."""
+    p, t = dat["pressure"], dat["temperature"]
+    td = th.dewpoint_from_specific_humidity(p, t, dat["specific_humidity"], opts.metpy_compat)
+    out = {}
+
+    def add_parcel(prefix, cc, prof):
+        out[prefix + "_cape"], out[prefix + "_cin"] = cc["cape"], cc["cin"]
+        li = lifted_index(prof)
+        out[prefix + "_lifted_index"] = li
+        out[prefix + "_dci"] = deep_convective_index(p, t, td, li)
+
+    cc, prof, _ = mixed_layer_cape_cin(p, t, td, opts, depth=100)
+    if min_set:
+        out["mixed_100_cape"], out["mixed_100_cin"] = cc["cape"], cc["cin"]
+        out["mixed_100_lifted_index"] = lifted_index(prof)
+    else:
+        add_parcel("mixed_100", cc, prof)
+        cc, prof, mu_parcel = most_unstable_cape_cin(p, t, td, opts, depth=250)
+        add_parcel("mu", cc, prof)
+        cc, prof, _ = mixed_layer_cape_cin(p, t, td, opts, depth=50)
+        add_parcel("mixed_50", cc, prof)
+        out["mu_mixing_ratio"] = th.saturation_mixing_ratio(mu_parcel["pressure"], mu_parcel["dewpoint"])
+    out["lapse_rate_700_500"] = lapse_rate(p, t, dat["height_asl"])
+    out["temp_500"] = isobar_temperature(p, t, 500)
+    out["freezing_level"] = freezing_level_height(t, dat["height_asl"])
+    out["melting_level"] = freezing_level_height(wet_bulb_temperature_fast(t, td), dat["height_asl"])
+    out.update(wind_shear(dat["surface_wind_u"], dat["surface_wind_v"], dat["wind_u"], dat["wind_v"],
+                          dat["wind_height_above_surface"], 6000))
+    if not min_set:
+        valid = ~(np.isnan(td).any(0) | np.isnan(p).any(0) | np.isnan(t).any(0) |
+                  np.isnan(dat["specific_humidity"]).any(0))                      # PF:1976-1983, 2098-2099
+        out = {k: np.where(valid, v, np.nan) for k, v in out.items()}
+    return out
+
+
 # --------------------------------------------------------------------------- suite
 def suite(pressure, temperature, dewpoint, opts, ml_depth=100, mu_depth=300, **kwargs):
     """The SB + ML + MU suite the benchmark metric is quoted on (the hot-path part of

@@ -253,3 +253,19 @@ def moist_lapse_ode(pressure, temperature, reference_pressure=None, solver="lsod
             raise ValueError(solver)
         out[sel] = [lut[v] for v in p[sel].tolist()]
     return out
+
+
+# ---- specific humidity front end (PF:1889, 1969, 2048-2049) -----------------------------------------
+def dewpoint_from_specific_humidity(pressure, temperature, specific_humidity, metpy_compat=METPY_COMPAT_DEFAULT):
+    """metpy.calc.dewpoint_from_specific_humidity.
+
+    MetPy 1.4.1 goes through relative humidity (w / ws(p, T), then dewpoint(rh * es(T)));
+    MetPy >= 1.6 through the vapour pressure e = p w / (eps + w) (the change noted in
+    environment_changes_eval.ipynb:278).  The >= 1.6 form is recalled, not verified.
+    """
+    with np.errstate(all="ignore"):
+        w = specific_humidity / (1 - specific_humidity)          # mixing_ratio_from_specific_humidity
+        if str(metpy_compat) in ("1.6.2", "162"):
+            return dewpoint_from_vapor_pressure(vapor_pressure(pressure, w))
+        rh = w / saturation_mixing_ratio(pressure, temperature)
+        return dewpoint_from_vapor_pressure(rh * saturation_vapor_pressure(temperature))

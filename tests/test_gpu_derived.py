@@ -108,3 +108,34 @@ def test_lifted_index_from_gpu_profile(ctx, soundings):
     prof = parcel.parcel_profile(p, p[0], t[0], td[0])               # as UT:1378-1384: no LCL level
     prof["environment_temperature"] = t
     assert abs(float(parcel.lifted_index(prof)["lifted_index"][0]) + 7.9176350) < 0.05
+
+
+@pytest.mark.parametrize("compat", ["1.4.1", "1.6.2"])
+def test_conv_properties_assembly(ctx, compat):
+    """conv_properties / min_conv_properties (PF:1872-2100) end to end from specific humidity, against
+    the oracle's assembly of the same steps."""
+    idx, cur = ctx.tables_get()
+    pl, tl = otab.default_grids()
+    tb = otab.AdiabatTables(pl, tl, idx, cur)
+    P, T, D, H = _cols(n=1200, L=45, seed=8, nan_columns=0.02, allnan_columns=0)
+    es_d = 6.112 * np.exp(17.67 * (D - 273.15) / (D - 29.65))
+    w = 0.6219569100577033 * es_d / (P - es_d)
+    rng = np.random.default_rng(2)
+    dat = {"pressure": P, "temperature": T, "specific_humidity": w / (1 + w), "height_asl": H,
+           "wind_u": rng.normal(5, 8, P.shape), "wind_v": rng.normal(0, 8, P.shape),
+           "wind_height_above_surface": H - H[0][None, :] + 10.0,
+           "surface_wind_u": rng.normal(2, 3, P.shape[1]), "surface_wind_v": rng.normal(0, 3, P.shape[1])}
+    opts = op.Options(op.MoistLapseLUT(tb), lcl_mode="converged", metpy_compat=compat)
+    for min_set in (False, True):
+        ora = op.conv_properties(dict(dat), opts, min_set=min_set)
+        got = (parcel.min_conv_properties(dict(dat), metpy_compat=compat) if min_set
+               else parcel.conv_properties(dict(dat), metpy_compat=compat))
+        assert set(ora) == set(got), set(ora) ^ set(got)
+        for k, v in ora.items():
+            g = np.asarray(got[k])
+            if v.dtype == bool:
+                assert np.array_equal(g.astype(bool), v), k
+            else:
+                assert np.array_equal(np.isnan(g), np.isnan(v)), k
+                ok = ~np.isnan(v)
+                assert np.allclose(g[ok], v[ok], rtol=1e-8, atol=1e-8), k

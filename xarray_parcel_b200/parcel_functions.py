@@ -35,7 +35,8 @@ __all__ = ["load_moist_adiabat_lookups", "lookup_tables_loaded", "moist_adiabat_
            "mixed_parcel", "most_unstable_parcel", "mix_layer", "from_most_unstable_parcel",
            "parcel_suite", "Dataset", "linear_interp", "log_interp", "lifted_index",
            "deep_convective_index", "isobar_temperature", "lapse_rate", "freezing_level_height",
-           "melting_level_height", "wet_bulb_temperature_fast", "wind_shear"]
+           "melting_level_height", "wet_bulb_temperature_fast", "wind_shear",
+           "dewpoint_from_specific_humidity", "conv_properties", "min_conv_properties"]
 
 KAPPA = 0.28571428571428564       # metpy.constants.kappa (PF:313)
 
@@ -738,3 +739,106 @@ def wind_shear(surface_wind_u, surface_wind_v, wind_u, wind_v, height, shear_hei
            "shear_magnitude": torch.sqrt(shear_u ** 2 + shear_v ** 2),
            "positive_shear": torch.sqrt(hu ** 2 + hv ** 2) > torch.sqrt(su ** 2 + sv ** 2)}
     return lay.dataset({k: lay.wrap_scalar(x if on_gpu else x.cpu(), None) for k, x in out.items()})
+
+
+def dewpoint_from_specific_humidity(pressure, temperature, specific_humidity, metpy_compat="1.4.1"):
+    """metpy.calc.dewpoint_from_specific_humidity as the reference calls it (PF:1889, 1969); elementwise on
+    the caller's array library.  MetPy 1.4.1 goes through relative humidity, MetPy >= 1.6 through the
+    vapour pressure (environment_changes_eval.ipynb:278) -- pass the version the data were made with."""
+    lib = torch if isinstance(temperature, torch.Tensor) else np
+    eps = 0.6219569100577033
+
+    def es(t):
+        return 6.112 * lib.exp(17.67 * (t - 273.15) / (t - 29.65))
+
+    def dewpoint(e):
+        v = lib.log(e / 6.112)
+        return 243.5 * v / (17.67 - v) + 273.15
+
+    w = specific_humidity / (1 - specific_humidity)
+    if str(metpy_compat) in ("1.6.2", "162"):
+        return dewpoint(pressure * w / (eps + w))
+    es_t = es(temperature)
+    rh = w / (eps * es_t / (pressure - es_t))
+    return dewpoint(rh * es_t)
+
+
+def _conv(dat, vert_dim, vert_axis, device, min_set, ignore_nans, metpy_compat):
+    p, t = dat["pressure"], dat["temperature"]
+    td = dewpoint_from_specific_humidity(p, t, dat["specific_humidity"], metpy_compat)
+    try:
+        dat["dewpoint"] = td                                        # the reference adds it to the caller's Dataset
+    except Exception:
+        pass
+    kw = dict(vert_dim=vert_dim, vert_axis=vert_axis, device=device)
+    out = {}
+
+    def merge(ds):
+        for k in ds:
+            out[k] = ds[k]
+
+    def parcel_block(prefix, cc, prof, desc):
+        merge(cc)
+        li = lifted_index(prof, prefix=prefix, description="Lifted index using " + desc, **kw)
+        merge(li)
+        if not min_set:
+            merge(deep_convective_index(p, t, td, li[prefix + "_lifted_index"], prefix=prefix,
+                                        description="Deep convective index using " + desc, **kw))
+
+    if not min_set:
+        cc, prof, mu_parcel = most_unstable_cape_cin(p, t, td, depth=250, prefix="mu", metpy_compat=metpy_compat, **kw)
+        parcel_block("mu", cc, prof, "most-unstable parcel in lowest 250 hPa.")
+        pp, pd = mu_parcel["pressure"], mu_parcel["dewpoint"]
+        lib = torch if isinstance(pp, torch.Tensor) else np
+        es_d = 6.112 * lib.exp(17.67 * (pd - 273.15) / (pd - 29.65))
+        out["mu_mixing_ratio"] = 0.6219569100577033 * es_d / (pp - es_d)          # PF:2047-2053
+    cc, prof, _ = mixed_layer_cape_cin(p, t, td, depth=100, prefix="mixed_100", metpy_compat=metpy_compat, **kw)
+    parcel_block("mixed_100", cc, prof, "fully-mixed lowest 100 hPa parcel.")
+    if not min_set:
+        cc, prof, _ = mixed_layer_cape_cin(p, t, td, depth=50, prefix="mixed_50", metpy_compat=metpy_compat, **kw)
+        parcel_block("mixed_50", cc, prof, "fully-mixed lowest 50 hPa parcel.")
+    out["lapse_rate_700_500"] = lapse_rate(p, t, dat["height_asl"], **kw)
+    out["temp_500"] = isobar_temperature(p, t, 500, **kw)
+    out["freezing_level"] = freezing_level_height(t, dat["height_asl"], **kw)
+    out["melting_level"], _ = melting_level_height(p, t, td, dat["height_asl"], **kw)
+    merge(wind_shear(dat["surface_wind_u"], dat["surface_wind_v"], dat["wind_u"], dat["wind_v"],
+                     dat["wind_height_above_surface"], shear_height=6000, **kw))
+    if not min_set and not ignore_nans:                              # PF:1976-1983, 2098-2099
+        lay = _Layout(t, vert_dim, vert_axis)
+        va = lay.vert_axis if lay.vert_axis is not None else 0
+        if lay.is_xr:
+            bad = (np.isnan(td).any(vert_dim) | np.isnan(p).any(vert_dim) | np.isnan(t).any(vert_dim) |
+                   np.isnan(dat["specific_humidity"]).any(vert_dim))
+            out = {k: v.where(~bad) for k, v in out.items()}
+        else:
+            lib = torch if isinstance(t, torch.Tensor) else np
+            bad = None
+            for x in (td, p, t, dat["specific_humidity"]):
+                b = lib.isnan(x).any(va) if x.ndim > 1 else lib.isnan(x).any()
+                bad = b if bad is None else (bad | b)
+            def mask(v):
+                if lib is torch:
+                    v = v.to(torch.float64) if v.dtype == torch.bool else v
+                    b = bad.to(v.device) if isinstance(bad, torch.Tensor) else bad
+                    return torch.where(b, torch.full_like(v, float("nan")), v)
+                v = v.astype(np.float64) if v.dtype == np.bool_ else v
+                return np.where(bad, np.nan, v)
+
+            out = {k: mask(v) for k, v in out.items()}
+    lay = _Layout(t, vert_dim, vert_axis)
+    return lay.dataset(out)
+
+
+def conv_properties(dat, vert_dim="model_level_number", ignore_nans=False, vert_axis=0, device=None,
+                    metpy_compat="1.4.1"):
+    """PF:1951-2100: MU (250 hPa) and mixed (100, 50 hPa) CAPE/CIN, lifted and deep-convective indices,
+    MU mixing ratio, 700-500 hPa lapse rate, 500 hPa temperature, freezing/melting level, 0-6 km shear.
+    ``dat``: Dataset/dict with pressure, temperature, specific_humidity, height_asl, wind_u, wind_v,
+    wind_height_above_surface (all [level, ...]) and surface_wind_u, surface_wind_v."""
+    return _conv(dat, vert_dim, vert_axis, device, False, ignore_nans, metpy_compat)
+
+
+def min_conv_properties(dat, vert_dim="model_level_number", vert_axis=0, device=None, metpy_compat="1.4.1"):
+    """PF:1872-1949: the minimal set (mixed-100 CAPE/CIN + lifted index, lapse rate, T500, freezing and
+    melting level, shear)."""
+    return _conv(dat, vert_dim, vert_axis, device, True, True, metpy_compat)
