@@ -43,7 +43,7 @@ extern "C" void hostsim_cape_cin(const double *p, const double *t, const double 
     xp::Tables tb = {index_grid, curves};
     xp::Opts o;
     o.vtc = iopts[0]; o.log_interp = iopts[1]; o.pos_neg = iopts[2]; o.post_zero = iopts[3];
-    o.compat = iopts[4]; o.ml_depth = ml_depth; o.mu_depth = mu_depth;
+    o.compat = iopts[4]; o.exact_only = 0; o.vote_mask = 0; o.ml_depth = ml_depth; o.mu_depth = mu_depth;
     uint32_t fl = 0;
     for (int64_t c = 0; c < n; ++c) {
         HostReader rd = {p1d ? p : p + c, t + c, td + c, n, p1d ? 1 : n, L};
@@ -76,6 +76,12 @@ struct HostRdF {
     int64_t stride() const { return ls; }
     static float ld(const float *p) { return *p; }
 };
+struct HostEnv {
+    static constexpr bool kStaged = true, kFullPass = true;
+    float v[xp::fast::kMaxLevels];
+    void put(int k, float x) { v[k] = x; }
+    float get(int k) const { return v[k]; }
+};
 struct HostCoefRow {
     const xp::fast::Coef *row;
     void advance() { row += xp::fast::kNI; }
@@ -94,7 +100,7 @@ extern "C" int hostsim_fast_suite(const float *p, const float *t, const float *t
     xp::Tables tb = {index_grid, curves};
     xp::Opts o;
     o.vtc = iopts[0]; o.log_interp = iopts[1]; o.pos_neg = iopts[2]; o.post_zero = iopts[3];
-    o.compat = iopts[4]; o.exact_only = 0; o.ml_depth = ml_depth; o.mu_depth = mu_depth;
+    o.compat = iopts[4]; o.exact_only = 0; o.vote_mask = 0; o.ml_depth = ml_depth; o.mu_depth = mu_depth;
     static xp::fast::Prep pr;
     xp::fast::compute_prep(p, 1, L, o, pr);
     if (!pr.ok) return 0;
@@ -105,8 +111,16 @@ extern "C" int hostsim_fast_suite(const float *p, const float *t, const float *t
     for (int64_t c = 0; c < n; ++c) {
         HostRdF rd = {t + c, td + c, n};
         xp::fast::FResult r[3];
-        redo[c] = (o.vtc && o.compat == 141 && o.pos_neg) ? xp::fast::suite_column<7u, 1>(rd, cf, pr, tb, o, r)
-                                              : xp::fast::suite_column<7u, 0>(rd, cf, pr, tb, o, r);
+        // even columns: environment staged + early termination; odd columns: recomputed in the sweep
+        if (c & 1) {
+            xp::fast::EnvRecompute env;
+            redo[c] = (o.vtc && o.compat == 141 && o.pos_neg) ? xp::fast::suite_column<7u, 1>(rd, cf, pr, tb, o, env, r)
+                                                              : xp::fast::suite_column<7u, 0>(rd, cf, pr, tb, o, env, r);
+        } else {
+            HostEnv env;
+            redo[c] = (o.vtc && o.compat == 141 && o.pos_neg) ? xp::fast::suite_column<7u, 1>(rd, cf, pr, tb, o, env, r)
+                                                              : xp::fast::suite_column<7u, 0>(rd, cf, pr, tb, o, env, r);
+        }
         for (int q = 0; q < 3; ++q) {
             const float vals[12] = {r[q].cape, r[q].cin, r[q].lcl_p, r[q].lcl_t, r[q].lcl_tv, r[q].lfc_p,
                                     r[q].lfc_t, r[q].el_p, r[q].el_t, r[q].par_p, r[q].par_t, r[q].par_td};
@@ -141,7 +155,7 @@ extern "C" int hostsim_fast_suite_pcol(const float *p, const float *t, const flo
     xp::Tables tb = {index_grid, curves};
     xp::Opts o;
     o.vtc = iopts[0]; o.log_interp = iopts[1]; o.pos_neg = iopts[2]; o.post_zero = iopts[3];
-    o.compat = iopts[4]; o.exact_only = 0; o.ml_depth = ml_depth; o.mu_depth = mu_depth;
+    o.compat = iopts[4]; o.exact_only = 0; o.vote_mask = 0; o.ml_depth = ml_depth; o.mu_depth = mu_depth;
     for (int64_t c = 0; c < n; ++c) {
         HostRdP rd = {p + c, t + c, td + c, n};
         xp::fast::FResult r[3];

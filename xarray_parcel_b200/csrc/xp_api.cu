@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -89,6 +90,12 @@ Opts to_opts(const xp_options *o) {
     r.ml_depth = d.mixed_layer_depth;
     r.mu_depth = d.most_unstable_depth;
     r.exact_only = d.exact_only != 0;
+    static int vote_mask = -1;
+    if (vote_mask < 0) {
+        const char *e = getenv("XP_FAST_VOTE_MASK");
+        vote_mask = e ? (atoi(e) & 15) : 3;
+    }
+    r.vote_mask = vote_mask;
     return r;
 }
 

@@ -28,6 +28,7 @@ struct Tables {
 struct Opts {
     int vtc, log_interp, pos_neg, post_zero, compat;
     int exact_only;      // 1: never take the float32 fast path
+    int vote_mask;       // fast path: early-termination vote every (vote_mask + 1) iterations (tuning)
     double ml_depth, mu_depth;
 };
 

@@ -84,7 +84,19 @@ constexpr int kFastThreads = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <unsigned KINDS, int MODE, int THREADS>
+// Per-thread column of the environment curve in shared memory: element (level k, thread t) at
+// base[k * blockDim.x + t] -- consecutive threads hit consecutive banks.
+struct EnvSmem {
+    static constexpr bool kStaged = true, kFullPass = true;
+    float *base;
+    int stride;
+    __device__ __forceinline__ void put(int k, float v) { base[k * stride] = v; }
+    __device__ __forceinline__ float get(int k) const { return base[k * stride]; }
+};
+
+// STAGED: 0 = environment recomputed in the sweep; 1 = environment curve staged in shared memory + early
+// termination; 2 = recomputed, with a first pass over all levels for the early-termination bound.
+template <unsigned KINDS, int MODE, int THREADS, int STAGED>
 __global__ void __launch_bounds__(THREADS, 1) suite_fast_kernel(const __grid_constant__ FastParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
@@ -135,12 +147,25 @@ __global__ void __launch_bounds__(THREADS, 1) suite_fast_kernel(const __grid_con
         }
     }
     const SmemCoef cf{s_coef};
+    float *s_env = reinterpret_cast<float *>(s_coef + (size_t)pr.n_table * fast::kNI);
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < prm.n; base += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t col = base + threadIdx.x;
-        if (col >= prm.n) continue;
+        // lanes past the end redo the last column (warp-uniform votes need every lane) and do not store
+        const bool valid = base + threadIdx.x < prm.n;
+        const int64_t col = valid ? base + threadIdx.x : prm.n - 1;
         const GlobalRd rd{prm.t + col, prm.td + col, prm.ls};
         fast::FResult res[3];
-        const unsigned redo = fast::suite_column<KINDS, MODE>(rd, cf, pr, prm.tb, prm.o, res);
+        unsigned redo;
+        if (STAGED == 1) {
+            EnvSmem env{s_env + threadIdx.x, (int)blockDim.x};
+            redo = fast::suite_column<KINDS, MODE>(rd, cf, pr, prm.tb, prm.o, env, res);
+        } else if (STAGED == 2) {
+            fast::EnvMinOnly env;
+            redo = fast::suite_column<KINDS, MODE>(rd, cf, pr, prm.tb, prm.o, env, res);
+        } else {
+            fast::EnvRecompute env;
+            redo = fast::suite_column<KINDS, MODE>(rd, cf, pr, prm.tb, prm.o, env, res);
+        }
+        if (!valid) continue;
         if (KINDS & 1u) store_fast(prm.outs[0], col, res[0]);
         if (KINDS & 2u) store_fast(prm.outs[1], col, res[1]);
         if (KINDS & 4u) store_fast(prm.outs[2], col, res[2]);
@@ -263,31 +288,36 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
     fp.prep = prep; fp.coef = coef; fp.tb = tb; fp.o = o; fp.kinds = (unsigned)kind_mask;
     for (int q = 0; q < 3; ++q) fp.outs[q] = outs[q];
     fp.list = list; fp.list_count = count;
-    const size_t smem = ((sizeof(Prep) + 127) & ~(size_t)127) + (size_t)cols.L * fast::kNI * sizeof(Coef);
-    // threads per CTA (one CTA per SM): 512 x 128 registers by default; XP_FAST_THREADS=640 trades
-    // registers (102) for 20 resident warps (tuning knob, read once)
-    static int threads = 0;
-    if (!threads) {
-        const char *e = getenv("XP_FAST_THREADS");
-        threads = (e && atoi(e) == 640) ? 640 : kFastThreads;
+    // shared memory: Prep | coefficient table | (staged) the environment curve of every thread
+    const size_t smem_table = ((sizeof(Prep) + 127) & ~(size_t)127) + (size_t)cols.L * fast::kNI * sizeof(Coef);
+    const size_t smem_env = (size_t)cols.L * kFastThreads * sizeof(float);
+    static int staged_ok = -1;
+    if (staged_ok < 0) {
+        const char *e = getenv("XP_FAST_STAGED");
+        staged_ok = e ? atoi(e) : 0;       // default 0: measured fastest
     }
+    int staged = staged_ok;
+    if (staged == 1 && smem_table + smem_env + 256 > (size_t)227 * 1024) staged = 0;
+    const size_t smem = smem_table + (staged == 1 ? smem_env : 0);
+    const int threads = kFastThreads;      // one 512-thread CTA per SM (128 registers per thread)
     const int64_t tiles = (cols.n + threads - 1) / threads;
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
-    static size_t smem_set[2][2][8] = {};
-#define XP_FAST_LAUNCH(K, M, T)                                                                                \
-    do {                                                                                                       \
-        if (smem > smem_set[T == 640][M][K]) {                                                                 \
-            if (cudaFuncSetAttribute(suite_fast_kernel<K, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                     (int)smem) != cudaSuccess)                                                \
-                return -1;                                                                                     \
-            smem_set[T == 640][M][K] = smem;                                                                   \
-        }                                                                                                      \
-        suite_fast_kernel<K, M, T><<<grid, T, smem, stream>>>(fp);                                             \
+    static size_t smem_set[3][2][1][8] = {};
+#define XP_FAST_LAUNCH(K, M, S)                                                                                  \
+    do {                                                                                                         \
+        if (smem > smem_set[S][M][0][K]) {                                                                       \
+            if (cudaFuncSetAttribute(suite_fast_kernel<K, M, kFastThreads, S>,                                   \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)     \
+                return -1;                                                                                       \
+            smem_set[S][M][0][K] = smem;                                                                         \
+        }                                                                                                        \
+        suite_fast_kernel<K, M, kFastThreads, S><<<grid, kFastThreads, smem, stream>>>(fp);                      \
     } while (0)
-#define XP_FAST_CASE(K)                                                                   \
-    case K:                                                                               \
-        if (threads == 640) { if (mode) XP_FAST_LAUNCH(K, 1, 640); else XP_FAST_LAUNCH(K, 0, 640); } \
-        else { if (mode) XP_FAST_LAUNCH(K, 1, 512); else XP_FAST_LAUNCH(K, 0, 512); }     \
+#define XP_FAST_CASE(K)                                                                           \
+    case K:                                                                                       \
+        if (staged == 1) { if (mode) XP_FAST_LAUNCH(K, 1, 1); else XP_FAST_LAUNCH(K, 0, 1); }     \
+        else if (staged == 2) { if (mode) XP_FAST_LAUNCH(K, 1, 2); else XP_FAST_LAUNCH(K, 0, 2); }\
+        else { if (mode) XP_FAST_LAUNCH(K, 1, 0); else XP_FAST_LAUNCH(K, 0, 0); }                 \
         break;
     switch (kind_mask & 7) {
         XP_FAST_CASE(1) XP_FAST_CASE(2) XP_FAST_CASE(3) XP_FAST_CASE(4) XP_FAST_CASE(5) XP_FAST_CASE(6) XP_FAST_CASE(7)

@@ -31,6 +31,7 @@ constexpr float kDecisionEps = 6e-4f;       // K: |parcel - environment| below t
 constexpr float kThetaEMargin = 4e-6f;      // ln(theta_e) gap below this is a most-unstable tie
 constexpr float kCrossSlope = 0.5f;         // K per unit ln p: a crossing with |d0 - d1| < kCrossSlope * dx is too
                                             // shallow to place within 1e-3 relative in pressure in float32
+constexpr float kStopMargin = 1.0f;          // K: early-termination margin below the coldest environment level
 constexpr unsigned kRedoMuIsSb = 8u;         // redo-mask bit (== kListMuIsSb): write the SB exact result to the MU outputs too
 constexpr double kSaturationMargin = 2e-3;
 // margins for a parcel that is itself only float32-accurate (`approx`; currently unused: all parcels are
@@ -146,6 +147,25 @@ XP_HD Coef compute_coef(const Prep &pr, const float *curves, int k, int m) {
     c.c3 = (float)(-y[0] / 6 + y[1] / 2 - y[2] / 2 + y[3] / 6);
     return c;
 }
+
+// warp-uniform vote (the host simulation runs one column at a time)
+#if defined(__CUDACC__)
+#define XP_WARP_ALL(x) __all_sync(0xffffffffu, (x))
+#else
+#define XP_WARP_ALL(x) (x)
+#endif
+
+// Environment-curve policies of suite_column (see there).
+struct EnvRecompute {                 // environment recomputed in the sweep, no early termination
+    static constexpr bool kStaged = false, kFullPass = false;
+    XP_HD void put(int, float) {}
+    XP_HD float get(int) const { return 0.0f; }
+};
+struct EnvMinOnly {                   // first pass over all levels for the coldest environment level only
+    static constexpr bool kStaged = false, kFullPass = true;
+    XP_HD void put(int, float) {}
+    XP_HD float get(int) const { return 0.0f; }
+};
 
 // ---- float32 primitives (MUFU on the device) -------------------------------------------------
 #if defined(__CUDACC__)
@@ -453,21 +473,62 @@ XP_HD void parcel_iteration(FParcel &c, int it, bool last, const CoefRow &cprev,
 // KINDS: bit 0 SB, 1 ML, 2 MU.  MODE 1: the reference's default options (virtual temperature
 // correction, MetPy 1.4.1 formulas, pos_cape_neg_cin) folded in at compile time; MODE 0: run time.
 // Returns the mask of kinds that the exact path must recompute.
-template <unsigned KINDS, int MODE, class Rd, class Cf>
+//
+// Env: where the environment curve lives between the first pass and the sweep.
+//   Env::kStaged = true : `env.put(k, b)` / `env.get(k)` is a per-thread column in shared memory; the first
+//     pass runs over ALL levels (reading T/Td once), stores the environment curve and its minimum, and the
+//     sweep (a) reads it back instead of recomputing it and (b) stops -- warp-uniformly -- as soon as every
+//     parcel of every lane is above its LCL and colder than the coldest environment level by
+//     kStopMargin: no crossing and no positive area can follow, so with pos_cape_neg_cin (MODE 1)
+//     nothing the outputs depend on changes any more.
+//   Env::kStaged = false: the environment is recomputed in the sweep from T/Td (no shared memory needed).
+template <unsigned KINDS, int MODE, class Rd, class Cf, class Env>
 XP_HD unsigned suite_column(const Rd &rd, const Cf &cf, const Prep &pr, const Tables &tb, const Opts &o,
-                            FResult res[3]) {
+                            Env &env, FResult res[3]) {
     unsigned redo = 0;
     float nanacc = 0.0f;                   // becomes NaN if any T/Td read is NaN or infinite
+    const bool vtc = (MODE == 1) ? true : (o.vtc != 0);
+    const int compat = (MODE == 1) ? 141 : o.compat;
+    const int nt = pr.n_table;
+    float b_min = 1e30f;
     // ---- pre-pass over the lowest levels: mixed-layer means (float64) and most-unstable argmax ----
     double sum_th = 0.0, sum_w = 0.0;
     float best = -1e30f, second = -1e30f, mu_t = 0.0f, mu_td = 0.0f;
     int k_mu = 0;
-    const int n_pre = max((KINDS & 4u) ? pr.K_mu : 0, (KINDS & 2u) ? pr.n_ml_w : 0);
-    for (int k = 0; k < n_pre; ++k) {
-        const float t = rd.T(k), td = rd.Td(k);
+    const int n_low = max((KINDS & 4u) ? pr.K_mu : 0, (KINDS & 2u) ? pr.n_ml_w : 0);
+    const int n_pre = Env::kFullPass ? nt : n_low;
+    const float *tp0 = rd.tptr(0), *tdp0 = rd.tdptr(0);
+    const int64_t ls = rd.stride();
+    // T/Td are fetched kPre levels ahead (this pass has little arithmetic per level to hide the
+    // HBM latency behind): a ring of registers refilled one chunk at a time
+    constexpr int kPre = 4;
+    float tq[kPre], tdq[kPre], tn[kPre], tdn[kPre];
+#pragma unroll
+    for (int j = 0; j < kPre; ++j) {
+        tn[j] = tdn[j] = 0.0f;
+        if (j < n_pre) { tn[j] = Rd::ld(tp0 + (int64_t)j * ls); tdn[j] = Rd::ld(tdp0 + (int64_t)j * ls); }
+    }
+    for (int k0 = 0; k0 < n_pre; k0 += kPre) {
+#pragma unroll
+        for (int j = 0; j < kPre; ++j) { tq[j] = tn[j]; tdq[j] = tdn[j]; }
+        tp0 += (int64_t)kPre * ls; tdp0 += (int64_t)kPre * ls;
+#pragma unroll
+        for (int j = 0; j < kPre; ++j)
+            if (k0 + kPre + j < n_pre) { tn[j] = Rd::ld(tp0 + (int64_t)j * ls); tdn[j] = Rd::ld(tdp0 + (int64_t)j * ls); }
+#pragma unroll
+      for (int j = 0; j < kPre; ++j) {
+        const int k = k0 + j;
+        if (k >= n_pre) break;
+        const float t = tq[j], td = tdq[j];
         nanacc = f_fma(t, 0.0f, f_fma(td, 0.0f, nanacc));
         const float p = pr.p[k];
         const float e = f_es(td);
+        if (Env::kFullPass) {                                                     // environment curve, PF:839-843
+            const float b = vtc ? f_tv(t, f_mixing_ratio(f_es(t), e, p, compat)) : t;
+            if (Env::kStaged) env.put(k, b);
+            b_min = fminf(b_min, b);
+        }
+        if (k >= n_low) continue;
         const float ipe = f_rcp(p - e);
         const float r = kEpsF * e * ipe;                 // saturation mixing ratio of the dewpoint (PF:258)
         if ((KINDS & 2u) && k < pr.n_ml_w) {
@@ -491,6 +552,7 @@ XP_HD unsigned suite_column(const Rd &rd, const Cf &cf, const Prep &pr, const Ta
             if (v > best) { second = best; best = v; k_mu = k; mu_t = t; mu_td = td; }   // ties: larger p (PF:128)
             else if (v > second) second = v;
         }
+      }
     }
     // ---- parcels --------------------------------------------------------------------------------
     FParcel sb, ml, mu;
@@ -512,29 +574,26 @@ XP_HD unsigned suite_column(const Rd &rd, const Cf &cf, const Prep &pr, const Ta
         res[2].par_p = pr.p[k_mu]; res[2].par_t = mu_t; res[2].par_td = mu_td; res[2].shift = k_mu;
     }
     // ---- the sweep --------------------------------------------------------------------------------------
-    const int nt = pr.n_table;
-    const bool vtc = (MODE == 1) ? true : (o.vtc != 0);
-    const int compat = (MODE == 1) ? 141 : o.compat;
     const float *lp_p = pr.p + 1, *lp_x = pr.lnp + 1, *lp_k = pr.pk + 1;      // level `it` of the axis constants
     float b_prv = 0.0f, x_prv = pr.lnp[0], p_prv = pr.p[0];
     const float *tp = rd.tptr(1), *tdp = rd.tdptr(1);
-    const int64_t ls = rd.stride();
-    float t_nxt = Rd::ld(tp), td_nxt = Rd::ld(tdp);
+    float t_nxt = 0.0f, td_nxt = 0.0f;
+    if (!Env::kStaged) { t_nxt = Rd::ld(tp); td_nxt = Rd::ld(tdp); }
     auto crow = cf.row(0);
+    const float stop_below = b_min - kStopMargin;
     for (int it = 1; it <= nt; ++it) {
         const bool last = (it == nt);
-        const float t = t_nxt, td = td_nxt;
-        tp += ls; tdp += ls;
-        if (it + 1 < nt) { t_nxt = Rd::ld(tp); td_nxt = Rd::ld(tdp); }          // prefetch the next level
         float b_cur = 0.0f, x_cur = x_prv, pk_cur = 0.0f, p_cur = p_prv;
-        if (!last) {
-            nanacc = f_fma(t, 0.0f, f_fma(td, 0.0f, nanacc));
-            p_cur = *lp_p++; x_cur = *lp_x++; pk_cur = *lp_k++;
-            if (vtc) {
-                const float es_t = f_es(t), es_td = f_es(td);
-                b_cur = f_tv(t, f_mixing_ratio(es_t, es_td, p_cur, compat));    // PF:839-843
-            } else {
-                b_cur = t;
+        if (Env::kStaged) {
+            if (!last) { p_cur = *lp_p++; x_cur = *lp_x++; pk_cur = *lp_k++; b_cur = env.get(it); }
+        } else {
+            const float t = t_nxt, td = td_nxt;
+            tp += ls; tdp += ls;
+            if (it + 1 < nt) { t_nxt = Rd::ld(tp); td_nxt = Rd::ld(tdp); }      // prefetch the next level
+            if (!last) {
+                nanacc = f_fma(t, 0.0f, f_fma(td, 0.0f, nanacc));
+                p_cur = *lp_p++; x_cur = *lp_x++; pk_cur = *lp_k++;
+                b_cur = vtc ? f_tv(t, f_mixing_ratio(f_es(t), f_es(td), p_cur, compat)) : t;   // PF:839-843
             }
         }
         if (KINDS & 1u) parcel_iteration<MODE>(sb, it, last, crow, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
@@ -542,6 +601,18 @@ XP_HD unsigned suite_column(const Rd &rd, const Cf &cf, const Prep &pr, const Ta
         if (KINDS & 4u) parcel_iteration<MODE>(mu, it, last, crow, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
         b_prv = b_cur; x_prv = x_cur; p_prv = p_cur;
         crow.advance();
+        if (Env::kFullPass && MODE == 1) {
+            // a parcel is finished when it is above its LCL and colder than every environment level
+            // (its curve only cools with height); parcels already bound for the exact path do not count
+            bool done = true;
+            if (KINDS & 1u) done = done && (sb.bad || (it > sb.ka && sb.aprev < stop_below));
+            if (KINDS & 2u) done = done && (ml.bad || (it > ml.ka && ml.aprev < stop_below));
+            if (KINDS & 4u) done = done && (mu.bad || (it > mu.ka && it > mu.kfirst && mu.aprev < stop_below));
+#if defined(XP_HOST_SIM) && defined(XP_DEBUG_STOP)
+            if (done) { XP_DEBUG_STOP(it); }
+#endif
+            if ((it & o.vote_mask) == 0 && XP_WARP_ALL(done)) break;
+        }
     }
     // ---- results ---------------------------------------------------------------------------------------
     const bool nan_seen = !(nanacc == 0.0f);

@@ -23,6 +23,8 @@ XP_HD float adiabat_temperature_f32(const float *__restrict__ curve, int j, floa
 
 struct PColParcel : FParcel {
     const float *curve;         // row of this parcel's adiabat in the curve table (ascending pressure)
+    float f0, f1;               // the two table nodes bracketing the pressure of the previous level,
+                                // gathered one iteration ahead so that the L2 latency is hidden
 };
 
 // Per-parcel set-up for per-column pressure.  Rd: float P(k), T(k), Td(k).
@@ -38,7 +40,7 @@ XP_HD void setup_parcel_pcol(const Rd &rd, int L, const Tables &tb, const Opts &
     const int adiabat = adiabat_cell(tb, lp, lt, edge);                // PF:554-557
     if (adiabat <= 0) pc.bad = true;
     pc.curve = tb.curves + (size_t)(adiabat > 0 ? adiabat - 1 : 0) * kNP;
-    pc.m = 0; pc.f = 0.0f;
+    pc.m = 0; pc.f = 0.0f; pc.f0 = pc.f1 = 0.0f;
     const float p0f = (float)p0, t0f = (float)t0, td0f = (float)td0;
     const float lpf = (float)lp, ltf = (float)lt;
     pc.lcl_p = lpf; pc.lcl_t = ltf;
@@ -80,12 +82,14 @@ XP_HD void setup_parcel_pcol(const Rd &rd, int L, const Tables &tb, const Opts &
 // One parcel, one iteration (row schedule of xp_fast.cuh).  (j_prv, w_prv): table node and weight
 // of the pressure of level it-1.
 template <int MODE>
-XP_HD void parcel_iteration_pcol(PColParcel &c, int it, bool last, int j_prv, float w_prv, float pk_cur,
+XP_HD void parcel_iteration_pcol(PColParcel &c, int it, bool last, int j_cur, float w_prv, float pk_cur,
                                  float p_prv, float x_cur, float x_prv, float b_cur, float b_prv, bool vtc) {
     const bool above = it > c.ka;
     const bool is_lcl = it == c.ka;
+    const float f0 = c.f0, f1 = c.f1;
+    c.f0 = XP_LDG(c.curve + j_cur); c.f1 = XP_LDG(c.curve + j_cur + 1);         // for the next iteration
     if (it < c.kfirst || (last && !above)) return;
-    const float tm = adiabat_temperature_f32(c.curve, j_prv, w_prv);           // PF:585-592
+    const float tm = f_fma(f1 - f0, w_prv, f0);                                // np.interp, PF:585-592
     const float es = f_es(tm);
     const float a_m = vtc ? f_tv(tm, kEpsF * es * f_rcp(p_prv - es)) : tm;      // PF:760
     const float a_d = c.c_dryv * pk_cur;                                        // PF:742
@@ -189,6 +193,15 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
     const bool vtc = (MODE == 1) ? true : (o.vtc != 0);
     const int compat = (MODE == 1) ? 141 : o.compat;
     float b_prv = 0.0f, x_prv = x_sfc, p_prv = p_sfc;
+    float w_prv;
+    {   // node/weight of the surface pressure and the first gathers
+        const float s0 = (p_sfc - 2.5f) * 2.0f;
+        const int j0 = min(max((int)s0, 0), kNP - 2);
+        w_prv = s0 - (float)j0;
+        if (KINDS & 1u) { sb.f0 = XP_LDG(sb.curve + j0); sb.f1 = XP_LDG(sb.curve + j0 + 1); }
+        if (KINDS & 2u) { ml.f0 = XP_LDG(ml.curve + j0); ml.f1 = XP_LDG(ml.curve + j0 + 1); }
+        if (KINDS & 4u) { mu.f0 = XP_LDG(mu.curve + j0); mu.f1 = XP_LDG(mu.curve + j0 + 1); }
+    }
     const float *ppp = rd.pptr(1), *tp = rd.tptr(1), *tdp = rd.tdptr(1);
     const int64_t ls = rd.stride(), pls = rd.pstride();
     float p_nxt = Rd::ld(ppp), t_nxt = Rd::ld(tp), td_nxt = Rd::ld(tdp);
@@ -197,16 +210,17 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
         const float p_cur0 = p_nxt, t = t_nxt, td = td_nxt;
         ppp += pls; tp += ls; tdp += ls;
         if (it + 1 < L) { p_nxt = Rd::ld(ppp); t_nxt = Rd::ld(tp); td_nxt = Rd::ld(tdp); }
-        // table node of the previous level's pressure (shared by the parcels), PF:585-592
-        const float s_prv = (p_prv - 2.5f) * 2.0f;
-        int j_prv = (int)s_prv;                                     // floor: s_prv >= 0 inside the table
-        j_prv = min(max(j_prv, 0), kNP - 2);
-        const float w_prv = s_prv - (float)j_prv;
-        float b_cur = 0.0f, x_cur = x_prv, pk_cur = 0.0f, p_cur = p_prv;
+        float b_cur = 0.0f, x_cur = x_prv, pk_cur = 0.0f, p_cur = p_prv, w_cur = w_prv;
+        int j_cur = 0;
         if (!last) {
             nanacc = f_fma(p_cur0, 0.0f, f_fma(t, 0.0f, f_fma(td, 0.0f, nanacc)));
             p_cur = p_cur0;
             if (!(p_cur < p_prv) || !(p_cur >= 2.5f)) bad_axis = true;
+            // table node and weight of this level's pressure (shared by the parcels; used by the
+            // lagging rows of the next iteration), PF:585-592
+            const float s_cur = (p_cur - 2.5f) * 2.0f;
+            j_cur = min(max((int)s_cur, 0), kNP - 2);
+            w_cur = s_cur - (float)j_cur;
             const float l2p = f_lg2(p_cur);
             x_cur = kLn2 * l2p; pk_cur = f_ex2((float)kKappa * l2p);
             if (vtc) {
@@ -216,10 +230,10 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
                 b_cur = t;
             }
         }
-        if (KINDS & 1u) parcel_iteration_pcol<MODE>(sb, it, last, j_prv, w_prv, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
-        if (KINDS & 2u) parcel_iteration_pcol<MODE>(ml, it, last, j_prv, w_prv, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
-        if (KINDS & 4u) parcel_iteration_pcol<MODE>(mu, it, last, j_prv, w_prv, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
-        b_prv = b_cur; x_prv = x_cur; p_prv = p_cur;
+        if (KINDS & 1u) parcel_iteration_pcol<MODE>(sb, it, last, j_cur, w_prv, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
+        if (KINDS & 2u) parcel_iteration_pcol<MODE>(ml, it, last, j_cur, w_prv, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
+        if (KINDS & 4u) parcel_iteration_pcol<MODE>(mu, it, last, j_cur, w_prv, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
+        b_prv = b_cur; x_prv = x_cur; p_prv = p_cur; w_prv = w_cur;
     }
     // ---- results ----------------------------------------------------------------------------------------------
     const bool nan_seen = !(nanacc == 0.0f) || bad_axis;
