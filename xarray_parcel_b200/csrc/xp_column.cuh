@@ -292,24 +292,36 @@ XP_HD void lift_parcel(const Levels &lv, double p0, double t0, double td0, const
         inserted = true;
     };
 
-    for (int v = 0; v < n; ++v) {
-        double p, t, td;
-        lv.get(v, p, t, td);
-        if (!inserted && !(p >= lcl_p)) emit_lcl(!isnan(p), p, t, td);          // PF:965-966
+    // Row evaluation (independent of the sweep state) is issued one level ahead of its use so that its
+    // long dependent chains (exp / pow / table gathers) overlap the sweep of the previous row.
+    struct RowEval { double p, t, td, env_tv, tp, tvp; };
+    auto eval_row = [&](int v) {
+        RowEval e;
+        lv.get(v, e.p, e.t, e.td);
         // environment (PF:839-843)
-        const double env_tv = virtual_temperature(t, mixing_ratio_t_td(t, td, p, o.compat));
+        e.env_tv = virtual_temperature(e.t, mixing_ratio_t_td(e.t, e.td, e.p, o.compat));
         // parcel (PF:742-777)
-        double tp, wp;
-        const double above = (adiabat > 0) ? adiabat_temperature(curve, p) : qnan();
-        if (p >= lcl_p) tp = dry_lapse(p, t0, p0); else tp = above;             // PF:767
-        if (p <= lcl_p) wp = sat_mixing_ratio(p, above); else wp = w_parcel;    // PF:760, 773
-        const double tvp = virtual_temperature(tp, wp);
+        double wp;
+        const double above = (adiabat > 0) ? adiabat_temperature(curve, e.p) : qnan();
+        if (e.p >= lcl_p) e.tp = dry_lapse(e.p, t0, p0); else e.tp = above;     // PF:767
+        if (e.p <= lcl_p) wp = sat_mixing_ratio(e.p, above); else wp = w_parcel;    // PF:760, 773
+        e.tvp = virtual_temperature(e.tp, wp);
+        return e;
+    };
+    RowEval cur = {qnan(), qnan(), qnan(), qnan(), qnan(), qnan()};
+    if (n > 0) cur = eval_row(0);
+    for (int v = 0; v < n; ++v) {
+        RowEval nxt = cur;
+        if (v + 1 < n) nxt = eval_row(v + 1);
+        const double p = cur.p, t = cur.t, td = cur.td;
+        if (!inserted && !(p >= lcl_p)) emit_lcl(!isnan(p), p, t, td);          // PF:965-966
         // insert_level maps every variable at a NaN-pressure level to NaN (PF:963, 988)
-        ProfileRow row = {p, tp, tvp, t, env_tv, td};
+        ProfileRow row = {p, cur.tp, cur.tvp, t, cur.env_tv, td};
         if (isnan(p)) row = {qnan(), qnan(), qnan(), qnan(), qnan(), qnan()};
         prof.put(row_idx++, row);
         sw.emit(row.p, o.vtc ? row.tv : row.t, o.vtc ? row.env_tv : row.env_t, false);
         if (!isnan(p)) { have_prev = true; pb = p; tb_ = t; tdb = td; }
+        cur = nxt;
     }
     if (!inserted) emit_lcl(false, qnan(), qnan(), qnan());
     sw.finish(r, o.post_zero);

@@ -36,7 +36,7 @@ struct FastParams {
     Opts o;
     unsigned kinds;
     OutArg<float> outs[3];
-    uint32_t *list;          // [n] entries: column | redo-mask << 28 (bits 0-2 kinds, bit 3 MU == SB)
+    uint32_t *list;          // 3 regions of n entries (see ListParams)
     uint32_t *list_count;
 };
 
@@ -120,8 +120,7 @@ __global__ void __launch_bounds__(THREADS, 1) suite_fast_kernel(const __grid_con
         // the axis does not qualify: every column goes to the exact path
         for (int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; col < prm.n;
              col += (int64_t)gridDim.x * blockDim.x) {
-            const uint32_t slot = atomicAdd(prm.list_count, 1u);
-            prm.list[slot] = (uint32_t)col | (prm.kinds << 28);
+            push_redo(prm.list, prm.list_count, prm.n, col, prm.kinds);
         }
         return;
     }
@@ -169,10 +168,7 @@ __global__ void __launch_bounds__(THREADS, 1) suite_fast_kernel(const __grid_con
         if (KINDS & 1u) store_fast(prm.outs[0], col, res[0]);
         if (KINDS & 2u) store_fast(prm.outs[1], col, res[1]);
         if (KINDS & 4u) store_fast(prm.outs[2], col, res[2]);
-        if (redo) {
-            const uint32_t slot = atomicAdd(prm.list_count, 1u);
-            prm.list[slot] = (uint32_t)col | (redo << 28);
-        }
+        if (redo) push_redo(prm.list, prm.list_count, prm.n, col, redo);
     }
 }
 
@@ -214,10 +210,7 @@ __global__ void __launch_bounds__(kPColThreads, 2) suite_fast_pcol_kernel(const 
     if (KINDS & 1u) store_fast(prm.outs[0], col, res[0]);
     if (KINDS & 2u) store_fast(prm.outs[1], col, res[1]);
     if (KINDS & 4u) store_fast(prm.outs[2], col, res[2]);
-    if (redo) {
-        const uint32_t slot = atomicAdd(prm.list_count, 1u);
-        prm.list[slot] = (uint32_t)col | (redo << 28);
-    }
+    if (redo) push_redo(prm.list, prm.list_count, prm.n, col, redo);
 }
 
 }  // namespace
@@ -225,7 +218,7 @@ __global__ void __launch_bounds__(kPColThreads, 2) suite_fast_pcol_kernel(const 
 size_t fast_scratch_bytes(int64_t n) {
     // Prep | coef table | list counter | list
     return ((sizeof(Prep) + 255) & ~(size_t)255) + (size_t)fast::kMaxLevels * fast::kNI * sizeof(Coef) + 256 +
-           (size_t)n * sizeof(uint32_t);
+           3 * (size_t)n * sizeof(uint32_t);
 }
 
 bool fast_eligible(const ColsArg<float> &cols, int kind_mask, const OutArg<float> *outs) {
@@ -253,12 +246,12 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
     off += 256;
     uint32_t *list = reinterpret_cast<uint32_t *>(base + off);
 
-    cudaMemsetAsync(count, 0, sizeof(uint32_t), stream);
+    cudaMemsetAsync(count, 0, 4 * sizeof(uint32_t), stream);
     const int mode = (o.vtc && o.compat == 141 && o.pos_neg) ? 1 : 0;
     ListParams lp;
     lp.cols = cols; lp.tb = tb; lp.o = o;
     for (int q = 0; q < 3; ++q) lp.outs[q] = outs[q];
-    lp.list = list; lp.list_count = count; lp.flags = flags;
+    lp.list = list; lp.list_count = count; lp.capacity = cols.n; lp.flags = flags;
     if (!cols.p1d) {
         // per-column pressure: no shared-memory table, adiabats gathered from the curve table
         PColParams pp;
@@ -335,7 +328,7 @@ uint32_t fast_last_list_count(void *scratch, cudaStream_t stream) {
     unsigned char *base = static_cast<unsigned char *>(scratch);
     size_t off = ((sizeof(Prep) + 255) & ~(size_t)255) + (size_t)fast::kMaxLevels * fast::kNI * sizeof(Coef);
     uint32_t v = 0;
-    cudaMemcpyAsync(&v, base + off, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(&v, base + off + 3 * sizeof(uint32_t), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
     cudaStreamSynchronize(stream);
     return v;
 }

@@ -134,15 +134,15 @@ struct NoProf {
     __device__ __forceinline__ void put(int, const ProfileRow &) const {}
 };
 
-// One thread per (list entry, parcel kind) item; kind-major item order keeps the kind uniform in a warp.
+// One thread per (column, parcel kind) item.
 __global__ void __launch_bounds__(128) suite_list_kernel(const __grid_constant__ ListParams prm) {
-    const uint32_t count = *prm.list_count;
-    if (count == 0) return;
-    for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < (uint64_t)count * 3u;
+    const uint32_t c0 = prm.list_count[0], c1 = prm.list_count[1], c2 = prm.list_count[2];
+    const uint64_t total = (uint64_t)c0 + c1 + c2;
+    for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
          it += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t e = prm.list[it % count];
-        const int kind = (int)(it / count);
-        if (!((e >> (28 + kind)) & 1u)) continue;
+        const int kind = it < c0 ? 0 : (it < (uint64_t)c0 + c1 ? 1 : 2);
+        const uint64_t idx = it - (kind == 0 ? 0 : (kind == 1 ? c0 : (uint64_t)c0 + c1));
+        const uint32_t e = prm.list[(uint64_t)kind * prm.capacity + idx];
         const bool also_mu = kind == 0 && ((e >> 28) & kListMuIsSb);
         const int64_t col = (int64_t)(e & 0x0fffffffu);
         const GlobalReader<float> rd = make_reader(prm.cols, col);

@@ -65,10 +65,12 @@ void launch_cape_cin_base(const T *pressure, const T *env_t, const T *parcel_t, 
                           int64_t n, const T *lfc_p, const T *el_p, const Opts &o, T *cape, T *cin,
                           cudaStream_t stream);
 
-// Exact (float64) recomputation of the columns the float32 fast paths hand over: `list` holds
-// column | mask << 28 (mask bits 0-2: SB/ML/MU to recompute, bit 3: also write the SB result to the
-// MU outputs), `list_count` the number of entries (device memory).  Lives in xp_kernels.cu because
-// that file is compiled without FMA contraction.
+// Exact (float64) recomputation of the (column, parcel kind) items the float32 fast paths hand over.
+// `list` has one region of `capacity` entries per kind (SB, ML, MU); an entry is the column index, in
+// the SB region OR-ed with kListMuIsSb << 28 when the SB result must also be written to the MU outputs.
+// `list_count[0..2]` = entries per kind, `list_count[3]` = columns with at least one entry (device
+// memory).  Dense per-kind regions keep every lane of the fix-up kernel busy and its warps kind-uniform.
+// Lives in xp_kernels.cu because that file is compiled without FMA contraction.
 struct ListParams {
     ColsArg<float> cols;
     Tables tb;
@@ -76,9 +78,19 @@ struct ListParams {
     OutArg<float> outs[3];
     const uint32_t *list;
     const uint32_t *list_count;
+    int64_t capacity;
     uint32_t *flags;
 };
 constexpr unsigned kListMuIsSb = 8u;
+
+// Append the items of one column (redo: bits 0-2 kinds, bit 3 = kListMuIsSb).
+__device__ __forceinline__ void push_redo(uint32_t *list, uint32_t *count, int64_t capacity, int64_t col,
+                                          unsigned redo) {
+    if (redo & 1u) list[atomicAdd(count + 0, 1u)] = (uint32_t)col | ((redo & kListMuIsSb) << 28);
+    if (redo & 2u) list[capacity + atomicAdd(count + 1, 1u)] = (uint32_t)col;
+    if (redo & 4u) list[2 * capacity + atomicAdd(count + 2, 1u)] = (uint32_t)col;
+    atomicAdd(count + 3, 1u);
+}
 void launch_suite_list(const ListParams &lp, int sm_count, cudaStream_t stream);
 
 // Float32 fast path of the suite on a shared pressure axis (xp_fast.cu / xp_fast.cuh): prep +
