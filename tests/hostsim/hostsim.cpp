@@ -148,10 +148,24 @@ struct HostRdP {
 };
 }  // namespace
 
+namespace {
+struct HostProfW {
+    static constexpr bool kEnabled = true;
+    float *base;       // [3 kinds][6 fields][L+1][n]
+    int64_t n, col;
+    int L;
+    void put(int q, int row, float p, float tp, float tv, float et, float etv, float etd) const {
+        const float v[6] = {p, tp, tv, et, etv, etd};
+        if (row < 0 || row > L) __builtin_trap();          // the device writer drops such rows; here they are bugs
+        for (int f = 0; f < 6; ++f) base[(((int64_t)q * 6 + f) * (L + 1) + row) * n + col] = v[f];
+    }
+};
+}  // namespace
+
 extern "C" int hostsim_fast_suite_pcol(const float *p, const float *t, const float *td, int64_t n, int L,
                                        const int *iopts, double ml_depth, double mu_depth,
                                        const uint16_t *index_grid, const float *curves, float *out,
-                                       int32_t *shift, uint32_t *redo) {
+                                       int32_t *shift, uint32_t *redo, float *prof) {
     xp::Tables tb = {index_grid, curves};
     xp::Opts o;
     o.vtc = iopts[0]; o.log_interp = iopts[1]; o.pos_neg = iopts[2]; o.post_zero = iopts[3];
@@ -159,8 +173,16 @@ extern "C" int hostsim_fast_suite_pcol(const float *p, const float *t, const flo
     for (int64_t c = 0; c < n; ++c) {
         HostRdP rd = {p + c, t + c, td + c, n};
         xp::fast::FResult r[3];
-        redo[c] = (o.vtc && o.compat == 141 && o.pos_neg) ? xp::fast::suite_column_pcol<7u, 1>(rd, L, tb, o, r)
-                                                          : xp::fast::suite_column_pcol<7u, 0>(rd, L, tb, o, r);
+        const bool m1 = o.vtc && o.compat == 141 && o.pos_neg;
+        if (prof) {
+            HostProfW pw = {prof, n, c, L};
+            redo[c] = m1 ? xp::fast::suite_column_pcol<7u, 1>(rd, L, tb, o, pw, r)
+                         : xp::fast::suite_column_pcol<7u, 0>(rd, L, tb, o, pw, r);
+        } else {
+            xp::fast::NoProfile np;
+            redo[c] = m1 ? xp::fast::suite_column_pcol<7u, 1>(rd, L, tb, o, np, r)
+                         : xp::fast::suite_column_pcol<7u, 0>(rd, L, tb, o, np, r);
+        }
         for (int q = 0; q < 3; ++q) {
             const float vals[12] = {r[q].cape, r[q].cin, r[q].lcl_p, r[q].lcl_t, r[q].lcl_tv, r[q].lfc_p,
                                     r[q].lfc_t, r[q].el_p, r[q].el_t, r[q].par_p, r[q].par_t, r[q].par_td};

@@ -82,7 +82,7 @@ def cape_cin(p, t, td, tables, kind="sb", explicit=None, vtc=True, lcl_interp="l
 
 
 def fast_suite(p, t, td, tables, vtc=True, lcl_interp="log", pos_cape_neg_cin=True, post_zero_cin=False,
-               metpy_compat=141, ml_depth=100.0, mu_depth=300.0):
+               metpy_compat=141, ml_depth=100.0, mu_depth=300.0, profile=False):
     """Run the host-compiled float32 fast path on a shared pressure axis p [L] (xp_fast.cuh) or
     per-column pressure p [L, N] (xp_fast_pcol.cuh) and float32 [L, N] T/Td.  Returns ({kind: {field: float32 [N], 'level_shift'}}, redo mask [N]) or None
     if the axis does not qualify."""
@@ -104,13 +104,19 @@ def fast_suite(p, t, td, tables, vtc=True, lcl_interp="log", pos_cape_neg_cin=Tr
     l = lib()
     fn = l.hostsim_fast_suite if p.ndim == 1 else l.hostsim_fast_suite_pcol
     fn.restype = ctypes.c_int
-    ok = fn(ptr(p), ptr(t), ptr(td), ctypes.c_int64(N), ctypes.c_int(L), iopts,
-                              ctypes.c_double(ml_depth), ctypes.c_double(mu_depth), ptr(idx), ptr(cur),
-                              ptr(out), ptr(shift), ptr(redo))
+    args = [ptr(p), ptr(t), ptr(td), ctypes.c_int64(N), ctypes.c_int(L), iopts, ctypes.c_double(ml_depth),
+            ctypes.c_double(mu_depth), ptr(idx), ptr(cur), ptr(out), ptr(shift), ptr(redo)]
+    prof = None
+    if p.ndim == 2:
+        prof = np.full((3, 6, L + 1, N), -12345.0, dtype=np.float32) if profile else None
+        args.append(ptr(prof) if prof is not None else None)
+    ok = fn(*args)
     if not ok:
         return None
     res = {}
     for q, kind in enumerate(("sb", "ml", "mu")):
         res[kind] = {k: out[q, i] for i, k in enumerate(SCALARS)}
         res[kind]["level_shift"] = shift[q]
+        if prof is not None:
+            res[kind]["profile"] = {k: prof[q, i] for i, k in enumerate(PROFILE)}
     return res, redo

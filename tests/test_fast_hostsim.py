@@ -100,6 +100,34 @@ def test_fast_suite_per_column_pressure(oracle_tables, o):
     assert np.array_equal(res["ml"]["level_shift"][keep], k_ml[keep])
 
 
+@pytest.mark.parametrize("vtc", [True, False])
+def test_fast_profile_rows_per_column_pressure(oracle_tables, vtc):
+    """Profile rows (parcel_profile_with_lcl, PF:806-931) written by the per-column fast path, for the
+    columns it keeps: every row of every kind against the oracle, NaN padding included."""
+    p, t, td = synth.model_level_columns(1500, 50, seed=31, nan_columns=0.05, allnan_columns=0.02)
+    P, T, D = [a.numpy().astype(np.float64) for a in (p, t, td)]
+    opts = op.Options(op.MoistLapseLUT(oracle_tables), lcl_mode="converged")
+    res, redo = hs.fast_suite(p.numpy(), t.numpy(), td.numpy(), oracle_tables, vtc=vtc, profile=True)
+    fns = {"sb": op.surface_based_cape_cin, "ml": op.mixed_layer_cape_cin, "mu": op.most_unstable_cape_cin}
+    L = T.shape[0]
+    for q, kind in enumerate(("sb", "ml", "mu")):
+        prof = fns[kind](P, T, D, opts, virtual_temperature_correction=vtc)[1]
+        keep = ((redo >> q) & 1) == 0
+        if kind == "mu":
+            keep &= (redo & 8) == 0
+        n = prof["pressure"].shape[0]            # the oracle trims levels that are NaN in every column
+        for k in hs.PROFILE:
+            a = res[kind]["profile"][k].astype(np.float64)[:, keep]
+            b = np.full((L + 1, keep.sum()), np.nan)
+            b[:n] = prof[k][:, keep]
+            assert not (a == -12345.0).any(), f"{kind} {k}: rows left unwritten"
+            if b.shape[1] == 0:
+                continue
+            assert np.array_equal(np.isnan(a), np.isnan(b)), f"{kind} {k}: NaN pattern differs"
+            ok = ~np.isnan(b)
+            assert np.allclose(a[ok], b[ok], rtol=3e-6, atol=0), (kind, k, np.abs(a[ok] - b[ok]).max())
+
+
 def test_fast_suite_per_column_pressure_depths_and_90_levels(oracle_tables):
     p, t, td = synth.model_level_columns(3000, 90, seed=22, nan_columns=0, allnan_columns=0, saturated=0)
     P, T, D = [a.numpy().astype(np.float64) for a in (p, t, td)]

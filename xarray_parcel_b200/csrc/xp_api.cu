@@ -222,7 +222,9 @@ xp_status run_host(xp_context *ctx, const xp_columns *cols, int kind_mask,
     int64_t C = (int64_t)((size_t)256 << 20) / (int64_t)per_col;
     C = std::max<int64_t>(1024, (C / 1024) * 1024);
     C = std::min<int64_t>(C, ((N + 1023) / 1024) * 1024);
-    const size_t need = (size_t)C * per_col + 4096;
+    // every carved array is padded to 256 B: at most 3 inputs + 3 explicit + 4 x (12 scalars + shift + 6
+    // profiles) = 82 arrays
+    const size_t need = (size_t)C * per_col + 96 * 256;
     if (need > ctx->slot_bytes) {
         for (int s = 0; s < xp_context::kSlots; ++s) {
             if (ctx->slot_buf[s]) { cudaFree(ctx->slot_buf[s]); ctx->slot_buf[s] = nullptr; }

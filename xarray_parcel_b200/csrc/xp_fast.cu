@@ -200,13 +200,40 @@ struct PColParams {
 
 constexpr int kPColThreads = 256;
 
-template <unsigned KINDS, int MODE>
+// parcel_profile_with_lcl rows (PF:806-931) of the fast path: [L+1][N] arrays per kind, NULL = not wanted
+struct ProfileWriter {
+    static constexpr bool kEnabled = true;
+    const OutArg<float> *outs;
+    int64_t col;
+    int L;
+    __device__ __forceinline__ void put(int q, int row, float p, float tp, float tv, float et, float etv,
+                                        float etd) const {
+        if ((unsigned)row > (unsigned)L) return;          // rows 0..L exist
+        const OutArg<float> &o = outs[q];
+        const int64_t off = (int64_t)row * o.prof_ls + col;
+        if (o.prof_p) o.prof_p[off] = p;
+        if (o.prof_t) o.prof_t[off] = tp;
+        if (o.prof_tv) o.prof_tv[off] = tv;
+        if (o.prof_et) o.prof_et[off] = et;
+        if (o.prof_etv) o.prof_etv[off] = etv;
+        if (o.prof_etd) o.prof_etd[off] = etd;
+    }
+};
+
+template <unsigned KINDS, int MODE, bool PROFILE>
 __global__ void __launch_bounds__(kPColThreads, 2) suite_fast_pcol_kernel(const __grid_constant__ PColParams prm) {
     const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= prm.n) return;
     const PColRd rd{prm.p + col, prm.t + col, prm.td + col, prm.ls, prm.pls};
     fast::FResult res[3];
-    const unsigned redo = fast::suite_column_pcol<KINDS, MODE>(rd, prm.L, prm.tb, prm.o, res);
+    unsigned redo;
+    if (PROFILE) {
+        ProfileWriter pw{prm.outs, col, prm.L};
+        redo = fast::suite_column_pcol<KINDS, MODE>(rd, prm.L, prm.tb, prm.o, pw, res);
+    } else {
+        fast::NoProfile np;
+        redo = fast::suite_column_pcol<KINDS, MODE>(rd, prm.L, prm.tb, prm.o, np, res);
+    }
     if (KINDS & 1u) store_fast(prm.outs[0], col, res[0]);
     if (KINDS & 2u) store_fast(prm.outs[1], col, res[1]);
     if (KINDS & 4u) store_fast(prm.outs[2], col, res[2]);
@@ -221,15 +248,20 @@ size_t fast_scratch_bytes(int64_t n) {
            3 * (size_t)n * sizeof(uint32_t);
 }
 
+static bool wants_profile(int kind_mask, const OutArg<float> *outs) {
+    for (int q = 0; q < 3; ++q) {
+        if (!((kind_mask >> q) & 1)) continue;
+        const OutArg<float> &o = outs[q];
+        if (o.prof_p || o.prof_t || o.prof_tv || o.prof_et || o.prof_etv || o.prof_etd) return true;
+    }
+    return false;
+}
+
 bool fast_eligible(const ColsArg<float> &cols, int kind_mask, const OutArg<float> *outs) {
     if (cols.L < 3 || cols.n >= (int64_t)1 << 28) return false;
     if (cols.p1d && cols.L > fast::kMaxLevels) return false;
     if (kind_mask & ~(kSB | kML | kMU)) return false;
-    for (int q = 0; q < 3; ++q) {
-        if (!((kind_mask >> q) & 1)) continue;
-        const OutArg<float> &o = outs[q];
-        if (o.prof_p || o.prof_t || o.prof_tv || o.prof_et || o.prof_etv || o.prof_etd) return false;
-    }
+    if (cols.p1d && wants_profile(kind_mask, outs)) return false;   // shared-axis kernel: scalars only
     return true;
 }
 
@@ -260,10 +292,16 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
         for (int q = 0; q < 3; ++q) pp.outs[q] = outs[q];
         pp.list = list; pp.list_count = count;
         const unsigned g = (unsigned)((cols.n + kPColThreads - 1) / kPColThreads);
+        const bool profile = wants_profile(kind_mask, outs);
 #define XP_PCOL_CASE(K)                                                                          \
     case K:                                                                                      \
-        if (mode) suite_fast_pcol_kernel<K, 1><<<g, kPColThreads, 0, stream>>>(pp);              \
-        else suite_fast_pcol_kernel<K, 0><<<g, kPColThreads, 0, stream>>>(pp);                   \
+        if (profile) {                                                                           \
+            if (mode) suite_fast_pcol_kernel<K, 1, true><<<g, kPColThreads, 0, stream>>>(pp);    \
+            else suite_fast_pcol_kernel<K, 0, true><<<g, kPColThreads, 0, stream>>>(pp);         \
+        } else {                                                                                 \
+            if (mode) suite_fast_pcol_kernel<K, 1, false><<<g, kPColThreads, 0, stream>>>(pp);   \
+            else suite_fast_pcol_kernel<K, 0, false><<<g, kPColThreads, 0, stream>>>(pp);        \
+        }                                                                                        \
         break;
         switch (kind_mask & 7) {
             XP_PCOL_CASE(1) XP_PCOL_CASE(2) XP_PCOL_CASE(3) XP_PCOL_CASE(4) XP_PCOL_CASE(5) XP_PCOL_CASE(6) XP_PCOL_CASE(7)

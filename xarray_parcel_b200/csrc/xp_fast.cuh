@@ -155,6 +155,14 @@ XP_HD Coef compute_coef(const Prep &pr, const float *curves, int k, int m) {
 #define XP_WARP_ALL(x) (x)
 #endif
 
+// Profile-output policies (parcel_profile_with_lcl rows, PF:806-931).  kEnabled = false compiles the row
+// bookkeeping away; the kernels provide a writer with
+//   put(kind, row, p, parcel T, parcel Tv, environment T, environment Tv, environment Td).
+struct NoProfile {
+    static constexpr bool kEnabled = false;
+    XP_HD void put(int, int, float, float, float, float, float, float) const {}
+};
+
 // Environment-curve policies of suite_column (see there).
 struct EnvRecompute {                 // environment recomputed in the sweep, no early termination
     static constexpr bool kStaged = false, kFullPass = false;
@@ -276,6 +284,8 @@ struct FParcel {
     float x_lcl, a_lcl, b_lcl;  // the inserted LCL row
     float lcl_p, lcl_t, lcl_tv;
     bool bad;                   // must go to the exact path
+    // profile output only (dead otherwise): unfolded dry adiabat, parcel mixing ratio, environment at the LCL
+    float c_dry, w_par, lcl_env_t, lcl_env_td, lcl_env_tv;
     // sweep state (float32 version of Sweep in xp_column.cuh)
     float xprev, dprev, aprev;  // ln p, parcel - environment, parcel curve at the previous row
     float pos, tot;             // running sums of the positive areas and of all areas (ln p units)

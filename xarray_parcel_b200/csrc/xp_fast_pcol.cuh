@@ -49,6 +49,8 @@ XP_HD void setup_parcel_pcol(const Rd &rd, int L, const Tables &tb, const Opts &
     const float w_parcel = f_mixing_ratio(f_es(t0f), f_es(td0f), p0f, o.compat);   // PF:748
     const float c_dry = t0f * f_ex2(-(float)kKappa * f_lg2(p0f));               // T0 / p0^kappa, PF:291-316
     pc.c_dryv = o.vtc ? c_dry * f_fma(0.608f, w_parcel, 1.0f) : c_dry;
+    pc.c_dry = c_dry; pc.w_par = w_parcel;
+    pc.lcl_env_t = pc.lcl_env_td = pc.lcl_env_tv = f_qnan();
     sweep_init(pc, x_start, o.vtc ? f_tv(t0f, w_parcel) : t0f);
     // LCL position among the levels of the lifted column (insert_level PF:965-966): exact in float64
     int ka = knext;
@@ -76,14 +78,19 @@ XP_HD void setup_parcel_pcol(const Rd &rd, int L, const Tables &tb, const Opts &
     pc.x_lcl = x_l;
     pc.a_lcl = o.vtc ? pc.lcl_tv : ltf;
     pc.b_lcl = o.vtc ? etv : te;
+    pc.lcl_env_t = te; pc.lcl_env_td = tde; pc.lcl_env_tv = etv;
     if (!(te == te) || !(tde == tde)) pc.bad = true;
 }
 
-// One parcel, one iteration (row schedule of xp_fast.cuh).  (j_prv, w_prv): table node and weight
-// of the pressure of level it-1.
-template <int MODE>
+// Environment of a level as the profile rows need it.
+struct EnvLevel { float p, t, td, tv; };
+
+// One parcel, one iteration (row schedule of xp_fast.cuh).  j_cur: table node of the pressure of level
+// `it` (gathered for the next iteration); w_prv: interpolation weight of level it-1.
+template <int MODE, class Prof>
 XP_HD void parcel_iteration_pcol(PColParcel &c, int it, bool last, int j_cur, float w_prv, float pk_cur,
-                                 float p_prv, float x_cur, float x_prv, float b_cur, float b_prv, bool vtc) {
+                                 float p_prv, float x_cur, float x_prv, float b_cur, float b_prv, bool vtc,
+                                 const EnvLevel &e_cur, const EnvLevel &e_prv, int q, Prof &prof) {
     const bool above = it > c.ka;
     const bool is_lcl = it == c.ka;
     const float f0 = c.f0, f1 = c.f1;
@@ -91,17 +98,24 @@ XP_HD void parcel_iteration_pcol(PColParcel &c, int it, bool last, int j_cur, fl
     if (it < c.kfirst || (last && !above)) return;
     const float tm = f_fma(f1 - f0, w_prv, f0);                                // np.interp, PF:585-592
     const float es = f_es(tm);
-    const float a_m = vtc ? f_tv(tm, kEpsF * es * f_rcp(p_prv - es)) : tm;      // PF:760
+    const float tv_m = f_tv(tm, kEpsF * es * f_rcp(p_prv - es));                // PF:760, 775
+    const float a_m = vtc ? tv_m : tm;
     const float a_d = c.c_dryv * pk_cur;                                        // PF:742
     const float a = is_lcl ? c.a_lcl : (above ? a_m : a_d);
     const float b = is_lcl ? c.b_lcl : (above ? b_prv : b_cur);
     const float x = is_lcl ? c.x_lcl : (above ? x_prv : x_cur);
+    if (Prof::kEnabled) {                                                       // PF:806-931 row of this iteration
+        const int row = it - c.kfirst + 1;
+        if (is_lcl) prof.put(q, row, c.lcl_p, c.lcl_t, c.lcl_tv, c.lcl_env_t, c.lcl_env_tv, c.lcl_env_td);
+        else if (above) prof.put(q, row, e_prv.p, tm, tv_m, e_prv.t, e_prv.tv, e_prv.td);
+        else { const float tp = c.c_dry * pk_cur; prof.put(q, row, e_cur.p, tp, f_tv(tp, c.w_par), e_cur.t, e_cur.tv, e_cur.td); }
+    }
     sweep_step<MODE>(c, it, x, a, b, is_lcl, above);
 }
 
 // The suite for one column with its own pressure profile.  Returns the redo mask (see suite_column).
-template <unsigned KINDS, int MODE, class Rd>
-XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Opts &o, FResult res[3]) {
+template <unsigned KINDS, int MODE, class Rd, class Prof>
+XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Opts &o, Prof &prof, FResult res[3]) {
     unsigned redo = 0;
     float nanacc = 0.0f;
     bool bad_axis = false;                 // pressure not finite / not strictly decreasing / outside the table
@@ -180,7 +194,7 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
         const double depth = fabs(top_ml - bottom);                              // PF:158-159
         const double mp_t = (1. / depth) * sum_th * exner(bottom);               // PF:161, 268-269
         const double mp_td = dewpoint_from_e(vapor_pressure(bottom, (1. / depth) * sum_w));   // PF:275-282
-        if (!ml_done) redo |= 2u;              // no level above the mixed layer: exact path
+        if (!ml_done || K_ml < 1) { redo |= 2u; K_ml = max(K_ml, 1); }   // no level above / NaN layer: exact path
         setup_parcel_pcol(rd, L, tb, o, bottom, mp_t, mp_td, x_sfc, K_ml, ml);
         res[1].par_p = p_sfc; res[1].par_t = (float)mp_t; res[1].par_td = (float)mp_td; res[1].shift = K_ml;
     }
@@ -192,6 +206,16 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
     // ---- the sweep ----------------------------------------------------------------------------------------
     const bool vtc = (MODE == 1) ? true : (o.vtc != 0);
     const int compat = (MODE == 1) ? 141 : o.compat;
+    if (Prof::kEnabled) {       // start rows: the parcel level itself (environment == parcel there)
+        auto row0 = [&](const PColParcel &c, int q, const FResult &r) {
+            const float tv0 = f_tv(r.par_t, c.w_par);
+            prof.put(q, 0, r.par_p, r.par_t, tv0, r.par_t, tv0, r.par_td);
+        };
+        if (KINDS & 1u) row0(sb, 0, res[0]);
+        if (KINDS & 2u) row0(ml, 1, res[1]);
+        if (KINDS & 4u) row0(mu, 2, res[2]);
+    }
+    EnvLevel e_prv = {p_sfc, t_sfc, td_sfc, 0.0f};
     float b_prv = 0.0f, x_prv = x_sfc, p_prv = p_sfc;
     float w_prv;
     {   // node/weight of the surface pressure and the first gathers
@@ -211,6 +235,7 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
         ppp += pls; tp += ls; tdp += ls;
         if (it + 1 < L) { p_nxt = Rd::ld(ppp); t_nxt = Rd::ld(tp); td_nxt = Rd::ld(tdp); }
         float b_cur = 0.0f, x_cur = x_prv, pk_cur = 0.0f, p_cur = p_prv, w_cur = w_prv;
+        EnvLevel e_cur = e_prv;
         int j_cur = 0;
         if (!last) {
             nanacc = f_fma(p_cur0, 0.0f, f_fma(t, 0.0f, f_fma(td, 0.0f, nanacc)));
@@ -223,17 +248,26 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
             w_cur = s_cur - (float)j_cur;
             const float l2p = f_lg2(p_cur);
             x_cur = kLn2 * l2p; pk_cur = f_ex2((float)kKappa * l2p);
-            if (vtc) {
+            if (vtc || Prof::kEnabled) {
                 const float es_t = f_es(t), es_td = f_es(td);
-                b_cur = f_tv(t, f_mixing_ratio(es_t, es_td, p_cur, compat));    // PF:839-843
-            } else {
-                b_cur = t;
+                e_cur.tv = f_tv(t, f_mixing_ratio(es_t, es_td, p_cur, compat));  // PF:839-843
             }
+            b_cur = vtc ? e_cur.tv : t;
+            e_cur.p = p_cur; e_cur.t = t; e_cur.td = td;
         }
-        if (KINDS & 1u) parcel_iteration_pcol<MODE>(sb, it, last, j_cur, w_prv, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
-        if (KINDS & 2u) parcel_iteration_pcol<MODE>(ml, it, last, j_cur, w_prv, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
-        if (KINDS & 4u) parcel_iteration_pcol<MODE>(mu, it, last, j_cur, w_prv, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc);
-        b_prv = b_cur; x_prv = x_cur; p_prv = p_cur; w_prv = w_cur;
+        if (KINDS & 1u) parcel_iteration_pcol<MODE>(sb, it, last, j_cur, w_prv, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc, e_cur, e_prv, 0, prof);
+        if (KINDS & 2u) parcel_iteration_pcol<MODE>(ml, it, last, j_cur, w_prv, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc, e_cur, e_prv, 1, prof);
+        if (KINDS & 4u) parcel_iteration_pcol<MODE>(mu, it, last, j_cur, w_prv, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc, e_cur, e_prv, 2, prof);
+        b_prv = b_cur; x_prv = x_cur; p_prv = p_cur; w_prv = w_cur; e_prv = e_cur;
+    }
+    if (Prof::kEnabled) {       // rows above the lifted column are NaN (PF:1552, 1637: levels dropped below)
+        const float qn = f_qnan();
+        auto pad = [&](const PColParcel &c, int q) {
+            for (int row = L - c.kfirst + 2; row <= L; ++row) prof.put(q, row, qn, qn, qn, qn, qn, qn);
+        };
+        if (KINDS & 1u) pad(sb, 0);
+        if (KINDS & 2u) pad(ml, 1);
+        if (KINDS & 4u) pad(mu, 2);
     }
     // ---- results ----------------------------------------------------------------------------------------------
     const bool nan_seen = !(nanacc == 0.0f) || bad_axis;
@@ -245,7 +279,8 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
     if (KINDS & 1u) wrap(sb, res[0], 1u);
     if (KINDS & 2u) wrap(ml, res[1], 2u);
     if (KINDS & 4u) wrap(mu, res[2], 4u);
-    if ((KINDS & 5u) == 5u && (redo & 4u) && k_mu == 0 && !nan_seen && (best - second >= kThetaEMargin))
+    if (!Prof::kEnabled && (KINDS & 5u) == 5u && (redo & 4u) && k_mu == 0 && !nan_seen &&
+        (best - second >= kThetaEMargin))
         redo = (redo & ~4u) | 1u | kRedoMuIsSb;
     return redo;
 }
