@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../xarray_parcel_b200/csrc/xp_fast_pcol.cuh"
+#include "../../xarray_parcel_b200/csrc/xp_fast6.cuh"
 
 namespace {
 
@@ -108,11 +109,24 @@ extern "C" int hostsim_fast_suite(const float *p, const float *t, const float *t
     for (int k = 0; k < pr.n_table; ++k)
         for (int m = 0; m < xp::fast::kNI; ++m) coef[(size_t)k * xp::fast::kNI + m] = xp::fast::compute_coef(pr, curves, k, m);
     HostCoef cf = {coef.data()};
+    // default options: the v6 sweep on the virtual-temperature table (xp_fast6.cuh) -- what the kernel runs
+    const bool m1 = o.vtc && o.compat == 141 && o.pos_neg;
+    std::vector<xp::fast::Coef> coef_tv;
+    if (m1) {
+        coef_tv.resize((size_t)L * xp::fast::kNI);
+        for (int k = 0; k < pr.n_table; ++k)
+            for (int m = 0; m < xp::fast::kNI; ++m)
+                coef_tv[(size_t)k * xp::fast::kNI + m] = xp::fast::compute_coef_tv(pr, curves, k, m);
+    }
+    HostCoef cf_tv = {coef_tv.data()};
     for (int64_t c = 0; c < n; ++c) {
         HostRdF rd = {t + c, td + c, n};
         xp::fast::FResult r[3];
-        // even columns: environment staged + early termination; odd columns: recomputed in the sweep
-        if (c & 1) {
+        // default options: v6 sweep on columns 2, 3 mod 4 (the generic sweep keeps 0, 1 mod 4);
+        // other options: even columns environment staged + early termination, odd columns recomputed
+        if (m1 && (c & 3) >= 2) {
+            redo[c] = xp::fast::suite_column6<7u>(rd, cf_tv, pr, tb, o, r);
+        } else if (c & 1) {
             xp::fast::EnvRecompute env;
             redo[c] = (o.vtc && o.compat == 141 && o.pos_neg) ? xp::fast::suite_column<7u, 1>(rd, cf, pr, tb, o, env, r)
                                                               : xp::fast::suite_column<7u, 0>(rd, cf, pr, tb, o, env, r);

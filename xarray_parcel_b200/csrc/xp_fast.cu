@@ -4,6 +4,7 @@
 
 #include "xp_fast.cuh"
 #include "xp_fast_pcol.cuh"
+#include "xp_fast6.cuh"
 #include "xp_kernels.cuh"
 
 namespace xp {
@@ -20,10 +21,12 @@ __global__ void fast_prep_kernel(const float *__restrict__ p, int64_t pls, int L
     if (threadIdx.x == 0) fast::compute_prep_axis(L, o, *out);
 }
 
-__global__ void fast_coef_kernel(const Prep *__restrict__ prep, const float *__restrict__ curves, Coef *__restrict__ coef) {
+// tv = 1: cubics of the saturated parcel's VIRTUAL temperature (v6 sweep, xp_fast6.cuh); 0: of its temperature
+__global__ void fast_coef_kernel(const Prep *__restrict__ prep, const float *__restrict__ curves, Coef *__restrict__ coef,
+                                 int tv) {
     const int k = blockIdx.x, m = threadIdx.x;
     if (!prep->ok || k >= prep->n_table || m >= fast::kNI) return;
-    coef[(size_t)k * fast::kNI + m] = fast::compute_coef(*prep, curves, k, m);
+    coef[(size_t)k * fast::kNI + m] = tv ? fast::compute_coef_tv(*prep, curves, k, m) : fast::compute_coef(*prep, curves, k, m);
 }
 
 // ---- the fast suite kernel ---------------------------------------------------------------------------------------
@@ -154,7 +157,10 @@ __global__ void __launch_bounds__(THREADS, 1) suite_fast_kernel(const __grid_con
         const GlobalRd rd{prm.t + col, prm.td + col, prm.ls};
         fast::FResult res[3];
         unsigned redo;
-        if (STAGED == 1) {
+        if (MODE == 1 && STAGED == 0) {
+            // default options: the v6 sweep on the virtual-temperature table (xp_fast6.cuh)
+            redo = fast::suite_column6<KINDS>(rd, cf, pr, prm.tb, prm.o, res);
+        } else if (STAGED == 1) {
             EnvSmem env{s_env + threadIdx.x, (int)blockDim.x};
             redo = fast::suite_column<KINDS, MODE>(rd, cf, pr, prm.tb, prm.o, env, res);
         } else if (STAGED == 2) {
@@ -312,7 +318,6 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
         return 2;
     }
     fast_prep_kernel<<<1, 64, 0, stream>>>(cols.p, cols.pls, cols.L, o, prep);
-    fast_coef_kernel<<<cols.L, fast::kNI, 0, stream>>>(prep, tb.curves, coef);
 
     FastParams fp;
     fp.t = cols.t; fp.td = cols.td; fp.n = cols.n; fp.ls = cols.ls;
@@ -329,6 +334,7 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
     }
     int staged = staged_ok;
     if (staged == 1 && smem_table + smem_env + 256 > (size_t)227 * 1024) staged = 0;
+    fast_coef_kernel<<<cols.L, fast::kNI, 0, stream>>>(prep, tb.curves, coef, (mode == 1 && staged == 0) ? 1 : 0);
     const size_t smem = smem_table + (staged == 1 ? smem_env : 0);
     const int threads = kFastThreads;      // one 512-thread CTA per SM (128 registers per thread)
     const int64_t tiles = (cols.n + threads - 1) / threads;
