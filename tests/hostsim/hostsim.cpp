@@ -76,12 +76,19 @@ struct HostRdF {
     const float *tdptr(int k) const { return td + (int64_t)k * ls; }
     int64_t stride() const { return ls; }
     static float ld(const float *p) { return *p; }
+    static void prefetch(const float *) {}
 };
 struct HostEnv {
     static constexpr bool kStaged = true, kFullPass = true;
     float v[xp::fast::kMaxLevels];
     void put(int k, float x) { v[k] = x; }
     float get(int k) const { return v[k]; }
+};
+struct HostStash {
+    float t[xp::fast::kMaxLevels], td[xp::fast::kMaxLevels];
+    int capacity() const { return xp::fast::kMaxLevels; }
+    void put(int k, float a, float b) { t[k] = a; td[k] = b; }
+    void get(int k, float &a, float &b) const { a = t[k]; b = td[k]; }
 };
 struct HostCoefRow {
     const xp::fast::Coef *row;
@@ -125,7 +132,14 @@ extern "C" int hostsim_fast_suite(const float *p, const float *t, const float *t
         // default options: v6 sweep on columns 2, 3 mod 4 (the generic sweep keeps 0, 1 mod 4);
         // other options: even columns environment staged + early termination, odd columns recomputed
         if (m1 && (c & 3) >= 2) {
-            redo[c] = xp::fast::suite_column6<7u>(rd, cf_tv, pr, tb, o, r);
+            // column 2 mod 4: T/Td of the lowest levels stashed by the pre-pass; 3 mod 4: no stash
+            if ((c & 3) == 2) {
+                HostStash st;
+                redo[c] = xp::fast::suite_column6<7u>(rd, cf_tv, pr, tb, o, st, r);
+            } else {
+                xp::fast::NoStash st;
+                redo[c] = xp::fast::suite_column6<7u>(rd, cf_tv, pr, tb, o, st, r);
+            }
         } else if (c & 1) {
             xp::fast::EnvRecompute env;
             redo[c] = (o.vtc && o.compat == 141 && o.pos_neg) ? xp::fast::suite_column<7u, 1>(rd, cf, pr, tb, o, env, r)
@@ -205,4 +219,13 @@ extern "C" int hostsim_fast_suite_pcol(const float *p, const float *t, const flo
         }
     }
     return 1;
+}
+
+// LCL solvers of the fast paths on n parcels: which = 0 lcl_fast (xp_fast.cuh), 1 lcl_fast6 (xp_fast6.cuh).
+extern "C" void hostsim_lcl_fast(const double *p, const double *t, const double *td, int64_t n, int which,
+                                 double *lcl_p, double *lcl_t) {
+    for (int64_t i = 0; i < n; ++i) {
+        if (which == 0) xp::fast::lcl_fast(p[i], t[i], td[i], lcl_p[i], lcl_t[i]);
+        else xp::fast::lcl_fast6(p[i], t[i], td[i], lcl_p[i], lcl_t[i]);
+    }
 }

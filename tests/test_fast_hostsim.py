@@ -159,3 +159,25 @@ def test_fast_path_refuses_bad_axes(oracle_tables):
     for p in ([1000, 900, 900, 700, 500], [900, 1000, 800, 700, 600], [1200, 1000, 800, 700, 600],
               [1000, np.nan, 800, 700, 600]):
         assert hs.fast_suite(np.array(p, dtype=np.float32), t, t - 5, oracle_tables) is None
+
+
+@pytest.mark.parametrize("which", [0, 1], ids=["lcl_fast", "lcl_fast6"])
+def test_fast_lcl_solvers_reach_the_converged_fixed_point(which):
+    """float32 Newton + one float64 step (xp_fast.cuh / xp_fast6.cuh) against the converged fixed point of
+    metpy.calc.lcl (oracle, PF:644): the agreement must be far below the 0.5 hPa x 0.02 K table cell, so that
+    the cell of the LCL is the reference's except within ~1e-8 of a cell edge."""
+    import ctypes
+    from oracle import thermo as th
+    rng = np.random.default_rng(11)
+    n = 200_000
+    p = rng.uniform(600.0, 1050.0, n)
+    t = rng.uniform(240.0, 315.0, n)
+    td = t - np.concatenate([rng.uniform(2e-3, 1.0, n // 4), rng.uniform(1.0, 45.0, n - n // 4)])
+    lp, lt = np.empty(n), np.empty(n)
+    fn = hs.lib().hostsim_lcl_fast
+    fn.restype = None
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    fn(ptr(p), ptr(t), ptr(td), ctypes.c_int64(n), ctypes.c_int(which), ptr(lp), ptr(lt))
+    rp, rt = th.lcl(p, t, td, mode="converged")
+    assert np.abs(lp / rp - 1).max() < 2e-11
+    assert np.abs(lt - rt).max() < 2e-9

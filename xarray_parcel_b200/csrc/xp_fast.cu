@@ -41,6 +41,7 @@ struct FastParams {
     OutArg<float> outs[3];
     uint32_t *list;          // 3 regions of n entries (see ListParams)
     uint32_t *list_count;
+    int stash_levels;        // levels of T/Td per thread that fit in shared memory after the table (v6 sweep)
 };
 
 struct GlobalRd {
@@ -52,6 +53,7 @@ struct GlobalRd {
     __device__ __forceinline__ const float *tdptr(int k) const { return td + (int64_t)k * ls; }
     __device__ __forceinline__ int64_t stride() const { return ls; }
     static __device__ __forceinline__ float ld(const float *p) { return __ldg(p); }
+    static __device__ __forceinline__ void prefetch(const float *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 };
 
 struct SmemCoefRow {
@@ -95,6 +97,16 @@ struct EnvSmem {
     int stride;
     __device__ __forceinline__ void put(int k, float v) { base[k * stride] = v; }
     __device__ __forceinline__ float get(int k) const { return base[k * stride]; }
+};
+
+// T/Td of the lowest levels of every thread's column: element (level k, T|Td, thread) at
+// base[(2 k + which) * blockDim.x + thread] -- conflict-free.
+struct StashSmem {
+    float *base;
+    int stride, cap;
+    __device__ __forceinline__ int capacity() const { return cap; }
+    __device__ __forceinline__ void put(int k, float t, float td) { base[(2 * k) * stride] = t; base[(2 * k + 1) * stride] = td; }
+    __device__ __forceinline__ void get(int k, float &t, float &td) const { t = base[(2 * k) * stride]; td = base[(2 * k + 1) * stride]; }
 };
 
 // STAGED: 0 = environment recomputed in the sweep; 1 = environment curve staged in shared memory + early
@@ -158,8 +170,10 @@ __global__ void __launch_bounds__(THREADS, 1) suite_fast_kernel(const __grid_con
         fast::FResult res[3];
         unsigned redo;
         if (MODE == 1 && STAGED == 0) {
-            // default options: the v6 sweep on the virtual-temperature table (xp_fast6.cuh)
-            redo = fast::suite_column6<KINDS>(rd, cf, pr, prm.tb, prm.o, res);
+            // default options: the v6 sweep on the virtual-temperature table (xp_fast6.cuh); the shared
+            // memory left after the table stashes T/Td of the lowest levels of every thread's column
+            StashSmem st{s_env + threadIdx.x, (int)blockDim.x, prm.stash_levels};
+            redo = fast::suite_column6<KINDS>(rd, cf, pr, prm.tb, prm.o, st, res);
         } else if (STAGED == 1) {
             EnvSmem env{s_env + threadIdx.x, (int)blockDim.x};
             redo = fast::suite_column<KINDS, MODE>(rd, cf, pr, prm.tb, prm.o, env, res);
@@ -335,7 +349,17 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
     int staged = staged_ok;
     if (staged == 1 && smem_table + smem_env + 256 > (size_t)227 * 1024) staged = 0;
     fast_coef_kernel<<<cols.L, fast::kNI, 0, stream>>>(prep, tb.curves, coef, (mode == 1 && staged == 0) ? 1 : 0);
-    const size_t smem = smem_table + (staged == 1 ? smem_env : 0);
+    size_t smem = smem_table + (staged == 1 ? smem_env : 0);
+    fp.stash_levels = 0;
+    if (mode == 1 && staged == 0) {
+        // v6 sweep: stash as many of the lowest levels as fit (at most 16: the pre-pass depth of real axes)
+        const size_t per_level = 2 * sizeof(float) * kFastThreads;
+        const size_t room = (size_t)227 * 1024 - 256 - smem_table;
+        int lv = (int)(room / per_level);
+        lv = lv > 16 ? 16 : lv;
+        fp.stash_levels = lv;
+        smem += (size_t)lv * per_level;
+    }
     const int threads = kFastThreads;      // one 512-thread CTA per SM (128 registers per thread)
     const int64_t tiles = (cols.n + threads - 1) / threads;
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);

@@ -153,23 +153,168 @@ XP_HD void sweep_finish6(const FParcel &s, const Cf &cf, const Prep &pr, const O
     r.lcl_p = s.lcl_p; r.lcl_t = s.lcl_t; r.lcl_tv = s.lcl_tv;
 }
 
-// Shared per-level state of the sweep.
+// ---- LCL (metpy.calc.lcl fixed point, PF:644), cheaper float64 polish -------------------------------------------
+// Same scheme as lcl_fast (xp_fast.cuh): float32 Newton on F(q) = q - (tdp(v0 + ln q)/T)^3.5, then ONE float64
+// Newton step.  Here only the RESIDUAL F is evaluated in float64 (one log, reciprocals and a square root by
+// float32-seeded Newton iterations, no IEEE division); its derivative is the float32 one, whose 1e-6 relative
+// error enters the step (|dq| ~ 1e-7 q) at second order.
+XP_HD double rcp64(double y) {
+    double r = (double)f_rcp((float)y);
+    r = fma(fma(-y, r, 1.0), r, r);
+    return fma(fma(-y, r, 1.0), r, r);
+}
+XP_HD double sqrt64(double y) {               // y ~ 1
+#if defined(__CUDACC__)
+    double r = (double)rsqrtf((float)y);
+#else
+    double r = 1.0 / sqrt(y);
+#endif
+    r = r * fma(-0.5 * y, r * r, 1.5);
+    r = r * fma(-0.5 * y, r * r, 1.5);
+    return y * r;
+}
+XP_HD void lcl_fast6(double p0, double t, double td, double &lcl_p, double &lcl_t) {
+    const double v0 = 17.67 * (td - 273.15) * rcp64(td - 29.65);
+    const float v0f = (float)v0, rt = f_rcp((float)t);
+    float q = 1.0f, dF = 1.0f, dtdp = 0.0f;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const float v = f_fma(kLn2, f_lg2(q), v0f);
+        const float iv = f_rcp(17.67f - v);
+        const float tdp = f_fma(243.5f * v, iv, 273.15f);
+        const float r = tdp * rt;
+        const float r35 = r * r * r * f_sqrt(r);
+        dtdp = 243.5f * 17.67f * iv * iv;                               // d tdp / d v
+        dF = 1.0f - 3.5f * r35 * dtdp * f_rcp(tdp * q);                 // d/dq: r35 * 3.5 * (dtdp/tdp) * (1/q)
+        q = q - (q - r35) * f_rcp(dF);
+    }
+    // (dF, dtdp belong to the previous iterate: they differ from the ones at q by ~1e-6 relative)
+    const double qd = (double)q;
+    const double v = v0 + log(qd);
+    const double tdp = 243.5 * v * rcp64(17.67 - v) + 273.15;
+    const double r = tdp * rcp64(t);
+    const double r35 = r * r * r * sqrt64(r);
+    const double dq = (qd - r35) * (double)f_rcp(dF);
+    // tdp at the polished q, first order (|dq| ~ 1e-7: the second-order term is < 1e-11 K)
+    lcl_t = tdp - (double)(dtdp * f_rcp(q)) * dq;
+    lcl_p = p0 * (qd - dq);
+}
+
+// ---- parcel set-up in three stages, so that the three parcels of a column overlap their latencies -------------------
+// (setup_parcel of xp_fast.cuh does the same work for one parcel start to end.)
+//   A  LCL solve (arithmetic only)
+//   B  issue the gathers: table cell of the LCL, T/Td of the two levels bracketing the LCL
+//   C  everything that consumes them
+struct Setup6 {
+    double lp, lt;              // LCL (float64-polished)
+    double p0, t0, td0;         // parcel (replaced by a dummy when the parcel is bound for the exact path)
+    int adiabat;                // table cell -> adiabat number (gathered)
+    float ta, tda, tb_, tdb;    // T/Td of the levels after / before the LCL
+    bool before_is_start;
+};
+
+XP_HD void setup6_a(double p0, double t0, double td0, FParcel &pc, Setup6 &u) {
+    pc.bad = false;
+    // saturated / supersaturated / NaN parcels: exact path (see setup_parcel)
+    if (!(t0 - td0 >= kSaturationMargin) || !(p0 > 0.0)) { pc.bad = true; t0 = 280.0; td0 = 270.0; p0 = 1000.0; }
+    u.p0 = p0; u.t0 = t0; u.td0 = td0;
+    lcl_fast6(p0, t0, td0, u.lp, u.lt);
+}
+
+// `lev(k, t, td)` reads T/Td of level k.
+template <class Lev>
+XP_HD void setup6_b(const Lev &lev, const Prep &pr, const Tables &tb, int knext, FParcel &pc, Setup6 &u) {
+    float edge;
+    u.adiabat = adiabat_cell(tb, u.lp, u.lt, edge);                   // PF:554-557 (2-byte gather)
+    // LCL position among the levels of the lifted column (insert_level PF:965-966).  The axis is float32 data,
+    // so comparing it with the float32-rounded LCL pressure decides every case except equality.
+    const float lpf = (float)u.lp;
+    int ka = knext;
+#pragma unroll
+    for (int step = 32; step > 0; step >>= 1) {
+        const int k2 = ka + step;
+        const bool ok = k2 <= pr.L && pr.p[min(k2, kMaxLevels) - 1] >= lpf;
+        ka = ok ? k2 : ka;
+    }
+    pc.kfirst = knext;
+    u.before_is_start = (ka == knext);
+    const int kb = ka - 1;
+    // LCL above the table top, or (to float32) exactly on a level: exact path
+    if (ka >= pr.n_table || pr.p[kb] == lpf || pr.p[min(ka, pr.L - 1)] == lpf) { pc.bad = true; ka = pr.n_table; }
+    pc.ka = ka;
+    const int kl = min(ka, pr.L - 1);
+    lev(kl, u.ta, u.tda);
+    lev(max(kl - 1, 0), u.tb_, u.tdb);
+}
+
+XP_HD void setup6_c(const Prep &pr, const Opts &o, int kstart, FParcel &pc, const Setup6 &u) {
+    const int a0 = u.adiabat - 1;
+    pc.m = a0 / kNodeStride;
+    if (u.adiabat <= 0 || pc.m < kFirstInterval || pc.m > kLastInterval) { pc.bad = true; pc.m = kFirstInterval; }
+    pc.f = (float)(a0 - pc.m * kNodeStride) * (1.0f / kNodeStride);
+    const float p0f = (float)u.p0, t0f = (float)u.t0, td0f = (float)u.td0;
+    const float lpf = (float)u.lp, ltf = (float)u.lt;
+    pc.lcl_p = lpf; pc.lcl_t = ltf;
+    const float es_l = f_es(ltf);
+    pc.lcl_tv = f_tv(ltf, f_mixing_ratio(es_l, es_l, lpf, 141));                   // PF:653-657
+    const float w_parcel = f_mixing_ratio(f_es(t0f), f_es(td0f), p0f, 141);        // PF:748
+    pc.c_dryv = t0f * f_rcp(pr.pk[kstart]) * f_fma(0.608f, w_parcel, 1.0f);        // PF:291-316, 767-775
+    sweep_init6(pc, pr.lnp[kstart]);
+    pc.x_lcl = pr.lnp[kstart]; pc.a_lcl = pc.b_lcl = 0.0f;
+    if (pc.ka >= pr.n_table) return;                                               // bound for the exact path
+    // environment at the LCL (PF:1774-1806): "before" = last level with p >= lcl_p (the start row when the LCL
+    // is below the first swept level), "after" = level ka
+    const int ka = pc.ka, kb = ka - 1;
+    float tb_ = u.tb_, tdb = u.tdb, xb = o.log_interp ? pr.lnp[kb] : pr.p[kb];
+    if (u.before_is_start) { tb_ = t0f; tdb = td0f; xb = o.log_interp ? pr.lnp[kstart] : pr.p[kstart]; }
+    const float xa = o.log_interp ? pr.lnp[ka] : pr.p[ka];
+    const float x_l = kLn2 * f_lg2(lpf);
+    const float at = o.log_interp ? x_l : lpf;
+    const float g = (at - xb) * f_rcp(xa - xb);
+    const float te = f_fma(u.ta - tb_, g, tb_), tde = f_fma(u.tda - tdb, g, tdb);   // PF:1802
+    const float etv = f_tv(te, f_mixing_ratio(f_es(te), f_es(tde), lpf, 141));      // PF:916-920
+    pc.x_lcl = x_l;
+    pc.a_lcl = pc.lcl_tv;
+    pc.b_lcl = pc.lcl_tv - etv;                                                    // v6: the LCL row as a difference
+    if (!(te == te) || !(tde == tde)) pc.bad = true;
+}
+
+// Per-thread stash of the T/Td of the lowest levels (filled by the pre-pass, read by the parcel set-up and
+// by the first iterations of the sweep).  The kernel keeps it in shared memory.
+struct NoStash {
+    XP_HD int capacity() const { return 0; }
+    XP_HD void put(int, float, float) const {}
+    XP_HD void get(int, float &t, float &td) const { t = td = 0.0f; }
+};
+
+// Shared per-level state of the sweep: axis constants of level `it`, T/Td one level ahead in registers and
+// kL2Ahead levels ahead as L2 prefetches (the register load then costs an L2 hit, which one iteration hides).
+constexpr int kL2Ahead = 4;
 template <class Rd>
 struct Sweep6 {
-    const float *lp_x, *lp_k, *lp_p;      // axis constants of level `it`
-    const float *tp, *tdp;                // T/Td of level it + 1 (prefetch)
+    const float *lp_x, *lp_k, *lp_p;
+    const float *tp, *tdp;                // T/Td of the level after the prefetched one
     int64_t ls;
-    float t_nxt, td_nxt;
+    int k_pf;                             // level that tp/tdp point at
+    float t_n1, td_n1;                    // prefetched: the next global level
     float b_prv, x_prv;
 };
 
-// Iterations [it0, it1) of the sweep for the parcels in KACT (subset of KINDS); it1 <= nt - 1 + 1.
-template <unsigned KACT, bool GUARD_MU, class Rd, class CoefRow>
-XP_HD void sweep_segment6(Sweep6<Rd> &s, CoefRow &crow, int it0, int it1, int nt, FParcel &sb, FParcel &ml, FParcel &mu) {
+// Iterations [it0, it1) of the sweep for the parcels in KACT (subset of KINDS).  FROM_STASH: T/Td of these
+// levels come from the stash (it1 <= stash levels) instead of the global prefetch pipeline.
+template <unsigned KACT, bool GUARD_MU, class Rd, class CoefRow, class Stash>
+XP_HD void sweep_segment6(Sweep6<Rd> &s, CoefRow &crow, const Stash &stash, bool from_stash, int it0, int it1, int nt,
+                          FParcel &sb, FParcel &ml, FParcel &mu) {
     for (int it = it0; it < it1; ++it) {
-        const float t = s.t_nxt, td = s.td_nxt;
-        s.tp += s.ls; s.tdp += s.ls;
-        if (it + 1 < nt) { s.t_nxt = Rd::ld(s.tp); s.td_nxt = Rd::ld(s.tdp); }      // prefetch the next level
+        float t, td;
+        if (from_stash) {
+            stash.get(it, t, td);
+        } else {
+            t = s.t_n1; td = s.td_n1;
+            if (s.k_pf < nt) { s.t_n1 = Rd::ld(s.tp); s.td_n1 = Rd::ld(s.tdp); }      // one level ahead
+            if (s.k_pf + kL2Ahead < nt) { Rd::prefetch(s.tp + kL2Ahead * s.ls); Rd::prefetch(s.tdp + kL2Ahead * s.ls); }
+            s.tp += s.ls; s.tdp += s.ls; ++s.k_pf;
+        }
         const float p_cur = *s.lp_p++, x_cur = *s.lp_x++, pk_cur = *s.lp_k++;
         const float b_cur = f_tv(t, f_mixing_ratio(f_es(t), f_es(td), p_cur, 141));   // PF:839-843
         if (KACT & 1u) step6<false>(sb, it, crow.at(sb.m), pk_cur, x_cur, s.x_prv, b_cur, s.b_prv);
@@ -182,19 +327,33 @@ XP_HD void sweep_segment6(Sweep6<Rd> &s, CoefRow &crow, int it0, int it1, int nt
 
 // The whole suite for one column, default options.  Interfaces as suite_column (xp_fast.cuh); `cf` must be
 // the VIRTUAL-temperature table (compute_coef_tv).  Returns the mask of kinds for the exact path.
-template <unsigned KINDS, class Rd, class Cf>
+template <unsigned KINDS, class Rd, class Cf, class Stash>
 XP_HD unsigned suite_column6(const Rd &rd, const Cf &cf, const Prep &pr, const Tables &tb, const Opts &o,
-                             FResult res[3]) {
+                             Stash &stash, FResult res[3]) {
     unsigned redo = 0;
     float nanacc = 0.0f;                   // becomes NaN if a T/Td read of the pre-pass is NaN or infinite
     const int nt = pr.n_table;
+    const int n_low = max(1, max((KINDS & 4u) ? pr.K_mu : 0, (KINDS & 2u) ? pr.n_ml_w : 0));
+    const int64_t ls = rd.stride();
+    // the stash is used only if it holds every pre-pass level (then the sweep starts from it too)
+    const int n_stash = (stash.capacity() >= n_low) ? n_low : 0;
+    // start the global prefetch pipeline of the sweep now: its first levels arrive during the pre-pass
+    Sweep6<Rd> s;
+    {
+        const int k0 = (n_stash > 0) ? n_stash : 1;          // first level the sweep reads from global memory
+        s.tp = rd.tptr(k0); s.tdp = rd.tdptr(k0); s.ls = ls;
+        s.t_n1 = s.td_n1 = 0.0f;
+        if (k0 < nt) { s.t_n1 = Rd::ld(s.tp); s.td_n1 = Rd::ld(s.tdp); }
+#pragma unroll
+        for (int j = 1; j <= kL2Ahead; ++j)
+            if (k0 + j < nt) { Rd::prefetch(s.tp + j * ls); Rd::prefetch(s.tdp + j * ls); }
+        s.tp += ls; s.tdp += ls; s.k_pf = k0 + 1;
+    }
     // ---- pre-pass over the lowest levels: mixed-layer means (float64) and most-unstable argmax ----
     double sum_th = 0.0, sum_w = 0.0;
-    float best = -1e30f, second = -1e30f, mu_t = 0.0f, mu_td = 0.0f;
+    float best = -1e30f, second = -1e30f, mu_t = 0.0f, mu_td = 0.0f, t_sfc = 0.0f, td_sfc = 0.0f;
     int k_mu = 0;
-    const int n_low = max((KINDS & 4u) ? pr.K_mu : 0, (KINDS & 2u) ? pr.n_ml_w : 0);
     const float *tp0 = rd.tptr(0), *tdp0 = rd.tdptr(0);
-    const int64_t ls = rd.stride();
     constexpr int kPre = 4;
     float tq[kPre], tdq[kPre], tn[kPre], tdn[kPre];
 #pragma unroll
@@ -214,6 +373,8 @@ XP_HD unsigned suite_column6(const Rd &rd, const Cf &cf, const Prep &pr, const T
             const int k = k0 + j;
             if (k >= n_low) break;
             const float t = tq[j], td = tdq[j];
+            if (k == 0) { t_sfc = t; td_sfc = td; }
+            if (k < n_stash) stash.put(k, t, td);
             nanacc = f_fma(t, 0.0f, f_fma(td, 0.0f, nanacc));
             const float p = pr.p[k];
             const float e = f_es(td);
@@ -240,43 +401,54 @@ XP_HD unsigned suite_column6(const Rd &rd, const Cf &cf, const Prep &pr, const T
             }
         }
     }
-    // ---- parcels --------------------------------------------------------------------------------
+    // ---- parcels: staged so that the LCL solves, the gathers and their consumers overlap --------------
     FParcel sb, ml, mu;
-    const float t_sfc = rd.T(0), td_sfc = rd.Td(0);
-    nanacc = f_fma(t_sfc, 0.0f, f_fma(td_sfc, 0.0f, nanacc));
-    Opts od = o; od.vtc = 1; od.compat = 141; od.pos_neg = 1;
-    if (KINDS & 1u) {
-        setup_parcel(rd, pr, tb, od, pr.p0, (double)t_sfc, (double)td_sfc, 0, 1, false, sb);
-        res[0].par_p = pr.p[0]; res[0].par_t = t_sfc; res[0].par_td = td_sfc; res[0].shift = 0;
-    }
+    Setup6 u_sb, u_ml, u_mu;
+    auto lev = [&](int k, float &t, float &td) {
+        if (k < n_stash) stash.get(k, t, td);
+        else { t = rd.T(k); td = rd.Td(k); }
+    };
+    double mp_t = 0.0, mp_td = 0.0;
+    if (KINDS & 1u) setup6_a(pr.p0, (double)t_sfc, (double)td_sfc, sb, u_sb);
     if (KINDS & 2u) {
-        const double mp_t = sum_th * pr.exner0;                                  // PF:268-269
-        const double mp_td = dewpoint_from_e(vapor_pressure(pr.p0, sum_w));      // PF:275-282
-        setup_parcel(rd, pr, tb, od, pr.p0, mp_t, mp_td, 0, pr.K_ml, false, ml);
-        res[1].par_p = pr.p[0]; res[1].par_t = (float)mp_t; res[1].par_td = (float)mp_td; res[1].shift = pr.K_ml;
+        mp_t = sum_th * pr.exner0;                                               // PF:268-269
+        mp_td = dewpoint_from_e(vapor_pressure(pr.p0, sum_w));                   // PF:275-282
+        setup6_a(pr.p0, mp_t, mp_td, ml, u_ml);
     }
     if (KINDS & 4u) {
         if (!(best - second >= kThetaEMargin)) redo |= 4u;                       // argmax within float32 error
-        setup_parcel(rd, pr, tb, od, pr.p64[k_mu], (double)mu_t, (double)mu_td, k_mu, k_mu + 1, false, mu);
+        setup6_a(pr.p64[k_mu], (double)mu_t, (double)mu_td, mu, u_mu);
+    }
+    if (KINDS & 1u) setup6_b(lev, pr, tb, 1, sb, u_sb);
+    if (KINDS & 2u) setup6_b(lev, pr, tb, pr.K_ml, ml, u_ml);
+    if (KINDS & 4u) setup6_b(lev, pr, tb, k_mu + 1, mu, u_mu);
+    if (KINDS & 1u) {
+        setup6_c(pr, o, 0, sb, u_sb);
+        res[0].par_p = pr.p[0]; res[0].par_t = t_sfc; res[0].par_td = td_sfc; res[0].shift = 0;
+    }
+    if (KINDS & 2u) {
+        setup6_c(pr, o, 0, ml, u_ml);
+        res[1].par_p = pr.p[0]; res[1].par_t = (float)mp_t; res[1].par_td = (float)mp_td; res[1].shift = pr.K_ml;
+    }
+    if (KINDS & 4u) {
+        setup6_c(pr, o, k_mu, mu, u_mu);
         res[2].par_p = pr.p[k_mu]; res[2].par_t = mu_t; res[2].par_td = mu_td; res[2].shift = k_mu;
     }
-    // v6 state: the LCL row as a difference, zeroed sums, start row of each parcel
-    if (KINDS & 1u) { sb.b_lcl = sb.a_lcl - sb.b_lcl; sweep_init6(sb, pr.lnp[0]); }
-    if (KINDS & 2u) { ml.b_lcl = ml.a_lcl - ml.b_lcl; sweep_init6(ml, pr.lnp[0]); }
-    if (KINDS & 4u) { mu.b_lcl = mu.a_lcl - mu.b_lcl; sweep_init6(mu, pr.lnp[0]); }
     // ---- the sweep --------------------------------------------------------------------------------------
-    Sweep6<Rd> s;
     s.lp_p = pr.p + 1; s.lp_x = pr.lnp + 1; s.lp_k = pr.pk + 1;
-    s.tp = rd.tptr(1); s.tdp = rd.tdptr(1); s.ls = ls;
-    s.t_nxt = Rd::ld(s.tp); s.td_nxt = Rd::ld(s.tdp);
     s.b_prv = 0.0f; s.x_prv = pr.lnp[0];
     auto crow = cf.row(0);
-    // segment bounds: the mixed-layer parcel joins at K_ml; most-unstable parcels have all started by K_mu
+    // segment bounds: the mixed-layer parcel joins at K_ml; most-unstable parcels have all started by K_mu;
+    // levels below n_stash come from the stash
     const int it_a = (KINDS & 2u) ? min(pr.K_ml, nt) : 1;
     const int it_b = (KINDS & 4u) ? max(it_a, min(pr.K_mu, nt)) : it_a;
-    sweep_segment6<KINDS & 5u, true>(s, crow, 1, it_a, nt, sb, ml, mu);
-    sweep_segment6<KINDS, true>(s, crow, it_a, it_b, nt, sb, ml, mu);
-    sweep_segment6<KINDS, false>(s, crow, it_b, nt, nt, sb, ml, mu);
+    const bool fs = n_stash > 0;
+    // with a stash the first n_stash levels come from it (n_stash = n_low >= it_b), the rest from the
+    // global prefetch pipeline, which was started at level n_stash
+    const int it_c = fs ? max(it_b, min(n_stash, nt)) : it_b;
+    sweep_segment6<KINDS & 5u, true>(s, crow, stash, fs, 1, it_a, nt, sb, ml, mu);
+    sweep_segment6<KINDS, true>(s, crow, stash, fs, it_a, it_c, nt, sb, ml, mu);
+    sweep_segment6<KINDS, false>(s, crow, stash, false, it_c, nt, nt, sb, ml, mu);
     // last iteration: no level `nt`; every parcel that is not bound for the exact path is above its LCL
     {
         const float big = 1e30f;
