@@ -78,6 +78,15 @@ struct HostRdF {
     static float ld(const float *p) { return *p; }
     static void prefetch(const float *) {}
 };
+struct HostRd6 {                       // v6 sweep: 32-bit element offsets from the array bases
+    const float *t, *td;
+    uint32_t col, lstride;
+    uint32_t off0() const { return col; }
+    uint32_t ls() const { return lstride; }
+    float ldT(uint32_t off) const { return t[off]; }
+    float ldTd(uint32_t off) const { return td[off]; }
+    void prefetch(uint32_t) const {}
+};
 struct HostEnv {
     static constexpr bool kStaged = true, kFullPass = true;
     float v[xp::fast::kMaxLevels];
@@ -133,12 +142,13 @@ extern "C" int hostsim_fast_suite(const float *p, const float *t, const float *t
         // other options: even columns environment staged + early termination, odd columns recomputed
         if (m1 && (c & 3) >= 2) {
             // column 2 mod 4: T/Td of the lowest levels stashed by the pre-pass; 3 mod 4: no stash
+            const HostRd6 rd6 = {t, td, (uint32_t)c, (uint32_t)n};
             if ((c & 3) == 2) {
                 HostStash st;
-                redo[c] = xp::fast::suite_column6<7u>(rd, cf_tv, pr, tb, o, st, r);
+                redo[c] = xp::fast::suite_column6<7u>(rd6, cf_tv, pr, tb, o, st, r);
             } else {
                 xp::fast::NoStash st;
-                redo[c] = xp::fast::suite_column6<7u>(rd, cf_tv, pr, tb, o, st, r);
+                redo[c] = xp::fast::suite_column6<7u>(rd6, cf_tv, pr, tb, o, st, r);
             }
         } else if (c & 1) {
             xp::fast::EnvRecompute env;

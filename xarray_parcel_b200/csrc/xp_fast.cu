@@ -56,6 +56,20 @@ struct GlobalRd {
     static __device__ __forceinline__ void prefetch(const float *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 };
 
+// v6 sweep: 32-bit element offsets from the array bases (see Sweep6 in xp_fast6.cuh)
+struct GlobalRd32 {
+    const float *t, *td;
+    uint32_t col, lstride;
+    __device__ __forceinline__ uint32_t off0() const { return col; }
+    __device__ __forceinline__ uint32_t ls() const { return lstride; }
+    __device__ __forceinline__ float ldT(uint32_t off) const { return __ldg(t + off); }
+    __device__ __forceinline__ float ldTd(uint32_t off) const { return __ldg(td + off); }
+    __device__ __forceinline__ void prefetch(uint32_t off) const {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(t + off));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(td + off));
+    }
+};
+
 struct SmemCoefRow {
     const Coef *row;
     __device__ __forceinline__ void advance() { row += fast::kNI; }
@@ -173,7 +187,8 @@ __global__ void __launch_bounds__(THREADS, 1) suite_fast_kernel(const __grid_con
             // default options: the v6 sweep on the virtual-temperature table (xp_fast6.cuh); the shared
             // memory left after the table stashes T/Td of the lowest levels of every thread's column
             StashSmem st{s_env + threadIdx.x, (int)blockDim.x, prm.stash_levels};
-            redo = fast::suite_column6<KINDS>(rd, cf, pr, prm.tb, prm.o, st, res);
+            const GlobalRd32 rd32{prm.t, prm.td, (uint32_t)col, (uint32_t)prm.ls};
+            redo = fast::suite_column6<KINDS>(rd32, cf, pr, prm.tb, prm.o, st, res);
         } else if (STAGED == 1) {
             EnvSmem env{s_env + threadIdx.x, (int)blockDim.x};
             redo = fast::suite_column<KINDS, MODE>(rd, cf, pr, prm.tb, prm.o, env, res);
@@ -348,6 +363,8 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
     }
     int staged = staged_ok;
     if (staged == 1 && smem_table + smem_env + 256 > (size_t)227 * 1024) staged = 0;
+    // the v6 sweep addresses T/Td with 32-bit element offsets; larger arrays take the generic sweep (variant 2)
+    if (mode == 1 && staged == 0 && (uint64_t)cols.n + (uint64_t)cols.L * (uint64_t)cols.ls >= ((uint64_t)1 << 32)) staged = 2;
     fast_coef_kernel<<<cols.L, fast::kNI, 0, stream>>>(prep, tb.curves, coef, (mode == 1 && staged == 0) ? 1 : 0);
     size_t smem = smem_table + (staged == 1 ? smem_env : 0);
     fp.stash_levels = 0;

@@ -290,12 +290,14 @@ struct NoStash {
 // Shared per-level state of the sweep: axis constants of level `it`, T/Td one level ahead in registers and
 // kL2Ahead levels ahead as L2 prefetches (the register load then costs an L2 hit, which one iteration hides).
 constexpr int kL2Ahead = 4;
-template <class Rd>
+// T/Td are addressed as base[off] with a 32-bit element offset off = column + level * level_stride from the
+// (warp-uniform) array bases -- one integer add per level instead of 64-bit pointer arithmetic per array; the
+// launcher takes this path only when every offset fits 32 bits.  Rd: ldT(off), ldTd(off), prefetch(off), ls(), off0().
 struct Sweep6 {
     const float *lp_x, *lp_k, *lp_p;
-    const float *tp, *tdp;                // T/Td of the level after the prefetched one
-    int64_t ls;
-    int k_pf;                             // level that tp/tdp point at
+    uint32_t off;                         // offset of the level after the prefetched one
+    uint32_t ls;
+    int k_pf;                             // that level
     float t_n1, td_n1;                    // prefetched: the next global level
     float b_prv, x_prv;
 };
@@ -303,7 +305,7 @@ struct Sweep6 {
 // Iterations [it0, it1) of the sweep for the parcels in KACT (subset of KINDS).  FROM_STASH: T/Td of these
 // levels come from the stash (it1 <= stash levels) instead of the global prefetch pipeline.
 template <unsigned KACT, bool GUARD_MU, class Rd, class CoefRow, class Stash>
-XP_HD void sweep_segment6(Sweep6<Rd> &s, CoefRow &crow, const Stash &stash, bool from_stash, int it0, int it1, int nt,
+XP_HD void sweep_segment6(const Rd &rd, Sweep6 &s, CoefRow &crow, const Stash &stash, bool from_stash, int it0, int it1, int nt,
                           FParcel &sb, FParcel &ml, FParcel &mu) {
     for (int it = it0; it < it1; ++it) {
         float t, td;
@@ -311,9 +313,9 @@ XP_HD void sweep_segment6(Sweep6<Rd> &s, CoefRow &crow, const Stash &stash, bool
             stash.get(it, t, td);
         } else {
             t = s.t_n1; td = s.td_n1;
-            if (s.k_pf < nt) { s.t_n1 = Rd::ld(s.tp); s.td_n1 = Rd::ld(s.tdp); }      // one level ahead
-            if (s.k_pf + kL2Ahead < nt) { Rd::prefetch(s.tp + kL2Ahead * s.ls); Rd::prefetch(s.tdp + kL2Ahead * s.ls); }
-            s.tp += s.ls; s.tdp += s.ls; ++s.k_pf;
+            if (s.k_pf < nt) { s.t_n1 = rd.ldT(s.off); s.td_n1 = rd.ldTd(s.off); }    // one level ahead
+            if (s.k_pf + kL2Ahead < nt) rd.prefetch(s.off + kL2Ahead * s.ls);
+            s.off += s.ls; ++s.k_pf;
         }
         const float p_cur = *s.lp_p++, x_cur = *s.lp_x++, pk_cur = *s.lp_k++;
         const float b_cur = f_tv(t, f_mixing_ratio(f_es(t), f_es(td), p_cur, 141));   // PF:839-843
@@ -334,40 +336,40 @@ XP_HD unsigned suite_column6(const Rd &rd, const Cf &cf, const Prep &pr, const T
     float nanacc = 0.0f;                   // becomes NaN if a T/Td read of the pre-pass is NaN or infinite
     const int nt = pr.n_table;
     const int n_low = max(1, max((KINDS & 4u) ? pr.K_mu : 0, (KINDS & 2u) ? pr.n_ml_w : 0));
-    const int64_t ls = rd.stride();
+    const uint32_t ls = rd.ls();
     // the stash is used only if it holds every pre-pass level (then the sweep starts from it too)
     const int n_stash = (stash.capacity() >= n_low) ? n_low : 0;
     // start the global prefetch pipeline of the sweep now: its first levels arrive during the pre-pass
-    Sweep6<Rd> s;
+    Sweep6 s;
     {
         const int k0 = (n_stash > 0) ? n_stash : 1;          // first level the sweep reads from global memory
-        s.tp = rd.tptr(k0); s.tdp = rd.tdptr(k0); s.ls = ls;
+        s.off = rd.off0() + (uint32_t)k0 * ls; s.ls = ls;
         s.t_n1 = s.td_n1 = 0.0f;
-        if (k0 < nt) { s.t_n1 = Rd::ld(s.tp); s.td_n1 = Rd::ld(s.tdp); }
+        if (k0 < nt) { s.t_n1 = rd.ldT(s.off); s.td_n1 = rd.ldTd(s.off); }
 #pragma unroll
         for (int j = 1; j <= kL2Ahead; ++j)
-            if (k0 + j < nt) { Rd::prefetch(s.tp + j * ls); Rd::prefetch(s.tdp + j * ls); }
-        s.tp += ls; s.tdp += ls; s.k_pf = k0 + 1;
+            if (k0 + j < nt) rd.prefetch(s.off + (uint32_t)j * ls);
+        s.off += ls; s.k_pf = k0 + 1;
     }
     // ---- pre-pass over the lowest levels: mixed-layer means (float64) and most-unstable argmax ----
     double sum_th = 0.0, sum_w = 0.0;
     float best = -1e30f, second = -1e30f, mu_t = 0.0f, mu_td = 0.0f, t_sfc = 0.0f, td_sfc = 0.0f;
     int k_mu = 0;
-    const float *tp0 = rd.tptr(0), *tdp0 = rd.tdptr(0);
+    uint32_t off0 = rd.off0();
     constexpr int kPre = 4;
     float tq[kPre], tdq[kPre], tn[kPre], tdn[kPre];
 #pragma unroll
     for (int j = 0; j < kPre; ++j) {
         tn[j] = tdn[j] = 0.0f;
-        if (j < n_low) { tn[j] = Rd::ld(tp0 + (int64_t)j * ls); tdn[j] = Rd::ld(tdp0 + (int64_t)j * ls); }
+        if (j < n_low) { tn[j] = rd.ldT(off0 + (uint32_t)j * ls); tdn[j] = rd.ldTd(off0 + (uint32_t)j * ls); }
     }
     for (int k0 = 0; k0 < n_low; k0 += kPre) {
 #pragma unroll
         for (int j = 0; j < kPre; ++j) { tq[j] = tn[j]; tdq[j] = tdn[j]; }
-        tp0 += (int64_t)kPre * ls; tdp0 += (int64_t)kPre * ls;
+        off0 += (uint32_t)kPre * ls;
 #pragma unroll
         for (int j = 0; j < kPre; ++j)
-            if (k0 + kPre + j < n_low) { tn[j] = Rd::ld(tp0 + (int64_t)j * ls); tdn[j] = Rd::ld(tdp0 + (int64_t)j * ls); }
+            if (k0 + kPre + j < n_low) { tn[j] = rd.ldT(off0 + (uint32_t)j * ls); tdn[j] = rd.ldTd(off0 + (uint32_t)j * ls); }
 #pragma unroll
         for (int j = 0; j < kPre; ++j) {
             const int k = k0 + j;
@@ -406,7 +408,7 @@ XP_HD unsigned suite_column6(const Rd &rd, const Cf &cf, const Prep &pr, const T
     Setup6 u_sb, u_ml, u_mu;
     auto lev = [&](int k, float &t, float &td) {
         if (k < n_stash) stash.get(k, t, td);
-        else { t = rd.T(k); td = rd.Td(k); }
+        else { const uint32_t o_ = rd.off0() + (uint32_t)k * ls; t = rd.ldT(o_); td = rd.ldTd(o_); }
     };
     double mp_t = 0.0, mp_td = 0.0;
     if (KINDS & 1u) setup6_a(pr.p0, (double)t_sfc, (double)td_sfc, sb, u_sb);
@@ -446,9 +448,9 @@ XP_HD unsigned suite_column6(const Rd &rd, const Cf &cf, const Prep &pr, const T
     // with a stash the first n_stash levels come from it (n_stash = n_low >= it_b), the rest from the
     // global prefetch pipeline, which was started at level n_stash
     const int it_c = fs ? max(it_b, min(n_stash, nt)) : it_b;
-    sweep_segment6<KINDS & 5u, true>(s, crow, stash, fs, 1, it_a, nt, sb, ml, mu);
-    sweep_segment6<KINDS, true>(s, crow, stash, fs, it_a, it_c, nt, sb, ml, mu);
-    sweep_segment6<KINDS, false>(s, crow, stash, false, it_c, nt, nt, sb, ml, mu);
+    sweep_segment6<KINDS & 5u, true>(rd, s, crow, stash, fs, 1, it_a, nt, sb, ml, mu);
+    sweep_segment6<KINDS, true>(rd, s, crow, stash, fs, it_a, it_c, nt, sb, ml, mu);
+    sweep_segment6<KINDS, false>(rd, s, crow, stash, false, it_c, nt, nt, sb, ml, mu);
     // last iteration: no level `nt`; every parcel that is not bound for the exact path is above its LCL
     {
         const float big = 1e30f;
