@@ -35,9 +35,10 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile the CUDA sources into xarray_parcel_b200/libxparcel.so.  Returns the path."""
-    if not force and not is_stale():
+def build(force=False, verbose=False, extra_flags=(), lib_out=None):
+    """Compile the CUDA sources into xarray_parcel_b200/libxparcel.so.  Returns the path.
+    `extra_flags` / `lib_out` build an experimental variant next to it (A/B runs: XP_LIB_PATH selects it)."""
+    if lib_out is None and not force and not is_stale():
         return LIB_PATH
     nvcc = find_nvcc()
     objdir = os.path.join(HERE, "build")
@@ -45,7 +46,7 @@ def build(force=False, verbose=False):
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", f".{os.getpid()}.o"))
-        cmd = [nvcc] + NVCC_COMMON + PER_FILE_FLAGS.get(src, []) + (["-Xptxas", "-v"] if verbose else [])
+        cmd = [nvcc] + NVCC_COMMON + PER_FILE_FLAGS.get(src, []) + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
         cmd += ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
     objs, log = [], ""
@@ -55,16 +56,17 @@ def build(force=False, verbose=False):
         if pr.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n" + out + err)
         objs.append(obj)
-    tmp = LIB_PATH + f".tmp{os.getpid()}"
+    target = lib_out or LIB_PATH
+    tmp = target + f".tmp{os.getpid()}"
     res = subprocess.run([nvcc] + LINK_FLAGS + ["-o", tmp] + objs, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
-    os.replace(tmp, LIB_PATH)
+    os.replace(tmp, target)
     for o in objs:
         os.remove(o)
     if verbose:
         print(log)
-    return LIB_PATH
+    return target
 
 
 if __name__ == "__main__":

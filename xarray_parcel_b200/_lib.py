@@ -77,7 +77,7 @@ def load_library():
     with _lib_lock:
         if _lib is not None:
             return _lib
-        path = _build.LIB_PATH
+        path = os.environ.get("XP_LIB_PATH") or _build.LIB_PATH      # XP_LIB_PATH: an experimental build (A/B runs)
         if not os.path.exists(path):
             raise XparcelError(f"{path} is missing: build the CUDA library first "
                                "(python -m xarray_parcel_b200._build); there is no CPU fallback")

@@ -352,55 +352,44 @@ XP_HD unsigned suite_column6(const Rd &rd, const Cf &cf, const Prep &pr, const T
         s.off += ls; s.k_pf = k0 + 1;
     }
     // ---- pre-pass over the lowest levels: mixed-layer means (float64) and most-unstable argmax ----
+    // (a rolled loop -- the float64 code below is long and every copy of it costs instruction-cache misses;
+    //  the levels are asked for up front as L2 prefetches and then loaded one level ahead)
     double sum_th = 0.0, sum_w = 0.0;
-    float best = -1e30f, second = -1e30f, mu_t = 0.0f, mu_td = 0.0f, t_sfc = 0.0f, td_sfc = 0.0f;
+    float best = -1e30f, second = -1e30f, mu_t = 0.0f, mu_td = 0.0f;
     int k_mu = 0;
     uint32_t off0 = rd.off0();
-    constexpr int kPre = 4;
-    float tq[kPre], tdq[kPre], tn[kPre], tdn[kPre];
-#pragma unroll
-    for (int j = 0; j < kPre; ++j) {
-        tn[j] = tdn[j] = 0.0f;
-        if (j < n_low) { tn[j] = rd.ldT(off0 + (uint32_t)j * ls); tdn[j] = rd.ldTd(off0 + (uint32_t)j * ls); }
-    }
-    for (int k0 = 0; k0 < n_low; k0 += kPre) {
-#pragma unroll
-        for (int j = 0; j < kPre; ++j) { tq[j] = tn[j]; tdq[j] = tdn[j]; }
-        off0 += (uint32_t)kPre * ls;
-#pragma unroll
-        for (int j = 0; j < kPre; ++j)
-            if (k0 + kPre + j < n_low) { tn[j] = rd.ldT(off0 + (uint32_t)j * ls); tdn[j] = rd.ldTd(off0 + (uint32_t)j * ls); }
-#pragma unroll
-        for (int j = 0; j < kPre; ++j) {
-            const int k = k0 + j;
-            if (k >= n_low) break;
-            const float t = tq[j], td = tdq[j];
-            if (k == 0) { t_sfc = t; td_sfc = td; }
-            if (k < n_stash) stash.put(k, t, td);
-            nanacc = f_fma(t, 0.0f, f_fma(td, 0.0f, nanacc));
-            const float p = pr.p[k];
-            const float e = f_es(td);
-            const float ipe = f_rcp(p - e);
-            const float r = kEpsF * e * ipe;                 // saturation mixing ratio of the dewpoint (PF:258)
-            if ((KINDS & 2u) && k < pr.n_ml_w) {
-                // mixed_parcel PF:253-258 in float64 (see suite_column)
-                const double e64 = sat_vapor_pressure((double)td);
-                sum_th += pr.mlw[k] * ((double)t * pr.thfac[k]);
-                sum_w += pr.mlw[k] * (kEps * e64 / (pr.p64[k] - e64));
-            }
-            if ((KINDS & 4u) && k < pr.K_mu) {
-                // ln(theta_e), Bolton (1980) eq. 39 as in metpy.calc.equivalent_potential_temperature (PF:123)
-                const float l2t = f_lg2(t), l2td = f_lg2(td);
-                const float t_l = 56.0f + f_rcp(f_rcp(td - 56.0f) + (l2t - l2td) * (kLn2 / 800.0f));
-                const float it_l = f_rcp(t_l);
-                float v = l2t * kLn2;                                                   // ln T
-                v = f_fma((float)kKappa * kLn2, f_lg2(1000.0f * ipe), v);               // + kappa ln(1000/(p-e))
-                v = f_fma(0.28f * r * kLn2, l2t - f_lg2(t_l), v);                       // + 0.28 r ln(T/t_l)
-                v = f_fma(r * f_fma(0.448f, r, 1.0f), f_fma(3036.0f, it_l, -1.78f), v);
-                nanacc = f_fma(v, 0.0f, nanacc);
-                if (v > best) { second = best; best = v; k_mu = k; mu_t = t; mu_td = td; }   // ties: larger p (PF:128)
-                else if (v > second) second = v;
-            }
+    for (int k = 1; k < n_low; ++k) rd.prefetch(off0 + (uint32_t)k * ls);
+    const float t_sfc = rd.ldT(off0), td_sfc = rd.ldTd(off0);
+    float t_nx = t_sfc, td_nx = td_sfc;
+#pragma unroll 1
+    for (int k = 0; k < n_low; ++k) {
+        const float t = t_nx, td = td_nx;
+        off0 += ls;
+        if (k + 1 < n_low) { t_nx = rd.ldT(off0); td_nx = rd.ldTd(off0); }
+        if (k < n_stash) stash.put(k, t, td);
+        nanacc = f_fma(t, 0.0f, f_fma(td, 0.0f, nanacc));
+        const float p = pr.p[k];
+        const float e = f_es(td);
+        const float ipe = f_rcp(p - e);
+        const float r = kEpsF * e * ipe;                 // saturation mixing ratio of the dewpoint (PF:258)
+        if ((KINDS & 2u) && k < pr.n_ml_w) {
+            // mixed_parcel PF:253-258 in float64 (see suite_column)
+            const double e64 = sat_vapor_pressure((double)td);
+            sum_th += pr.mlw[k] * ((double)t * pr.thfac[k]);
+            sum_w += pr.mlw[k] * (kEps * e64 / (pr.p64[k] - e64));
+        }
+        if ((KINDS & 4u) && k < pr.K_mu) {
+            // ln(theta_e), Bolton (1980) eq. 39 as in metpy.calc.equivalent_potential_temperature (PF:123)
+            const float l2t = f_lg2(t), l2td = f_lg2(td);
+            const float t_l = 56.0f + f_rcp(f_rcp(td - 56.0f) + (l2t - l2td) * (kLn2 / 800.0f));
+            const float it_l = f_rcp(t_l);
+            float v = l2t * kLn2;                                                   // ln T
+            v = f_fma((float)kKappa * kLn2, f_lg2(1000.0f * ipe), v);               // + kappa ln(1000/(p-e))
+            v = f_fma(0.28f * r * kLn2, l2t - f_lg2(t_l), v);                       // + 0.28 r ln(T/t_l)
+            v = f_fma(r * f_fma(0.448f, r, 1.0f), f_fma(3036.0f, it_l, -1.78f), v);
+            nanacc = f_fma(v, 0.0f, nanacc);
+            if (v > best) { second = best; best = v; k_mu = k; mu_t = t; mu_td = td; }   // ties: larger p (PF:128)
+            else if (v > second) second = v;
         }
     }
     // ---- parcels: staged so that the LCL solves, the gathers and their consumers overlap --------------
