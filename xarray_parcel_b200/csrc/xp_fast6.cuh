@@ -374,9 +374,11 @@ XP_HD unsigned suite_column6(const Rd &rd, const Cf &cf, const Prep &pr, const T
         const float r = kEpsF * e * ipe;                 // saturation mixing ratio of the dewpoint (PF:258)
         if ((KINDS & 2u) && k < pr.n_ml_w) {
             // mixed_parcel PF:253-258 in float64 (see suite_column)
-            const double e64 = sat_vapor_pressure((double)td);
+            // (reciprocals by float32-seeded Newton steps, ~1e-16 relative: no IEEE division)
+            const double tdd = (double)td;
+            const double e64 = kSat0 * exp(17.67 * (tdd - 273.15) * rcp64(tdd - 29.65));
             sum_th += pr.mlw[k] * ((double)t * pr.thfac[k]);
-            sum_w += pr.mlw[k] * (kEps * e64 / (pr.p64[k] - e64));
+            sum_w += pr.mlw[k] * (kEps * e64 * rcp64(pr.p64[k] - e64));
         }
         if ((KINDS & 4u) && k < pr.K_mu) {
             // ln(theta_e), Bolton (1980) eq. 39 as in metpy.calc.equivalent_potential_temperature (PF:123)
