@@ -208,6 +208,29 @@ def test_fast_path_vs_exact_path(ctx, gpu_tables):
     assert torch.equal(a["sb"]["cape"].view(torch.int32), b["sb"]["cape"].view(torch.int32))
 
 
+@pytest.mark.parametrize("depths", [(100.0, 300.0), (400.0, 100.0), (60.0, 60.0)], ids=lambda d: f"ml{d[0]:.0f}-mu{d[1]:.0f}")
+def test_fast_path_kind_pairs_and_depths(ctx, depths):
+    """Shared-axis fast path (v6 sweep, xp_fast6.cuh): every pair of parcel kinds is bit-identical to the
+    three-kind call (the sweep segments differ with the set of live parcels), for the default layer depths
+    and for depths that reorder / merge the segment bounds (mixed layer deeper than the most-unstable
+    search); and the three-kind call agrees with the float64 exact kernel."""
+    p, t, td = synth.era5_columns(60_000, seed=91, device="cuda", nan_columns=0.002)
+    opts = dict(mixed_layer_depth=depths[0], most_unstable_depth=depths[1])
+    full = ctx.cape_cin(p, t, td, kinds=("sb", "ml", "mu"), options=_lib.make_options(**opts))
+    assert 0 <= ctx.last_exact_count() < 0.05 * t.shape[1]
+    for pair in (("sb", "ml"), ("sb", "mu"), ("ml", "mu")):
+        two = ctx.cape_cin(p, t, td, kinds=pair, options=_lib.make_options(**opts))
+        for kind in pair:
+            for f in _lib.SCALAR_FIELDS:
+                assert torch.equal(two[kind][f].view(torch.int32), full[kind][f].view(torch.int32)), (pair, kind, f)
+            assert torch.equal(two[kind]["level_shift"], full[kind]["level_shift"])
+    exact = ctx.cape_cin(p, t, td, kinds=("sb", "ml", "mu"), options=_lib.make_options(exact_only=True, **opts))
+    for kind in ("sb", "ml", "mu"):
+        ex = {kind + "_" + f: exact[kind][f].double().cpu().numpy() for f in FIELDS}
+        _check(full[kind], ex, kind + "_", "fast", what=f"fast vs exact {depths}: ")
+        assert torch.equal(full[kind]["level_shift"], exact[kind]["level_shift"])
+
+
 def test_single_kind_calls_equal_suite(ctx):
     """xp_cape_cin per kind == xp_suite (bit-exact)."""
     p, t, td = synth.model_level_columns(5000, 70, seed=21, device="cuda")
