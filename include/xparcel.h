@@ -208,6 +208,51 @@ xp_status xp_level_crossing(xp_context *ctx, const void *coords, int64_t coords_
                             int32_t n_levels, int64_t n_columns, int32_t dtype, double level,
                             void *output, void *stream);
 
+/* ---- pointwise helpers around the hot path (callers and front end) -----------------
+ * All arrays hold `n` points of `dtype` in device memory (any shape, flattened); one thread per point. */
+
+/* metpy.calc.dewpoint_from_specific_humidity as the reference calls it in conv_properties /
+ * min_conv_properties (PF:1889, 1969).  metpy_compat = 141: via relative humidity (MetPy 1.4.1);
+ * 162: via the vapour pressure (MetPy >= 1.6, environment_changes_eval.ipynb:278). */
+xp_status xp_dewpoint_from_specific_humidity(xp_context *ctx, const void *pressure, const void *temperature,
+                                             const void *specific_humidity, int64_t n, int32_t dtype,
+                                             int32_t metpy_compat, void *dewpoint, void *stream);
+/* metpy.calc.saturation_mixing_ratio(pressure, temperature) (PF:258; mu_mixing_ratio PF:2047-2053). */
+xp_status xp_saturation_mixing_ratio(xp_context *ctx, const void *pressure, const void *temperature, int64_t n,
+                                     int32_t dtype, void *mixing_ratio, void *stream);
+/* dry_lapse (PF:291-316): parcel_temperature * (pressure / parcel_pressure) ** kappa, all three [n]. */
+xp_status xp_dry_lapse(xp_context *ctx, const void *pressure, const void *parcel_temperature,
+                       const void *parcel_pressure, int64_t n, int32_t dtype, void *temperature, void *stream);
+/* mixing_ratio (PF:684-710): relative humidity from the dewpoint, then the mixing ratio from it
+ * (metpy_compat 141 / 162: the two MetPy forms of mixing_ratio_from_relative_humidity). */
+xp_status xp_mixing_ratio(xp_context *ctx, const void *temperature, const void *dewpoint, const void *pressure,
+                          int64_t n, int32_t dtype, int32_t metpy_compat, void *mixing_ratio, void *stream);
+/* virtual_temperature (PF:782-804): temperature * (1 + epsilon * mixing_ratio), epsilon = 0.608 in the reference. */
+xp_status xp_virtual_temperature(xp_context *ctx, const void *temperature, const void *mixing_ratio, int64_t n,
+                                 int32_t dtype, double epsilon, void *virtual_temperature, void *stream);
+/* wet_bulb_temperature (PF:389-445, Normand's rule): lcl (PF:609-682) of every point, then moist_lapse
+ * (PF:525-607, lookup tables) from the LCL back to the point's pressure.  Needs the tables. */
+xp_status xp_wet_bulb_temperature(xp_context *ctx, const void *pressure, const void *temperature,
+                                  const void *dewpoint, int64_t n, int32_t dtype, void *wet_bulb, void *stream);
+/* significant_hail_parameter (PF:2261-2306): units as the reference's arguments (mixing ratio kg/kg,
+ * lapse K/km negative for decreasing temperature, temp_500 K, shear m/s, flh m). */
+xp_status xp_significant_hail_parameter(xp_context *ctx, const void *mucape, const void *mixing_ratio,
+                                        const void *lapse, const void *temp_500, const void *shear,
+                                        const void *flh, int64_t n, int32_t dtype, void *ship, void *stream);
+/* storm_proxies (PF:2323-2407) on the variables conv_properties returns. */
+typedef struct xp_proxy_inputs {
+    const void *mixed_100_cape, *mixed_50_cape, *mu_cape, *shear_magnitude;
+    const void *mixed_100_lifted_index, *mixed_100_dci;
+    const void *positive_shear;            /* `dtype` values, 0 = false (NaN counts as true, like NumPy) */
+    const void *mixed_50_cin, *mixed_100_cin, *lapse_rate_700_500, *mu_mixing_ratio, *temp_500, *freezing_level;
+} xp_proxy_inputs;
+typedef struct xp_proxy_outputs {          /* uint8 [n] each, 1 = proxy triggered; any may be NULL */
+    uint8_t *craven2004, *kunz2007, *trapp2007, *marsh2009, *allen2011, *allen2014, *eccel2012, *mohr2013, *ship_0_1;
+    void *ship;                            /* `dtype` [n] */
+} xp_proxy_outputs;
+xp_status xp_storm_proxies(xp_context *ctx, const xp_proxy_inputs *in, int64_t n, int32_t dtype,
+                           const xp_proxy_outputs *out, void *stream);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* Number of kernels this library has launched on ctx since creation. */
 uint64_t xp_launch_count(const xp_context *ctx);

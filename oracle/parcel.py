@@ -709,6 +709,69 @@ def wet_bulb_temperature_fast(temperature, dewpoint):
     return temperature - (1 / 3) * (temperature - dewpoint)
 
 
+def wet_bulb_temperature(pressure, temperature, dewpoint, opts):
+    """PF:389-445 (Normand's rule): lcl of every point, then moist_lapse from the LCL back to the point's
+    pressure.  The reference loops over levels and calls moist_lapse on one level at a time; per point that
+    is ``opts.moist_lapse(p, lcl_t, lcl_p)`` with a one-level profile."""
+    shp = np.shape(temperature)
+    p = np.broadcast_to(np.asarray(pressure, dtype=np.float64), shp).ravel()
+    t = np.asarray(temperature, dtype=np.float64).ravel()
+    td = np.asarray(dewpoint, dtype=np.float64).ravel()
+    out = np.full(p.shape, np.nan)
+    ok = ~(np.isnan(p) | np.isnan(t) | np.isnan(td))
+    if ok.any():
+        l = lcl(p[ok], t[ok], td[ok], opts)
+        out[ok] = opts.moist_lapse(p[ok][None, :], l["lcl_temperature"], l["lcl_pressure"])[0]
+    return out.reshape(shp)
+
+
+def significant_hail_parameter(mucape, mixing_ratio, lapse, temp_500, shear, flh):
+    """PF:2261-2306, xarray ``.where(cond, other)`` semantics (a failed comparison, also with NaN, takes
+    ``other``; without ``other`` it gives NaN)."""
+    with np.errstate(invalid="ignore"):
+        mixing_ratio = mixing_ratio * 1e3
+        lapse = -lapse
+        temp_500 = temp_500 - 273.15
+        shear = where(shear >= 7, shear)
+        shear = where(shear <= 27, shear)
+        mixing_ratio = where(mixing_ratio >= 11, mixing_ratio)
+        mixing_ratio = where(mixing_ratio <= 13.6, mixing_ratio)
+        temp_500 = where(temp_500 <= -5.5, temp_500, -5.5)
+        ship = mucape * mixing_ratio * lapse * -temp_500 * shear / 42000000
+        ship = where(mucape >= 1300, ship, ship * (mucape / 1300))
+        ship = where(lapse >= 5.8, ship, ship * (lapse / 5.8))
+        ship = where(flh >= 2400, ship, ship * (flh / 2400))
+    return ship
+
+
+def storm_proxies(dat):
+    """PF:2323-2407 on a dict of [N] arrays as conv_properties returns them."""
+    with np.errstate(invalid="ignore"):
+        s06 = dat["shear_magnitude"]
+        ml100 = where(dat["mixed_100_cape"] >= 0, dat["mixed_100_cape"])
+        ml50 = where(dat["mixed_50_cape"] >= 0, dat["mixed_50_cape"])
+        mu = where(dat["mu_cape"] >= 0, dat["mu_cape"])
+        out = {}
+        out["proxy_Craven2004"] = (ml100 * s06) >= 20000
+        out["proxy_Kunz2007"] = np.logical_or(dat["mixed_100_lifted_index"] <= -2.07,
+                                              np.logical_or(mu >= 1474, dat["mixed_100_dci"] >= 25.7))
+        tr = np.logical_and(ml100 * s06 >= 10000, ml100 >= 100)
+        tr = np.logical_and(tr, s06 >= 5)
+        out["proxy_Trapp2007"] = np.logical_and(tr, dat["positive_shear"])
+        out["proxy_Marsh2009"] = (ml100 * s06) >= 10000
+        out["proxy_Allen2011"] = ml50 * s06 ** 1.67 >= 25000
+        al = np.logical_and(out["proxy_Allen2011"], dat["mixed_50_cin"] > -25)
+        al = np.logical_and(al, s06 > 7.5)
+        out["proxy_Allen2014"] = np.logical_and(al, dat["lapse_rate_700_500"] < -6.5)
+        out["proxy_Eccel2012"] = np.logical_and(ml100 * s06 > 10000, dat["mixed_100_cin"] > -50)
+        mo = np.logical_or(dat["mixed_100_lifted_index"] <= -1.6, ml100 >= 439)
+        out["proxy_Mohr2013"] = np.logical_or(mo, dat["mixed_100_dci"] >= 26.4)
+        out["ship"] = significant_hail_parameter(mu, dat["mu_mixing_ratio"], dat["lapse_rate_700_500"],
+                                                 dat["temp_500"], s06, dat["freezing_level"])
+        out["proxy_SHIP_0.1"] = out["ship"] > 0.1
+    return out
+
+
 def wind_shear(surface_wind_u, surface_wind_v, wind_u, wind_v, height, shear_height=6000):
     """PF:2216-2259."""
     N = wind_u.shape[1]

@@ -139,3 +139,89 @@ def test_conv_properties_assembly(ctx, compat):
                 assert np.array_equal(np.isnan(g), np.isnan(v)), k
                 ok = ~np.isnan(v)
                 assert np.allclose(g[ok], v[ok], rtol=1e-8, atol=1e-8), k
+
+
+# ---- pointwise kernels ------------------------------------------------------------------
+def test_pointwise_thermo_against_oracle(ctx):
+    """dry_lapse PF:291-316, mixing_ratio PF:684-710, virtual_temperature PF:782-804, q -> Td (PF:1889,
+    1969; both MetPy forms) and the saturation mixing ratio, through the reference-facing functions."""
+    from oracle import thermo as th
+    P, T, D, _ = _cols(n=3000, L=40, nan_columns=0.05)
+    for compat in ("1.4.1", "1.6.2"):
+        w = th.mixing_ratio_from_t_td(T, D, P, compat)
+        _same(parcel.mixing_ratio(T, D, P, metpy_compat=compat), w, rtol=1e-12)
+        q = w / (1 + w)
+        _same(parcel.dewpoint_from_specific_humidity(P, T, q, metpy_compat=compat),
+              th.dewpoint_from_specific_humidity(P, T, q, compat), rtol=1e-12)
+    _same(parcel.virtual_temperature(T, w), th.virtual_temperature(T, w), rtol=1e-15)
+    _same(parcel.dry_lapse(P, T[0], P[0]), th.dry_lapse(P, T[0][None, :], P[0][None, :]), rtol=1e-13)
+    _same(parcel.dry_lapse(P, T[0]), th.dry_lapse(P, T[0][None, :], np.max(P, axis=0, keepdims=True)), rtol=1e-13)
+    _same(ctx.saturation_mixing_ratio(torch.from_numpy(P).cuda(), torch.from_numpy(D).cuda()).cpu().numpy(),
+          th.saturation_mixing_ratio(P, D), rtol=1e-13)
+    # float32 tensors on the device stay float32 tensors on the device
+    r = parcel.mixing_ratio(torch.from_numpy(T).float().cuda(), torch.from_numpy(D).float().cuda(),
+                            torch.from_numpy(P).float().cuda())
+    assert r.is_cuda and r.dtype == torch.float32
+    w141 = th.mixing_ratio_from_t_td(T, D, P, "1.4.1")
+    ok = ~np.isnan(w141)
+    assert np.allclose(r.cpu().numpy()[ok], w141[ok], rtol=2e-5)    # float32 inputs (T, Td rounded to ~2e-5 K)
+
+
+def test_wet_bulb_temperature_against_oracle(ctx, ):
+    """wet_bulb_temperature PF:389-445 (Normand's rule) = lcl + moist_lapse on the lookup tables per point."""
+    idx, cur = ctx.tables_get()
+    pl, tl = otab.default_grids()
+    opts = op.Options(op.MoistLapseLUT(otab.AdiabatTables(pl, tl, idx, cur)), lcl_mode="converged")
+    P, T, D, H = _cols(n=600, L=30, seed=9, nan_columns=0.05)
+    ora = op.wet_bulb_temperature(P, T, D, opts)
+    got = parcel.wet_bulb_temperature(P, T, D)
+    a = np.asarray(got)
+    assert np.array_equal(np.isnan(a), np.isnan(ora))
+    ok = ~np.isnan(ora)
+    # the table cell of an LCL within rounding of a cell edge may differ: one 0.02 K adiabat step at most
+    assert np.abs(a[ok] - ora[ok]).max() < 0.05
+    assert (np.abs(a[ok] - ora[ok]) > 1e-9).mean() < 1e-3
+    # between dewpoint and temperature, up to the table resolution (the nearest 0.5 hPa node is coarse aloft)
+    low = ok & (P > 400.0)
+    assert (a[low] <= T[low] + 0.1).all() and (a[low] >= D[low] - 0.1).all()
+    ml, wb = parcel.melting_level_height(P, T, D, H, fast=False)
+    _same(np.asarray(wb), a)
+    _same(np.asarray(ml), op.freezing_level_height(a, H), rtol=1e-12)
+
+
+def _proxy_fields(n, seed):
+    rng = np.random.default_rng(seed)
+    f = {"mixed_100_cape": rng.uniform(-50, 3000, n), "mixed_50_cape": rng.uniform(-50, 3000, n),
+         "mu_cape": rng.uniform(-50, 4000, n), "shear_magnitude": rng.uniform(0, 40, n),
+         "mixed_100_lifted_index": rng.uniform(-8, 6, n), "mixed_100_dci": rng.uniform(0, 45, n),
+         "positive_shear": (rng.uniform(0, 1, n) > 0.3).astype(np.float64),
+         "mixed_50_cin": rng.uniform(-100, 0, n), "mixed_100_cin": rng.uniform(-120, 0, n),
+         "lapse_rate_700_500": rng.uniform(-9, -4, n), "mu_mixing_ratio": rng.uniform(0.004, 0.018, n),
+         "temp_500": rng.uniform(250, 272, n), "freezing_level": rng.uniform(1000, 5000, n)}
+    for k in f:                       # NaNs everywhere, threshold values exactly hit
+        f[k][rng.uniform(0, 1, n) < 0.03] = np.nan
+    f["shear_magnitude"][:6] = [7.0, 27.0, 5.0, 7.5, 6.999, 27.001]
+    f["mu_cape"][6:9] = [1300.0, 1474.0, 1299.0]
+    f["freezing_level"][9:11] = [2400.0, 2399.0]
+    f["mu_mixing_ratio"][11:15] = [0.011, 0.0136, 0.0109, 0.01361]
+    return f
+
+
+def test_significant_hail_parameter_and_storm_proxies(ctx):
+    """significant_hail_parameter PF:2261-2306 and storm_proxies PF:2323-2407: flags bit-exact, SHIP to
+    rounding, NaN inputs and values exactly on the thresholds included."""
+    f = _proxy_fields(20_000, 4)
+    ora = op.storm_proxies(f)
+    got = parcel.storm_proxies(f)
+    for k in _lib.PROXY_FLAGS:
+        assert np.array_equal(np.asarray(got[k]).astype(bool), np.asarray(ora[k]).astype(bool)), k
+    _same(got["ship"], ora["ship"], rtol=1e-14)
+    ship = parcel.significant_hail_parameter(f["mu_cape"], f["mu_mixing_ratio"], f["lapse_rate_700_500"],
+                                             f["temp_500"], f["shear_magnitude"], f["freezing_level"])
+    _same(ship, op.significant_hail_parameter(f["mu_cape"], f["mu_mixing_ratio"], f["lapse_rate_700_500"],
+                                              f["temp_500"], f["shear_magnitude"], f["freezing_level"]), rtol=1e-14)
+    # device tensors in, device tensors out
+    dev = {k: torch.from_numpy(v).cuda() for k, v in f.items()}
+    got = parcel.storm_proxies(dev)
+    assert got["proxy_Kunz2007"].is_cuda and got["proxy_Kunz2007"].dtype == torch.bool
+    assert np.array_equal(got["proxy_Allen2014"].cpu().numpy(), ora["proxy_Allen2014"])

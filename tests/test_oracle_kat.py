@@ -428,3 +428,55 @@ def test_derived_index_restatements():
     assert_almost_equal(ws["shear_v"], -6.0, 9)
     assert ws["positive_shear"].all()
     assert_almost_equal(op.wet_bulb_temperature_fast(t, td), t - 4.0 / 3.0, 12)                     # PF:364-387
+
+
+def test_significant_hail_parameter_hand_values():
+    """PF:2261-2306 against values worked by hand from the SPC formula the reference cites
+    (https://www.spc.noaa.gov/exper/mesoanalysis/help/help_sigh.html)."""
+    from oracle import parcel as op
+    # all thresholds met: SHIP = 2500 * 12 * 7 * 15 * 20 / 42e6 = 1.5
+    one = lambda v: np.array([float(v)])
+    s = op.significant_hail_parameter(one(2500), one(0.012), one(-7.0), one(258.15), one(20), one(3000))
+    assert abs(s[0] - 1.5) < 1e-12
+    # MUCAPE < 1300 scales by MUCAPE/1300; lapse < 5.8 by lapse/5.8; freezing level < 2400 by flh/2400
+    s = op.significant_hail_parameter(one(650), one(0.012), one(-5.0), one(258.15), one(20), one(1200))
+    base = 650 * 12 * 5.0 * 15 * 20 / 42e6
+    assert abs(s[0] - base * 0.5 * (5.0 / 5.8) * 0.5) < 1e-12
+    # T500 warmer than -5.5 C is taken as -5.5 C (also when it is NaN); shear / mixing ratio outside their windows -> NaN
+    s = op.significant_hail_parameter(one(2500), one(0.012), one(-7.0), one(270.15), one(20), one(3000))
+    assert abs(s[0] - 2500 * 12 * 7 * 5.5 * 20 / 42e6) < 1e-12
+    s = op.significant_hail_parameter(one(2500), one(0.012), one(-7.0), one(np.nan), one(20), one(3000))
+    assert abs(s[0] - 2500 * 12 * 7 * 5.5 * 20 / 42e6) < 1e-12
+    for shear, mr in ((6.9, 0.012), (27.1, 0.012), (20, 0.0109), (20, 0.0137)):
+        assert np.isnan(op.significant_hail_parameter(one(2500), one(mr), one(-7.0), one(258.15), one(shear), one(3000))[0])
+
+
+def test_storm_proxies_hand_values():
+    """PF:2323-2407: one column per proxy, triggered exactly at its published threshold."""
+    from oracle import parcel as op
+    base = {"mixed_100_cape": 0.0, "mixed_50_cape": 0.0, "mu_cape": 0.0, "shear_magnitude": 0.0,
+            "mixed_100_lifted_index": 5.0, "mixed_100_dci": 0.0, "positive_shear": 1.0, "mixed_50_cin": -100.0,
+            "mixed_100_cin": -100.0, "lapse_rate_700_500": -5.0, "mu_mixing_ratio": 0.005, "temp_500": 260.0,
+            "freezing_level": 3000.0}
+
+    def run(**kw):
+        d = {k: np.array([float(kw.get(k, v))]) for k, v in base.items()}
+        return {k: v[0] for k, v in op.storm_proxies(d).items()}
+
+    none = run()
+    assert not any(bool(none[k]) for k in none if k.startswith("proxy_"))
+    assert run(mixed_100_cape=1000, shear_magnitude=20)["proxy_Craven2004"]
+    assert not run(mixed_100_cape=999, shear_magnitude=20)["proxy_Craven2004"]
+    assert run(mixed_100_lifted_index=-2.07)["proxy_Kunz2007"] and run(mu_cape=1474)["proxy_Kunz2007"]
+    assert run(mixed_100_dci=25.7)["proxy_Kunz2007"] and not run(mixed_100_dci=25.6)["proxy_Kunz2007"]
+    assert run(mixed_100_cape=1000, shear_magnitude=10)["proxy_Trapp2007"]
+    assert not run(mixed_100_cape=1000, shear_magnitude=10, positive_shear=0)["proxy_Trapp2007"]
+    assert run(mixed_100_cape=1000, shear_magnitude=10)["proxy_Marsh2009"]
+    assert run(mixed_50_cape=25000 / 10 ** 1.67 + 1e-9, shear_magnitude=10)["proxy_Allen2011"]
+    assert run(mixed_50_cape=1000, shear_magnitude=10, mixed_50_cin=-20, lapse_rate_700_500=-7)["proxy_Allen2014"]
+    assert not run(mixed_50_cape=1000, shear_magnitude=7.5, mixed_50_cin=-20, lapse_rate_700_500=-7)["proxy_Allen2014"]
+    assert run(mixed_100_cape=1001, shear_magnitude=10, mixed_100_cin=-49)["proxy_Eccel2012"]
+    assert run(mixed_100_cape=439)["proxy_Mohr2013"] and run(mixed_100_dci=26.4)["proxy_Mohr2013"]
+    # negative CAPE is ignored (NaN): no proxy from it
+    assert not run(mixed_100_cape=-5, shear_magnitude=-5000)["proxy_Craven2004"]
+    assert run(mu_cape=2500, mu_mixing_ratio=0.012, lapse_rate_700_500=-7, temp_500=258.15, shear_magnitude=20)["proxy_SHIP_0.1"]

@@ -59,7 +59,23 @@ EXPORTS = ["xp_version", "xp_create", "xp_destroy", "xp_last_error", "xp_take_fl
            "xp_tables_loaded", "xp_cape_cin", "xp_suite", "xp_lcl", "xp_moist_lapse",
            "xp_parcel_profile", "xp_lfc_el", "xp_cape_cin_base", "xp_launch_count",
            "xp_last_kernel_ms", "xp_last_exact_count", "xp_interp_levels",
-           "xp_level_crossing"]
+           "xp_level_crossing", "xp_dewpoint_from_specific_humidity", "xp_saturation_mixing_ratio",
+           "xp_dry_lapse", "xp_mixing_ratio", "xp_virtual_temperature", "xp_wet_bulb_temperature",
+           "xp_significant_hail_parameter", "xp_storm_proxies"]
+
+PROXY_INPUTS = ["mixed_100_cape", "mixed_50_cape", "mu_cape", "shear_magnitude", "mixed_100_lifted_index",
+                "mixed_100_dci", "positive_shear", "mixed_50_cin", "mixed_100_cin", "lapse_rate_700_500",
+                "mu_mixing_ratio", "temp_500", "freezing_level"]
+PROXY_FLAGS = ["proxy_Craven2004", "proxy_Kunz2007", "proxy_Trapp2007", "proxy_Marsh2009", "proxy_Allen2011",
+               "proxy_Allen2014", "proxy_Eccel2012", "proxy_Mohr2013", "proxy_SHIP_0.1"]
+
+
+class XpProxyInputs(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in PROXY_INPUTS]
+
+
+class XpProxyOutputs(ctypes.Structure):
+    _fields_ = [(f"flag{i}", c_void_p) for i in range(9)] + [("ship", c_void_p)]
 
 
 class XparcelError(RuntimeError):
@@ -120,6 +136,19 @@ def load_library():
                                          c_void_p, c_double, c_int32, c_void_p]
         lib.xp_level_crossing.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32,
                                           c_int64, c_int32, c_double, c_void_p, c_void_p]
+        lib.xp_dewpoint_from_specific_humidity.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                                           c_int32, c_void_p, c_void_p]
+        lib.xp_saturation_mixing_ratio.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
+        lib.xp_dry_lapse.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
+        lib.xp_mixing_ratio.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p,
+                                        c_void_p]
+        lib.xp_virtual_temperature.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_double, c_void_p,
+                                               c_void_p]
+        lib.xp_wet_bulb_temperature.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p,
+                                                c_void_p]
+        lib.xp_significant_hail_parameter.argtypes = [c_void_p] + [c_void_p] * 6 + [c_int64, c_int32, c_void_p, c_void_p]
+        lib.xp_storm_proxies.argtypes = [c_void_p, ctypes.POINTER(XpProxyInputs), c_int64, c_int32,
+                                         ctypes.POINTER(XpProxyOutputs), c_void_p]
         lib.xp_launch_count.argtypes = [c_void_p]
         lib.xp_launch_count.restype = ctypes.c_uint64
         lib.xp_last_kernel_ms.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_float)]
@@ -439,6 +468,68 @@ class Context:
                                         out.data_ptr(), self._stream())
         self._check(st, "xp_level_crossing")
         return out
+
+
+    # ---- pointwise helpers (device tensors of one shape and dtype) -------------------------------------
+    def _pointwise(self, fn_name, inputs, extra=()):
+        """Call lib.<fn_name>(ctx, *inputs, n, dtype, *extra, out, stream) on broadcast, contiguous inputs."""
+        dt = inputs[0].dtype
+        xs = [x.to(dt) for x in inputs]
+        xs = [x.contiguous() for x in torch.broadcast_tensors(*xs)]
+        out = torch.empty_like(xs[0])
+        st = getattr(self.lib, fn_name)(self.handle, *[x.data_ptr() for x in xs], xs[0].numel(), _dtype_code(xs[0]),
+                                        *extra, out.data_ptr(), self._stream())
+        self._check(st, fn_name)
+        return out
+
+    def dewpoint_from_specific_humidity(self, pressure, temperature, specific_humidity, metpy_compat="1.4.1"):
+        compat = {"1.4.1": 141, "1.6.2": 162, 141: 141, 162: 162, "141": 141, "162": 162}[metpy_compat]
+        # dtype follows the temperature
+        pressure = pressure.to(temperature.dtype)
+        return self._pointwise("xp_dewpoint_from_specific_humidity", [pressure, temperature, specific_humidity],
+                               (compat,))
+
+    def saturation_mixing_ratio(self, pressure, temperature):
+        return self._pointwise("xp_saturation_mixing_ratio", [pressure, temperature])
+
+    def dry_lapse(self, pressure, parcel_temperature, parcel_pressure):
+        return self._pointwise("xp_dry_lapse", [pressure, parcel_temperature, parcel_pressure])
+
+    def mixing_ratio(self, temperature, dewpoint, pressure, metpy_compat="1.4.1"):
+        compat = {"1.4.1": 141, "1.6.2": 162, 141: 141, 162: 162, "141": 141, "162": 162}[metpy_compat]
+        return self._pointwise("xp_mixing_ratio", [temperature, dewpoint, pressure], (compat,))
+
+    def virtual_temperature(self, temperature, mixing_ratio, epsilon=0.608):
+        dt = temperature.dtype
+        t, w = [x.contiguous() for x in torch.broadcast_tensors(temperature, mixing_ratio.to(dt))]
+        out = torch.empty_like(t)
+        st = self.lib.xp_virtual_temperature(self.handle, t.data_ptr(), w.data_ptr(), t.numel(), _dtype_code(t),
+                                             float(epsilon), out.data_ptr(), self._stream())
+        self._check(st, "xp_virtual_temperature")
+        return out
+
+    def wet_bulb_temperature(self, pressure, temperature, dewpoint):
+        return self._pointwise("xp_wet_bulb_temperature", [pressure, temperature, dewpoint])
+
+    def significant_hail_parameter(self, mucape, mixing_ratio, lapse, temp_500, shear, flh):
+        return self._pointwise("xp_significant_hail_parameter", [mucape, mixing_ratio, lapse, temp_500, shear, flh])
+
+    def storm_proxies(self, fields):
+        """``fields``: dict of the PROXY_INPUTS tensors (one shape).  Returns dict of 9 bool tensors + 'ship'."""
+        dt = fields["mixed_100_cape"].dtype
+        xs = [fields[k].to(dt) for k in PROXY_INPUTS]
+        xs = [x.contiguous() for x in torch.broadcast_tensors(*xs)]
+        n = xs[0].numel()
+        flags = [torch.empty(xs[0].shape, dtype=torch.uint8, device=xs[0].device) for _ in PROXY_FLAGS]
+        ship = torch.empty_like(xs[0])
+        inp = XpProxyInputs(*[x.data_ptr() for x in xs])
+        outp = XpProxyOutputs(*([f.data_ptr() for f in flags] + [ship.data_ptr()]))
+        st = self.lib.xp_storm_proxies(self.handle, ctypes.byref(inp), n, _dtype_code(xs[0]), ctypes.byref(outp),
+                                       self._stream())
+        self._check(st, "xp_storm_proxies")
+        res = {k: f.bool() for k, f in zip(PROXY_FLAGS, flags)}
+        res["ship"] = ship
+        return res
 
 
 _contexts = {}

@@ -642,6 +642,138 @@ xp_status xp_level_crossing(xp_context *ctx, const void *coords, int64_t coords_
     return check_cuda(ctx, cudaGetLastError(), "level_crossing kernel launch");
 }
 
+xp_status xp_dewpoint_from_specific_humidity(xp_context *ctx, const void *pressure, const void *temperature,
+                                             const void *specific_humidity, int64_t n, int32_t dtype,
+                                             int32_t metpy_compat, void *dewpoint, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (n == 0) return XP_OK;
+    if (!pressure || !temperature || !specific_humidity || !dewpoint || n < 0 || (metpy_compat != 141 && metpy_compat != 162))
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad dewpoint_from_specific_humidity arguments");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    XP_DISPATCH(dtype,
+                launch_dewpoint_from_q<float>((const float *)pressure, (const float *)temperature, (const float *)specific_humidity, n, metpy_compat, (float *)dewpoint, st),
+                launch_dewpoint_from_q<double>((const double *)pressure, (const double *)temperature, (const double *)specific_humidity, n, metpy_compat, (double *)dewpoint, st));
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "dewpoint_from_specific_humidity kernel launch");
+}
+
+xp_status xp_saturation_mixing_ratio(xp_context *ctx, const void *pressure, const void *temperature, int64_t n,
+                                     int32_t dtype, void *mixing_ratio, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (n == 0) return XP_OK;
+    if (!pressure || !temperature || !mixing_ratio || n < 0)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad saturation_mixing_ratio arguments");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    XP_DISPATCH(dtype,
+                launch_sat_mixing_ratio<float>((const float *)pressure, (const float *)temperature, n, (float *)mixing_ratio, st),
+                launch_sat_mixing_ratio<double>((const double *)pressure, (const double *)temperature, n, (double *)mixing_ratio, st));
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "saturation_mixing_ratio kernel launch");
+}
+
+xp_status xp_dry_lapse(xp_context *ctx, const void *pressure, const void *parcel_temperature,
+                       const void *parcel_pressure, int64_t n, int32_t dtype, void *temperature, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (n == 0) return XP_OK;
+    if (!pressure || !parcel_temperature || !parcel_pressure || !temperature || n < 0)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad dry_lapse arguments");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    XP_DISPATCH(dtype,
+                launch_dry_lapse<float>((const float *)pressure, (const float *)parcel_temperature, (const float *)parcel_pressure, n, (float *)temperature, st),
+                launch_dry_lapse<double>((const double *)pressure, (const double *)parcel_temperature, (const double *)parcel_pressure, n, (double *)temperature, st));
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "dry_lapse kernel launch");
+}
+
+xp_status xp_mixing_ratio(xp_context *ctx, const void *temperature, const void *dewpoint, const void *pressure,
+                          int64_t n, int32_t dtype, int32_t metpy_compat, void *mixing_ratio, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (n == 0) return XP_OK;
+    if (!temperature || !dewpoint || !pressure || !mixing_ratio || n < 0 || (metpy_compat != 141 && metpy_compat != 162))
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad mixing_ratio arguments");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    XP_DISPATCH(dtype,
+                launch_mixing_ratio<float>((const float *)temperature, (const float *)dewpoint, (const float *)pressure, n, metpy_compat, (float *)mixing_ratio, st),
+                launch_mixing_ratio<double>((const double *)temperature, (const double *)dewpoint, (const double *)pressure, n, metpy_compat, (double *)mixing_ratio, st));
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "mixing_ratio kernel launch");
+}
+
+xp_status xp_virtual_temperature(xp_context *ctx, const void *temperature, const void *mixing_ratio, int64_t n,
+                                 int32_t dtype, double epsilon, void *virtual_temperature, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (n == 0) return XP_OK;
+    if (!temperature || !mixing_ratio || !virtual_temperature || n < 0)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad virtual_temperature arguments");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    XP_DISPATCH(dtype,
+                launch_virtual_temperature<float>((const float *)temperature, (const float *)mixing_ratio, n, epsilon, (float *)virtual_temperature, st),
+                launch_virtual_temperature<double>((const double *)temperature, (const double *)mixing_ratio, n, epsilon, (double *)virtual_temperature, st));
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "virtual_temperature kernel launch");
+}
+
+xp_status xp_wet_bulb_temperature(xp_context *ctx, const void *pressure, const void *temperature,
+                                  const void *dewpoint, int64_t n, int32_t dtype, void *wet_bulb, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (!ctx->tables) return fail(ctx, XP_ERR_TABLES_NOT_LOADED, "Call load_moist_adiabat_lookups first.");
+    if (n == 0) return XP_OK;
+    if (!pressure || !temperature || !dewpoint || !wet_bulb || n < 0)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad wet_bulb_temperature arguments");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const Tables tb = {ctx->d_index, ctx->d_curves};
+    XP_DISPATCH(dtype,
+                launch_wet_bulb<float>((const float *)pressure, (const float *)temperature, (const float *)dewpoint, n, tb, (float *)wet_bulb, st),
+                launch_wet_bulb<double>((const double *)pressure, (const double *)temperature, (const double *)dewpoint, n, tb, (double *)wet_bulb, st));
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "wet_bulb_temperature kernel launch");
+}
+
+xp_status xp_significant_hail_parameter(xp_context *ctx, const void *mucape, const void *mixing_ratio,
+                                        const void *lapse, const void *temp_500, const void *shear,
+                                        const void *flh, int64_t n, int32_t dtype, void *ship, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (n == 0) return XP_OK;
+    if (!mucape || !mixing_ratio || !lapse || !temp_500 || !shear || !flh || !ship || n < 0)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad significant_hail_parameter arguments");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const void *in[6] = {mucape, mixing_ratio, lapse, temp_500, shear, flh};
+    XP_DISPATCH(dtype,
+                launch_ship<float>((const float *const *)in, n, (float *)ship, st),
+                launch_ship<double>((const double *const *)in, n, (double *)ship, st));
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "significant_hail_parameter kernel launch");
+}
+
+xp_status xp_storm_proxies(xp_context *ctx, const xp_proxy_inputs *in, int64_t n, int32_t dtype,
+                           const xp_proxy_outputs *out, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (n == 0) return XP_OK;
+    if (!in || !out || n < 0) return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad storm_proxies arguments");
+    const void *iv[13] = {in->mixed_100_cape, in->mixed_50_cape, in->mu_cape, in->shear_magnitude,
+                          in->mixed_100_lifted_index, in->mixed_100_dci, in->positive_shear, in->mixed_50_cin,
+                          in->mixed_100_cin, in->lapse_rate_700_500, in->mu_mixing_ratio, in->temp_500,
+                          in->freezing_level};
+    for (int k = 0; k < 13; ++k)
+        if (!iv[k]) return fail(ctx, XP_ERR_INVALID_ARGUMENT, "storm_proxies: NULL input");
+    uint8_t *fl[9] = {out->craven2004, out->kunz2007, out->trapp2007, out->marsh2009, out->allen2011,
+                      out->allen2014, out->eccel2012, out->mohr2013, out->ship_0_1};
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    XP_DISPATCH(dtype,
+                launch_storm_proxies<float>((const float *const *)iv, fl, (float *)out->ship, n, st),
+                launch_storm_proxies<double>((const double *const *)iv, fl, (double *)out->ship, n, st));
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "storm_proxies kernel launch");
+}
+
 uint64_t xp_launch_count(const xp_context *ctx) { return ctx ? ctx->launches : 0; }
 
 xp_status xp_last_exact_count(xp_context *ctx, int64_t *out_count) {

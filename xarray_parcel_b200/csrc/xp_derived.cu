@@ -8,6 +8,7 @@
 // One thread per column, float64 arithmetic in the reference's operation order (no FMA contraction),
 // level-major inputs so each level read of a warp is one coalesced line.
 #include "xp_kernels.cuh"
+#include "xp_parcels.cuh"
 
 namespace xp {
 
@@ -105,7 +106,198 @@ __global__ void level_crossing_kernel(const __grid_constant__ CrossParams<T> prm
     prm.out[i] = (T)best;
 }
 
+// ---- pointwise kernels around the hot path ------------------------------------------------------
+// One thread per point, float64 arithmetic in the reference's operation order, grid-stride.
+
+// metpy.calc.dewpoint_from_specific_humidity as the reference calls it (PF:1889, 1969): MetPy 1.4.1 goes
+// through the relative humidity, MetPy >= 1.6 through the vapour pressure (environment_changes_eval.ipynb:278).
+template <typename T>
+__global__ void dewpoint_from_q_kernel(const T *p, const T *t, const T *q, int64_t n, int compat, T *out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double pp = (double)p[i], tt = (double)t[i], qq = (double)q[i];
+        const double w = qq / (1 - qq);                                  // mixing_ratio_from_specific_humidity
+        double e;
+        if (compat == 162) {
+            e = pp * w / (kEps + w);                                     // vapor_pressure(p, w)
+        } else {
+            const double es_t = sat_vapor_pressure(tt);
+            const double rh = w / (kEps * es_t / (pp - es_t));           // relative_humidity_from_mixing_ratio
+            e = rh * es_t;
+        }
+        out[i] = (T)dewpoint_from_e(e);
+    }
+}
+
+// metpy.calc.saturation_mixing_ratio(p, T) (PF:258; the most-unstable parcel's mixing ratio PF:2047-2053)
+template <typename T>
+__global__ void sat_mixing_ratio_kernel(const T *p, const T *t, int64_t n, T *out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (T)sat_mixing_ratio((double)p[i], (double)t[i]);
+}
+
+// dry_lapse (PF:291-316), mixing_ratio (PF:684-710), virtual_temperature (PF:782-804) as the reference exposes them
+template <typename T>
+__global__ void dry_lapse_kernel(const T *p, const T *t0, const T *p0, int64_t n, T *out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (T)dry_lapse((double)p[i], (double)t0[i], (double)p0[i]);
+}
+template <typename T>
+__global__ void mixing_ratio_kernel(const T *t, const T *td, const T *p, int64_t n, int compat, T *out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (T)mixing_ratio_t_td((double)t[i], (double)td[i], (double)p[i], compat);
+}
+template <typename T>
+__global__ void virtual_temperature_kernel(const T *t, const T *w, int64_t n, double epsilon, T *out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (T)((double)t[i] * (1 + epsilon * (double)w[i]));
+}
+
+// wet_bulb_temperature by Normand's rule (PF:389-445): lift every point to its LCL (PF:609-682), then bring
+// it back down the moist adiabat of the lookup tables to its own pressure (moist_lapse PF:525-607).
+template <typename T>
+__global__ void wet_bulb_kernel(const T *p, const T *t, const T *td, int64_t n, Tables tb, T *out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double pp = (double)p[i], tt = (double)t[i], dd = (double)td[i];
+        double r = qnan();
+        if (!(isnan(pp) || isnan(tt) || isnan(dd))) {                    // PF:627-634, 680
+            double lp, lt;
+            lcl_solve(pp, tt, dd, lp, lt);
+            const int adiabat = adiabat_lookup(tb, lp, lt);              // PF:554-557
+            if (adiabat > 0) r = adiabat_temperature(tb.curves + (size_t)(adiabat - 1) * kNP, pp);
+        }
+        out[i] = (T)r;
+    }
+}
+
+// significant_hail_parameter (PF:2261-2306), xarray .where semantics: a failed comparison (also with NaN)
+// takes the `other` branch.
+__device__ __forceinline__ double ship_value(double mucape, double mr, double lapse, double t500, double shear,
+                                             double flh) {
+    mr = mr * 1e3;
+    lapse = -lapse;
+    t500 = t500 - 273.15;
+    if (!(shear >= 7)) shear = qnan();
+    if (!(shear <= 27)) shear = qnan();
+    if (!(mr >= 11)) mr = qnan();
+    if (!(mr <= 13.6)) mr = qnan();
+    if (!(t500 <= -5.5)) t500 = -5.5;
+    double ship = mucape * mr * lapse * -t500 * shear / 42000000;
+    if (!(mucape >= 1300)) ship = ship * (mucape / 1300);
+    if (!(lapse >= 5.8)) ship = ship * (lapse / 5.8);
+    if (!(flh >= 2400)) ship = ship * (flh / 2400);
+    return ship;
+}
+
+template <typename T>
+__global__ void ship_kernel(const T *mucape, const T *mr, const T *lapse, const T *t500, const T *shear, const T *flh,
+                            int64_t n, T *out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (T)ship_value((double)mucape[i], (double)mr[i], (double)lapse[i], (double)t500[i], (double)shear[i],
+                               (double)flh[i]);
+}
+
+// storm_proxies (PF:2323-2407).  Inputs in the order of ProxyIn; outputs: 9 flags (uint8) in the order of the
+// reference's `proxies` dict, and SHIP.
+template <typename T>
+struct ProxyParams {
+    const T *in[13];
+    uint8_t *flag[9];
+    T *ship;
+    int64_t n;
+};
+enum ProxyIn { kMl100Cape, kMl50Cape, kMuCape, kS06, kMl100Li, kMl100Dci, kPosShear, kMl50Cin, kMl100Cin, kLapse,
+               kMuMr, kT500, kFlh };
+
+template <typename T>
+__global__ void storm_proxies_kernel(const __grid_constant__ ProxyParams<T> prm) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < prm.n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v[13];
+#pragma unroll
+        for (int k = 0; k < 13; ++k) v[k] = (double)prm.in[k][i];
+        // negative CAPE is ignored (PF:2337-2339)
+        const double ml100 = (v[kMl100Cape] >= 0) ? v[kMl100Cape] : qnan();
+        const double ml50 = (v[kMl50Cape] >= 0) ? v[kMl50Cape] : qnan();
+        const double mu = (v[kMuCape] >= 0) ? v[kMuCape] : qnan();
+        const double s06 = v[kS06];
+        const bool pos_shear = !(v[kPosShear] == 0.0);                   // numpy truthiness (NaN is true)
+        const bool craven = (ml100 * s06) >= 20000;                                          // PF:2345
+        const bool kunz = (v[kMl100Li] <= -2.07) || ((mu >= 1474) || (v[kMl100Dci] >= 25.7));   // PF:2348-2350
+        bool trapp = ((ml100 * s06) >= 10000) && (ml100 >= 100);                             // PF:2353-2357
+        trapp = trapp && (s06 >= 5);
+        trapp = trapp && pos_shear;
+        const bool marsh = (ml100 * s06) >= 10000;                                           // PF:2360
+        const bool allen11 = (ml50 * pow(s06, 1.67)) >= 25000;                               // PF:2363
+        bool allen14 = allen11 && (v[kMl50Cin] > -25);                                       // PF:2366-2371
+        allen14 = allen14 && (s06 > 7.5);
+        allen14 = allen14 && (v[kLapse] < -6.5);
+        const bool eccel = ((ml100 * s06) > 10000) && (v[kMl100Cin] > -50);                  // PF:2374-2375
+        bool mohr = (v[kMl100Li] <= -1.6) || (ml100 >= 439);                                 // PF:2378-2381
+        mohr = mohr || (v[kMl100Dci] >= 26.4);
+        const double ship = ship_value(mu, v[kMuMr], v[kLapse], v[kT500], s06, v[kFlh]);     // PF:2384-2389
+        const bool flags[9] = {craven, kunz, trapp, marsh, allen11, allen14, eccel, mohr, ship > 0.1};
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+            if (prm.flag[k]) prm.flag[k][i] = flags[k] ? 1 : 0;
+        if (prm.ship) prm.ship[i] = (T)ship;
+    }
+}
+
+inline unsigned pointwise_grid(int64_t n) {
+    const int64_t g = (n + 255) / 256;
+    return (unsigned)(g < 148 * 16 ? g : 148 * 16);
+}
+
 }  // namespace
+
+template <typename T>
+void launch_dewpoint_from_q(const T *p, const T *t, const T *q, int64_t n, int compat, T *out, cudaStream_t stream) {
+    if (n > 0) dewpoint_from_q_kernel<T><<<pointwise_grid(n), 256, 0, stream>>>(p, t, q, n, compat, out);
+}
+template <typename T>
+void launch_sat_mixing_ratio(const T *p, const T *t, int64_t n, T *out, cudaStream_t stream) {
+    if (n > 0) sat_mixing_ratio_kernel<T><<<pointwise_grid(n), 256, 0, stream>>>(p, t, n, out);
+}
+template <typename T>
+void launch_dry_lapse(const T *p, const T *t0, const T *p0, int64_t n, T *out, cudaStream_t stream) {
+    if (n > 0) dry_lapse_kernel<T><<<pointwise_grid(n), 256, 0, stream>>>(p, t0, p0, n, out);
+}
+template <typename T>
+void launch_mixing_ratio(const T *t, const T *td, const T *p, int64_t n, int compat, T *out, cudaStream_t stream) {
+    if (n > 0) mixing_ratio_kernel<T><<<pointwise_grid(n), 256, 0, stream>>>(t, td, p, n, compat, out);
+}
+template <typename T>
+void launch_virtual_temperature(const T *t, const T *w, int64_t n, double epsilon, T *out, cudaStream_t stream) {
+    if (n > 0) virtual_temperature_kernel<T><<<pointwise_grid(n), 256, 0, stream>>>(t, w, n, epsilon, out);
+}
+template <typename T>
+void launch_wet_bulb(const T *p, const T *t, const T *td, int64_t n, const Tables &tb, T *out, cudaStream_t stream) {
+    if (n > 0) wet_bulb_kernel<T><<<pointwise_grid(n), 256, 0, stream>>>(p, t, td, n, tb, out);
+}
+template <typename T>
+void launch_ship(const T *const *in6, int64_t n, T *out, cudaStream_t stream) {
+    if (n > 0) ship_kernel<T><<<pointwise_grid(n), 256, 0, stream>>>(in6[0], in6[1], in6[2], in6[3], in6[4], in6[5], n, out);
+}
+template <typename T>
+void launch_storm_proxies(const T *const *in13, uint8_t *const *flags9, T *ship, int64_t n, cudaStream_t stream) {
+    if (n <= 0) return;
+    ProxyParams<T> p;
+    for (int k = 0; k < 13; ++k) p.in[k] = in13[k];
+    for (int k = 0; k < 9; ++k) p.flag[k] = flags9[k];
+    p.ship = ship; p.n = n;
+    storm_proxies_kernel<T><<<pointwise_grid(n), 256, 0, stream>>>(p);
+}
+#define XP_INST_POINTWISE(T)                                                                                          \
+    template void launch_dewpoint_from_q<T>(const T *, const T *, const T *, int64_t, int, T *, cudaStream_t);        \
+    template void launch_sat_mixing_ratio<T>(const T *, const T *, int64_t, T *, cudaStream_t);                       \
+    template void launch_dry_lapse<T>(const T *, const T *, const T *, int64_t, T *, cudaStream_t);                   \
+    template void launch_mixing_ratio<T>(const T *, const T *, const T *, int64_t, int, T *, cudaStream_t);           \
+    template void launch_virtual_temperature<T>(const T *, const T *, int64_t, double, T *, cudaStream_t);            \
+    template void launch_wet_bulb<T>(const T *, const T *, const T *, int64_t, const Tables &, T *, cudaStream_t);    \
+    template void launch_ship<T>(const T *const *, int64_t, T *, cudaStream_t);                                       \
+    template void launch_storm_proxies<T>(const T *const *, uint8_t *const *, T *, int64_t, cudaStream_t);
+XP_INST_POINTWISE(float)
+XP_INST_POINTWISE(double)
+#undef XP_INST_POINTWISE
 
 template <typename T>
 void launch_interp_levels(const T *coords, int64_t cls, int c1d, const T *const *x, T *const *out, int n_fields,

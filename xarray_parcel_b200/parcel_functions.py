@@ -466,6 +466,37 @@ def _back(t, template):
     return t.cpu().numpy()
 
 
+def _pointwise(method, args, template=0, name=None, attrs=None, device=None, **kw):
+    """Run a pointwise Context method (``_lib.Context.<method>``: one CUDA thread per point) on broadcast
+    inputs and hand the result back as the template's array type (DataArray / torch / NumPy)."""
+    ctx = _lib.get_context(device)
+    tmpl = args[template]
+    if _xr is not None and any(isinstance(a, _xr.DataArray) for a in args):
+        xa = _xr.broadcast(*[a if isinstance(a, _xr.DataArray) else _xr.DataArray(a) for a in args])
+        tmpl = xa[template]
+        args = [a.data for a in xa]
+    dt = None
+    for a in args:
+        if isinstance(a, torch.Tensor) and a.dtype in (torch.float32, torch.float64):
+            dt = a.dtype
+            break
+        if isinstance(a, np.ndarray) and a.dtype == np.float32:
+            dt = torch.float32
+            break
+    dev = [_to_dev(a, dtype=dt or torch.float64) for a in args]
+    res = getattr(ctx, method)(*dev, **kw)
+    if _xr is not None and isinstance(tmpl, _xr.DataArray):
+        out = tmpl.copy(data=res.cpu().numpy())
+        out.attrs = dict(attrs or {})
+        if name:
+            out.name = name
+        return out
+    raw = args[template]
+    if isinstance(raw, torch.Tensor):
+        return res if raw.is_cuda else res.cpu()
+    return res.cpu().numpy()
+
+
 def lcl(parcel_pressure, parcel_temperature, parcel_dewpoint, device=None, **kwargs):
     """PF:609-682.  Returns Dataset{lcl_pressure, lcl_temperature, lcl_virtual_temperature}."""
     ctx = _lib.get_context(device)
@@ -480,8 +511,8 @@ def lcl(parcel_pressure, parcel_temperature, parcel_dewpoint, device=None, **kwa
 
 
 def dry_lapse(pressure, parcel_temperature, parcel_pressure=None, vert_dim="model_level_number",
-              vert_axis=0):
-    """PF:291-316: T0 * (p / p0) ** kappa (elementwise; stays on the caller's array library)."""
+              vert_axis=0, device=None):
+    """PF:291-316: T0 * (p / p0) ** kappa (``xp_dry_lapse``, one thread per point)."""
     if parcel_pressure is None:
         if _xr is not None and isinstance(pressure, _xr.DataArray):
             parcel_pressure = pressure.max(vert_dim)
@@ -489,28 +520,22 @@ def dry_lapse(pressure, parcel_temperature, parcel_pressure=None, vert_dim="mode
             parcel_pressure = pressure.amax(dim=vert_axis, keepdim=True)
         else:
             parcel_pressure = np.max(pressure, axis=vert_axis, keepdims=True)
-    return parcel_temperature * (pressure / parcel_pressure) ** KAPPA
+    return _pointwise("dry_lapse", [pressure, parcel_temperature, parcel_pressure], name="temperature",
+                      attrs={"long_name": "Dry lapse rate temperature", "units": "K"}, device=device)
 
 
-def virtual_temperature(temperature, mixing_ratio, epsilon=0.608):
-    """PF:782-804."""
-    return temperature * (1 + epsilon * mixing_ratio)
+def virtual_temperature(temperature, mixing_ratio, epsilon=0.608, device=None):
+    """PF:782-804 (``xp_virtual_temperature``)."""
+    return _pointwise("virtual_temperature", [temperature, mixing_ratio], name="virtual_temperature",
+                      attrs={"long_name": "Virtual temperature", "units": "K"}, device=device, epsilon=epsilon)
 
 
-def mixing_ratio(temperature, dewpoint, pressure, metpy_compat="1.4.1"):
-    """PF:684-710 (elementwise; Bolton saturation vapour pressure as in MetPy <= 1.6)."""
-    lib = torch if isinstance(temperature, torch.Tensor) else np
-
-    def es(t):
-        return 6.112 * lib.exp(17.67 * (t - 273.15) / (t - 29.65))
-
-    eps = 0.6219569100577033
-    es_t = es(temperature)
-    rh = es(dewpoint) / es_t
-    ws = eps * es_t / (pressure - es_t)
-    if str(metpy_compat) in ("1.6.2", "162"):
-        return eps * ws * rh / (eps + ws * (1.0 - rh))
-    return rh * ws
+def mixing_ratio(temperature, dewpoint, pressure, metpy_compat="1.4.1", device=None):
+    """PF:684-710: relative humidity from the dewpoint, then mixing ratio from relative humidity
+    (``xp_mixing_ratio``; MetPy 1.4.1 or >= 1.6 form of mixing_ratio_from_relative_humidity)."""
+    return _pointwise("mixing_ratio", [temperature, dewpoint, pressure], name="mixing_ratio",
+                      attrs={"long_name": "Mixing ratio", "units": "kg kg$^{-1}$"}, device=device,
+                      metpy_compat=metpy_compat)
 
 
 def moist_lapse(pressure, parcel_temperature, parcel_pressure=None, vert_dim="model_level_number",
@@ -717,11 +742,24 @@ def wet_bulb_temperature_fast(temperature, dewpoint):
     return temperature - (1 / 3) * (temperature - dewpoint)
 
 
+def wet_bulb_temperature(pressure, temperature, dewpoint, vert_dim="model_level_number", device=None):
+    """PF:389-445, Normand's rule: every point is lifted to its LCL (PF:609-682) and brought back down the
+    moist adiabat of the lookup tables to its own pressure (``xp_wet_bulb_temperature``: one thread per
+    point instead of the reference's Python loop over levels)."""
+    lookup_tables_loaded(device)
+    return _pointwise("wet_bulb_temperature", [pressure, temperature, dewpoint], template=1,
+                      name="wet_bulb_temperature", attrs={"long_name": "Wet bulb temperature", "units": "K"},
+                      device=device)
+
+
 def melting_level_height(pressure, temperature, dewpoint, height, fast=True, vert_dim="model_level_number",
                          vert_axis=0, device=None):
-    """PF:2162-2191 with fast=True (wet bulb by the 1/3 rule).  Returns (melting level height, wet bulb)."""
-    assert fast, "fast=False (Normand wet-bulb, PF:389-445) is not implemented"
-    wb = wet_bulb_temperature_fast(temperature, dewpoint)
+    """PF:2162-2191: lowest height at which the wet-bulb temperature (1/3 rule with fast=True, Normand's
+    rule otherwise) crosses 273.15 K.  Returns (melting level height, wet bulb)."""
+    if fast:
+        wb = wet_bulb_temperature_fast(temperature, dewpoint)
+    else:
+        wb = wet_bulb_temperature(pressure, temperature, dewpoint, vert_dim=vert_dim, device=device)
     return freezing_level_height(wb, height, vert_dim=vert_dim, vert_axis=vert_axis, device=device), wb
 
 
@@ -741,31 +779,81 @@ def wind_shear(surface_wind_u, surface_wind_v, wind_u, wind_v, height, shear_hei
     return lay.dataset({k: lay.wrap_scalar(x if on_gpu else x.cpu(), None) for k, x in out.items()})
 
 
-def dewpoint_from_specific_humidity(pressure, temperature, specific_humidity, metpy_compat="1.4.1"):
-    """metpy.calc.dewpoint_from_specific_humidity as the reference calls it (PF:1889, 1969); elementwise on
-    the caller's array library.  MetPy 1.4.1 goes through relative humidity, MetPy >= 1.6 through the
-    vapour pressure (environment_changes_eval.ipynb:278) -- pass the version the data were made with."""
-    lib = torch if isinstance(temperature, torch.Tensor) else np
-    eps = 0.6219569100577033
+def dewpoint_from_specific_humidity(pressure, temperature, specific_humidity, metpy_compat="1.4.1", device=None):
+    """metpy.calc.dewpoint_from_specific_humidity as the reference calls it (PF:1889, 1969), on the GPU
+    (``xp_dewpoint_from_specific_humidity``).  MetPy 1.4.1 goes through relative humidity, MetPy >= 1.6 through
+    the vapour pressure (environment_changes_eval.ipynb:278) -- pass the version the data were made with."""
+    return _pointwise("dewpoint_from_specific_humidity", [pressure, temperature, specific_humidity], template=1,
+                      name="dewpoint", attrs={"long_name": "Dewpoint temperature", "units": "K"}, device=device,
+                      metpy_compat=str(metpy_compat))
 
-    def es(t):
-        return 6.112 * lib.exp(17.67 * (t - 273.15) / (t - 29.65))
 
-    def dewpoint(e):
-        v = lib.log(e / 6.112)
-        return 243.5 * v / (17.67 - v) + 273.15
+def significant_hail_parameter(mucape, mixing_ratio, lapse, temp_500, shear, flh, device=None):
+    """PF:2261-2306 (https://www.spc.noaa.gov/exper/mesoanalysis/help/help_sigh.html): MU CAPE [J/kg], MU parcel
+    mixing ratio [kg/kg], 700-500 hPa lapse rate [K/km], 500 hPa temperature [K], 0-6 km shear [m/s],
+    freezing level height [m]  (``xp_significant_hail_parameter``)."""
+    return _pointwise("significant_hail_parameter", [mucape, mixing_ratio, lapse, temp_500, shear, flh],
+                      name="ship", attrs={"long_name": "Significant hail parameter",
+                                          "units": "J kg$^{-2}$ g K$^2$ km$^{-1}$ m s$^{-1}$"}, device=device)
 
-    w = specific_humidity / (1 - specific_humidity)
-    if str(metpy_compat) in ("1.6.2", "162"):
-        return dewpoint(pressure * w / (eps + w))
-    es_t = es(temperature)
-    rh = w / (eps * es_t / (pressure - es_t))
-    return dewpoint(rh * es_t)
+
+_PROXY_NAMES = {"proxy_Craven2004": "Craven 2004", "proxy_Kunz2007": "Kunz 2007", "proxy_Trapp2007": "Trapp 2007",
+                "proxy_Marsh2009": "Marsh 2009", "proxy_Allen2011": "Allen 2011", "proxy_Allen2014": "Allen 2014",
+                "proxy_Eccel2012": "Eccel 2012", "proxy_Mohr2013": "Mohr 2013", "proxy_SHIP_0.1": "SHIP > 0.1"}
+
+
+def storm_proxies(dat, device=None):
+    """PF:2323-2407: the nine storm proxies (True = triggered) and SHIP from the variables ``conv_properties``
+    returns (``xp_storm_proxies``, one thread per column)."""
+    ctx = _lib.get_context(device)
+    names = {k: ("shear_magnitude" if k == "shear_magnitude" else k) for k in _lib.PROXY_INPUTS}
+    raw = {k: dat[names[k]] for k in _lib.PROXY_INPUTS}
+    tmpl = raw["mixed_100_cape"]
+    is_xr = _xr is not None and isinstance(tmpl, _xr.DataArray)
+    if is_xr:
+        xa = _xr.broadcast(*[raw[k] for k in _lib.PROXY_INPUTS])
+        tmpl = xa[0]
+        raw = {k: a.data for k, a in zip(_lib.PROXY_INPUTS, xa)}
+    src = raw["mixed_100_cape"]
+    if isinstance(src, torch.Tensor):
+        dt = src.dtype if src.dtype in (torch.float32, torch.float64) else torch.float64
+    else:
+        dt = torch.float32 if np.asarray(src).dtype == np.float32 else torch.float64
+    dev = {}
+    for k, v in raw.items():
+        if isinstance(v, torch.Tensor):
+            dev[k] = v.to(dt).cuda()
+        else:
+            dev[k] = torch.as_tensor(np.asarray(v).astype(np.float64)).to(dt).cuda()
+    res = ctx.storm_proxies(dev)
+    out = {}
+    for k, v in res.items():
+        if is_xr:
+            da = tmpl.copy(data=v.cpu().numpy())
+            da.attrs = {}
+            da.name = k
+            out[k] = da
+        elif isinstance(src, torch.Tensor):
+            out[k] = v if src.is_cuda else v.cpu()
+        else:
+            out[k] = v.cpu().numpy()
+    if is_xr:
+        ds = _xr.Dataset(out)
+        for k, val in _PROXY_NAMES.items():
+            ds[k].attrs["long_name"] = "Proxy " + val
+        ds["ship"].attrs["long_name"] = "Significant hail parameter (SHIP)"
+        ds["ship"].attrs["units"] = "J kg$^{-2}$ g K$^2$ km$^{-1}$ m s$^{-1}$"
+        return ds
+    ds = Dataset(out)
+    ds.var_attrs = {k: {"long_name": "Proxy " + val} for k, val in _PROXY_NAMES.items()}
+    ds.var_attrs["ship"] = {"long_name": "Significant hail parameter (SHIP)",
+                            "units": "J kg$^{-2}$ g K$^2$ km$^{-1}$ m s$^{-1}$"}
+    return ds
 
 
 def _conv(dat, vert_dim, vert_axis, device, min_set, ignore_nans, metpy_compat):
     p, t = dat["pressure"], dat["temperature"]
-    td = dewpoint_from_specific_humidity(p, t, dat["specific_humidity"], metpy_compat)
+    td = dewpoint_from_specific_humidity(p, t, dat["specific_humidity"], metpy_compat, device=device)
     try:
         dat["dewpoint"] = td                                        # the reference adds it to the caller's Dataset
     except Exception:
@@ -788,10 +876,8 @@ def _conv(dat, vert_dim, vert_axis, device, min_set, ignore_nans, metpy_compat):
     if not min_set:
         cc, prof, mu_parcel = most_unstable_cape_cin(p, t, td, depth=250, prefix="mu", metpy_compat=metpy_compat, **kw)
         parcel_block("mu", cc, prof, "most-unstable parcel in lowest 250 hPa.")
-        pp, pd = mu_parcel["pressure"], mu_parcel["dewpoint"]
-        lib = torch if isinstance(pp, torch.Tensor) else np
-        es_d = 6.112 * lib.exp(17.67 * (pd - 273.15) / (pd - 29.65))
-        out["mu_mixing_ratio"] = 0.6219569100577033 * es_d / (pp - es_d)          # PF:2047-2053
+        out["mu_mixing_ratio"] = _pointwise("saturation_mixing_ratio", [mu_parcel["pressure"], mu_parcel["dewpoint"]],
+                                            name="mu_mixing_ratio", device=device)   # PF:2047-2053
     cc, prof, _ = mixed_layer_cape_cin(p, t, td, depth=100, prefix="mixed_100", metpy_compat=metpy_compat, **kw)
     parcel_block("mixed_100", cc, prof, "fully-mixed lowest 100 hPa parcel.")
     if not min_set:
