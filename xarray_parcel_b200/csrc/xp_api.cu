@@ -218,8 +218,16 @@ xp_status run_host(xp_context *ctx, const xp_columns *cols, int kind_mask,
         per_col += (size_t)n_scalar[k] * es + (q->level_shift ? 4 : 0) + (size_t)n_prof[k] * (L + 1) * es;
     }
     if (kind_mask & kEX) per_col += 3 * es;
-    // block size: ~256 MB per slot, multiple of 1024 columns
-    int64_t C = (int64_t)((size_t)256 << 20) / (int64_t)per_col;
+    // block size: ~256 MB per slot (XP_HOST_BLOCK_MB overrides), multiple of 1024 columns.  Measured on the B200
+    // box (ERA5 suite, 1.33 GB per call): 256 MB 160.6 M columns/s, 128 MB 155.5, 64 MB 151.3, 32 MB 126.3 --
+    // the per-block copies (2 strided H2D, ~40 D2H) cost more than the shorter pipeline fill/drain saves.
+    static int block_mb = -1;
+    if (block_mb < 0) {
+        const char *e = getenv("XP_HOST_BLOCK_MB");
+        block_mb = e ? atoi(e) : 256;
+        if (block_mb < 1 || block_mb > 4096) block_mb = 256;
+    }
+    int64_t C = (int64_t)((size_t)block_mb << 20) / (int64_t)per_col;
     C = std::max<int64_t>(1024, (C / 1024) * 1024);
     C = std::min<int64_t>(C, ((N + 1023) / 1024) * 1024);
     // every carved array is padded to 256 B: at most 3 inputs + 3 explicit + 4 x (12 scalars + shift + 6
