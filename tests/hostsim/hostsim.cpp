@@ -11,6 +11,7 @@
 
 #include "../../xarray_parcel_b200/csrc/xp_fast_pcol.cuh"
 #include "../../xarray_parcel_b200/csrc/xp_fast6.cuh"
+#include "../../xarray_parcel_b200/csrc/xp_fast_pcol6.cuh"
 
 namespace {
 
@@ -187,6 +188,24 @@ struct HostRdP {
 }  // namespace
 
 namespace {
+struct HostRdP6 {                      // pcol v6 sweep: 32-bit element offsets from the array bases
+    const float *p, *t, *td;
+    uint32_t col, lstride;
+    uint32_t off0() const { return col; }
+    uint32_t ls() const { return lstride; }
+    uint32_t pls() const { return lstride; }
+    float ldP(uint32_t off) const { return p[off]; }
+    float ldT(uint32_t off) const { return t[off]; }
+    float ldTd(uint32_t off) const { return td[off]; }
+    void prefetch(uint32_t, uint32_t) const {}
+};
+struct HostStash3 {
+    float p[128], t[128], td[128];
+    int cap;
+    int capacity() const { return cap; }
+    void put(int k, float a, float b, float c) { p[k] = a; t[k] = b; td[k] = c; }
+    void get(int k, float &a, float &b, float &c) const { a = p[k]; b = t[k]; c = td[k]; }
+};
 struct HostProfW {
     static constexpr bool kEnabled = true;
     float *base;       // [3 kinds][6 fields][L+1][n]
@@ -216,6 +235,17 @@ extern "C" int hostsim_fast_suite_pcol(const float *p, const float *t, const flo
             HostProfW pw = {prof, n, c, L};
             redo[c] = m1 ? xp::fast::suite_column_pcol<7u, 1>(rd, L, tb, o, pw, r)
                          : xp::fast::suite_column_pcol<7u, 0>(rd, L, tb, o, pw, r);
+        } else if (m1 && (c % 3) != 0) {
+            // default options, no profile: the v6 sweep (xp_fast_pcol6.cuh) on two columns out of three, with a
+            // stash of 36 levels (the kernel's), of 5 levels (search and sweep cross its end) or none
+            const HostRdP6 rd6 = {p, t, td, (uint32_t)c, (uint32_t)n};
+            if ((c % 3) == 1) {
+                HostStash3 st; st.cap = (c % 2) ? 36 : 5;
+                redo[c] = xp::fast::suite_column_pcol6<7u>(rd6, L, tb, o, st, r);
+            } else {
+                xp::fast::NoStash3 st;
+                redo[c] = xp::fast::suite_column_pcol6<7u>(rd6, L, tb, o, st, r);
+            }
         } else {
             xp::fast::NoProfile np;
             redo[c] = m1 ? xp::fast::suite_column_pcol<7u, 1>(rd, L, tb, o, np, r)

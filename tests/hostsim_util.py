@@ -21,7 +21,7 @@ KINDS = {"sb": 0, "ml": 1, "mu": 2, "explicit": 3}
 
 
 def build():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("xp_math.cuh", "xp_column.cuh", "xp_parcels.cuh", "xp_fast.cuh", "xp_fast_pcol.cuh", "xp_fast6.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("xp_math.cuh", "xp_column.cuh", "xp_parcels.cuh", "xp_fast.cuh", "xp_fast_pcol.cuh", "xp_fast6.cuh", "xp_fast_pcol6.cuh")]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     os.makedirs(BUILD, exist_ok=True)

@@ -1,11 +1,24 @@
 // xp_fast.cu -- sm_100a kernels of the float32 fast path (see xp_fast.cuh) and of the exact-path
 // fix-up over the compact list of columns whose decisions were uncertain in float32.
+#include <algorithm>
 #include <cstdlib>
 
 #include "xp_fast.cuh"
 #include "xp_fast_pcol.cuh"
 #include "xp_fast6.cuh"
+#include "xp_fast_pcol6.cuh"
 #include "xp_kernels.cuh"
+
+// Streaming read of column data (each element is used once): evict-first in L2 so that it does not push the
+// moist-adiabat tables (gathered many times) out.  XP_STREAM_LOADS=0 at build time restores plain loads.
+#ifndef XP_STREAM_LOADS
+#define XP_STREAM_LOADS 1
+#endif
+#if XP_STREAM_LOADS
+#define XP_LDSTREAM(ptr) __ldcs(ptr)
+#else
+#define XP_LDSTREAM(ptr) __ldg(ptr)
+#endif
 
 namespace xp {
 
@@ -275,6 +288,56 @@ __global__ void __launch_bounds__(kPColThreads, 2) suite_fast_pcol_kernel(const 
     if (redo) push_redo(prm.list, prm.list_count, prm.n, col, redo);
 }
 
+// ---- per-column pressure, v6 sweep (xp_fast_pcol6.cuh): default options, scalar outputs ----------------------
+struct PColRd32 {
+    const float *p, *t, *td;
+    uint32_t col, lstride, plstride;
+    __device__ __forceinline__ uint32_t off0() const { return col; }
+    __device__ __forceinline__ uint32_t ls() const { return lstride; }
+    __device__ __forceinline__ uint32_t pls() const { return plstride; }
+    __device__ __forceinline__ float ldP(uint32_t off) const { return XP_LDSTREAM(p + off); }
+    __device__ __forceinline__ float ldT(uint32_t off) const { return XP_LDSTREAM(t + off); }
+    __device__ __forceinline__ float ldTd(uint32_t off) const { return XP_LDSTREAM(td + off); }
+    __device__ __forceinline__ void prefetch(uint32_t offp, uint32_t off) const {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + offp));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(t + off));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(td + off));
+    }
+};
+
+// p/T/Td of the lowest levels of every thread's column: element (level k, which, thread) at
+// base[(3 k + which) * blockDim.x + thread] -- conflict-free.
+struct StashSmem3 {
+    float *base;
+    int stride, cap;
+    __device__ __forceinline__ int capacity() const { return cap; }
+    __device__ __forceinline__ void put(int k, float p, float t, float td) {
+        base[(3 * k) * stride] = p; base[(3 * k + 1) * stride] = t; base[(3 * k + 2) * stride] = td;
+    }
+    __device__ __forceinline__ void get(int k, float &p, float &t, float &td) const {
+        p = base[(3 * k) * stride]; t = base[(3 * k + 1) * stride]; td = base[(3 * k + 2) * stride];
+    }
+};
+
+constexpr int kPCol6Threads = 256;
+constexpr int kPCol6StashLevels = 8;       // 8 levels x 3 arrays x 4 B x 256 threads = 24 KB per CTA (more levels cost occupancy: measured)
+
+template <unsigned KINDS>
+__global__ void __launch_bounds__(kPCol6Threads, 2) suite_fast_pcol6_kernel(const __grid_constant__ PColParams prm,
+                                                                            int stash_levels) {
+    extern __shared__ __align__(16) float s_stash[];
+    const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= prm.n) return;
+    const PColRd32 rd{prm.p, prm.t, prm.td, (uint32_t)col, (uint32_t)prm.ls, (uint32_t)prm.pls};
+    StashSmem3 st{s_stash + threadIdx.x, (int)blockDim.x, stash_levels};
+    fast::FResult res[3];
+    const unsigned redo = fast::suite_column_pcol6<KINDS>(rd, prm.L, prm.tb, prm.o, st, res);
+    if (KINDS & 1u) store_fast(prm.outs[0], col, res[0]);
+    if (KINDS & 2u) store_fast(prm.outs[1], col, res[1]);
+    if (KINDS & 4u) store_fast(prm.outs[2], col, res[2]);
+    if (redo) push_redo(prm.list, prm.list_count, prm.n, col, redo);
+}
+
 }  // namespace
 
 size_t fast_scratch_bytes(int64_t n) {
@@ -328,6 +391,36 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
         pp.list = list; pp.list_count = count;
         const unsigned g = (unsigned)((cols.n + kPColThreads - 1) / kPColThreads);
         const bool profile = wants_profile(kind_mask, outs);
+        // default options, scalar outputs, 32-bit element offsets: the v6 sweep (xp_fast_pcol6.cuh)
+        static int pcol6 = -1;
+        if (pcol6 < 0) { const char *e = getenv("XP_PCOL6"); pcol6 = e ? atoi(e) : 1; }
+        const uint64_t span = (uint64_t)cols.n + (uint64_t)cols.L * (uint64_t)std::max(cols.ls, cols.pls);
+        // Measured on the B200: 1 M x 70 surface-based 934 vs 862 M columns/s for the generic
+        // sweep; with the mixed-layer parcel the generic sweep wins (595 vs 507: it skips that parcel's rows below
+        // the layer top with a nearly warp-uniform branch), so only the surface-based kernel is dispatched here
+        // unless XP_PCOL6=2 forces the v6 sweep for every kind.
+        if (pcol6 && ((kind_mask & 7) == 1 || pcol6 == 2) && mode && !profile && span < ((uint64_t)1 << 32)) {
+            const int lv = kPCol6StashLevels;
+            const size_t smem6 = (size_t)lv * 3 * sizeof(float) * kPCol6Threads;
+            const unsigned g6 = (unsigned)((cols.n + kPCol6Threads - 1) / kPCol6Threads);
+            static bool attr_set[8] = {};
+#define XP_PCOL6_CASE(K)                                                                                          \
+    case K:                                                                                                       \
+        if (!attr_set[K]) {                                                                                       \
+            if (cudaFuncSetAttribute(suite_fast_pcol6_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                     (int)((size_t)kPCol6StashLevels * 3 * sizeof(float) * kPCol6Threads)) != cudaSuccess) return -1; \
+            attr_set[K] = true;                                                                                   \
+        }                                                                                                         \
+        suite_fast_pcol6_kernel<K><<<g6, kPCol6Threads, smem6, stream>>>(pp, lv);                                 \
+        break;
+            switch (kind_mask & 7) {
+                XP_PCOL6_CASE(1) XP_PCOL6_CASE(2) XP_PCOL6_CASE(3) XP_PCOL6_CASE(4) XP_PCOL6_CASE(5) XP_PCOL6_CASE(6) XP_PCOL6_CASE(7)
+                default: return -1;
+            }
+#undef XP_PCOL6_CASE
+            launch_suite_list(lp, sm_count, stream);
+            return 2;
+        }
 #define XP_PCOL_CASE(K)                                                                          \
     case K:                                                                                      \
         if (profile) {                                                                           \

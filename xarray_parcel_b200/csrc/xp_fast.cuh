@@ -56,6 +56,7 @@ struct Prep {
     double thfac[kMaxLevels];     // (1000/p)^kappa  (potential temperature factor, PF:253)
     double p64[kMaxLevels];
     float p[kMaxLevels], lnp[kMaxLevels], pk[kMaxLevels];   // p, ln p, p^kappa
+    float plk[kMaxLevels][4];                               // the same three, packed per level (one 16-byte load)
 };
 
 // ---- per-call constants of the shared pressure axis ----------------------------------------------------
@@ -66,6 +67,7 @@ XP_HD void compute_prep_level(const float *p, int64_t pls, int k, Prep &pr) {
     pr.p[k] = (float)pk;
     pr.lnp[k] = (float)log(pk);
     pr.pk[k] = (float)pow(pk, kKappa);
+    pr.plk[k][0] = pr.p[k]; pr.plk[k][1] = pr.lnp[k]; pr.plk[k][2] = pr.pk[k]; pr.plk[k][3] = 0.0f;
     pr.thfac[k] = 1.0 / exner(pk);                                   // PF:253 theta = T / exner(p)
     pr.mlw[k] = 0.0;
 }

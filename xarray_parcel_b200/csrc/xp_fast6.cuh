@@ -56,22 +56,23 @@ XP_HD void sweep_init6(FParcel &c, float x0) {
     c.min_abs_d = 1e30f; c.min_slope = 1e30f; c.max_d_above = -1e30f;
 }
 
-// One row of one parcel at iteration `it` (row schedule: see FParcel in xp_fast.cuh).
-//   cc      cubic of level it-1 for this parcel's adiabat interval
-//   *_cur   level it, *_prv level it-1:  pk = p^kappa, x = ln p, b = environment virtual temperature
-// GUARD: the parcel may start above this row (most-unstable parcel): rows it < kfirst are neutral.
-template <bool GUARD>
-XP_HD void step6(FParcel &c, int it, const Coef &cc, float pk_cur, float x_cur, float x_prv, float b_cur,
-                 float b_prv) {
+// One row of one parcel at iteration `it` (row schedule: see FParcel in xp_fast.cuh), given
+//   d_m   parcel - environment on the moist adiabat at level it-1 (PF:585-592)
+//   d_d   parcel - environment on the dry adiabat at level it     (PF:742)
+//   x_cur / x_prv   ln p of level it / it-1
+// GUARD 0: the parcel is live at every row.  1: rows it < kfirst are neutral and leave xprev at the row's
+// ln p (most-unstable parcel on a shared axis: its start row is the level below kfirst).  2: rows it < kfirst
+// are neutral and leave xprev untouched (per-column pressure: xprev was set to the parcel's start row).
+template <int GUARD>
+XP_HD void step6_core(FParcel &c, int it, float d_m, float d_d, float x_cur, float x_prv) {
     const bool above = it > c.ka, is_lcl = it == c.ka;
-    const float d_m = cubic_at(cc, c.f) - b_prv;                  // moist adiabat (PF:585-592), level it-1
-    const float d_d = f_fma(c.c_dryv, pk_cur, -b_cur);            // dry adiabat (PF:742), level it
     float d = above ? d_m : d_d;
     d = is_lcl ? c.b_lcl : d;
     float x = above ? x_prv : x_cur;
     x = is_lcl ? c.x_lcl : x;
     bool active = true;
     if (GUARD) { active = it >= c.kfirst; d = active ? d : 0.0f; }
+    if (GUARD == 2) x = active ? x : c.xprev;
     const float dx = c.xprev - x;
     const float h = 0.5f * dx;
     const float den = c.dprev - d;
@@ -101,6 +102,15 @@ XP_HD void step6(FParcel &c, int it, const Coef &cc, float pk_cur, float x_cur, 
     c.min_abs_d = fminf(c.min_abs_d, (!GUARD || active) ? fabsf(d) : 1e30f);
     c.min_slope = fminf(c.min_slope, cross ? f_fma(-kCrossSlope, dx, fabsf(den)) : 1e30f);
     c.xprev = x; c.dprev = d;
+}
+
+// Shared pressure axis: the moist adiabat comes from the shared-memory cubic of level it-1 (`cc`);
+// *_cur = level it, *_prv = level it-1: pk = p^kappa, x = ln p, b = environment virtual temperature.
+// GUARD: the parcel may start above this row (most-unstable parcel).
+template <bool GUARD>
+XP_HD void step6(FParcel &c, int it, const Coef &cc, float pk_cur, float x_cur, float x_prv, float b_cur,
+                 float b_prv) {
+    step6_core<GUARD ? 1 : 0>(c, it, cubic_at(cc, c.f) - b_prv, f_fma(c.c_dryv, pk_cur, -b_cur), x_cur, x_prv);
 }
 
 // ln p and parcel virtual temperature of a crossing found at iteration `itc` (> ka) with fraction fr.
@@ -294,7 +304,7 @@ constexpr int kL2Ahead = 4;
 // (warp-uniform) array bases -- one integer add per level instead of 64-bit pointer arithmetic per array; the
 // launcher takes this path only when every offset fits 32 bits.  Rd: ldT(off), ldTd(off), prefetch(off), ls(), off0().
 struct Sweep6 {
-    const float *lp_x, *lp_k, *lp_p;
+    const float *lp;                      // packed axis constants {p, ln p, p^kappa, -} of level `it`
     uint32_t off;                         // offset of the level after the prefetched one
     uint32_t ls;
     int k_pf;                             // that level
@@ -317,7 +327,8 @@ XP_HD void sweep_segment6(const Rd &rd, Sweep6 &s, CoefRow &crow, const Stash &s
             if (s.k_pf + kL2Ahead < nt) rd.prefetch(s.off + kL2Ahead * s.ls);
             s.off += s.ls; ++s.k_pf;
         }
-        const float p_cur = *s.lp_p++, x_cur = *s.lp_x++, pk_cur = *s.lp_k++;
+        const float p_cur = s.lp[0], x_cur = s.lp[1], pk_cur = s.lp[2];
+        s.lp += 4;
         const float b_cur = f_tv(t, f_mixing_ratio(f_es(t), f_es(td), p_cur, 141));   // PF:839-843
         if (KACT & 1u) step6<false>(sb, it, crow.at(sb.m), pk_cur, x_cur, s.x_prv, b_cur, s.b_prv);
         if (KACT & 2u) step6<false>(ml, it, crow.at(ml.m), pk_cur, x_cur, s.x_prv, b_cur, s.b_prv);
@@ -428,7 +439,7 @@ XP_HD unsigned suite_column6(const Rd &rd, const Cf &cf, const Prep &pr, const T
         res[2].par_p = pr.p[k_mu]; res[2].par_t = mu_t; res[2].par_td = mu_td; res[2].shift = k_mu;
     }
     // ---- the sweep --------------------------------------------------------------------------------------
-    s.lp_p = pr.p + 1; s.lp_x = pr.lnp + 1; s.lp_k = pr.pk + 1;
+    s.lp = &pr.plk[1][0];
     s.b_prv = 0.0f; s.x_prv = pr.lnp[0];
     auto crow = cf.row(0);
     // segment bounds: the mixed-layer parcel joins at K_ml; most-unstable parcels have all started by K_mu;
