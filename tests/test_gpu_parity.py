@@ -231,6 +231,31 @@ def test_fast_path_kind_pairs_and_depths(ctx, depths):
         assert torch.equal(full[kind]["level_shift"], exact[kind]["level_shift"])
 
 
+@pytest.mark.parametrize("L", [24, 37, 50, 56])
+def test_fast_path_other_shared_axes(ctx, L):
+    """Shared-axis fast path on axes that are not ERA5's: few levels (the lowest-level stash covers most of the
+    column), 50 / 56 levels (the coefficient table leaves no room for the stash: every level from global
+    memory), uneven spacing, mixed-layer top between levels -- against the float64 exact kernel."""
+    rng = np.random.default_rng(100 + L)
+    inner = np.sort(rng.uniform(110, 1008, L - 6))[::-1]
+    p = np.concatenate([[1012.0], inner, [80.0, 40.0, 12.0, 4.0, 1.5]]).astype(np.float32)
+    assert p.size == L and (np.diff(p) < 0).all()
+    N = 40_000
+    z = 7.5 * np.log(1012.0 / p.astype(np.float64))[:, None]
+    t0 = rng.uniform(275, 306, N); lapse = rng.uniform(5.5, 9.2, N)
+    T = np.maximum(t0[None, :] - lapse[None, :] * z, rng.uniform(198, 222, N)[None, :]).astype(np.float32)
+    D = (T - (rng.uniform(0.5, 18, N)[None, :] + 1.5 * z)).astype(np.float32)
+    pd, td_, dd = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (p, T, D)]
+    fast = ctx.cape_cin(pd, td_, dd, kinds=("sb", "ml", "mu"))
+    n_exact = ctx.last_exact_count()
+    assert 0 <= n_exact < 0.06 * N, n_exact
+    exact = ctx.cape_cin(pd, td_, dd, kinds=("sb", "ml", "mu"), options=_lib.make_options(exact_only=True))
+    for kind in ("sb", "ml", "mu"):
+        ex = {kind + "_" + f: exact[kind][f].double().cpu().numpy() for f in FIELDS}
+        _check(fast[kind], ex, kind + "_", "fast", what=f"fast vs exact, {L} levels: ")
+        assert torch.equal(fast[kind]["level_shift"], exact[kind]["level_shift"])
+
+
 def test_single_kind_calls_equal_suite(ctx):
     """xp_cape_cin per kind == xp_suite: bit-exact where both run the same sweep (ML, MU); the surface-based
     call on per-column pressure runs the v6 sweep (xp_fast_pcol6.cuh: same decisions, float32 rounding of the
