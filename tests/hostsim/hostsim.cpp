@@ -269,3 +269,8 @@ extern "C" void hostsim_lcl_fast(const double *p, const double *t, const double 
         else xp::fast::lcl_fast6(p[i], t[i], td[i], lcl_p[i], lcl_t[i]);
     }
 }
+
+// Branch-free float64 log / exp of the v6 fast path (xp_fast6.cuh): which = 0 log, 1 exp.
+extern "C" void hostsim_fast_math64(const double *x, int64_t n, int which, double *y) {
+    for (int64_t i = 0; i < n; ++i) y[i] = which == 0 ? xp::fast::log64_fast(x[i]) : xp::fast::exp64_fast(x[i]);
+}

@@ -181,3 +181,23 @@ def test_fast_lcl_solvers_reach_the_converged_fixed_point(which):
     rp, rt = th.lcl(p, t, td, mode="converged")
     assert np.abs(lp / rp - 1).max() < 2e-11
     assert np.abs(lt - rt).max() < 2e-9
+
+
+def test_branch_free_log_exp_accuracy():
+    """log64_fast / exp64_fast (xp_fast6.cuh) over the argument ranges of the path: the LCL solve needs ~1e-12."""
+    import ctypes
+    rng = np.random.default_rng(5)
+    fn = hs.lib().hostsim_fast_math64
+    fn.restype = None
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    x = np.concatenate([rng.uniform(0.02, 1.0, 200_000), rng.uniform(1e-3, 50.0, 100_000),
+                        np.array([1.0, 0.5, 2.0, np.sqrt(2.0), np.nextafter(np.sqrt(2.0), 2), 0.7071067811865476])])
+    y = np.empty_like(x)
+    fn(ptr(x), ctypes.c_int64(x.size), ctypes.c_int(0), ptr(y))
+    ref = np.log(x)
+    assert np.abs(y - ref).max() <= 4e-16 + 4e-16 * np.abs(ref).max()
+    assert np.abs((y - ref)[np.abs(ref) > 1e-3] / ref[np.abs(ref) > 1e-3]).max() < 2e-15
+    x = np.concatenate([rng.uniform(-45.0, 8.0, 300_000), np.array([0.0, -0.3465, 0.3466, 1.0, -1.0])])
+    y = np.empty_like(x)
+    fn(ptr(x), ctypes.c_int64(x.size), ctypes.c_int(1), ptr(y))
+    assert np.abs(y / np.exp(x) - 1).max() < 1e-15

@@ -55,6 +55,7 @@ struct FastParams {
     uint32_t *list;          // 3 regions of n entries (see ListParams)
     uint32_t *list_count;
     int stash_levels;        // levels of T/Td per thread that fit in shared memory after the table (v6 sweep)
+    int dense_out;           // the requested outputs are exactly the 9 scalars per kind + parcel p/T/Td of ML, MU
 };
 
 struct GlobalRd {
@@ -110,6 +111,14 @@ __device__ __forceinline__ void store_fast(const OutArg<float> &o, int64_t col, 
     if (o.par_t) o.par_t[col] = r.par_t;
     if (o.par_td) o.par_td[col] = r.par_td;
     if (o.shift) o.shift[col] = r.shift;
+}
+
+// Every scalar output of the kind is requested (the usual case): no pointer checks.
+__device__ __forceinline__ void store_fast_all(const OutArg<float> &o, int64_t col, const fast::FResult &r, bool parcel) {
+    o.cape[col] = r.cape; o.cin[col] = r.cin;
+    o.lcl_p[col] = r.lcl_p; o.lcl_t[col] = r.lcl_t; o.lcl_tv[col] = r.lcl_tv;
+    o.lfc_p[col] = r.lfc_p; o.lfc_t[col] = r.lfc_t; o.el_p[col] = r.el_p; o.el_t[col] = r.el_t;
+    if (parcel) { o.par_p[col] = r.par_p; o.par_t[col] = r.par_t; o.par_td[col] = r.par_td; }
 }
 
 constexpr int kFastThreads = 512;
@@ -213,9 +222,16 @@ __global__ void __launch_bounds__(THREADS, 1) suite_fast_kernel(const __grid_con
             redo = fast::suite_column<KINDS, MODE>(rd, cf, pr, prm.tb, prm.o, env, res);
         }
         if (!valid) continue;
-        if (KINDS & 1u) store_fast(prm.outs[0], col, res[0]);
-        if (KINDS & 2u) store_fast(prm.outs[1], col, res[1]);
-        if (KINDS & 4u) store_fast(prm.outs[2], col, res[2]);
+        if (prm.dense_out) {
+            // cape .. el_temperature of every kind, parcel p/T/Td of ML and MU, nothing else
+            if (KINDS & 1u) store_fast_all(prm.outs[0], col, res[0], false);
+            if (KINDS & 2u) store_fast_all(prm.outs[1], col, res[1], true);
+            if (KINDS & 4u) store_fast_all(prm.outs[2], col, res[2], true);
+        } else {
+            if (KINDS & 1u) store_fast(prm.outs[0], col, res[0]);
+            if (KINDS & 2u) store_fast(prm.outs[1], col, res[1]);
+            if (KINDS & 4u) store_fast(prm.outs[2], col, res[2]);
+        }
         if (redo) push_redo(prm.list, prm.list_count, prm.n, col, redo);
     }
 }
@@ -446,6 +462,14 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
     fp.prep = prep; fp.coef = coef; fp.tb = tb; fp.o = o; fp.kinds = (unsigned)kind_mask;
     for (int q = 0; q < 3; ++q) fp.outs[q] = outs[q];
     fp.list = list; fp.list_count = count;
+    fp.dense_out = 1;
+    for (int q = 0; q < 3; ++q) {
+        if (!((kind_mask >> q) & 1)) continue;
+        const OutArg<float> &oq = outs[q];
+        const bool nine = oq.cape && oq.cin && oq.lcl_p && oq.lcl_t && oq.lcl_tv && oq.lfc_p && oq.lfc_t && oq.el_p && oq.el_t;
+        const bool par = oq.par_p && oq.par_t && oq.par_td, no_par = !oq.par_p && !oq.par_t && !oq.par_td;
+        if (!nine || oq.shift || (q == 0 ? !no_par : !par)) fp.dense_out = 0;
+    }
     // shared memory: Prep | coefficient table | (staged) the environment curve of every thread
     const size_t smem_table = ((sizeof(Prep) + 127) & ~(size_t)127) + (size_t)cols.L * fast::kNI * sizeof(Coef);
     const size_t smem_env = (size_t)cols.L * kFastThreads * sizeof(float);
