@@ -31,6 +31,7 @@ constexpr float kDecisionEps = 6e-4f;       // K: |parcel - environment| below t
 constexpr float kThetaEMargin = 4e-6f;      // ln(theta_e) gap below this is a most-unstable tie
 constexpr float kCrossSlope = 0.5f;         // K per unit ln p: a crossing with |d0 - d1| < kCrossSlope * dx is too
                                             // shallow to place within 1e-3 relative in pressure in float32
+constexpr double kTopCheckHpa = 125.0;       // v6 sweep: early termination is considered above this pressure
 constexpr float kStopMargin = 1.0f;          // K: early-termination margin below the coldest environment level
 constexpr unsigned kRedoMuIsSb = 8u;         // redo-mask bit (== kListMuIsSb): write the SB exact result to the MU outputs too
 constexpr double kSaturationMargin = 2e-3;
@@ -49,7 +50,9 @@ struct Prep {
     int K_ml;               // number of levels in the mixed layer (p >= bottom - depth); first kept level of the ML column
     int n_ml_w;             // number of levels with a non-zero mixed-layer weight (K_ml or K_ml + 1)
     int K_mu;               // number of levels in the most-unstable search layer
-    int pad0, pad1;
+    int k_top;              // first level above kTopCheckHpa (n_table when there are fewer than 3): from here on the
+                            // v6 sweep may stop once no parcel of the warp can meet the environment again
+    int pad1;
     double exner0;          // (p[0]/1000)^kappa
     double p0;              // p[0]
     double mlw[kMaxLevels];       // mixed-layer trapezoid weights / depth (PF:137-162 with get_layer PF:63-100)
@@ -124,6 +127,11 @@ XP_HD void compute_prep_axis(int L, const Opts &o, Prep &pr) {
         if (d < best) { best = d; kt = k; }                              // ties keep the larger pressure
     }
     pr.K_mu = kt + 1;
+    {
+        int k_top = n_table;
+        for (int k = n_table - 1; k >= 0 && pr.p64[k] < kTopCheckHpa; --k) k_top = k;
+        pr.k_top = (n_table - k_top >= 3) ? k_top : n_table;
+    }
     if (pr.K_mu > n_table || K_ml >= n_table || n_table < 3) ok = false;
     pr.ok = ok ? 1 : 0;
 }

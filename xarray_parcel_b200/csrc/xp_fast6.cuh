@@ -401,6 +401,40 @@ XP_HD void sweep_segment6(const Rd &rd, Sweep6 &s, CoefRow &crow, const Stash &s
     }
 }
 
+// The top of the sweep, iterations [it0, nt) with it0 > k_top: as sweep_segment6 (no guards, global pipeline), but
+// after every iteration the warp checks whether it can stop.  A parcel is finished when it is above its LCL,
+// colder than the environment, and its virtual temperature (which only falls with height along the moist
+// adiabat) is more than kStopMargin below `tmin_top`, the coldest environment TEMPERATURE (<= virtual
+// temperature) of all levels from k_top up: no crossing and no positive area can follow, and with
+// pos_cape_neg_cin nothing the outputs depend on changes any more (PF:1329-1388; the negative area above the
+// last crossing is never used).  Returns true if the sweep stopped early.
+template <unsigned KINDS, class Rd, class CoefRow>
+XP_HD bool sweep_top6(const Rd &rd, Sweep6 &s, CoefRow &crow, int it0, int nt, float tmin_top,
+                      FParcel &sb, FParcel &ml, FParcel &mu) {
+    const float stop_below = tmin_top - kStopMargin;
+    for (int it = it0; it < nt; ++it) {
+        const float t = s.t_n1, td = s.td_n1;
+        if (s.k_pf < nt) { s.t_n1 = rd.ldT(s.off); s.td_n1 = rd.ldTd(s.off); }
+        if (s.k_pf + kL2Ahead < nt) rd.prefetch(s.off + kL2Ahead * s.ls);
+        s.off += s.ls; ++s.k_pf;
+        const float p_cur = s.lp[0], x_cur = s.lp[1], pk_cur = s.lp[2];
+        s.lp += 4;
+        const float b_cur = f_tv(t, f_mixing_ratio(f_es(t), f_es(td), p_cur, 141));   // PF:839-843
+        if (KINDS & 1u) step6<false>(sb, it, crow.at(sb.m), pk_cur, x_cur, s.x_prv, b_cur, s.b_prv);
+        if (KINDS & 2u) step6<false>(ml, it, crow.at(ml.m), pk_cur, x_cur, s.x_prv, b_cur, s.b_prv);
+        if (KINDS & 4u) step6<false>(mu, it, crow.at(mu.m), pk_cur, x_cur, s.x_prv, b_cur, s.b_prv);
+        // the row just processed by a parcel above its LCL is level it-1: its curve there is dprev + b_prv
+        bool done = true;
+        if (KINDS & 1u) done = done && (sb.bad || (it > sb.ka && sb.dprev < 0.0f && sb.dprev + s.b_prv < stop_below));
+        if (KINDS & 2u) done = done && (ml.bad || (it > ml.ka && ml.dprev < 0.0f && ml.dprev + s.b_prv < stop_below));
+        if (KINDS & 4u) done = done && (mu.bad || (it > mu.ka && mu.dprev < 0.0f && mu.dprev + s.b_prv < stop_below));
+        s.b_prv = b_cur; s.x_prv = x_cur;
+        crow.advance();
+        if (XP_WARP_ALL(done)) return true;
+    }
+    return false;
+}
+
 // The whole suite for one column, default options.  Interfaces as suite_column (xp_fast.cuh); `cf` must be
 // the VIRTUAL-temperature table (compute_coef_tv).  Returns the mask of kinds for the exact path.
 template <unsigned KINDS, class Rd, class Cf, class Stash>
@@ -518,9 +552,21 @@ XP_HD unsigned suite_column6(const Rd &rd, const Cf &cf, const Prep &pr, const T
     const int it_c = fs ? max(it_b, min(n_stash, nt)) : it_b;
     sweep_segment6<KINDS & 5u, true>(rd, s, crow, stash, fs, 1, it_a, nt, sb, ml, mu);
     sweep_segment6<KINDS, true>(rd, s, crow, stash, fs, it_a, it_c, nt, sb, ml, mu);
-    sweep_segment6<KINDS, false>(rd, s, crow, stash, false, it_c, nt, nt, sb, ml, mu);
+    // the top of the column (levels above kTopCheckHpa): the coldest environment temperature up there bounds what
+    // a parcel can still meet; T/Td of those levels are read here (L2 keeps them for the sweep) -- their NaNs
+    // must be seen even if the sweep stops below them
+    const int it_d = max(it_c, min(pr.k_top + 1, nt));
+    float tmin_top = 1e30f;
+    for (int k = pr.k_top; k < nt; ++k) {
+        const uint32_t o_ = rd.off0() + (uint32_t)k * ls;
+        const float t = rd.ldT(o_), td = rd.ldTd(o_);
+        nanacc = f_fma(t, 0.0f, f_fma(td, 0.0f, nanacc));
+        tmin_top = fminf(tmin_top, t);
+    }
+    sweep_segment6<KINDS, false>(rd, s, crow, stash, false, it_c, it_d, nt, sb, ml, mu);
+    const bool stopped = sweep_top6<KINDS>(rd, s, crow, it_d, nt, tmin_top, sb, ml, mu);
     // last iteration: no level `nt`; every parcel that is not bound for the exact path is above its LCL
-    {
+    if (!stopped) {
         const float big = 1e30f;
         if (KINDS & 1u) step6<false>(sb, nt, crow.at(sb.m), 0.0f, s.x_prv, s.x_prv, big, s.b_prv);
         if (KINDS & 2u) step6<false>(ml, nt, crow.at(ml.m), 0.0f, s.x_prv, s.x_prv, big, s.b_prv);
