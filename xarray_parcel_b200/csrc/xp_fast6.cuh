@@ -459,6 +459,8 @@ XP_HD unsigned suite_column6(const Rd &rd, const Cf &cf, const Prep &pr, const T
             if (k0 + j < nt) rd.prefetch(s.off + (uint32_t)j * ls);
         s.off += ls; s.k_pf = k0 + 1;
     }
+    // the levels above kTopCheckHpa are read right before the sweep (early-termination bound): ask L2 for them now
+    for (int k = pr.k_top; k < nt; ++k) rd.prefetch(rd.off0() + (uint32_t)k * ls);
     // ---- pre-pass over the lowest levels: mixed-layer means (float64) and most-unstable argmax ----
     // (a rolled loop -- the float64 code below is long and every copy of it costs instruction-cache misses;
     //  the levels are asked for up front as L2 prefetches and then loaded one level ahead)
@@ -501,6 +503,16 @@ XP_HD unsigned suite_column6(const Rd &rd, const Cf &cf, const Prep &pr, const T
             if (v > best) { second = best; best = v; k_mu = k; mu_t = t; mu_td = td; }   // ties: larger p (PF:128)
             else if (v > second) second = v;
         }
+    }
+    // the top of the column (levels above kTopCheckHpa): the coldest environment temperature up there bounds what
+    // a parcel can still meet (sweep_top6).  Read here, with the parcel set-up behind them to hide the latency
+    // (L2 keeps the lines for the sweep); their NaNs must be seen even if the sweep stops below them.
+    float tmin_top = 1e30f;
+    for (int k = pr.k_top; k < nt; ++k) {
+        const uint32_t o_ = rd.off0() + (uint32_t)k * ls;
+        const float t = rd.ldT(o_), td = rd.ldTd(o_);
+        nanacc = f_fma(t, 0.0f, f_fma(td, 0.0f, nanacc));
+        tmin_top = fminf(tmin_top, t);
     }
     // ---- parcels: staged so that the LCL solves, the gathers and their consumers overlap --------------
     FParcel sb, ml, mu;
@@ -552,17 +564,7 @@ XP_HD unsigned suite_column6(const Rd &rd, const Cf &cf, const Prep &pr, const T
     const int it_c = fs ? max(it_b, min(n_stash, nt)) : it_b;
     sweep_segment6<KINDS & 5u, true>(rd, s, crow, stash, fs, 1, it_a, nt, sb, ml, mu);
     sweep_segment6<KINDS, true>(rd, s, crow, stash, fs, it_a, it_c, nt, sb, ml, mu);
-    // the top of the column (levels above kTopCheckHpa): the coldest environment temperature up there bounds what
-    // a parcel can still meet; T/Td of those levels are read here (L2 keeps them for the sweep) -- their NaNs
-    // must be seen even if the sweep stops below them
     const int it_d = max(it_c, min(pr.k_top + 1, nt));
-    float tmin_top = 1e30f;
-    for (int k = pr.k_top; k < nt; ++k) {
-        const uint32_t o_ = rd.off0() + (uint32_t)k * ls;
-        const float t = rd.ldT(o_), td = rd.ldTd(o_);
-        nanacc = f_fma(t, 0.0f, f_fma(td, 0.0f, nanacc));
-        tmin_top = fminf(tmin_top, t);
-    }
     sweep_segment6<KINDS, false>(rd, s, crow, stash, false, it_c, it_d, nt, sb, ml, mu);
     const bool stopped = sweep_top6<KINDS>(rd, s, crow, it_d, nt, tmin_top, sb, ml, mu);
     // last iteration: no level `nt`; every parcel that is not bound for the exact path is above its LCL
