@@ -31,7 +31,10 @@ constexpr float kDecisionEps = 6e-4f;       // K: |parcel - environment| below t
 constexpr float kThetaEMargin = 4e-6f;      // ln(theta_e) gap below this is a most-unstable tie
 constexpr float kCrossSlope = 0.5f;         // K per unit ln p: a crossing with |d0 - d1| < kCrossSlope * dx is too
                                             // shallow to place within 1e-3 relative in pressure in float32
-constexpr double kTopCheckHpa = 125.0;       // v6 sweep: early termination is considered above this pressure
+#ifndef XP_TOP_CHECK_HPA
+#define XP_TOP_CHECK_HPA 125.0
+#endif
+constexpr double kTopCheckHpa = XP_TOP_CHECK_HPA;   // v6 sweep: early termination is considered above this pressure
 constexpr float kStopMargin = 1.0f;          // K: early-termination margin below the coldest environment level
 constexpr unsigned kRedoMuIsSb = 8u;         // redo-mask bit (== kListMuIsSb): write the SB exact result to the MU outputs too
 constexpr double kSaturationMargin = 2e-3;
