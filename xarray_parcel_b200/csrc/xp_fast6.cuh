@@ -249,9 +249,17 @@ XP_HD double exp64_fast(double x) {
 XP_HD void lcl_fast6(double p0, double t, double td, double &lcl_p, double &lcl_t) {
     const double v0 = 17.67 * (td - 273.15) * rcp64(td - 29.65);
     const float v0f = (float)v0, rt = f_rcp((float)t);
-    float q = 1.0f, dF = 1.0f, dtdp = 0.0f;
+    // start from Bolton's (1980) LCL temperature, good to ~0.1 K: q0 = (t_l / T)^3.5 is within ~1e-3 of the root,
+    // two Newton steps reach float32 rounding
+    float q, dF = 1.0f, dtdp = 0.0f;
+    {
+        const float tf = (float)t, tdf = (float)td;
+        const float l2t = f_lg2(tf);
+        const float t_l = 56.0f + f_rcp(f_rcp(tdf - 56.0f) + (l2t - f_lg2(tdf)) * (kLn2 / 800.0f));
+        q = f_ex2(3.5f * (f_lg2(t_l) - l2t));
+    }
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < 2; ++it) {
         const float v = f_fma(kLn2, f_lg2(q), v0f);
         const float iv = f_rcp(17.67f - v);
         const float tdp = f_fma(243.5f * v, iv, 273.15f);
