@@ -225,3 +225,16 @@ def test_significant_hail_parameter_and_storm_proxies(ctx):
     got = parcel.storm_proxies(dev)
     assert got["proxy_Kunz2007"].is_cuda and got["proxy_Kunz2007"].dtype == torch.bool
     assert np.array_equal(got["proxy_Allen2014"].cpu().numpy(), ora["proxy_Allen2014"])
+
+
+def test_wet_bulb_reference_known_answers(ctx):
+    """The reference's own wet-bulb known answers (unit_tests.py:79-104) through the CUDA path: the lookup
+    tables quantise the LCL to 0.5 hPa x 0.02 K cells, so these hold to ~2 decimals (as the reference's LUT
+    mode does for its moist-lapse tests, unit_tests.py:106-112), not to the 5-7 of the exact-ODE mode."""
+    wb = parcel.wet_bulb_temperature(np.array([1000.0]), np.array([25 + 273.15]), np.array([15 + 273.15]))
+    assert abs(float(wb[0]) - (18.3432116 + 273.15)) < 0.03
+    wb = parcel.wet_bulb_temperature(np.array([850.0]), np.array([17.6 + 273.15]), np.array([17.6 + 273.15]))
+    assert abs(float(wb[0]) - (17.6 + 273.15)) < 0.03
+    wb = parcel.wet_bulb_temperature(np.array([1013.0, 1000.0, 990.0]), np.array([25.0, 20.0, 15.0]) + 273.15,
+                                     np.array([20.0, 15.0, 10.0]) + 273.15)
+    assert np.abs(np.asarray(wb) - (np.array([21.44487, 16.73673, 12.06554]) + 273.15)).max() < 0.03

@@ -480,3 +480,22 @@ def test_storm_proxies_hand_values():
     # negative CAPE is ignored (NaN): no proxy from it
     assert not run(mixed_100_cape=-5, shear_magnitude=-5000)["proxy_Craven2004"]
     assert run(mu_cape=2500, mu_mixing_ratio=0.012, lapse_rate_700_500=-7, temp_500=258.15, shear_magnitude=20)["proxy_SHIP_0.1"]
+
+
+# ---- wet bulb (Normand's rule), UT:79-104 ------------------------------------------------------------------
+def test_wet_bulb_temperature(soundings):                        # UT:79-87
+    s = soundings["test_wet_bulb_temperature"]
+    val = op.wet_bulb_temperature(col(s["levels"]), col(s["temp"]), col(s["dewp"]), ODE)
+    assert_almost_equal(val[0, 0], s["truth"], 5)
+
+
+def test_wet_bulb_temperature_saturated(soundings):              # UT:89-96
+    s = soundings["test_wet_bulb_temperature_saturated"]
+    val = op.wet_bulb_temperature(col(s["levels"]), col(s["temp"]), col(s["dewp"]), ODE)
+    assert_almost_equal(val[0, 0], 17.6 + K, 7)
+
+
+def test_wet_bulb_temperature_1d(soundings):                     # UT:98-104 (defined, not run upstream)
+    s = soundings["test_wet_bulb_temperature_1d"]
+    val = op.wet_bulb_temperature(col(s["pressures"]), col(s["temperatures"]), col(s["dewpoints"]), ODE)
+    assert_array_almost_equal(val[:, 0], np.array([21.44487, 16.73673, 12.06554]) + K, 5)
