@@ -19,8 +19,18 @@
 #pragma once
 #include "xp_fast.cuh"
 
+#ifndef XP_PREPASS_UNROLL
+#define XP_PREPASS_UNROLL 1
+#endif
+
+#ifndef XP_PREPASS_UNROLL
+#define XP_PREPASS_UNROLL 1
+#endif
+
 namespace xp {
 namespace fast {
+
+constexpr int kPrepassUnroll = XP_PREPASS_UNROLL;    // the pre-pass loop is rolled: its float64 body is long
 
 // coef[k][m] of the VIRTUAL temperature of the saturated parcel on adiabat (m-1..m+2)*64 at level k
 XP_HD Coef compute_coef_tv(const Prep &pr, const float *curves, int k, int m) {
@@ -479,7 +489,7 @@ XP_HD unsigned suite_column6(const Rd &rd, const Cf &cf, const Prep &pr, const T
     for (int k = 1; k < n_low; ++k) rd.prefetch(off0 + (uint32_t)k * ls);
     const float t_sfc = rd.ldT(off0), td_sfc = rd.ldTd(off0);
     float t_nx = t_sfc, td_nx = td_sfc;
-#pragma unroll 1
+#pragma unroll(kPrepassUnroll)
     for (int k = 0; k < n_low; ++k) {
         const float t = t_nx, td = td_nx;
         off0 += ls;
