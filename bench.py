@@ -258,6 +258,12 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
     torch.cuda.set_device(local)
+    # one process per GPU: stay on the CPU cores / NUMA node next to it (the e2e path is PCIe-bound and its pinned
+    # staging buffers are placed by first touch); XP_BENCH_NO_BIND=1 keeps the inherited affinity
+    cpus = None
+    if not os.environ.get("XP_BENCH_NO_BIND"):
+        from xarray_parcel_b200.partition import bind_host_thread_to_device
+        cpus = bind_host_thread_to_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -370,7 +376,8 @@ def run_b200(args):
                        "parcels": list(kinds), "io_dtype": "f32",
                        "pressure": "shared 1-D axis" if spec["p1d"] else "per column",
                        "l2": f"inputs {b_in / 1e6:.0f} MB per step > 126 MB L2, no flush needed",
-                       "sharding": "column blocks, one per GPU, no collective"},
+                       "sharding": "column blocks, one per GPU, no collective",
+                       "host_cpus_rank0": (f"{len(cpus)} cores next to the GPU (NVML affinity)" if cpus else "inherited")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "timer": "host wall clock around xp_suite(mem=HOST), max over ranks",
                     "checksum_matches_device_run": abs(e2e_check - dev_check) <= 1e-6 * max(1.0, abs(dev_check))},

@@ -45,3 +45,37 @@ def gather_columns(local, n_columns, group=None, align=32):
     dist.all_gather(parts, pad, group=group)
     out = torch.cat(parts, dim=-1)
     return out[..., :n_columns]
+
+
+def bind_host_thread_to_device(device):
+    """Pin the calling process to the CPU cores (and thereby the NUMA node) next to CUDA device `device`.
+
+    The host-memory path (``xp_suite(mem=XP_MEM_HOST)``) is PCIe-bound; with one process per GPU on a
+    multi-socket box its staging buffers should live on the socket the GPU hangs off, or the copies of
+    several ranks meet on the inter-socket link.  Call this BEFORE allocating (pinned) host buffers: first
+    touch then places them on the local node.  Returns the CPU list, or None if NVML is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device)
+        handle = None
+        uuid = getattr(props, "uuid", None)
+        if uuid is not None:
+            try:
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except Exception:
+                handle = None
+        if handle is None:
+            bus = "%08x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, n_words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
