@@ -525,12 +525,26 @@ XP_HD unsigned suite_column6(const Rd &rd, const Cf &cf, const Prep &pr, const T
     // the top of the column (levels above kTopCheckHpa): the coldest environment temperature up there bounds what
     // a parcel can still meet (sweep_top6).  Read here, with the parcel set-up behind them to hide the latency
     // (L2 keeps the lines for the sweep); their NaNs must be seen even if the sweep stops below them.
-    float tmin_top = 1e30f;
+    float tmin_top = 1e30f, tmax_top = -1e30f;
     for (int k = pr.k_top; k < nt; ++k) {
         const uint32_t o_ = rd.off0() + (uint32_t)k * ls;
         const float t = rd.ldT(o_), td = rd.ldTd(o_);
         nanacc = f_fma(t, 0.0f, f_fma(td, 0.0f, nanacc));
         tmin_top = fminf(tmin_top, t);
+        tmax_top = fmaxf(tmax_top, t);
+    }
+    // the bound rests on virtual temperature >= temperature, i.e. on a non-negative mixing ratio
+    // eps es(Td)/(p - es(T)) (PF:684-710): that needs es(T) < p at every one of these levels.  Where the
+    // stratopause is warm enough for es(T) to reach the lowest pressure swept, the sweep runs to the top.
+    // There the float32 mixing ratio also loses its accuracy as es(T) comes close to p (the reference's formula is
+    // singular at es(T) = p): columns with a level within 5 % of that go to the exact path.
+    bool singular = false;
+    if (nt > pr.k_top && !(f_es(tmax_top) < 0.5f * pr.p[nt - 1])) {
+        tmin_top = -1e30f;
+        for (int k = pr.k_top; k < nt; ++k) {
+            const float pk = pr.p[k];
+            if (fabsf(pk - f_es(rd.ldT(rd.off0() + (uint32_t)k * ls))) < 0.05f * pk) singular = true;
+        }
     }
     // ---- parcels: staged so that the LCL solves, the gathers and their consumers overlap --------------
     FParcel sb, ml, mu;
@@ -595,7 +609,7 @@ XP_HD unsigned suite_column6(const Rd &rd, const Cf &cf, const Prep &pr, const T
     // ---- results ---------------------------------------------------------------------------------------
     // A NaN/Inf T or Td in the pre-pass levels poisons nanacc; one in the swept levels makes the area
     // sums of every parcel that sweeps it non-finite (each parcel sweeps every level above its start).
-    bool nan_seen = !(nanacc == 0.0f);
+    bool nan_seen = !(nanacc == 0.0f) || singular;
     if (KINDS & 1u) nan_seen = nan_seen || !(sb.pos - sb.tot < 3e38f);
     if (KINDS & 2u) nan_seen = nan_seen || !(ml.pos - ml.tot < 3e38f);
     if (KINDS & 4u) nan_seen = nan_seen || !(mu.pos - mu.tot < 3e38f);
