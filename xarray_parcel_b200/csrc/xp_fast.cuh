@@ -302,45 +302,56 @@ XP_HD double exp64_fast(double x) {
 }
 
 
-// ---- LCL (metpy.calc.lcl fixed point, PF:644) ----------------------------------------------------
-// With w = eps es(Td)/(p0 - es(Td)) the vapour pressure of the lifted parcel is e(p) = es(Td) p/p0, so
-//   v(q) = ln(e/6.112) = v0 + ln q,   v0 = 17.67 (Td - 273.15)/(Td - 29.65),  q = p/p0
-//   tdp(v) = 243.5 v/(17.67 - v) + 273.15
-// and the fixed point is F(q) = q - (tdp(v(q))/T)^3.5 = 0.  Newton in float32 from q = 1, then ONE
-// Newton step in float64: the result agrees with the fully converged iteration to ~1e-12 relative,
-// which is what makes the table-cell selection below identical to the reference's.
-XP_HD void lcl_fast(double p0, double t, double td, double &lcl_p, double &lcl_t) {
-    const double v0 = 17.67 * (td - 273.15) / (td - 29.65);
-    // float32 Newton
+// ---- LCL (metpy.calc.lcl fixed point, PF:644), cheaper float64 polish -------------------------------------------
+// Same scheme as lcl_fast (xp_fast.cuh): float32 Newton on F(q) = q - (tdp(v0 + ln q)/T)^3.5, then ONE float64
+// Newton step.  Here only the RESIDUAL F is evaluated in float64 (one log, reciprocals and a square root by
+// float32-seeded Newton iterations, no IEEE division); its derivative is the float32 one, whose 1e-6 relative
+// error enters the step (|dq| ~ 1e-7 q) at second order.
+XP_HD void lcl_fast6(double p0, double t, double td, double &lcl_p, double &lcl_t) {
+    const double v0 = 17.67 * (td - 273.15) * rcp64(td - 29.65);
     const float v0f = (float)v0, rt = f_rcp((float)t);
-    float q = 1.0f;
+    // start from Bolton's (1980) LCL temperature, good to ~0.1 K: q0 = (t_l / T)^3.5 is within ~1e-3 of the root,
+    // two Newton steps reach float32 rounding
+    float q, dF = 1.0f, dtdp = 0.0f;
+    {
+        const float tf = (float)t, tdf = (float)td;
+        const float l2t = f_lg2(tf);
+        const float t_l = 56.0f + f_rcp(f_rcp(tdf - 56.0f) + (l2t - f_lg2(tdf)) * (kLn2 / 800.0f));
+        q = f_ex2(3.5f * (f_lg2(t_l) - l2t));
+    }
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < 2; ++it) {
         const float v = f_fma(kLn2, f_lg2(q), v0f);
         const float iv = f_rcp(17.67f - v);
         const float tdp = f_fma(243.5f * v, iv, 273.15f);
         const float r = tdp * rt;
         const float r35 = r * r * r * f_sqrt(r);
-        const float dtdp = 243.5f * 17.67f * iv * iv;                   // d tdp / d v
-        const float dF = 1.0f - 3.5f * r35 * dtdp * f_rcp(tdp * q);     // d/dq: r35 * 3.5 * (dtdp/tdp) * (1/q)
+        dtdp = 243.5f * 17.67f * iv * iv;                               // d tdp / d v
+        dF = 1.0f - 3.5f * r35 * dtdp * f_rcp(tdp * q);                 // d/dq: r35 * 3.5 * (dtdp/tdp) * (1/q)
         q = q - (q - r35) * f_rcp(dF);
     }
-    // float64 polish
-    double qd = (double)q;
-    {
-        const double v = v0 + log(qd);
-        const double iv = 1.0 / (17.67 - v);
-        const double tdp = 243.5 * v * iv + 273.15;
-        const double r = tdp / t;
-        const double r35 = r * r * r * sqrt(r);
-        const double dtdp = 243.5 * 17.67 * iv * iv;
-        const double dF = 1.0 - 3.5 * r35 * dtdp / (tdp * qd);
-        const double dq = (qd - r35) / dF;
-        qd = qd - dq;
-        // tdp at the polished q, first order (|dq| ~ 1e-6: the second-order term is < 1e-11 K)
-        lcl_t = tdp - dtdp * dq / qd;
-    }
-    lcl_p = p0 * qd;
+    // (dF, dtdp belong to the previous iterate: they differ from the ones at q by ~1e-6 relative)
+    const double qd = (double)q;
+    const double v = v0 + log64_fast(qd);
+    const double tdp = 243.5 * v * rcp64(17.67 - v) + 273.15;
+    const double r = tdp * rcp64(t);
+    const double r35 = r * r * r * sqrt64(r);
+    const double dq = (qd - r35) * (double)f_rcp(dF);
+    // tdp at the polished q, first order (|dq| ~ 1e-7: the second-order term is < 1e-11 K)
+    lcl_t = tdp - (double)(dtdp * f_rcp(q)) * dq;
+    lcl_p = p0 * (qd - dq);
+}
+
+// (the first version of the solver -- four Newton steps from q = 1, libm float64 polish -- gave the same LCL to
+// 2e-11; every fast path now uses the cheaper one)
+XP_HD void lcl_fast(double p0, double t, double td, double &lcl_p, double &lcl_t) { lcl_fast6(p0, t, td, lcl_p, lcl_t); }
+
+// mixed_parcel's last steps (PF:268-282) with the branch-free float64 helpers: temperature = theta * exner(p0),
+// dewpoint = dewpoint(vapor_pressure(p0, w)).
+XP_HD void mixed_parcel_t_td(double p0, double theta, double w, double &t, double &td) {
+    t = theta * exp64_fast(kKappa * log64_fast(p0 * 1e-3));                      // PF:268-269
+    const double val = log64_fast(p0 * w * rcp64(kEps + w) * (1.0 / kSat0));     // PF:275-282
+    td = 243.5 * val * rcp64(17.67 - val) + kZeroC;
 }
 
 // ---- table cell of the LCL (PF:554-557 .sel(method='nearest')) --------------------------------------------

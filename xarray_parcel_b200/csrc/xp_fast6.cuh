@@ -173,46 +173,6 @@ XP_HD void sweep_finish6(const FParcel &s, const Cf &cf, const Prep &pr, const O
     r.lcl_p = s.lcl_p; r.lcl_t = s.lcl_t; r.lcl_tv = s.lcl_tv;
 }
 
-// ---- LCL (metpy.calc.lcl fixed point, PF:644), cheaper float64 polish -------------------------------------------
-// Same scheme as lcl_fast (xp_fast.cuh): float32 Newton on F(q) = q - (tdp(v0 + ln q)/T)^3.5, then ONE float64
-// Newton step.  Here only the RESIDUAL F is evaluated in float64 (one log, reciprocals and a square root by
-// float32-seeded Newton iterations, no IEEE division); its derivative is the float32 one, whose 1e-6 relative
-// error enters the step (|dq| ~ 1e-7 q) at second order.
-XP_HD void lcl_fast6(double p0, double t, double td, double &lcl_p, double &lcl_t) {
-    const double v0 = 17.67 * (td - 273.15) * rcp64(td - 29.65);
-    const float v0f = (float)v0, rt = f_rcp((float)t);
-    // start from Bolton's (1980) LCL temperature, good to ~0.1 K: q0 = (t_l / T)^3.5 is within ~1e-3 of the root,
-    // two Newton steps reach float32 rounding
-    float q, dF = 1.0f, dtdp = 0.0f;
-    {
-        const float tf = (float)t, tdf = (float)td;
-        const float l2t = f_lg2(tf);
-        const float t_l = 56.0f + f_rcp(f_rcp(tdf - 56.0f) + (l2t - f_lg2(tdf)) * (kLn2 / 800.0f));
-        q = f_ex2(3.5f * (f_lg2(t_l) - l2t));
-    }
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const float v = f_fma(kLn2, f_lg2(q), v0f);
-        const float iv = f_rcp(17.67f - v);
-        const float tdp = f_fma(243.5f * v, iv, 273.15f);
-        const float r = tdp * rt;
-        const float r35 = r * r * r * f_sqrt(r);
-        dtdp = 243.5f * 17.67f * iv * iv;                               // d tdp / d v
-        dF = 1.0f - 3.5f * r35 * dtdp * f_rcp(tdp * q);                 // d/dq: r35 * 3.5 * (dtdp/tdp) * (1/q)
-        q = q - (q - r35) * f_rcp(dF);
-    }
-    // (dF, dtdp belong to the previous iterate: they differ from the ones at q by ~1e-6 relative)
-    const double qd = (double)q;
-    const double v = v0 + log64_fast(qd);
-    const double tdp = 243.5 * v * rcp64(17.67 - v) + 273.15;
-    const double r = tdp * rcp64(t);
-    const double r35 = r * r * r * sqrt64(r);
-    const double dq = (qd - r35) * (double)f_rcp(dF);
-    // tdp at the polished q, first order (|dq| ~ 1e-7: the second-order term is < 1e-11 K)
-    lcl_t = tdp - (double)(dtdp * f_rcp(q)) * dq;
-    lcl_p = p0 * (qd - dq);
-}
-
 // ---- parcel set-up in three stages, so that the three parcels of a column overlap their latencies -------------------
 // (setup_parcel of xp_fast.cuh does the same work for one parcel start to end.)
 //   A  LCL solve (arithmetic only)

@@ -195,8 +195,8 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
     }
     if (KINDS & 2u) {
         const double depth = fabs(top_ml - bottom);                              // PF:158-159
-        const double mp_t = (1. / depth) * sum_th * exner(bottom);               // PF:161, 268-269
-        const double mp_td = dewpoint_from_e(vapor_pressure(bottom, (1. / depth) * sum_w));   // PF:275-282
+        double mp_t, mp_td;
+        mixed_parcel_t_td(bottom, (1. / depth) * sum_th, (1. / depth) * sum_w, mp_t, mp_td);   // PF:161, 268-282
         if (!ml_done || K_ml < 1) { redo |= 2u; K_ml = max(K_ml, 1); }   // no level above / NaN layer: exact path
         setup_parcel_pcol(rd, L, tb, o, bottom, mp_t, mp_td, x_sfc, K_ml, ml);
         res[1].par_p = p_sfc; res[1].par_t = (float)mp_t; res[1].par_td = (float)mp_td; res[1].shift = K_ml;

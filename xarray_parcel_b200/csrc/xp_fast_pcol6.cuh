@@ -269,8 +269,7 @@ XP_HD unsigned suite_column_pcol6(const Rd &rd, int L, const Tables &tb, const O
     if (KINDS & 1u) stage_a(bottom, (double)t_sfc, (double)td_sfc, sb, u_sb);
     if (KINDS & 2u) {
         const double depth = fabs(top_ml - bottom);                              // PF:158-159
-        mp_t = (1. / depth) * sum_th * exner(bottom);                            // PF:161, 268-269
-        mp_td = dewpoint_from_e(vapor_pressure(bottom, (1. / depth) * sum_w));   // PF:275-282
+        mixed_parcel_t_td(bottom, (1. / depth) * sum_th, (1. / depth) * sum_w, mp_t, mp_td);   // PF:161, 268-282
         if (!ml_done || K_ml < 1) { redo |= 2u; K_ml = max(K_ml, 1); }           // no level above / NaN layer: exact path
         stage_a(bottom, mp_t, mp_td, ml, u_ml);
     }
