@@ -53,12 +53,22 @@ XP_HD void setup_parcel_pcol(const Rd &rd, int L, const Tables &tb, const Opts &
     pc.lcl_env_t = pc.lcl_env_td = pc.lcl_env_tv = f_qnan();
     sweep_init(pc, x_start, o.vtc ? f_tv(t0f, w_parcel) : t0f);
     // LCL position among the levels of the lifted column (insert_level PF:965-966): exact in float64
+    // (the pressures are read four levels at a time: the loads of a chunk are independent, so the search costs one
+    //  memory round trip per four levels instead of one per level)
     int ka = knext;
     double pka = 0.0, pkb = p0;
-    while (ka < L) {
-        pka = (double)rd.P(ka);
-        if (!(pka >= lp)) break;
-        pkb = pka; ++ka;
+    bool found = false;
+    while (ka < L && !found) {
+        float pq[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pq[j] = (ka + j < L) ? rd.P(ka + j) : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (found || ka >= L) continue;
+            pka = (double)pq[j];
+            if (!(pka >= lp)) found = true;
+            else { pkb = pka; ++ka; }
+        }
     }
     pc.ka = ka;
     const bool before_is_start = (ka == knext);
@@ -131,8 +141,13 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
     bool ml_done = !(KINDS & 2u), mu_done = !(KINDS & 4u);
     float best = -1e30f, second = -1e30f, mu_t = 0.0f, mu_td = 0.0f, mu_p = p_sfc;
     int k_mu = 0;
+    float p_n1 = p_sfc, t_n1 = t_sfc, td_n1 = td_sfc, p_n2 = 0.0f, t_n2 = 0.0f, td_n2 = 0.0f;
+    if (1 < L) { p_n2 = rd.P(1); t_n2 = rd.T(1); td_n2 = rd.Td(1); }
     for (int k = 0; k < L && !(ml_done && mu_done); ++k) {
-        const float pf = rd.P(k), t = rd.T(k), td = rd.Td(k);
+        // levels are read two iterations ahead (this loop's float64 body hides one memory round trip, not two)
+        const float pf = p_n1, t = t_n1, td = td_n1;
+        p_n1 = p_n2; t_n1 = t_n2; td_n1 = td_n2;
+        if (k + 2 < L) { p_n2 = rd.P(k + 2); t_n2 = rd.T(k + 2); td_n2 = rd.Td(k + 2); }
         nanacc = f_fma(pf, 0.0f, f_fma(t, 0.0f, f_fma(td, 0.0f, nanacc)));
         const double p = (double)pf;
         if (k > 0 && !(p < pp)) bad_axis = true;
