@@ -407,14 +407,13 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
         pp.list = list; pp.list_count = count;
         const unsigned g = (unsigned)((cols.n + kPColThreads - 1) / kPColThreads);
         const bool profile = wants_profile(kind_mask, outs);
-        // default options, scalar outputs, 32-bit element offsets: the v6 sweep (xp_fast_pcol6.cuh)
+        // The v6 sweep for per-column pressure (xp_fast_pcol6.cuh) is kept for experiments (XP_PCOL6=1: surface-based
+        // parcel only, 2: every kind).  Measured on the B200 (1 M x 70 SB / 2.8 M x 70 SB+ML, M columns/s): generic
+        // sweep 1069 / 693, v6 sweep 938 / 506 -- since the generic sweep reads its pre-pass levels ahead and
+        // searches the LCL level in chunks of independent loads it wins everywhere, so it is the default.
         static int pcol6 = -1;
-        if (pcol6 < 0) { const char *e = getenv("XP_PCOL6"); pcol6 = e ? atoi(e) : 1; }
+        if (pcol6 < 0) { const char *e = getenv("XP_PCOL6"); pcol6 = e ? atoi(e) : 0; }
         const uint64_t span = (uint64_t)cols.n + (uint64_t)cols.L * (uint64_t)std::max(cols.ls, cols.pls);
-        // Measured on the B200: 1 M x 70 surface-based 934 vs 862 M columns/s for the generic
-        // sweep; with the mixed-layer parcel the generic sweep wins (595 vs 507: it skips that parcel's rows below
-        // the layer top with a nearly warp-uniform branch), so only the surface-based kernel is dispatched here
-        // unless XP_PCOL6=2 forces the v6 sweep for every kind.
         if (pcol6 && ((kind_mask & 7) == 1 || pcol6 == 2) && mode && !profile && span < ((uint64_t)1 << 32)) {
             const int lv = kPCol6StashLevels;
             const size_t smem6 = (size_t)lv * 3 * sizeof(float) * kPCol6Threads;
