@@ -139,6 +139,12 @@ def test_conv_properties_assembly(ctx, compat):
                 assert np.array_equal(np.isnan(g), np.isnan(v)), k
                 ok = ~np.isnan(v)
                 assert np.allclose(g[ok], v[ok], rtol=1e-8, atol=1e-8), k
+        if not min_set:
+            # the full chain the reference's users run: conv_properties -> storm_proxies (PF:2323-2407)
+            prox, prox_ora = parcel.storm_proxies(got), op.storm_proxies(ora)
+            for k in _lib.PROXY_FLAGS:
+                assert np.array_equal(np.asarray(prox[k]).astype(bool), np.asarray(prox_ora[k]).astype(bool)), k
+            _same(prox["ship"], prox_ora["ship"], rtol=1e-7)
 
 
 # ---- pointwise kernels ------------------------------------------------------------------
