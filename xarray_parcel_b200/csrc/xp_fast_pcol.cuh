@@ -53,11 +53,29 @@ XP_HD void setup_parcel_pcol(const Rd &rd, int L, const Tables &tb, const Opts &
     pc.lcl_env_t = pc.lcl_env_td = pc.lcl_env_tv = f_qnan();
     sweep_init(pc, x_start, o.vtc ? f_tv(t0f, w_parcel) : t0f);
     // LCL position among the levels of the lifted column (insert_level PF:965-966): exact in float64
-    // (the pressures are read four levels at a time: the loads of a chunk are independent, so the search costs one
-    //  memory round trip per four levels instead of one per level)
+    // (two memory round trips instead of one per level: eight independent probes four levels apart bracket the
+    //  LCL, four more loads resolve the bracket; columns whose LCL lies more than 32 levels up continue in chunks)
     int ka = knext;
     double pka = 0.0, pkb = p0;
     bool found = false;
+    {
+        float pq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pq[j] = (ka + 4 * j < L) ? rd.P(ka + 4 * j) : 0.0f;
+        int jc = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) jc += (jc == j && ka + 4 * j < L && (double)pq[j] >= lp) ? 1 : 0;
+        // probes 0 .. jc-1 are at or below the LCL (p >= lcl_p); the LCL level is among the four levels after probe jc-1
+        if (jc == 0) {
+            if (ka < L) { pka = (double)pq[0]; found = true; }
+        } else {
+            float pl = pq[0];
+#pragma unroll
+            for (int j = 1; j < 8; ++j) pl = (j == jc - 1) ? pq[j] : pl;
+            ka += 4 * (jc - 1);                               // a level with p >= lcl_p
+            pkb = (double)pl; ++ka;
+        }
+    }
     while (ka < L && !found) {
         float pq[4];
 #pragma unroll
