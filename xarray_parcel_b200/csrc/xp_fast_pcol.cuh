@@ -251,25 +251,42 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
         if (KINDS & 2u) row0(ml, 1, res[1]);
         if (KINDS & 4u) row0(mu, 2, res[2]);
     }
-    EnvLevel e_prv = {p_sfc, t_sfc, td_sfc, 0.0f};
-    float b_prv = 0.0f, x_prv = x_sfc, p_prv = p_sfc;
+    // Profile rows of ONE lifted kind (the reference's mixed_layer_cape_cin / most_unstable_cape_cin return the
+    // profile from the parcel's own start): row r of a column is written at iteration kfirst - 1 + r, and kfirst
+    // differs from lane to lane -- at any one time the 32 lanes of a warp would write 32 DIFFERENT rows, 4 bytes
+    // per 128-byte line, which the L2 turns into read-modify-write traffic (measured: 5.5 x the algorithmic reads).
+    // So the sweep of such a call is re-based per lane: iteration `it` visits level it + shift (shift =
+    // kfirst - 1), every lane writes row `it` at iteration `it` -- coalesced -- and the level reads are the ones
+    // that diverge (they only cost cache lines that the neighbouring lanes use a few iterations later).
+    int shift = 0;
+    if (Prof::kEnabled && (KINDS == 2u || KINDS == 4u)) {
+        PColParcel &c = (KINDS == 2u) ? ml : mu;
+        shift = min(max(c.kfirst - 1, 0), L - 1);
+        c.ka -= shift; c.kfirst -= shift;
+    }
+    const int Lq = L - shift;                         // levels from the first swept one's predecessor up
+    float p_s = p_sfc, t_s = t_sfc, td_s = td_sfc;
+    if (shift > 0) { p_s = rd.P(shift); t_s = rd.T(shift); td_s = rd.Td(shift); }
+    EnvLevel e_prv = {p_s, t_s, td_s, 0.0f};
+    float b_prv = 0.0f, x_prv = (shift > 0) ? kLn2 * f_lg2(p_s) : x_sfc, p_prv = p_s;
     float w_prv;
-    {   // node/weight of the surface pressure and the first gathers
-        const float s0 = (p_sfc - 2.5f) * 2.0f;
+    {   // node/weight of the pressure below the first swept level and the first gathers
+        const float s0 = (p_s - 2.5f) * 2.0f;
         const int j0 = min(max((int)s0, 0), kNP - 2);
         w_prv = s0 - (float)j0;
         if (KINDS & 1u) { sb.f0 = XP_LDG(sb.curve + j0); sb.f1 = XP_LDG(sb.curve + j0 + 1); }
         if (KINDS & 2u) { ml.f0 = XP_LDG(ml.curve + j0); ml.f1 = XP_LDG(ml.curve + j0 + 1); }
         if (KINDS & 4u) { mu.f0 = XP_LDG(mu.curve + j0); mu.f1 = XP_LDG(mu.curve + j0 + 1); }
     }
-    const float *ppp = rd.pptr(1), *tp = rd.tptr(1), *tdp = rd.tdptr(1);
+    const int k1 = min(1 + shift, L - 1);
+    const float *ppp = rd.pptr(k1), *tp = rd.tptr(k1), *tdp = rd.tdptr(k1);
     const int64_t ls = rd.stride(), pls = rd.pstride();
     float p_nxt = Rd::ld(ppp), t_nxt = Rd::ld(tp), td_nxt = Rd::ld(tdp);
-    for (int it = 1; it <= L; ++it) {
-        const bool last = (it == L);
+    for (int it = 1; it <= Lq; ++it) {
+        const bool last = (it == Lq);
         const float p_cur0 = p_nxt, t = t_nxt, td = td_nxt;
         ppp += pls; tp += ls; tdp += ls;
-        if (it + 1 < L) { p_nxt = Rd::ld(ppp); t_nxt = Rd::ld(tp); td_nxt = Rd::ld(tdp); }
+        if (it + 1 < Lq) { p_nxt = Rd::ld(ppp); t_nxt = Rd::ld(tp); td_nxt = Rd::ld(tdp); }
         float b_cur = 0.0f, x_cur = x_prv, pk_cur = 0.0f, p_cur = p_prv, w_cur = w_prv;
         EnvLevel e_cur = e_prv;
         int j_cur = 0;
@@ -299,7 +316,7 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
     if (Prof::kEnabled) {       // rows above the lifted column are NaN (PF:1552, 1637: levels dropped below)
         const float qn = f_qnan();
         auto pad = [&](const PColParcel &c, int q) {
-            for (int row = L - c.kfirst + 2; row <= L; ++row) prof.put(q, row, qn, qn, qn, qn, qn, qn);
+            for (int row = Lq - c.kfirst + 2; row <= L; ++row) prof.put(q, row, qn, qn, qn, qn, qn, qn);
         };
         if (KINDS & 1u) pad(sb, 0);
         if (KINDS & 2u) pad(ml, 1);
