@@ -208,6 +208,34 @@ xp_status xp_level_crossing(xp_context *ctx, const void *coords, int64_t coords_
                             int32_t n_levels, int64_t n_columns, int32_t dtype, double level,
                             void *output, void *stream);
 
+/* ---- layer primitives of the parcel selectors (device memory only) -----------------------------------
+ * xp_mixed_layer: mixed_layer (PF:137-162) of n_fields <= 4 variables [n_levels][n_columns]: the mass-weighted
+ * mean over the lowest `depth` hPa = trapz(x = 'pressure') (PF:164-206) over get_layer(interpolate=True)
+ * (PF:63-100; the layer top, bottom - depth, is interpolated in ln p and inserted, PF:85-90) divided by the
+ * pressure depth (PF:158-161).  `pressure_field` is the index of the field that is the pressure variable itself
+ * (its value at the inserted level is the top pressure, PF:87), or -1.  NaN areas are skipped like xarray's sum; columns must satisfy valid_data
+ * (PF:2308-2321: pressure decreasing with the level index), trailing NaN pressures end a column. */
+xp_status xp_mixed_layer(xp_context *ctx, const void *pressure, int64_t pressure_level_stride,
+                         int32_t pressure_is_1d, const void *const *fields, void *const *outputs, int32_t n_fields,
+                         int32_t pressure_field, int64_t level_stride, int32_t n_levels, int64_t n_columns,
+                         int32_t dtype, double depth, void *stream);
+/* xp_mixed_parcel: mixed_parcel (PF:229-289) with every variable of the Dataset the reference returns
+ * ([n_columns] each, any pointer may be NULL): theta and mixing_ratio (the layer means of PF:253/258),
+ * temperature (PF:268), vapour_pressure (PF:275), dewpoint (PF:280) and pressure (= level-0 pressure, PF:287). */
+typedef struct xp_mixed_parcel_out {
+    void *theta, *mixing_ratio, *temperature, *vapour_pressure, *dewpoint, *pressure;
+} xp_mixed_parcel_out;
+xp_status xp_mixed_parcel(xp_context *ctx, const void *pressure, int64_t pressure_level_stride,
+                          int32_t pressure_is_1d, const void *temperature, const void *dewpoint,
+                          int64_t level_stride, int32_t n_levels, int64_t n_columns, int32_t dtype, double depth,
+                          const xp_mixed_parcel_out *out, void *stream);
+/* xp_layer_bounds: the pressures that bound get_layer (PF:63-100): bottom = the column's largest pressure
+ * (PF:80); top = bottom - depth when interpolate != 0 (PF:84), else bound_pressure (PF:208-227): the level
+ * pressure closest to it, the larger one on a tie.  Either output may be NULL. */
+xp_status xp_layer_bounds(xp_context *ctx, const void *pressure, int64_t pressure_level_stride,
+                          int32_t pressure_is_1d, int32_t n_levels, int64_t n_columns, int32_t dtype, double depth,
+                          int32_t interpolate, void *bottom_pressure, void *top_pressure, void *stream);
+
 /* ---- pointwise helpers around the hot path (callers and front end) -----------------
  * All arrays hold `n` points of `dtype` in device memory (any shape, flattened); one thread per point. */
 

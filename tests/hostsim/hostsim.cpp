@@ -12,6 +12,7 @@
 #include "../../xarray_parcel_b200/csrc/xp_fast_pcol.cuh"
 #include "../../xarray_parcel_b200/csrc/xp_fast6.cuh"
 #include "../../xarray_parcel_b200/csrc/xp_fast_pcol6.cuh"
+#include "../../xarray_parcel_b200/csrc/xp_layers.cuh"
 
 namespace {
 
@@ -273,4 +274,49 @@ extern "C" void hostsim_lcl_fast(const double *p, const double *t, const double 
 // Branch-free float64 log / exp of the v6 fast path (xp_fast6.cuh): which = 0 log, 1 exp.
 extern "C" void hostsim_fast_math64(const double *x, int64_t n, int which, double *y) {
     for (int64_t i = 0; i < n; ++i) y[i] = which == 0 ? xp::fast::log64_fast(x[i]) : xp::fast::exp64_fast(x[i]);
+}
+
+// Layer primitives (xp_layers.cuh): mixed_layer of n_fields variables x [n_fields][L][n], mixed_parcel (out
+// [6][n]) and get_layer's bounds, column by column.
+extern "C" void hostsim_mixed_layer(const double *p, int p1d, const double *x, int n_fields, int64_t n, int L,
+                                    double depth, int pressure_field, double *out /*[n_fields][n]*/) {
+    for (int64_t c = 0; c < n; ++c) {
+        const double *pc = p1d ? p : p + c;
+        const int64_t pls = p1d ? 1 : n;
+        auto pressure_at = [&](int k) { return pc[(int64_t)k * pls]; };
+        for (int f0 = 0; f0 < n_fields; f0 += 4) {
+            auto load = [&](int k, double (&v)[4]) {
+                for (int f = 0; f < 4; ++f)
+                    v[f] = f0 + f < n_fields ? x[((int64_t)(f0 + f) * L + k) * n + c] : 0.0;
+            };
+            double bottom, top, mean[4];
+            xp::mixed_layer_means<4>(L, pressure_at, load, depth, bottom, top, mean,
+                                     pressure_field >= f0 && pressure_field < f0 + 4 ? pressure_field - f0 : -1);
+            for (int f = 0; f < 4 && f0 + f < n_fields; ++f) out[(int64_t)(f0 + f) * n + c] = mean[f];
+        }
+    }
+}
+
+extern "C" void hostsim_mixed_parcel(const double *p, int p1d, const double *t, const double *td, int64_t n, int L,
+                                     double depth, double *out /*[6][n]*/) {
+    for (int64_t c = 0; c < n; ++c) {
+        const double *pc = p1d ? p : p + c;
+        const int64_t pls = p1d ? 1 : n;
+        auto pressure_at = [&](int k) { return pc[(int64_t)k * pls]; };
+        auto t_at = [&](int k) { return t[(int64_t)k * n + c]; };
+        auto td_at = [&](int k) { return td[(int64_t)k * n + c]; };
+        double o[6];
+        xp::mixed_parcel_full(L, pressure_at, t_at, td_at, depth, o);
+        for (int f = 0; f < 6; ++f) out[(int64_t)f * n + c] = o[f];
+    }
+}
+
+extern "C" void hostsim_layer_bounds(const double *p, int p1d, int64_t n, int L, double depth, int interpolate,
+                                     double *bottom, double *top) {
+    for (int64_t c = 0; c < n; ++c) {
+        const double *pc = p1d ? p : p + c;
+        const int64_t pls = p1d ? 1 : n;
+        auto pressure_at = [&](int k) { return pc[(int64_t)k * pls]; };
+        xp::layer_bounds(L, pressure_at, depth, interpolate != 0, bottom[c], top[c]);
+    }
 }

@@ -21,7 +21,7 @@ KINDS = {"sb": 0, "ml": 1, "mu": 2, "explicit": 3}
 
 
 def build():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("xp_math.cuh", "xp_column.cuh", "xp_parcels.cuh", "xp_fast.cuh", "xp_fast_pcol.cuh", "xp_fast6.cuh", "xp_fast_pcol6.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("xp_math.cuh", "xp_column.cuh", "xp_parcels.cuh", "xp_fast.cuh", "xp_fast_pcol.cuh", "xp_fast6.cuh", "xp_fast_pcol6.cuh", "xp_layers.cuh")]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     os.makedirs(BUILD, exist_ok=True)
@@ -120,3 +120,40 @@ def fast_suite(p, t, td, tables, vtc=True, lcl_interp="log", pos_cape_neg_cin=Tr
         if prof is not None:
             res[kind]["profile"] = {k: prof[q, i] for i, k in enumerate(PROFILE)}
     return res, redo
+
+
+def mixed_layer(p, fields, depth=100.0, pressure_field=-1):
+    """xp_layers.cuh mixed_layer_means on float64 [L, N] fields; returns a list of [N] arrays."""
+    x = np.ascontiguousarray(np.stack(fields), dtype=np.float64)
+    F, L, N = x.shape
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    out = np.empty((F, N))
+    vp = ctypes.c_void_p
+    lib().hostsim_mixed_layer(vp(p.ctypes.data), int(p.ndim == 1), vp(x.ctypes.data), F, ctypes.c_int64(N), L,
+                              ctypes.c_double(depth), int(pressure_field), vp(out.ctypes.data))
+    return list(out)
+
+
+def mixed_parcel(p, t, td, depth=100.0):
+    """xp_layers.cuh mixed_parcel_full; dict of the six [N] variables of PF:229-289."""
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    td = np.ascontiguousarray(td, dtype=np.float64)
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    L, N = t.shape
+    out = np.empty((6, N))
+    vp = ctypes.c_void_p
+    lib().hostsim_mixed_parcel(vp(p.ctypes.data), int(p.ndim == 1), vp(t.ctypes.data), vp(td.ctypes.data),
+                               ctypes.c_int64(N), L, ctypes.c_double(depth), vp(out.ctypes.data))
+    names = ["theta", "mixing_ratio", "temperature", "vapour_pressure", "dewpoint", "pressure"]
+    return dict(zip(names, out))
+
+
+def layer_bounds(p, n_columns, depth=100.0, interpolate=True):
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    L = p.shape[0]
+    bottom, top = np.empty(n_columns), np.empty(n_columns)
+    vp = ctypes.c_void_p
+    lib().hostsim_layer_bounds(vp(p.ctypes.data), int(p.ndim == 1), ctypes.c_int64(n_columns), L,
+                               ctypes.c_double(depth), int(bool(interpolate)), vp(bottom.ctypes.data),
+                               vp(top.ctypes.data))
+    return bottom, top

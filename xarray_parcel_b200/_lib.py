@@ -61,13 +61,21 @@ EXPORTS = ["xp_version", "xp_create", "xp_destroy", "xp_last_error", "xp_take_fl
            "xp_last_kernel_ms", "xp_last_exact_count", "xp_interp_levels",
            "xp_level_crossing", "xp_dewpoint_from_specific_humidity", "xp_saturation_mixing_ratio",
            "xp_dry_lapse", "xp_mixing_ratio", "xp_virtual_temperature", "xp_wet_bulb_temperature",
-           "xp_significant_hail_parameter", "xp_storm_proxies"]
+           "xp_significant_hail_parameter", "xp_storm_proxies", "xp_mixed_layer", "xp_mixed_parcel",
+           "xp_layer_bounds"]
 
 PROXY_INPUTS = ["mixed_100_cape", "mixed_50_cape", "mu_cape", "shear_magnitude", "mixed_100_lifted_index",
                 "mixed_100_dci", "positive_shear", "mixed_50_cin", "mixed_100_cin", "lapse_rate_700_500",
                 "mu_mixing_ratio", "temp_500", "freezing_level"]
 PROXY_FLAGS = ["proxy_Craven2004", "proxy_Kunz2007", "proxy_Trapp2007", "proxy_Marsh2009", "proxy_Allen2011",
                "proxy_Allen2014", "proxy_Eccel2012", "proxy_Mohr2013", "proxy_SHIP_0.1"]
+
+
+MIXED_PARCEL_FIELDS = ["theta", "mixing_ratio", "temperature", "vapour_pressure", "dewpoint", "pressure"]
+
+
+class XpMixedParcelOut(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in MIXED_PARCEL_FIELDS]
 
 
 class XpProxyInputs(ctypes.Structure):
@@ -149,6 +157,13 @@ def load_library():
         lib.xp_significant_hail_parameter.argtypes = [c_void_p] + [c_void_p] * 6 + [c_int64, c_int32, c_void_p, c_void_p]
         lib.xp_storm_proxies.argtypes = [c_void_p, ctypes.POINTER(XpProxyInputs), c_int64, c_int32,
                                          ctypes.POINTER(XpProxyOutputs), c_void_p]
+        lib.xp_mixed_layer.argtypes = [c_void_p, c_void_p, c_int64, c_int32, ctypes.POINTER(c_void_p),
+                                       ctypes.POINTER(c_void_p), c_int32, c_int32, c_int64, c_int32, c_int64,
+                                       c_int32, c_double, c_void_p]
+        lib.xp_mixed_parcel.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_int32,
+                                        c_int64, c_int32, c_double, ctypes.POINTER(XpMixedParcelOut), c_void_p]
+        lib.xp_layer_bounds.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int64, c_int32, c_double,
+                                        c_int32, c_void_p, c_void_p, c_void_p]
         lib.xp_launch_count.argtypes = [c_void_p]
         lib.xp_launch_count.restype = ctypes.c_uint64
         lib.xp_last_kernel_ms.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_float)]
@@ -469,6 +484,59 @@ class Context:
         self._check(st, "xp_level_crossing")
         return out
 
+    # ---- layer primitives (xp_layers.cu) ---------------------------------------------------------------
+    def mixed_layer(self, pressure, fields, depth=100.0, pressure_field=-1):
+        """mixed_layer (PF:137-162) of up to 4 variables [L, N] per call (more: several calls).  ``pressure``:
+        [L, N] or shared [L]; ``pressure_field``: index of the variable that is the pressure itself, or -1.
+        Returns a list of [N] tensors."""
+        fields = [x.contiguous() for x in fields]
+        L, N = fields[0].shape
+        dt = fields[0].dtype
+        assert all(x.shape == (L, N) and x.dtype == dt for x in fields)
+        pressure = pressure.to(dt).contiguous()
+        p1d = pressure.dim() == 1
+        outs = []
+        for g in range(0, len(fields), 4):
+            grp = fields[g:g + 4]
+            o = [torch.empty((N,), dtype=dt, device=grp[0].device) for _ in grp]
+            fp = (c_void_p * len(grp))(*[x.data_ptr() for x in grp])
+            op = (c_void_p * len(grp))(*[x.data_ptr() for x in o])
+            st = self.lib.xp_mixed_layer(self.handle, pressure.data_ptr(), 1 if p1d else N, int(p1d), fp, op,
+                                         len(grp), pressure_field - g if g <= pressure_field < g + 4 else -1, N, L, N,
+                                         _dtype_code(grp[0]), float(depth), self._stream())
+            self._check(st, "xp_mixed_layer")
+            outs += o
+        return outs
+
+    def mixed_parcel(self, pressure, temperature, dewpoint, depth=100.0):
+        """mixed_parcel (PF:229-289): dict of the six [N] variables the reference returns."""
+        temperature = temperature.contiguous()
+        L, N = temperature.shape
+        dt = temperature.dtype
+        dewpoint = dewpoint.to(dt).contiguous()
+        pressure = pressure.to(dt).contiguous()
+        p1d = pressure.dim() == 1
+        outs = {n: torch.empty((N,), dtype=dt, device=temperature.device) for n in MIXED_PARCEL_FIELDS}
+        o = XpMixedParcelOut(*[outs[n].data_ptr() for n in MIXED_PARCEL_FIELDS])
+        st = self.lib.xp_mixed_parcel(self.handle, pressure.data_ptr(), 1 if p1d else N, int(p1d),
+                                      temperature.data_ptr(), dewpoint.data_ptr(), N, L, N, _dtype_code(temperature),
+                                      float(depth), ctypes.byref(o), self._stream())
+        self._check(st, "xp_mixed_parcel")
+        return outs
+
+    def layer_bounds(self, pressure, n_columns, depth=100.0, interpolate=True):
+        """(bottom, top) pressures of get_layer (PF:63-100; bound_pressure PF:208-227 when not interpolating)."""
+        pressure = pressure.contiguous()
+        p1d = pressure.dim() == 1
+        L = pressure.shape[0]
+        N = int(n_columns)
+        bottom = torch.empty((N,), dtype=pressure.dtype, device=pressure.device)
+        top = torch.empty_like(bottom)
+        st = self.lib.xp_layer_bounds(self.handle, pressure.data_ptr(), 1 if p1d else N, int(p1d), L, N,
+                                      _dtype_code(pressure), float(depth), int(bool(interpolate)),
+                                      bottom.data_ptr(), top.data_ptr(), self._stream())
+        self._check(st, "xp_layer_bounds")
+        return bottom, top
 
     # ---- pointwise helpers (device tensors of one shape and dtype) -------------------------------------
     def _pointwise(self, fn_name, inputs, extra=()):

@@ -650,6 +650,60 @@ xp_status xp_level_crossing(xp_context *ctx, const void *coords, int64_t coords_
     return check_cuda(ctx, cudaGetLastError(), "level_crossing kernel launch");
 }
 
+xp_status xp_mixed_layer(xp_context *ctx, const void *pressure, int64_t pressure_level_stride,
+                         int32_t pressure_is_1d, const void *const *fields, void *const *outputs, int32_t n_fields,
+                         int32_t pressure_field, int64_t level_stride, int32_t n_levels, int64_t n_columns,
+                         int32_t dtype, double depth, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (n_columns == 0) return XP_OK;
+    if (!pressure || !fields || !outputs || n_fields < 1 || n_fields > 4 || pressure_field >= n_fields || n_levels < 1 ||
+        n_columns < 0)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad mixed_layer arguments");
+    for (int f = 0; f < n_fields; ++f)
+        if (!fields[f] || !outputs[f]) return fail(ctx, XP_ERR_INVALID_ARGUMENT, "mixed_layer: NULL field/output");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    XP_DISPATCH(dtype,
+                launch_mixed_layer<float>((const float *)pressure, pressure_level_stride, pressure_is_1d, (const float *const *)fields, (float *const *)outputs, n_fields, pressure_field, level_stride, n_levels, n_columns, depth, st),
+                launch_mixed_layer<double>((const double *)pressure, pressure_level_stride, pressure_is_1d, (const double *const *)fields, (double *const *)outputs, n_fields, pressure_field, level_stride, n_levels, n_columns, depth, st));
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "mixed_layer kernel launch");
+}
+
+xp_status xp_mixed_parcel(xp_context *ctx, const void *pressure, int64_t pressure_level_stride,
+                          int32_t pressure_is_1d, const void *temperature, const void *dewpoint,
+                          int64_t level_stride, int32_t n_levels, int64_t n_columns, int32_t dtype, double depth,
+                          const xp_mixed_parcel_out *out, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (n_columns == 0) return XP_OK;
+    if (!pressure || !temperature || !dewpoint || !out || n_levels < 1 || n_columns < 0)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad mixed_parcel arguments");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    void *o6[6] = {out->theta, out->mixing_ratio, out->temperature, out->vapour_pressure, out->dewpoint, out->pressure};
+    XP_DISPATCH(dtype,
+                launch_mixed_parcel<float>((const float *)pressure, pressure_level_stride, pressure_is_1d, (const float *)temperature, (const float *)dewpoint, level_stride, n_levels, n_columns, depth, (float *const *)o6, st),
+                launch_mixed_parcel<double>((const double *)pressure, pressure_level_stride, pressure_is_1d, (const double *)temperature, (const double *)dewpoint, level_stride, n_levels, n_columns, depth, (double *const *)o6, st));
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "mixed_parcel kernel launch");
+}
+
+xp_status xp_layer_bounds(xp_context *ctx, const void *pressure, int64_t pressure_level_stride,
+                          int32_t pressure_is_1d, int32_t n_levels, int64_t n_columns, int32_t dtype, double depth,
+                          int32_t interpolate, void *bottom_pressure, void *top_pressure, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (n_columns == 0) return XP_OK;
+    if (!pressure || (!bottom_pressure && !top_pressure) || n_levels < 1 || n_columns < 0)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad layer_bounds arguments");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    XP_DISPATCH(dtype,
+                launch_layer_bounds<float>((const float *)pressure, pressure_level_stride, pressure_is_1d, n_levels, n_columns, depth, interpolate, (float *)bottom_pressure, (float *)top_pressure, st),
+                launch_layer_bounds<double>((const double *)pressure, pressure_level_stride, pressure_is_1d, n_levels, n_columns, depth, interpolate, (double *)bottom_pressure, (double *)top_pressure, st));
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "layer_bounds kernel launch");
+}
+
 xp_status xp_dewpoint_from_specific_humidity(xp_context *ctx, const void *pressure, const void *temperature,
                                              const void *specific_humidity, int64_t n, int32_t dtype,
                                              int32_t metpy_compat, void *dewpoint, void *stream) {

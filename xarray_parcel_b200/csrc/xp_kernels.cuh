@@ -113,6 +113,19 @@ template <typename T>
 void launch_level_crossing(const T *x, int64_t xls, int x1d, const T *a, int64_t ls, int L, int64_t n,
                            double level, T *out, cudaStream_t stream);
 
+// Layer primitives (xp_layers.cu): mixed_layer (PF:137-162) of up to 4 variables, mixed_parcel (PF:229-289) with
+// all six returned variables (out6 = theta, mixing_ratio, temperature, vapour_pressure, dewpoint, pressure; any
+// may be null) and get_layer's bottom/top pressures (PF:63-100, bound_pressure PF:208-227).
+template <typename T>
+void launch_mixed_layer(const T *p, int64_t pls, int p1d, const T *const *x, T *const *out, int n_fields,
+                        int pressure_field, int64_t ls, int L, int64_t n, double depth, cudaStream_t stream);
+template <typename T>
+void launch_mixed_parcel(const T *p, int64_t pls, int p1d, const T *t, const T *td, int64_t ls, int L, int64_t n,
+                         double depth, T *const *out6, cudaStream_t stream);
+template <typename T>
+void launch_layer_bounds(const T *p, int64_t pls, int p1d, int L, int64_t n, double depth, int interpolate,
+                         T *bottom, T *top, cudaStream_t stream);
+
 // Pointwise kernels (xp_derived.cu): q -> Td (PF:1889, 1969), saturation mixing ratio (PF:258, 2047-2053),
 // Normand wet-bulb temperature (PF:389-445), significant hail parameter (PF:2261-2306; in6 = mucape, mixing
 // ratio, lapse, temp_500, shear, flh) and storm proxies (PF:2323-2407; in13 in the order of ProxyIn in

@@ -368,10 +368,40 @@ def parcel_profile_with_lcl(pressure, temperature, dewpoint, parcel_pressure, pa
 
 def mixed_parcel(pressure, temperature, dewpoint, depth=100, vert_dim="model_level_number",
                  vert_axis=0, device=None, **kwargs):
-    """PF:229-289: Dataset{pressure, temperature, dewpoint} of the fully mixed lowest ``depth`` hPa."""
-    _, _, mp, _, _ = _run("ml", pressure, temperature, dewpoint, vert_dim, vert_axis, device, False,
-                          depth=depth, **kwargs)
-    return mp
+    """PF:229-289: Dataset{theta, mixing_ratio, temperature, vapour_pressure, dewpoint, pressure} of the fully
+    mixed lowest ``depth`` hPa (``xp_mixed_parcel``; pressure = the level-0 pressure, PF:287)."""
+    lay, ctx, p, t, td = _prepare(pressure, temperature, dewpoint, vert_dim, vert_axis, device)
+    on_gpu = t.is_cuda
+    res = ctx.mixed_parcel(p.cuda(), t.cuda(), td.cuda(), depth=depth)
+    return lay.dataset({k: lay.wrap_scalar(v if on_gpu else v.cpu(), k) for k, v in res.items()})
+
+
+def mixed_layer(dat, depth=100, vert_dim="model_level_number", vert_axis=0, device=None):
+    """PF:137-162: mass-weighted mean over the lowest ``depth`` hPa of every variable of ``dat`` (a Dataset or
+    dict that contains 'pressure'; like the reference's, the result also holds the mean of 'pressure' itself)."""
+    names = list(dat.data_vars) if hasattr(dat, "data_vars") else list(dat.keys())
+    assert "pressure" in names, "dat must contain pressure."
+    template = next((dat[k] for k in names if getattr(dat[k], "ndim", 0) > 1), dat["pressure"])
+    ctx = _lib.get_context(device)
+    lay, dtype, on_gpu = _layout_of(template, vert_dim, vert_axis)
+    blocks = _blocks(lay, [dat[k] for k in names], dtype)
+    pb = blocks[names.index("pressure")]
+    n = int(np.prod(lay.col_shape)) if lay.col_shape else 1
+    full = [b if b.dim() == 2 else b[:, None].expand(lay.L, n).contiguous() for b in blocks]
+    res = ctx.mixed_layer(pb, full, depth=depth, pressure_field=names.index("pressure"))
+    return lay.dataset({k: lay.wrap_scalar(v if on_gpu else v.cpu(), k) for k, v in zip(names, res)})
+
+
+def bound_pressure(pressure, bound=None, vert_dim="model_level_number", vert_axis=0, device=None, depth=None):
+    """PF:208-227 as get_layer(interpolate=False) uses it (PF:92-94): the level pressure closest to
+    ``bottom - depth``, the larger one on a tie.  Pass ``depth``; an arbitrary ``bound`` array is not supported."""
+    assert bound is None and depth is not None, "only bound = bottom pressure - depth (pass depth=) is implemented"
+    ctx = _lib.get_context(device)
+    lay, dtype, on_gpu = _layout_of(pressure, vert_dim, vert_axis)
+    (pb,) = _blocks(lay, [pressure], dtype)
+    n = int(np.prod(lay.col_shape)) if lay.col_shape else 1
+    _, top = ctx.layer_bounds(pb, n, depth=depth, interpolate=False)
+    return lay.wrap_scalar(top if on_gpu else top.cpu(), "pressure")
 
 
 def most_unstable_parcel(dat=None, depth=300, vert_dim="model_level_number", pressure=None,
