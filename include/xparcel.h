@@ -65,6 +65,8 @@ typedef enum {
  * xp_take_flags(). */
 #define XP_FLAG_TOP_TEMPERATURE_NAN 1u     /* PF:1149 */
 #define XP_FLAG_PRESSURES_NOT_UNIQUE 2u    /* PF:131  */
+#define XP_FLAG_PRESSURE_NOT_DECREASING 4u /* PF:2320, set by xp_valid_data */
+#define XP_FLAG_PRESSURE_ORDER_CHECKED 8u  /* xp_valid_data saw at least one non-NaN pressure difference */
 
 /* Environment columns: pressure/temperature/dewpoint [n_levels][n_columns]. */
 typedef struct {
@@ -235,6 +237,34 @@ xp_status xp_mixed_parcel(xp_context *ctx, const void *pressure, int64_t pressur
 xp_status xp_layer_bounds(xp_context *ctx, const void *pressure, int64_t pressure_level_stride,
                           int32_t pressure_is_1d, int32_t n_levels, int64_t n_columns, int32_t dtype, double depth,
                           int32_t interpolate, void *bottom_pressure, void *top_pressure, void *stream);
+
+/* ---- level primitives (device memory only; every array [n_levels][n_columns] unless noted) ----------------
+ * xp_insert_level: insert_level (PF:933-990) of n_fields <= 4 variables: `level_coord` / `level_values[f]`
+ * ([n_columns]) are inserted by coordinate VALUE (coordinates >= the new one stay, smaller ones move up one level,
+ * an equal coordinate is kept below the new level; NaN coordinates travel as the fill value -999 and come back as
+ * NaN).  Outputs have n_levels + 1 levels with stride `out_level_stride`; `coords_out` (or NULL) receives the
+ * coordinate variable itself. */
+xp_status xp_insert_level(xp_context *ctx, const void *coords, int64_t coords_level_stride, int32_t coords_is_1d,
+                          const void *level_coord, const void *const *fields, const void *const *level_values,
+                          void *const *outputs, int32_t n_fields, void *coords_out, int64_t level_stride,
+                          int64_t out_level_stride, int32_t n_levels, int64_t n_columns, int32_t dtype, void *stream);
+/* xp_shift_out_nans: shift_out_nans (PF:1699-1720): every field of a column moves down by the number of leading NaN
+ * levels of `ref_field`, NaN-padded at the top; `level_shift` ([n_columns] int32, or NULL) receives that number.
+ * Outputs must not alias the inputs. */
+xp_status xp_shift_out_nans(xp_context *ctx, const void *ref_field, const void *const *fields, void *const *outputs,
+                            int32_t n_fields, int64_t level_stride, int32_t n_levels, int64_t n_columns,
+                            int32_t dtype, int32_t *level_shift, void *stream);
+/* xp_trapz: trapz (PF:164-206): per column sum of |x[k+1] - x[k]| * (v[k] + v[k+1]) / 2 over the intervals whose
+ * `mask` byte (labelled by the lower level, [>= n_levels - 1][n_columns], or NULL) is non-zero; sign = +1 / -1 keeps
+ * only positive / negative areas (only_positive / only_negative), 0 all; NaN areas are skipped. */
+xp_status xp_trapz(xp_context *ctx, const void *x, int64_t x_level_stride, int32_t x_is_1d, const void *const *fields,
+                   void *const *outputs, int32_t n_fields, int64_t level_stride, int32_t n_levels, int64_t n_columns,
+                   int32_t dtype, const uint8_t *mask, int64_t mask_level_stride, int32_t sign, void *stream);
+/* xp_valid_data: the pressure check of valid_data (PF:2320: pressure.diff(vert_dim).max() < 0).  ORs
+ * XP_FLAG_PRESSURE_NOT_DECREASING (a difference >= 0 exists) and XP_FLAG_PRESSURE_ORDER_CHECKED (a non-NaN
+ * difference exists) into the context flags; read them with xp_take_flags(). */
+xp_status xp_valid_data(xp_context *ctx, const void *pressure, int64_t pressure_level_stride, int32_t pressure_is_1d,
+                        int32_t n_levels, int64_t n_columns, int32_t dtype, void *stream);
 
 /* ---- pointwise helpers around the hot path (callers and front end) -----------------
  * All arrays hold `n` points of `dtype` in device memory (any shape, flattened); one thread per point. */

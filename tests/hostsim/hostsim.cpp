@@ -13,6 +13,7 @@
 #include "../../xarray_parcel_b200/csrc/xp_fast6.cuh"
 #include "../../xarray_parcel_b200/csrc/xp_fast_pcol6.cuh"
 #include "../../xarray_parcel_b200/csrc/xp_layers.cuh"
+#include "../../xarray_parcel_b200/csrc/xp_levels.cuh"
 
 namespace {
 
@@ -319,4 +320,42 @@ extern "C" void hostsim_layer_bounds(const double *p, int p1d, int64_t n, int L,
         auto pressure_at = [&](int k) { return pc[(int64_t)k * pls]; };
         xp::layer_bounds(L, pressure_at, depth, interpolate != 0, bottom[c], top[c]);
     }
+}
+
+// Level primitives (xp_levels.cuh), column by column; one variable v [L][n] per call.
+extern "C" void hostsim_insert_level(const double *c, const double *v, const double *lev_c, const double *lev_v,
+                                     int64_t n, int L, double *out /*[L+1][n]*/) {
+    for (int64_t i = 0; i < n; ++i)
+        for (int j = 0; j <= L; ++j) {
+            const double c_j = j < L ? c[(int64_t)j * n + i] : xp::qnan(), c_jm = j >= 1 ? c[(int64_t)(j - 1) * n + i] : xp::qnan();
+            const double v_j = j < L ? v[(int64_t)j * n + i] : xp::qnan(), v_jm = j >= 1 ? v[(int64_t)(j - 1) * n + i] : xp::qnan();
+            out[(int64_t)j * n + i] = xp::insert_level_value(j, L, c_j, c_jm, v_j, v_jm, lev_c[i], lev_v[i]);
+        }
+}
+
+extern "C" void hostsim_shift_out_nans(const double *ref, const double *v, int64_t n, int L, double *out, int32_t *shift) {
+    for (int64_t i = 0; i < n; ++i) {
+        auto ref_at = [&](int k) { return ref[(int64_t)k * n + i]; };
+        const int k0 = xp::leading_nans(L, ref_at);
+        shift[i] = k0;
+        for (int j = 0; j < L; ++j) out[(int64_t)j * n + i] = j + k0 < L ? v[(int64_t)(j + k0) * n + i] : xp::qnan();
+    }
+}
+
+extern "C" void hostsim_trapz(const double *x, const double *v, const uint8_t *mask, int64_t n, int L, int sign, double *out) {
+    for (int64_t i = 0; i < n; ++i) {
+        auto x_at = [&](int k) { return x[(int64_t)k * n + i]; };
+        auto v_at = [&](int k) { return v[(int64_t)k * n + i]; };
+        auto use = [&](int k) { return !mask || mask[(int64_t)k * n + i] != 0; };
+        out[i] = xp::trapz_column(L, x_at, v_at, use, sign);
+    }
+}
+
+extern "C" int hostsim_pressure_order(const double *p, int64_t n, int L) {
+    int r = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        auto pressure_at = [&](int k) { return p[(int64_t)k * n + i]; };
+        r |= xp::pressure_order(L, pressure_at);
+    }
+    return r;
 }

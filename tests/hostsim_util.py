@@ -21,7 +21,7 @@ KINDS = {"sb": 0, "ml": 1, "mu": 2, "explicit": 3}
 
 
 def build():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("xp_math.cuh", "xp_column.cuh", "xp_parcels.cuh", "xp_fast.cuh", "xp_fast_pcol.cuh", "xp_fast6.cuh", "xp_fast_pcol6.cuh", "xp_layers.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("xp_math.cuh", "xp_column.cuh", "xp_parcels.cuh", "xp_fast.cuh", "xp_fast_pcol.cuh", "xp_fast6.cuh", "xp_fast_pcol6.cuh", "xp_layers.cuh", "xp_levels.cuh")]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     os.makedirs(BUILD, exist_ok=True)
@@ -157,3 +157,38 @@ def layer_bounds(p, n_columns, depth=100.0, interpolate=True):
                                ctypes.c_double(depth), int(bool(interpolate)), vp(bottom.ctypes.data),
                                vp(top.ctypes.data))
     return bottom, top
+
+
+def _vp(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def insert_level(c, v, lev_c, lev_v):
+    c, v, lev_c, lev_v = [np.ascontiguousarray(a, dtype=np.float64) for a in (c, v, lev_c, lev_v)]
+    L, N = c.shape
+    out = np.empty((L + 1, N))
+    lib().hostsim_insert_level(_vp(c), _vp(v), _vp(lev_c), _vp(lev_v), ctypes.c_int64(N), L, _vp(out))
+    return out
+
+
+def shift_out_nans(ref, v):
+    ref, v = [np.ascontiguousarray(a, dtype=np.float64) for a in (ref, v)]
+    L, N = ref.shape
+    out, shift = np.empty((L, N)), np.empty(N, dtype=np.int32)
+    lib().hostsim_shift_out_nans(_vp(ref), _vp(v), ctypes.c_int64(N), L, _vp(out), _vp(shift))
+    return out, shift
+
+
+def trapz(x, v, mask=None, sign=0):
+    x, v = [np.ascontiguousarray(a, dtype=np.float64) for a in (x, v)]
+    L, N = v.shape
+    m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+    out = np.empty(N)
+    lib().hostsim_trapz(_vp(x), _vp(v), _vp(m) if m is not None else None, ctypes.c_int64(N), L, int(sign), _vp(out))
+    return out
+
+
+def pressure_order(p):
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    L, N = p.shape
+    return int(lib().hostsim_pressure_order(_vp(p), ctypes.c_int64(N), L))

@@ -1,0 +1,79 @@
+"""CPU check of the level primitives' per-column code (xp_levels.cuh compiled for the host by tests/hostsim,
+test-only) against the oracle: insert_level (PF:933-990, incl. the reference's own known answer UT:1388-1411),
+shift_out_nans (PF:1699-1720), trapz (PF:164-206) and the pressure check of valid_data (PF:2320).  The GPU twin
+is tests/test_gpu_levels.py."""
+
+import numpy as np
+import pytest
+
+import hostsim_util as hs
+from oracle import parcel as op
+from xarray_parcel_b200 import synth
+
+
+def _same(a, b, rtol=1e-12):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    ok = ~np.isnan(b)
+    assert np.allclose(a[ok], b[ok], rtol=rtol, atol=0)
+
+
+def _columns(n=1500, L=40, seed=21):
+    p, t, td = synth.model_level_columns(n, L, seed=seed, nan_columns=0.1)
+    return [x.numpy().astype(np.float64) for x in (p, t, td)]
+
+
+def test_insert_level_against_oracle():
+    P, T, _ = _columns()
+    rng = np.random.default_rng(5)
+    N = P.shape[1]
+    lev_p = rng.uniform(50.0, 1100.0, N)             # inside, below and above the column
+    lev_p[:40] = P[rng.integers(0, P.shape[0], 40), np.arange(40)]     # exactly on a level (kept below, PF:955)
+    lev_p[40:50] = np.nan
+    lev_t = rng.uniform(200.0, 300.0, N)
+    P[5:9, 60:80] = np.nan                            # NaN coordinates inside a column (fill-value route)
+    ora = op.insert_level({"pressure": P, "temperature": T}, {"pressure": lev_p, "temperature": lev_t}, "pressure")
+    _same(hs.insert_level(P, P, lev_p, lev_p), ora["pressure"])
+    _same(hs.insert_level(P, T, lev_p, lev_t), ora["temperature"])
+
+
+def test_shift_out_nans_against_oracle():
+    P, T, _ = _columns(seed=22)
+    N = P.shape[1]
+    k = np.random.default_rng(6).integers(0, 6, N)
+    lead = np.arange(P.shape[0])[:, None] < k[None, :]
+    Pn = np.where(lead, np.nan, P)
+    Pn[:, :5] = np.nan                                # all-NaN columns
+    ora = op.shift_out_nans({"pressure": Pn, "temperature": T}, "pressure")
+    got_p, shift = hs.shift_out_nans(Pn, Pn)
+    got_t, _ = hs.shift_out_nans(Pn, T)
+    _same(got_p, ora["pressure"])
+    _same(got_t, ora["temperature"])
+    assert np.array_equal(shift[5:], np.where(np.isnan(P[0, 5:]), P.shape[0], k[5:]))
+
+
+@pytest.mark.parametrize("sign", [0, 1, -1])
+def test_trapz_against_oracle(sign):
+    P, T, D = _columns(seed=23)
+    V = T - D - 8.0                                   # changes sign
+    mask = np.random.default_rng(7).random(P.shape) < 0.7
+    for m in (None, mask):
+        ora = op.trapz({"pressure": P, "v": V}, "pressure", mask=m, only_positive=sign > 0, only_negative=sign < 0)
+        _same(hs.trapz(P, V, mask=m, sign=sign), ora["v"])
+        _same(hs.trapz(P, P, mask=m, sign=sign), ora["pressure"])
+    _same(hs.trapz(np.log(P), V, sign=sign),
+          op.trapz({"x": np.log(P), "v": V}, "x", only_positive=sign > 0, only_negative=sign < 0)["v"])
+
+
+def test_pressure_order():
+    P, _, _ = _columns(seed=24)
+    assert hs.pressure_order(P) == 2                  # valid: differences seen, none >= 0
+    Q = P.copy()
+    Q[[3, 4], 17] = Q[[4, 3], 17]
+    assert hs.pressure_order(Q) == 3
+    Q = P.copy()
+    Q[7, 3] = Q[6, 3]                                 # equal pressures are not "decreasing" (max < 0 fails)
+    assert hs.pressure_order(Q) & 1
+    assert hs.pressure_order(np.full((5, 3), np.nan)) == 0

@@ -21,6 +21,8 @@ XP_MEM_DEVICE, XP_MEM_HOST = 0, 1
 KIND = {"sb": 0, "ml": 1, "mu": 2, "explicit": 3}
 FLAG_TOP_TEMPERATURE_NAN = 1
 FLAG_PRESSURES_NOT_UNIQUE = 2
+FLAG_PRESSURE_NOT_DECREASING = 4
+FLAG_PRESSURE_ORDER_CHECKED = 8
 TABLE_NP, TABLE_NT, TABLE_NADIABATS = 2196, 7150, 14300
 
 SCALAR_FIELDS = ["cape", "cin", "lcl_pressure", "lcl_temperature", "lcl_virtual_temperature",
@@ -62,7 +64,7 @@ EXPORTS = ["xp_version", "xp_create", "xp_destroy", "xp_last_error", "xp_take_fl
            "xp_level_crossing", "xp_dewpoint_from_specific_humidity", "xp_saturation_mixing_ratio",
            "xp_dry_lapse", "xp_mixing_ratio", "xp_virtual_temperature", "xp_wet_bulb_temperature",
            "xp_significant_hail_parameter", "xp_storm_proxies", "xp_mixed_layer", "xp_mixed_parcel",
-           "xp_layer_bounds"]
+           "xp_layer_bounds", "xp_insert_level", "xp_shift_out_nans", "xp_trapz", "xp_valid_data"]
 
 PROXY_INPUTS = ["mixed_100_cape", "mixed_50_cape", "mu_cape", "shear_magnitude", "mixed_100_lifted_index",
                 "mixed_100_dci", "positive_shear", "mixed_50_cin", "mixed_100_cin", "lapse_rate_700_500",
@@ -164,6 +166,14 @@ def load_library():
                                         c_int64, c_int32, c_double, ctypes.POINTER(XpMixedParcelOut), c_void_p]
         lib.xp_layer_bounds.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int64, c_int32, c_double,
                                         c_int32, c_void_p, c_void_p, c_void_p]
+        PP = ctypes.POINTER(c_void_p)
+        lib.xp_insert_level.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, PP, PP, PP, c_int32, c_void_p,
+                                        c_int64, c_int64, c_int32, c_int64, c_int32, c_void_p]
+        lib.xp_shift_out_nans.argtypes = [c_void_p, c_void_p, PP, PP, c_int32, c_int64, c_int32, c_int64, c_int32,
+                                          c_void_p, c_void_p]
+        lib.xp_trapz.argtypes = [c_void_p, c_void_p, c_int64, c_int32, PP, PP, c_int32, c_int64, c_int32, c_int64,
+                                 c_int32, c_void_p, c_int64, c_int32, c_void_p]
+        lib.xp_valid_data.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int64, c_int32, c_void_p]
         lib.xp_launch_count.argtypes = [c_void_p]
         lib.xp_launch_count.restype = ctypes.c_uint64
         lib.xp_last_kernel_ms.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_float)]
@@ -537,6 +547,75 @@ class Context:
                                       bottom.data_ptr(), top.data_ptr(), self._stream())
         self._check(st, "xp_layer_bounds")
         return bottom, top
+    # ---- level primitives (xp_levels.cu) ---------------------------------------------------------------
+    @staticmethod
+    def _ptrs(tensors):
+        return (c_void_p * max(len(tensors), 1))(*[x.data_ptr() for x in tensors])
+
+    def insert_level(self, coords, level_coord, fields, level_values):
+        """insert_level (PF:933-990): ``coords`` [L, N] or [L]; ``level_coord`` [N]; ``fields`` list of [L, N] with
+        their values ``level_values`` (list of [N]) at the new level.  Returns (coords_out, [outputs]) with L + 1
+        levels."""
+        dt, dev = level_coord.dtype, level_coord.device
+        N = level_coord.shape[0]
+        coords = coords.to(dt).contiguous()
+        L = coords.shape[0]
+        c1d = coords.dim() == 1
+        fields = [x.to(dt).contiguous() for x in fields]
+        level_values = [x.to(dt).contiguous() for x in level_values]
+        assert len(fields) == len(level_values) and all(x.shape == (L, N) for x in fields)
+        cout = torch.empty((L + 1, N), dtype=dt, device=dev)
+        outs = [torch.empty((L + 1, N), dtype=dt, device=dev) for _ in fields]
+        for g in range(0, max(len(fields), 1), 4):
+            grp, lv, o = fields[g:g + 4], level_values[g:g + 4], outs[g:g + 4]
+            st = self.lib.xp_insert_level(self.handle, coords.data_ptr(), 1 if c1d else N, int(c1d),
+                                          level_coord.contiguous().data_ptr(), self._ptrs(grp), self._ptrs(lv),
+                                          self._ptrs(o), len(grp), cout.data_ptr() if g == 0 else None, N, N, L, N,
+                                          _dtype_code(level_coord), self._stream())
+            self._check(st, "xp_insert_level")
+        return cout, outs
+
+    def shift_out_nans(self, ref, fields):
+        """shift_out_nans (PF:1699-1720).  Returns ([shifted fields], level_shift int32 [N])."""
+        ref = ref.contiguous()
+        L, N = ref.shape
+        fields = [x.to(ref.dtype).contiguous() for x in fields]
+        outs = [torch.empty_like(x) for x in fields]
+        shift = torch.empty((N,), dtype=torch.int32, device=ref.device)
+        for g in range(0, max(len(fields), 1), 4):
+            grp, o = fields[g:g + 4], outs[g:g + 4]
+            st = self.lib.xp_shift_out_nans(self.handle, ref.data_ptr(), self._ptrs(grp), self._ptrs(o), len(grp), N,
+                                            L, N, _dtype_code(ref), shift.data_ptr(), self._stream())
+            self._check(st, "xp_shift_out_nans")
+        return outs, shift
+
+    def trapz(self, x, fields, mask=None, sign=0):
+        """trapz (PF:164-206) of the [L, N] ``fields`` along ``x`` ([L, N] or shared [L]); ``mask``: bool/uint8
+        [>= L-1, N] labelled by the lower level.  Returns a list of [N]."""
+        fields = [v.contiguous() for v in fields]
+        L, N = fields[0].shape
+        dt = fields[0].dtype
+        x = x.to(dt).contiguous()
+        x1d = x.dim() == 1
+        if mask is not None:
+            mask = mask.to(torch.uint8).contiguous()
+            assert mask.shape[0] >= L - 1 and mask.shape[1] == N
+        outs = [torch.empty((N,), dtype=dt, device=v.device) for v in fields]
+        for g in range(0, len(fields), 4):
+            grp, o = fields[g:g + 4], outs[g:g + 4]
+            st = self.lib.xp_trapz(self.handle, x.data_ptr(), 1 if x1d else N, int(x1d), self._ptrs(grp),
+                                   self._ptrs(o), len(grp), N, L, N, _dtype_code(grp[0]),
+                                   mask.data_ptr() if mask is not None else None, N, int(sign), self._stream())
+            self._check(st, "xp_trapz")
+        return outs
+
+    def valid_data(self, pressure, n_columns):
+        """The pressure check of valid_data (PF:2320); the verdict arrives through take_flags()."""
+        pressure = pressure.contiguous()
+        p1d = pressure.dim() == 1
+        st = self.lib.xp_valid_data(self.handle, pressure.data_ptr(), 1 if p1d else int(n_columns), int(p1d),
+                                    pressure.shape[0], int(n_columns), _dtype_code(pressure), self._stream())
+        self._check(st, "xp_valid_data")
 
     # ---- pointwise helpers (device tensors of one shape and dtype) -------------------------------------
     def _pointwise(self, fn_name, inputs, extra=()):

@@ -704,6 +704,80 @@ xp_status xp_layer_bounds(xp_context *ctx, const void *pressure, int64_t pressur
     return check_cuda(ctx, cudaGetLastError(), "layer_bounds kernel launch");
 }
 
+xp_status xp_insert_level(xp_context *ctx, const void *coords, int64_t coords_level_stride, int32_t coords_is_1d,
+                          const void *level_coord, const void *const *fields, const void *const *level_values,
+                          void *const *outputs, int32_t n_fields, void *coords_out, int64_t level_stride,
+                          int64_t out_level_stride, int32_t n_levels, int64_t n_columns, int32_t dtype, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (n_columns == 0) return XP_OK;
+    if (!coords || !level_coord || n_fields < 0 || n_fields > 4 || (n_fields == 0 && !coords_out) ||
+        (n_fields > 0 && (!fields || !level_values || !outputs)) || n_levels < 1 || n_columns < 0)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad insert_level arguments");
+    for (int f = 0; f < n_fields; ++f)
+        if (!fields[f] || !level_values[f] || !outputs[f])
+            return fail(ctx, XP_ERR_INVALID_ARGUMENT, "insert_level: NULL field/level/output");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    XP_DISPATCH(dtype,
+                launch_insert_level<float>((const float *)coords, coords_level_stride, coords_is_1d, (const float *)level_coord, (const float *const *)fields, (const float *const *)level_values, (float *const *)outputs, (float *)coords_out, n_fields, level_stride, out_level_stride, n_levels, n_columns, st),
+                launch_insert_level<double>((const double *)coords, coords_level_stride, coords_is_1d, (const double *)level_coord, (const double *const *)fields, (const double *const *)level_values, (double *const *)outputs, (double *)coords_out, n_fields, level_stride, out_level_stride, n_levels, n_columns, st));
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "insert_level kernel launch");
+}
+
+xp_status xp_shift_out_nans(xp_context *ctx, const void *ref_field, const void *const *fields, void *const *outputs,
+                            int32_t n_fields, int64_t level_stride, int32_t n_levels, int64_t n_columns,
+                            int32_t dtype, int32_t *level_shift, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (n_columns == 0) return XP_OK;
+    if (!ref_field || n_fields < 0 || n_fields > 4 || (n_fields == 0 && !level_shift) ||
+        (n_fields > 0 && (!fields || !outputs)) || n_levels < 1 || n_columns < 0)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad shift_out_nans arguments");
+    for (int f = 0; f < n_fields; ++f)
+        if (!fields[f] || !outputs[f] || fields[f] == outputs[f])
+            return fail(ctx, XP_ERR_INVALID_ARGUMENT, "shift_out_nans: NULL or aliased field/output");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    XP_DISPATCH(dtype,
+                launch_shift_out_nans<float>((const float *)ref_field, (const float *const *)fields, (float *const *)outputs, n_fields, level_stride, n_levels, n_columns, level_shift, st),
+                launch_shift_out_nans<double>((const double *)ref_field, (const double *const *)fields, (double *const *)outputs, n_fields, level_stride, n_levels, n_columns, level_shift, st));
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "shift_out_nans kernel launch");
+}
+
+xp_status xp_trapz(xp_context *ctx, const void *x, int64_t x_level_stride, int32_t x_is_1d, const void *const *fields,
+                   void *const *outputs, int32_t n_fields, int64_t level_stride, int32_t n_levels, int64_t n_columns,
+                   int32_t dtype, const uint8_t *mask, int64_t mask_level_stride, int32_t sign, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (n_columns == 0) return XP_OK;
+    if (!x || !fields || !outputs || n_fields < 1 || n_fields > 4 || n_levels < 1 || n_columns < 0 || sign < -1 || sign > 1)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad trapz arguments");
+    for (int f = 0; f < n_fields; ++f)
+        if (!fields[f] || !outputs[f]) return fail(ctx, XP_ERR_INVALID_ARGUMENT, "trapz: NULL field/output");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    XP_DISPATCH(dtype,
+                launch_trapz<float>((const float *)x, x_level_stride, x_is_1d, (const float *const *)fields, (float *const *)outputs, n_fields, level_stride, n_levels, n_columns, mask, mask_level_stride, sign, st),
+                launch_trapz<double>((const double *)x, x_level_stride, x_is_1d, (const double *const *)fields, (double *const *)outputs, n_fields, level_stride, n_levels, n_columns, mask, mask_level_stride, sign, st));
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "trapz kernel launch");
+}
+
+xp_status xp_valid_data(xp_context *ctx, const void *pressure, int64_t pressure_level_stride, int32_t pressure_is_1d,
+                        int32_t n_levels, int64_t n_columns, int32_t dtype, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (n_columns == 0) return XP_OK;
+    if (!pressure || n_levels < 1 || n_columns < 0) return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad valid_data arguments");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = pressure_is_1d ? 1 : n_columns;
+    XP_DISPATCH(dtype,
+                launch_pressure_order<float>((const float *)pressure, pressure_level_stride, pressure_is_1d, n_levels, n, ctx->d_flags, st),
+                launch_pressure_order<double>((const double *)pressure, pressure_level_stride, pressure_is_1d, n_levels, n, ctx->d_flags, st));
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "valid_data kernel launch");
+}
+
 xp_status xp_dewpoint_from_specific_humidity(xp_context *ctx, const void *pressure, const void *temperature,
                                              const void *specific_humidity, int64_t n, int32_t dtype,
                                              int32_t metpy_compat, void *dewpoint, void *stream) {

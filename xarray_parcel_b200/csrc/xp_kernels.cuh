@@ -126,6 +126,22 @@ template <typename T>
 void launch_layer_bounds(const T *p, int64_t pls, int p1d, int L, int64_t n, double depth, int interpolate,
                          T *bottom, T *top, cudaStream_t stream);
 
+// Level primitives (xp_levels.cu): insert_level (PF:933-990; outputs [L+1][N]), shift_out_nans (PF:1699-1720),
+// trapz (PF:164-206; mask labelled by the lower level, sign +1/-1 = only positive / only negative areas) and the
+// pressure-order check of valid_data (PF:2320; ORs kFlagPressure* into `flags`).
+template <typename T>
+void launch_insert_level(const T *coords, int64_t cls, int c1d, const T *lev_c, const T *const *x,
+                         const T *const *lev_x, T *const *out, T *coords_out, int n_fields, int64_t ls, int64_t ols,
+                         int L, int64_t n, cudaStream_t stream);
+template <typename T>
+void launch_shift_out_nans(const T *ref, const T *const *x, T *const *out, int n_fields, int64_t ls, int L,
+                           int64_t n, int32_t *shift, cudaStream_t stream);
+template <typename T>
+void launch_trapz(const T *x, int64_t xls, int x1d, const T *const *v, T *const *out, int n_fields, int64_t ls,
+                  int L, int64_t n, const uint8_t *mask, int64_t mls, int sign, cudaStream_t stream);
+template <typename T>
+void launch_pressure_order(const T *p, int64_t pls, int p1d, int L, int64_t n, uint32_t *flags, cudaStream_t stream);
+
 // Pointwise kernels (xp_derived.cu): q -> Td (PF:1889, 1969), saturation mixing ratio (PF:258, 2047-2053),
 // Normand wet-bulb temperature (PF:389-445), significant hail parameter (PF:2261-2306; in6 = mucape, mixing
 // ratio, lapse, temp_500, shear, flh) and storm proxies (PF:2323-2407; in13 in the order of ProxyIn in

@@ -1,0 +1,73 @@
+// xp_levels.cuh -- per-column level primitives of the parcel path on their own: insert_level (PF:933-990),
+// shift_out_nans (PF:1699-1720), trapz (PF:164-206) and the pressure-order check of valid_data (PF:2308-2321).
+// Host-compilable for tests/hostsim (see xp_math.cuh).
+#pragma once
+#include "xp_column.cuh"
+
+namespace xp {
+
+constexpr uint32_t kFlagPressureNotDecreasing = 4u;         // XP_FLAG_PRESSURE_NOT_DECREASING (PF:2320)
+constexpr uint32_t kFlagPressureOrderChecked = 8u;          // XP_FLAG_PRESSURE_ORDER_CHECKED
+constexpr double kInsertFill = -999.0;                       // insert_level's fill_value default (PF:934)
+
+// insert_level (PF:933-990), one output position j of 0..L for one variable.  c_j / c_jm: the coordinate at levels
+// j and j-1 (ignored where the level does not exist), v_j / v_jm: the variable there; lev_c / lev_v: coordinate
+// and value of the new level.  Value-based split: coordinates >= the new one stay in place ("below", PF:965),
+// coordinates < it move up one (PF:966-970), what is left is the new level (PF:985); NaN coordinates travel as the
+// fill value (with every variable of that level, PF:963) and come back as NaN (PF:988).
+XP_HD double insert_level_value(int j, int L, double c_j, double c_jm, double v_j, double v_jm, double lev_c,
+                                double lev_v) {
+    const bool nan_j = j < L && isnan(c_j), nan_jm = j >= 1 && isnan(c_jm);
+    const double cj = nan_j ? kInsertFill : c_j, cjm = nan_jm ? kInsertFill : c_jm;
+    const bool below = j < L && cj >= lev_c;
+    const bool above = j >= 1 && cjm < lev_c;
+    double val;
+    if (below) val = nan_j ? kInsertFill : v_j;
+    else if (above) val = nan_jm ? kInsertFill : v_jm;
+    else val = lev_v;
+    return val == kInsertFill ? qnan() : val;
+}
+
+// shift_out_nans (PF:1714-1718): the number of leading NaN levels of the reference variable (L if all are NaN:
+// the reference shifts L times and the column stays NaN).
+template <class RefAt>
+XP_HD int leading_nans(int L, RefAt ref_at) {
+    int k0 = 0;
+    while (k0 < L && isnan(ref_at(k0))) ++k0;
+    return k0;
+}
+
+// trapz (PF:164-206) of one variable: sum over k of |x[k+1] - x[k]| * (v[k] + v[k+1]) / 2, intervals labelled by
+// their lower level; `use(k)` is the mask (PF:193-196); sign > 0 keeps positive areas only, sign < 0 negative ones
+// (PF:200-204); NaN areas are skipped (xarray .sum, PF:206).
+template <class XAt, class VAt, class Use>
+XP_HD double trapz_column(int L, XAt x_at, VAt v_at, Use use, int sign) {
+    double sum = 0.0;
+    for (int k = 0; k + 1 < L; ++k) {
+        if (!use(k)) continue;
+        const double dx = fabs(x_at(k + 1) - x_at(k));          // PF:186
+        const double area = dx * ((v_at(k) + v_at(k + 1)) / 2);  // PF:188, 198
+        if (isnan(area)) continue;
+        if (sign > 0 && !(area > 0)) continue;
+        if (sign < 0 && !(area < 0)) continue;
+        sum += area;
+    }
+    return sum;
+}
+
+// valid_data (PF:2320): pressure.diff(vert_dim).max() < 0.  Returns bit 0 = a difference >= 0 exists,
+// bit 1 = a non-NaN difference exists (the reference's max skips NaN; with no valid difference it fails).
+template <class PressureAt>
+XP_HD int pressure_order(int L, PressureAt pressure_at) {
+    int r = 0;
+    double prev = L > 0 ? pressure_at(0) : qnan();
+    for (int k = 1; k < L; ++k) {
+        const double p = pressure_at(k);
+        const double d = p - prev;
+        if (!isnan(d)) { r |= 2; if (!(d < 0)) r |= 1; }
+        prev = p;
+    }
+    return r;
+}
+
+}  // namespace xp

@@ -379,7 +379,7 @@ def mixed_parcel(pressure, temperature, dewpoint, depth=100, vert_dim="model_lev
 def mixed_layer(dat, depth=100, vert_dim="model_level_number", vert_axis=0, device=None):
     """PF:137-162: mass-weighted mean over the lowest ``depth`` hPa of every variable of ``dat`` (a Dataset or
     dict that contains 'pressure'; like the reference's, the result also holds the mean of 'pressure' itself)."""
-    names = list(dat.data_vars) if hasattr(dat, "data_vars") else list(dat.keys())
+    names = _names(dat)
     assert "pressure" in names, "dat must contain pressure."
     template = next((dat[k] for k in names if getattr(dat[k], "ndim", 0) > 1), dat["pressure"])
     ctx = _lib.get_context(device)
@@ -390,6 +390,106 @@ def mixed_layer(dat, depth=100, vert_dim="model_level_number", vert_axis=0, devi
     full = [b if b.dim() == 2 else b[:, None].expand(lay.L, n).contiguous() for b in blocks]
     res = ctx.mixed_layer(pb, full, depth=depth, pressure_field=names.index("pressure"))
     return lay.dataset({k: lay.wrap_scalar(v if on_gpu else v.cpu(), k) for k, v in zip(names, res)})
+
+
+def _names(dat):
+    return list(dat.data_vars) if hasattr(dat, "data_vars") else list(dat.keys())
+
+
+def _full_blocks(lay, blocks):
+    n = int(np.prod(lay.col_shape)) if lay.col_shape else 1
+    return [b if b.dim() == 2 else b[:, None].expand(lay.L, n).contiguous() for b in blocks]
+
+
+def insert_level(d, level, coords, vert_dim="model_level_number", fill_value=-999, vert_axis=0, device=None):
+    """PF:933-990: insert ``level`` (values of ``coords`` and of the variables to keep, one per column) into the
+    vertically sorted ``d``; the result holds the keys of ``level`` on L + 1 levels."""
+    assert fill_value == -999, "only the reference's default fill_value is implemented"
+    keys = _names(level)
+    ctx = _lib.get_context(device)
+    lay, dtype, on_gpu = _layout_of(d[coords], vert_dim, vert_axis)
+    others = [k for k in keys if k != coords]
+    blocks = _full_blocks(lay, _blocks(lay, [d[coords]] + [d[k] for k in others], dtype))
+    lev = [lay.scalar_to_block(level[k], dtype).cuda().contiguous() for k in [coords] + others]
+    assert not bool((blocks[0] == fill_value).any()), "dataset d contains fill_value."          # PF:962
+    cout, outs = ctx.insert_level(blocks[0], lev[0], blocks[1:], lev[1:])
+    res = dict(zip([coords] + others, [cout] + outs))
+    return lay.dataset({k: lay.wrap_profile(res[k] if on_gpu else res[k].cpu(), k, lay.L + 1) for k in keys})
+
+
+def shift_out_nans(x, name, dim="model_level_number", vert_axis=0, device=None):
+    """PF:1699-1720: shift every variable of ``x`` down, column by column, until level 0 of ``name`` is not NaN."""
+    names = _names(x)
+    ctx = _lib.get_context(device)
+    lay, dtype, on_gpu = _layout_of(x[name], dim, vert_axis)
+    blocks = _full_blocks(lay, _blocks(lay, [x[k] for k in names], dtype))
+    outs, _ = ctx.shift_out_nans(blocks[names.index(name)], blocks)
+    return lay.dataset({k: lay.wrap_profile(o if on_gpu else o.cpu(), k, lay.L) for k, o in zip(names, outs)})
+
+
+def trapz(dat, x, dim="model_level_number", mask=None, only_positive=False, only_negative=False, vert_axis=0,
+          device=None):
+    """PF:164-206: trapezoidal integral of every variable of ``dat`` along its variable ``x``; ``mask`` selects the
+    intervals (labelled by their lower level)."""
+    assert not (only_positive and only_negative), "Only negative OR positive regions can be included in trapz."
+    names = _names(dat)
+    ctx = _lib.get_context(device)
+    template = next((dat[k] for k in names if getattr(dat[k], "ndim", 0) > 1), dat[x])
+    lay, dtype, on_gpu = _layout_of(template, dim, vert_axis)
+    blocks = _blocks(lay, [dat[k] for k in names], dtype)
+    xb = blocks[names.index(x)]
+    mb = None
+    if mask is not None:
+        m = mask.data if (_xr is not None and isinstance(mask, _xr.DataArray)) else mask
+        m = m if isinstance(m, torch.Tensor) else torch.as_tensor(np.asarray(m))
+        va = lay.vert_axis or 0
+        mb = m.movedim(va, 0).reshape(m.shape[va], -1).cuda() != 0
+    res = ctx.trapz(xb, _full_blocks(lay, blocks), mask=mb, sign=1 if only_positive else (-1 if only_negative else 0))
+    return lay.dataset({k: lay.wrap_scalar(v if on_gpu else v.cpu(), k) for k, v in zip(names, res)})
+
+
+def valid_data(dat, vert_dim="model_level_number", vert_axis=0, device=None):
+    """PF:2308-2321: True if the vertical index steps by one and the pressures decrease with the level number."""
+    if hasattr(dat, "coords") and vert_dim in getattr(dat, "coords", {}):
+        assert np.all(np.abs(np.diff(np.asarray(dat[vert_dim]))) == 1), "Index increments must all be 1."
+    ctx = _lib.get_context(device)
+    lay, dtype, _ = _layout_of(dat["pressure"], vert_dim, vert_axis)
+    (pb,) = _blocks(lay, [dat["pressure"]], dtype)
+    n = int(np.prod(lay.col_shape)) if lay.col_shape else 1
+    ctx.valid_data(pb, n)
+    flags = ctx.take_flags()
+    assert (flags & _lib.FLAG_PRESSURE_ORDER_CHECKED) and not (flags & _lib.FLAG_PRESSURE_NOT_DECREASING), \
+        "Pressures must decrease with increasing level number."
+    return True
+
+
+def get_layer(dat, depth=100, vert_dim="model_level_number", interpolate=True, vert_axis=0, device=None):
+    """PF:63-100: the lowest ``depth`` hPa of ``dat`` (which must contain 'pressure'), everything else NaN.  With
+    ``interpolate`` the layer top is interpolated in ln p and inserted (L + 1 levels), otherwise the top is the
+    level closest to it (bound_pressure)."""
+    names = _names(dat)
+    ctx = _lib.get_context(device)
+    lay, dtype, on_gpu = _layout_of(dat["pressure"], vert_dim, vert_axis)
+    blocks = _full_blocks(lay, _blocks(lay, [dat[k] for k in names], dtype))
+    pb = blocks[names.index("pressure")]
+    n = pb.shape[1]
+    bottom, top = ctx.layer_bounds(pb, n, depth=depth, interpolate=interpolate)
+    n_lev = lay.L
+    if interpolate:
+        others = [k for k in names if k != "pressure"]
+        ob = [blocks[names.index(k)] for k in others]
+        lev = []
+        for g in range(0, len(ob), 4):
+            lev += ctx.interp_levels(pb, ob[g:g + 4], top, log=True)                 # PF:85
+        cout, outs = ctx.insert_level(pb, top, ob, lev)                               # PF:87-90
+        res = dict(zip(["pressure"] + others, [cout] + outs))
+        blocks = [res[k] for k in names]
+        pb = cout
+        n_lev += 1
+    keep = (pb <= bottom[None, :]) & (pb >= top[None, :])                             # PF:97-98
+    nanv = torch.full((), float("nan"), dtype=pb.dtype, device=pb.device)
+    out = {k: torch.where(keep, b, nanv) for k, b in zip(names, blocks)}
+    return lay.dataset({k: lay.wrap_profile(v if on_gpu else v.cpu(), k, n_lev) for k, v in out.items()})
 
 
 def bound_pressure(pressure, bound=None, vert_dim="model_level_number", vert_axis=0, device=None, depth=None):
