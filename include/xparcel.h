@@ -260,6 +260,18 @@ xp_status xp_shift_out_nans(xp_context *ctx, const void *ref_field, const void *
 xp_status xp_trapz(xp_context *ctx, const void *x, int64_t x_level_stride, int32_t x_is_1d, const void *const *fields,
                    void *const *outputs, int32_t n_fields, int64_t level_stride, int32_t n_levels, int64_t n_columns,
                    int32_t dtype, const uint8_t *mask, int64_t mask_level_stride, int32_t sign, void *stream);
+/* xp_find_intersections: find_intersections (PF:992-1064) of the curves a and b over the coordinate x (ln x with
+ * log_x): for every interval between neighbouring levels whose sign(a - b) changes (a NaN sign counts as a change,
+ * PF:1022) the crossing point by linear interpolation (PF:1046-1050), split by direction (sign of a - b above the
+ * crossing, PF:1030).  Outputs are [n_levels - 1][n_columns] with stride out_level_stride (row r = the interval
+ * between levels r and r + 1, the reference's offset label r + 1), NaN where there is no crossing; any may be NULL. */
+typedef struct xp_intersections_out {
+    void *all_intersect_x, *all_intersect_y, *increasing_x, *increasing_y, *decreasing_x, *decreasing_y;
+} xp_intersections_out;
+xp_status xp_find_intersections(xp_context *ctx, const void *x, int64_t x_level_stride, int32_t x_is_1d, const void *a,
+                                const void *b, int64_t level_stride, int64_t out_level_stride, int32_t n_levels,
+                                int64_t n_columns, int32_t dtype, int32_t log_x, const xp_intersections_out *out,
+                                void *stream);
 /* xp_valid_data: the pressure check of valid_data (PF:2320: pressure.diff(vert_dim).max() < 0).  ORs
  * XP_FLAG_PRESSURE_NOT_DECREASING (a difference >= 0 exists) and XP_FLAG_PRESSURE_ORDER_CHECKED (a non-NaN
  * difference exists) into the context flags; read them with xp_take_flags(). */

@@ -351,6 +351,21 @@ extern "C" void hostsim_trapz(const double *x, const double *v, const uint8_t *m
     }
 }
 
+extern "C" void hostsim_find_intersections(const double *x, const double *a, const double *b, int64_t n, int L, int log_x,
+                                           double *out /*[3][L-1][n]: ix, iy, sign*/) {
+    for (int64_t i = 0; i < n; ++i)
+        for (int k = 1; k < L; ++k) {
+            double x0 = x[(int64_t)(k - 1) * n + i], x1 = x[(int64_t)k * n + i];
+            if (log_x) { x0 = log(x0); x1 = log(x1); }
+            double ix, iy, sc;
+            xp::interval_crossing(x0, x1, a[(int64_t)(k - 1) * n + i], a[(int64_t)k * n + i], b[(int64_t)(k - 1) * n + i],
+                                  b[(int64_t)k * n + i], log_x != 0, ix, iy, sc);
+            out[((int64_t)0 * (L - 1) + k - 1) * n + i] = ix;
+            out[((int64_t)1 * (L - 1) + k - 1) * n + i] = iy;
+            out[((int64_t)2 * (L - 1) + k - 1) * n + i] = sc;
+        }
+}
+
 extern "C" int hostsim_pressure_order(const double *p, int64_t n, int L) {
     int r = 0;
     for (int64_t i = 0; i < n; ++i) {

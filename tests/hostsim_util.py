@@ -192,3 +192,16 @@ def pressure_order(p):
     p = np.ascontiguousarray(p, dtype=np.float64)
     L, N = p.shape
     return int(lib().hostsim_pressure_order(_vp(p), ctypes.c_int64(N), L))
+
+
+def find_intersections(x, a, b, log_x=False):
+    """xp_levels.cuh interval_crossing over [L, N] arrays -> dict like oracle.parcel.find_intersections."""
+    x, a, b = [np.ascontiguousarray(v, dtype=np.float64) for v in (x, a, b)]
+    L, N = a.shape
+    out = np.empty((3, L - 1, N))
+    lib().hostsim_find_intersections(_vp(x), _vp(a), _vp(b), ctypes.c_int64(N), L, int(bool(log_x)), _vp(out))
+    ix, iy, sc = out
+    with np.errstate(invalid="ignore"):
+        return {"all_intersect_x": ix, "all_intersect_y": iy,
+                "increasing_x": np.where(sc > 0, ix, np.nan), "increasing_y": np.where(sc > 0, iy, np.nan),
+                "decreasing_x": np.where(sc < 0, ix, np.nan), "decreasing_y": np.where(sc < 0, iy, np.nan)}

@@ -115,3 +115,22 @@ def test_get_layer_against_oracle(ctx, interpolate, depth):
     got = parcel.get_layer(d, depth=depth, interpolate=interpolate)
     for key in d:
         _same(got[key], ora[key])
+
+
+@pytest.mark.parametrize("log_x", [False, True])
+def test_find_intersections_against_oracle(ctx, log_x):
+    P, T, D = _columns(seed=26)
+    A = T - 0.6 * (T - D) + 3.0 * np.sin(np.arange(P.shape[0]))[:, None]
+    A[7, :30] = T[7, :30]
+    ora = op.find_intersections(P, A, T, log_x=log_x)
+    got = parcel.find_intersections(P, A, T, log_x=log_x)
+    assert set(got.keys()) == set(ora.keys())
+    for k in ora:
+        _same(got[k], ora[k])
+    # shared 1-D coordinate, float32, crossing with a constant (the freezing level, PF:2153)
+    p1, t, _ = synth.era5_columns(2000, seed=10)
+    Pb = np.broadcast_to(p1.numpy().astype(np.float64)[:, None], t.shape)
+    t64 = t.numpy().astype(np.float64)
+    o2 = op.find_intersections(Pb, t64, np.full_like(t64, 273.0), log_x=log_x)
+    g2 = ctx.find_intersections(p1.cuda(), t.cuda(), torch.full((1, 1), 273.0, device="cuda"), log_x=log_x)
+    _same(g2["all_intersect_x"].cpu().numpy(), o2["all_intersect_x"], rtol=2e-4)

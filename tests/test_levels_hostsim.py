@@ -77,3 +77,14 @@ def test_pressure_order():
     Q[7, 3] = Q[6, 3]                                 # equal pressures are not "decreasing" (max < 0 fails)
     assert hs.pressure_order(Q) & 1
     assert hs.pressure_order(np.full((5, 3), np.nan)) == 0
+
+
+@pytest.mark.parametrize("log_x", [False, True])
+def test_find_intersections_against_oracle(log_x, soundings):
+    P, T, D = _columns(seed=26)
+    A = T - 0.6 * (T - D) + 3.0 * np.sin(np.arange(P.shape[0]))[:, None]          # crosses T several times
+    A[7, :30] = T[7, :30]                                                            # exact touches (sign 0)
+    ora = op.find_intersections(P, A, T, log_x=log_x)
+    got = hs.find_intersections(P, A, T, log_x=log_x)
+    for k in ora:
+        _same(got[k], ora[k])

@@ -64,7 +64,8 @@ EXPORTS = ["xp_version", "xp_create", "xp_destroy", "xp_last_error", "xp_take_fl
            "xp_level_crossing", "xp_dewpoint_from_specific_humidity", "xp_saturation_mixing_ratio",
            "xp_dry_lapse", "xp_mixing_ratio", "xp_virtual_temperature", "xp_wet_bulb_temperature",
            "xp_significant_hail_parameter", "xp_storm_proxies", "xp_mixed_layer", "xp_mixed_parcel",
-           "xp_layer_bounds", "xp_insert_level", "xp_shift_out_nans", "xp_trapz", "xp_valid_data"]
+           "xp_layer_bounds", "xp_insert_level", "xp_shift_out_nans", "xp_trapz", "xp_valid_data",
+           "xp_find_intersections"]
 
 PROXY_INPUTS = ["mixed_100_cape", "mixed_50_cape", "mu_cape", "shear_magnitude", "mixed_100_lifted_index",
                 "mixed_100_dci", "positive_shear", "mixed_50_cin", "mixed_100_cin", "lapse_rate_700_500",
@@ -78,6 +79,14 @@ MIXED_PARCEL_FIELDS = ["theta", "mixing_ratio", "temperature", "vapour_pressure"
 
 class XpMixedParcelOut(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in MIXED_PARCEL_FIELDS]
+
+
+INTERSECTION_FIELDS = ["all_intersect_x", "all_intersect_y", "increasing_x", "increasing_y", "decreasing_x",
+                       "decreasing_y"]
+
+
+class XpIntersectionsOut(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in INTERSECTION_FIELDS]
 
 
 class XpProxyInputs(ctypes.Structure):
@@ -174,6 +183,9 @@ def load_library():
         lib.xp_trapz.argtypes = [c_void_p, c_void_p, c_int64, c_int32, PP, PP, c_int32, c_int64, c_int32, c_int64,
                                  c_int32, c_void_p, c_int64, c_int32, c_void_p]
         lib.xp_valid_data.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int64, c_int32, c_void_p]
+        lib.xp_find_intersections.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_int64,
+                                              c_int32, c_int64, c_int32, c_int32, ctypes.POINTER(XpIntersectionsOut),
+                                              c_void_p]
         lib.xp_launch_count.argtypes = [c_void_p]
         lib.xp_launch_count.restype = ctypes.c_uint64
         lib.xp_last_kernel_ms.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_float)]
@@ -607,6 +619,22 @@ class Context:
                                    self._ptrs(o), len(grp), N, L, N, _dtype_code(grp[0]),
                                    mask.data_ptr() if mask is not None else None, N, int(sign), self._stream())
             self._check(st, "xp_trapz")
+        return outs
+
+    def find_intersections(self, x, a, b, log_x=False):
+        """find_intersections (PF:992-1064): dict of the six [L-1, N] arrays (row r = interval r..r+1)."""
+        a = a.contiguous()
+        L, N = a.shape
+        b = b.to(a.dtype).expand(L, N).contiguous()
+        x = x.to(a.dtype).contiguous()
+        x1d = x.dim() == 1
+        outs = {n: torch.full((max(L - 1, 0), N), float("nan"), dtype=a.dtype, device=a.device)
+                for n in INTERSECTION_FIELDS}
+        o = XpIntersectionsOut(*[outs[n].data_ptr() for n in INTERSECTION_FIELDS])
+        st = self.lib.xp_find_intersections(self.handle, x.data_ptr(), 1 if x1d else N, int(x1d), a.data_ptr(),
+                                            b.data_ptr(), N, N, L, N, _dtype_code(a), int(bool(log_x)),
+                                            ctypes.byref(o), self._stream())
+        self._check(st, "xp_find_intersections")
         return outs
 
     def valid_data(self, pressure, n_columns):

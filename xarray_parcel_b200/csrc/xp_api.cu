@@ -763,6 +763,25 @@ xp_status xp_trapz(xp_context *ctx, const void *x, int64_t x_level_stride, int32
     return check_cuda(ctx, cudaGetLastError(), "trapz kernel launch");
 }
 
+xp_status xp_find_intersections(xp_context *ctx, const void *x, int64_t x_level_stride, int32_t x_is_1d, const void *a,
+                                const void *b, int64_t level_stride, int64_t out_level_stride, int32_t n_levels,
+                                int64_t n_columns, int32_t dtype, int32_t log_x, const xp_intersections_out *out,
+                                void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (n_columns == 0) return XP_OK;
+    if (!x || !a || !b || !out || n_levels < 1 || n_columns < 0)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad find_intersections arguments");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    void *o6[6] = {out->all_intersect_x, out->all_intersect_y, out->increasing_x, out->increasing_y,
+                   out->decreasing_x, out->decreasing_y};
+    XP_DISPATCH(dtype,
+                launch_find_intersections<float>((const float *)x, x_level_stride, x_is_1d, (const float *)a, (const float *)b, level_stride, out_level_stride, n_levels, n_columns, log_x, (float *const *)o6, st),
+                launch_find_intersections<double>((const double *)x, x_level_stride, x_is_1d, (const double *)a, (const double *)b, level_stride, out_level_stride, n_levels, n_columns, log_x, (double *const *)o6, st));
+    ctx->launches += n_levels >= 2;
+    return check_cuda(ctx, cudaGetLastError(), "find_intersections kernel launch");
+}
+
 xp_status xp_valid_data(xp_context *ctx, const void *pressure, int64_t pressure_level_stride, int32_t pressure_is_1d,
                         int32_t n_levels, int64_t n_columns, int32_t dtype, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;

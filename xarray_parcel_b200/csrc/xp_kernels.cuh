@@ -139,6 +139,11 @@ void launch_shift_out_nans(const T *ref, const T *const *x, T *const *out, int n
 template <typename T>
 void launch_trapz(const T *x, int64_t xls, int x1d, const T *const *v, T *const *out, int n_fields, int64_t ls,
                   int L, int64_t n, const uint8_t *mask, int64_t mls, int sign, cudaStream_t stream);
+// find_intersections (PF:992-1064): out6 = all x, all y, increasing x, y, decreasing x, y, each [L-1][N] (row r =
+// the interval between levels r and r + 1, the reference's offset label r + 1), any may be null.
+template <typename T>
+void launch_find_intersections(const T *x, int64_t xls, int x1d, const T *a, const T *b, int64_t ls, int64_t ols,
+                               int L, int64_t n, int log_x, T *const *out6, cudaStream_t stream);
 template <typename T>
 void launch_pressure_order(const T *p, int64_t pls, int p1d, int L, int64_t n, uint32_t *flags, cudaStream_t stream);
 

@@ -1,6 +1,6 @@
 // xp_levels.cu -- level primitives of the parcel path as stand-alone column kernels (per-column code in
 // xp_levels.cuh): insert_level_kernel (PF:933-990), shift_out_nans_kernel (PF:1699-1720), trapz_kernel (PF:164-206)
-// and pressure_order_kernel (valid_data PF:2308-2321).  One thread per column, float64 arithmetic, level-major
+// pressure_order_kernel (valid_data PF:2308-2321) and find_intersections_kernel (PF:992-1064).  One thread per column, float64 arithmetic, level-major
 // arrays so every level access of a warp is one coalesced line; each input level is read once (insert_level keeps
 // the previous level in registers), each output level written once.
 #include "xp_kernels.cuh"
@@ -103,6 +103,41 @@ __global__ void trapz_kernel(const __grid_constant__ TrapzParams<T> prm) {
 }
 
 template <typename T>
+struct IntersectParams {
+    const T *x;                 // [L][N] or shared [L]
+    int64_t xls;
+    int x1d;
+    const T *a, *b;             // [L][N]
+    int64_t ls, ols;
+    int L;
+    int64_t n;
+    int log_x;
+    T *out[6];                  // all x, all y, increasing x, y, decreasing x, y: [L-1][N], any may be null
+};
+
+template <typename T>
+__global__ void find_intersections_kernel(const __grid_constant__ IntersectParams<T> prm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= prm.n) return;
+    const T *xc = prm.x1d ? prm.x : prm.x + i;
+    auto x_at = [&](int k) { const double v = (double)xc[(int64_t)k * prm.xls]; return prm.log_x ? log(v) : v; };
+    double x0 = x_at(0), a0 = (double)prm.a[i], b0 = (double)prm.b[i];
+    for (int k = 1; k < prm.L; ++k) {
+        const double x1 = x_at(k), a1 = (double)prm.a[(int64_t)k * prm.ls + i], b1 = (double)prm.b[(int64_t)k * prm.ls + i];
+        double ix, iy, sc;
+        interval_crossing(x0, x1, a0, a1, b0, b1, prm.log_x != 0, ix, iy, sc);
+        const int64_t o = (int64_t)(k - 1) * prm.ols + i;
+        if (prm.out[0]) prm.out[0][o] = (T)ix;
+        if (prm.out[1]) prm.out[1][o] = (T)iy;
+        if (prm.out[2]) prm.out[2][o] = (T)(sc > 0 ? ix : qnan());
+        if (prm.out[3]) prm.out[3][o] = (T)(sc > 0 ? iy : qnan());
+        if (prm.out[4]) prm.out[4][o] = (T)(sc < 0 ? ix : qnan());
+        if (prm.out[5]) prm.out[5][o] = (T)(sc < 0 ? iy : qnan());
+        x0 = x1; a0 = a1; b0 = b1;
+    }
+}
+
+template <typename T>
 __global__ void pressure_order_kernel(const T *p, int64_t pls, int p1d, int L, int64_t n, uint32_t *flags) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int r = 0;
@@ -158,6 +193,17 @@ void launch_trapz(const T *x, int64_t xls, int x1d, const T *const *v, T *const 
 }
 
 template <typename T>
+void launch_find_intersections(const T *x, int64_t xls, int x1d, const T *a, const T *b, int64_t ls, int64_t ols,
+                               int L, int64_t n, int log_x, T *const *out6, cudaStream_t stream) {
+    if (n <= 0 || L < 2) return;
+    IntersectParams<T> prm;
+    prm.x = x; prm.xls = xls; prm.x1d = x1d; prm.a = a; prm.b = b; prm.ls = ls; prm.ols = ols; prm.L = L; prm.n = n;
+    prm.log_x = log_x;
+    for (int f = 0; f < 6; ++f) prm.out[f] = out6[f];
+    find_intersections_kernel<T><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(prm);
+}
+
+template <typename T>
 void launch_pressure_order(const T *p, int64_t pls, int p1d, int L, int64_t n, uint32_t *flags, cudaStream_t stream) {
     if (n <= 0) return;
     pressure_order_kernel<T><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(p, pls, p1d, L, n, flags);
@@ -170,7 +216,9 @@ void launch_pressure_order(const T *p, int64_t pls, int p1d, int L, int64_t n, u
                                            int32_t *, cudaStream_t);                                                  \
     template void launch_trapz<T>(const T *, int64_t, int, const T *const *, T *const *, int, int64_t, int, int64_t, \
                                   const uint8_t *, int64_t, int, cudaStream_t);                                       \
-    template void launch_pressure_order<T>(const T *, int64_t, int, int, int64_t, uint32_t *, cudaStream_t);
+    template void launch_pressure_order<T>(const T *, int64_t, int, int, int64_t, uint32_t *, cudaStream_t);       \
+    template void launch_find_intersections<T>(const T *, int64_t, int, const T *, const T *, int64_t, int64_t, int, \
+                                               int64_t, int, T *const *, cudaStream_t);
 XP_INST_LEVELS(float)
 XP_INST_LEVELS(double)
 #undef XP_INST_LEVELS

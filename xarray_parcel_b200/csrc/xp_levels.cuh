@@ -55,6 +55,21 @@ XP_HD double trapz_column(int L, XAt x_at, VAt v_at, Use use, int sign) {
     return sum;
 }
 
+// find_intersections (PF:992-1064), one interval between two neighbouring levels.  x0 / x1 are the coordinates
+// (already ln x when log_x), a / b the two curves.  A sign change of a - b across the interval (NaN signs count as a
+// change, PF:1022) gives the crossing (ix, iy) by linear interpolation (PF:1046, 1050) and sign(a1 - b1) tells its
+// direction (PF:1030); otherwise everything is NaN.
+XP_HD void interval_crossing(double x0, double x1, double a0, double a1, double b0, double b1, bool log_x,
+                             double &ix, double &iy, double &sign_change) {
+    const double diff = sign_of(a1 - b1) - sign_of(a0 - b0);  // PF:1019
+    if (diff == 0) { ix = iy = sign_change = qnan(); return; }
+    sign_change = sign_of(a1 - b1);
+    const double dy0 = a0 - b0, dy1 = a1 - b1;
+    ix = (dy1 * x0 - dy0 * x1) / (dy1 - dy0);
+    iy = ((ix - x0) / (x1 - x0)) * (a1 - a0) + a0;
+    if (log_x) ix = exp(ix);                                  // PF:1053
+}
+
 // valid_data (PF:2320): pressure.diff(vert_dim).max() < 0.  Returns bit 0 = a difference >= 0 exists,
 // bit 1 = a non-NaN difference exists (the reference's max skips NaN; with no valid difference it fails).
 template <class PressureAt>

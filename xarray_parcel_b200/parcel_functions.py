@@ -448,6 +448,24 @@ def trapz(dat, x, dim="model_level_number", mask=None, only_positive=False, only
     return lay.dataset({k: lay.wrap_scalar(v if on_gpu else v.cpu(), k) for k, v in zip(names, res)})
 
 
+def find_intersections(x, a, b, dim="model_level_number", log_x=False, vert_axis=0, device=None):
+    """PF:992-1064: crossings of the curves ``a`` and ``b`` over ``x``.  Returns a Dataset of all_intersect_x/y,
+    increasing_x/y and decreasing_x/y on L - 1 levels labelled, like the reference's offset_dim, by the upper level
+    of each interval."""
+    ctx = _lib.get_context(device)
+    lay, dtype, on_gpu = _layout_of(a, dim, vert_axis)
+    xb, ab, bb = _blocks(lay, [x, a, b], dtype)
+    (ab, bb) = _full_blocks(lay, [ab, bb])
+    res = ctx.find_intersections(xb, ab, bb, log_x=log_x)
+    out = {}
+    for k, v in res.items():
+        w = lay.wrap_profile(v if on_gpu else v.cpu(), k, lay.L - 1)
+        if lay.is_xr:
+            w = w.assign_coords({dim: w[dim] + 1})                                     # PF:1026 offset labels
+        out[k] = w
+    return lay.dataset(out)
+
+
 def valid_data(dat, vert_dim="model_level_number", vert_axis=0, device=None):
     """PF:2308-2321: True if the vertical index steps by one and the pressures decrease with the level number."""
     if hasattr(dat, "coords") and vert_dim in getattr(dat, "coords", {}):
