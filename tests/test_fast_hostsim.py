@@ -112,11 +112,17 @@ def test_fast_profile_rows_per_column_pressure(oracle_tables, vtc):
     res, redo = hs.fast_suite(p.numpy(), t.numpy(), td.numpy(), oracle_tables, vtc=vtc, profile=True)
     fns = {"sb": op.surface_based_cape_cin, "ml": op.mixed_layer_cape_cin, "mu": op.most_unstable_cape_cin}
     L = T.shape[0]
+    seen_rows_ok = [0]
     for q, kind in enumerate(("sb", "ml", "mu")):
         prof = fns[kind](P, T, D, opts, virtual_temperature_correction=vtc)[1]
         keep = ((redo >> q) & 1) == 0
         if kind == "mu":
             keep &= (redo & 8) == 0
+        # columns handed over for a crossing decision alone keep their float32 rows (kRedoRowsOk): check them too
+        rows_ok = ((redo >> (4 + q)) & 1) == 1
+        assert not (rows_ok & keep).any() and rows_ok.sum() <= (~keep).sum()
+        seen_rows_ok[0] += int(rows_ok.sum())
+        keep = keep | rows_ok
         n = prof["pressure"].shape[0]            # the oracle trims levels that are NaN in every column
         for k in hs.PROFILE:
             a = res[kind]["profile"][k].astype(np.float64)[:, keep]
@@ -128,6 +134,7 @@ def test_fast_profile_rows_per_column_pressure(oracle_tables, vtc):
             assert np.array_equal(np.isnan(a), np.isnan(b)), f"{kind} {k}: NaN pattern differs"
             ok = ~np.isnan(b)
             assert np.allclose(a[ok], b[ok], rtol=3e-6, atol=0), (kind, k, np.abs(a[ok] - b[ok]).max())
+    assert seen_rows_ok[0] > 0                   # the case is exercised
 
 
 def test_fast_suite_per_column_pressure_depths_and_90_levels(oracle_tables):

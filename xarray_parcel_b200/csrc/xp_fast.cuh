@@ -36,6 +36,8 @@ constexpr float kCrossSlope = 0.5f;         // K per unit ln p: a crossing with 
 #endif
 constexpr double kTopCheckHpa = XP_TOP_CHECK_HPA;   // v6 sweep: early termination is considered above this pressure
 constexpr float kStopMargin = 1.0f;          // K: early-termination margin below the coldest environment level
+constexpr unsigned kRedoRowsOk = 16u;        // << kind (bits 4-6), profile calls only: the column is on the list for a crossing
+                                             // decision alone, its float32 profile rows stand and the fix-up rewrites scalars only
 constexpr unsigned kRedoMuIsSb = 8u;         // redo-mask bit (== kListMuIsSb): write the SB exact result to the MU outputs too
 constexpr double kSaturationMargin = 2e-3;
 // margins for a parcel that is itself only float32-accurate (`approx`; currently unused: all parcels are

@@ -144,7 +144,7 @@ XP_HD void parcel_iteration_pcol(PColParcel &c, int it, bool last, int j_cur, fl
 // The suite for one column with its own pressure profile.  Returns the redo mask (see suite_column).
 template <unsigned KINDS, int MODE, class Rd, class Prof>
 XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Opts &o, Prof &prof, FResult res[3]) {
-    unsigned redo = 0;
+    unsigned redo = 0, rows_exact = 0;       // rows_exact: kinds whose profile rows the exact path must rewrite too
     float nanacc = 0.0f;
     bool bad_axis = false;                 // pressure not finite / not strictly decreasing / outside the table
     const float p_sfc = rd.P(0), t_sfc = rd.T(0), td_sfc = rd.Td(0);
@@ -230,12 +230,12 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
         const double depth = fabs(top_ml - bottom);                              // PF:158-159
         double mp_t, mp_td;
         mixed_parcel_t_td(bottom, (1. / depth) * sum_th, (1. / depth) * sum_w, mp_t, mp_td);   // PF:161, 268-282
-        if (!ml_done || K_ml < 1) { redo |= 2u; K_ml = max(K_ml, 1); }   // no level above / NaN layer: exact path
+        if (!ml_done || K_ml < 1) { redo |= 2u; rows_exact |= 2u; K_ml = max(K_ml, 1); }   // no level above / NaN layer: exact path
         setup_parcel_pcol(rd, L, tb, o, bottom, mp_t, mp_td, x_sfc, K_ml, ml);
         res[1].par_p = p_sfc; res[1].par_t = (float)mp_t; res[1].par_td = (float)mp_td; res[1].shift = K_ml;
     }
     if (KINDS & 4u) {
-        if (!(best - second >= kThetaEMargin)) redo |= 4u;
+        if (!(best - second >= kThetaEMargin)) { redo |= 4u; rows_exact |= 4u; }
         setup_parcel_pcol(rd, L, tb, o, (double)mu_p, (double)mu_t, (double)mu_td, kLn2 * f_lg2(mu_p), k_mu + 1, mu);
         res[2].par_p = mu_p; res[2].par_t = mu_t; res[2].par_td = mu_td; res[2].shift = k_mu;
     }
@@ -328,6 +328,7 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
         sweep_finish<MODE>(c, o, r);
         const bool unc = !(c.min_abs_d >= kDecisionEps) || !(c.min_slope >= 0.0f);
         if (c.bad || unc || nan_seen) redo |= bit;
+        if (c.bad || nan_seen) rows_exact |= bit;
     };
     if (KINDS & 1u) wrap(sb, res[0], 1u);
     if (KINDS & 2u) wrap(ml, res[1], 2u);
@@ -335,6 +336,7 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
     if (!Prof::kEnabled && (KINDS & 5u) == 5u && (redo & 4u) && k_mu == 0 && !nan_seen &&
         (best - second >= kThetaEMargin))
         redo = (redo & ~4u) | 1u | kRedoMuIsSb;
+    if (Prof::kEnabled) redo |= ((redo & 7u) & ~rows_exact) * kRedoRowsOk;
     return redo;
 }
 

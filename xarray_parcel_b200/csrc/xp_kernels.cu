@@ -149,7 +149,8 @@ __global__ void __launch_bounds__(128) suite_list_kernel(const __grid_constant__
         ParcelResult r;
         double p0, t0, td0;
         int shift;
-        ProfWriter<float> np = make_writer(prm.outs[kind], col);       // profile rows too, where requested
+        ProfWriter<float> np = make_writer(prm.outs[kind], col);       // profile rows too, where requested ...
+        if ((e >> 28) & kListRowsOk) np.any = false;                   // ... unless the float32 rows stand
         run_column(rd, kind, prm.tb, prm.o, qnan(), qnan(), qnan(), r, p0, t0, td0, shift, np);
         for (int w = 0; w < (also_mu ? 2 : 1); ++w) store_result(prm.outs[w == 0 ? kind : 2], col, r, p0, t0, td0, shift);
         if (r.flags && prm.flags) atomicOr(prm.flags, r.flags);

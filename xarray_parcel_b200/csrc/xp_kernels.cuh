@@ -82,13 +82,14 @@ struct ListParams {
     uint32_t *flags;
 };
 constexpr unsigned kListMuIsSb = 8u;
+constexpr unsigned kListRowsOk = 1u;         // entry >> 28: the float32 profile rows of this item stand (scalars only)
 
-// Append the items of one column (redo: bits 0-2 kinds, bit 3 = kListMuIsSb).
+// Append the items of one column (redo: bits 0-2 kinds, bit 3 = kListMuIsSb, bits 4-6 = rows-ok per kind).
 __device__ __forceinline__ void push_redo(uint32_t *list, uint32_t *count, int64_t capacity, int64_t col,
                                           unsigned redo) {
-    if (redo & 1u) list[atomicAdd(count + 0, 1u)] = (uint32_t)col | ((redo & kListMuIsSb) << 28);
-    if (redo & 2u) list[capacity + atomicAdd(count + 1, 1u)] = (uint32_t)col;
-    if (redo & 4u) list[2 * capacity + atomicAdd(count + 2, 1u)] = (uint32_t)col;
+    if (redo & 1u) list[atomicAdd(count + 0, 1u)] = (uint32_t)col | ((redo & kListMuIsSb) << 28) | (((redo >> 4) & 1u) << 28);
+    if (redo & 2u) list[capacity + atomicAdd(count + 1, 1u)] = (uint32_t)col | (((redo >> 5) & 1u) << 28);
+    if (redo & 4u) list[2 * capacity + atomicAdd(count + 2, 1u)] = (uint32_t)col | (((redo >> 6) & 1u) << 28);
     atomicAdd(count + 3, 1u);
 }
 void launch_suite_list(const ListParams &lp, int sm_count, cudaStream_t stream);
