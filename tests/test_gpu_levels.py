@@ -134,3 +134,26 @@ def test_find_intersections_against_oracle(ctx, log_x):
     o2 = op.find_intersections(Pb, t64, np.full_like(t64, 273.0), log_x=log_x)
     g2 = ctx.find_intersections(p1.cuda(), t.cuda(), torch.full((1, 1), 273.0, device="cuda"), log_x=log_x)
     _same(g2["all_intersect_x"].cpu().numpy(), o2["all_intersect_x"], rtol=2e-4)
+
+
+@pytest.mark.parametrize("interpolator", ["log", "linear"])
+def test_add_lcl_to_profile_against_oracle(ctx, interpolator):
+    """PF:858-931 composed from the stand-alone kernels, against the oracle and against the fused kernel behind
+    parcel_profile_with_lcl."""
+    from oracle import tables as otab
+    from oracle import thermo as th
+    ctx.tables_build()
+    p, t, td = synth.model_level_columns(1500, 40, seed=27, nan_columns=0, allnan_columns=0)
+    P, T, D = [x.numpy().astype(np.float64) for x in (p, t, td)]
+    opts = op.Options(op.MoistLapseLUT(otab.load_tables()), lcl_mode="converged")
+    prof = op.parcel_profile(P, P[0], T[0], D[0], opts)
+    env = {"temperature": T, "virtual_temperature": th.virtual_temperature(T, op.mixing_ratio(T, D, P, opts)),
+           "dewpoint": D, "pressure": prof["pressure"]}
+    ora = op.add_lcl_to_profile(prof, env, interpolator, opts)
+    got = parcel.add_lcl_to_profile(prof, environment=env, interpolator=interpolator)
+    assert set(got.keys()) == set(ora.keys())
+    for k in ora:
+        _same(got[k], ora[k], rtol=1e-11)
+    fused = parcel.parcel_profile_with_lcl(P, T, D, P[0], T[0], D[0], lcl_interp=interpolator)
+    for k in ("pressure", "environment_temperature", "environment_dewpoint", "environment_virtual_temperature"):
+        _same(got[k], fused[k], rtol=1e-9)

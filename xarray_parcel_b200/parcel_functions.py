@@ -110,6 +110,29 @@ def moist_adiabat_tables(regenerate=False, cache=True, device=None, **kwargs):
     return ctx.tables_get()
 
 
+def moist_adiabat_lookup(pressure_levels=None, temperatures=None, pres_step=0.5, temp_step=0.02, device=None):
+    """PF:447-523 on the reference's default grids (pressures 1100 ... 2.5 hPa in 0.5 hPa steps, temperatures 173 ...
+    315.98 K in 0.02 K steps -- the only ones the CUDA builder and the kernels' table addressing support): builds the
+    tables on the GPU and returns (index_grid, curves) like ``moist_adiabat_tables``."""
+    if pressure_levels is not None:
+        ref = np.round(np.arange(1100, 2, step=-0.5), 1)
+        assert np.shape(pressure_levels) == ref.shape and np.allclose(pressure_levels, ref), \
+            "only the reference's default pressure_levels are supported"
+    if temperatures is not None:
+        ref = np.round(np.arange(173, 316, step=0.02), 2)
+        assert np.shape(temperatures) == ref.shape and np.allclose(temperatures, ref), \
+            "only the reference's default temperatures are supported"
+    assert pres_step == 0.5 and temp_step == 0.02, "only the reference's default steps are supported"
+    ctx = _lib.get_context(device)
+    ctx.tables_build()
+    return ctx.tables_get()
+
+
+def round_to(x, to, dp=2):
+    """PF:358-362: round ``x`` to the nearest ``to``, then to ``dp`` decimals (host helper of the table grid)."""
+    return np.round(np.round(np.asarray(x) / to) * to, dp)
+
+
 # ----------------------------------------------------------------------------- (un)wrapping
 class _Layout:
     """How an input field maps to level-major [L, N] blocks and how results map back."""
@@ -415,6 +438,43 @@ def insert_level(d, level, coords, vert_dim="model_level_number", fill_value=-99
     cout, outs = ctx.insert_level(blocks[0], lev[0], blocks[1:], lev[1:])
     res = dict(zip([coords] + others, [cout] + outs))
     return lay.dataset({k: lay.wrap_profile(res[k] if on_gpu else res[k].cpu(), k, lay.L + 1) for k in keys})
+
+
+def add_lcl_to_profile(profile, vert_dim="model_level_number", environment=None, interpolator="log", vert_axis=0,
+                       device=None, metpy_compat="1.4.1"):
+    """PF:858-931: insert the LCL level into a ``parcel_profile`` result (pressure, temperature,
+    virtual_temperature + lcl_*) and, if given, into the ``environment`` (interpolated at the LCL pressure, its
+    virtual temperature recomputed from the interpolated temperature and dewpoint, PF:911-920).  The fused kernel
+    behind ``parcel_profile_with_lcl`` does all of this in one pass; this is the step on its own, composed of
+    ``xp_insert_level``, ``xp_interp_levels``, ``xp_mixing_ratio`` and ``xp_virtual_temperature``."""
+    assert interpolator in ["linear", "log"], "interpolator must be linear or log"
+    ctx = _lib.get_context(device)
+    lay, dtype, on_gpu = _layout_of(profile["pressure"], vert_dim, vert_axis)
+    pv = ["pressure", "temperature", "virtual_temperature"]
+    pb, tb, tvb = _full_blocks(lay, _blocks(lay, [profile[k] for k in pv], dtype))
+    lcl = [lay.scalar_to_block(profile["lcl_" + k], dtype).cuda().contiguous() for k in pv]
+    assert not bool((pb == -999).any()), "dataset d contains fill_value."                       # PF:962
+    cout, (tout, tvout) = ctx.insert_level(pb, lcl[0], [tb, tvb], lcl[1:])                      # PF:884
+    fin = lambda v: v if on_gpu else v.cpu()
+    out = {k: lay.wrap_profile(fin(v), k, lay.L + 1) for k, v in zip(pv, (cout, tout, tvout))}
+    for k, v in zip(pv, lcl):
+        out["lcl_" + k] = lay.wrap_scalar(fin(v), "lcl_" + k)
+    if environment is not None:
+        names = [k for k in _names(environment) if k != "pressure"]
+        blocks = _full_blocks(lay, _blocks(lay, [environment["pressure"]] + [environment[k] for k in names], dtype))
+        eb, fields = blocks[0], blocks[1:]
+        lev = []
+        for g in range(0, len(fields), 4):
+            lev += ctx.interp_levels(eb, fields[g:g + 4], lcl[0], log=(interpolator == "log"))  # PF:899-906
+        if "virtual_temperature" in names:                                                      # PF:911-920
+            mr = ctx.mixing_ratio(lev[names.index("temperature")], lev[names.index("dewpoint")], lcl[0],
+                                  metpy_compat=metpy_compat)
+            lev[names.index("virtual_temperature")] = ctx.virtual_temperature(lev[names.index("temperature")], mr)
+        assert not bool((eb == -999).any()), "dataset d contains fill_value."
+        _, eouts = ctx.insert_level(eb, lcl[0], fields, lev)                                    # PF:923
+        for k, v in zip(names, eouts):
+            out["environment_" + k] = lay.wrap_profile(fin(v), "environment_" + k, lay.L + 1)
+    return lay.dataset(out)
 
 
 def shift_out_nans(x, name, dim="model_level_number", vert_axis=0, device=None):
