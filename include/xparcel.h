@@ -272,6 +272,11 @@ xp_status xp_find_intersections(xp_context *ctx, const void *x, int64_t x_level_
                                 const void *b, int64_t level_stride, int64_t out_level_stride, int32_t n_levels,
                                 int64_t n_columns, int32_t dtype, int32_t log_x, const xp_intersections_out *out,
                                 void *stream);
+/* xp_interp1d: interp1d_numba (PF:23-37), the reference's only natively compiled function: numpy.interp along the
+ * last (contiguous) axis.  at / out are [n_rows][m], fp is [n_rows][n], xp is [n_rows][n] or, with xp_is_1d, one
+ * shared [n]; xp must increase.  Points outside xp take the end values (the caller masks them, PF:598-600). */
+xp_status xp_interp1d(xp_context *ctx, const void *at, const void *xp, int32_t xp_is_1d, const void *fp, void *out,
+                      int64_t n_rows, int32_t m, int32_t n, int32_t dtype, void *stream);
 /* xp_valid_data: the pressure check of valid_data (PF:2320: pressure.diff(vert_dim).max() < 0).  ORs
  * XP_FLAG_PRESSURE_NOT_DECREASING (a difference >= 0 exists) and XP_FLAG_PRESSURE_ORDER_CHECKED (a non-NaN
  * difference exists) into the context flags; read them with xp_take_flags(). */

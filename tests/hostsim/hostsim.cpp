@@ -366,6 +366,12 @@ extern "C" void hostsim_find_intersections(const double *x, const double *a, con
         }
 }
 
+extern "C" void hostsim_interp1d(const double *at, const double *xp, const double *fp, int64_t m, int n, double *out) {
+    auto xp_at = [&](int k) { return xp[k]; };
+    auto fp_at = [&](int k) { return fp[k]; };
+    for (int64_t i = 0; i < m; ++i) out[i] = xp::interp1d_point(at[i], n, xp_at, fp_at);
+}
+
 extern "C" int hostsim_pressure_order(const double *p, int64_t n, int L) {
     int r = 0;
     for (int64_t i = 0; i < n; ++i) {

@@ -205,3 +205,10 @@ def find_intersections(x, a, b, log_x=False):
         return {"all_intersect_x": ix, "all_intersect_y": iy,
                 "increasing_x": np.where(sc > 0, ix, np.nan), "increasing_y": np.where(sc > 0, iy, np.nan),
                 "decreasing_x": np.where(sc < 0, ix, np.nan), "decreasing_y": np.where(sc < 0, iy, np.nan)}
+
+
+def interp1d(at, xp, fp):
+    at, xp, fp = [np.ascontiguousarray(v, dtype=np.float64) for v in (at, xp, fp)]
+    out = np.empty_like(at)
+    lib().hostsim_interp1d(_vp(at), _vp(xp), _vp(fp), ctypes.c_int64(at.size), int(xp.size), _vp(out))
+    return out

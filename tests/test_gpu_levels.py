@@ -157,3 +157,25 @@ def test_add_lcl_to_profile_against_oracle(ctx, interpolator):
     fused = parcel.parcel_profile_with_lcl(P, T, D, P[0], T[0], D[0], lcl_interp=interpolator)
     for k in ("pressure", "environment_temperature", "environment_dewpoint", "environment_virtual_temperature"):
         _same(got[k], fused[k], rtol=1e-9)
+
+
+def test_interp1d_is_numpy_interp(ctx):
+    """interp1d_numba (PF:23-37) through xp_interp1d: rows of moist-adiabat-like curves on a shared and on a per-row
+    xp, against numpy.interp row by row (bit-exact in float64)."""
+    rng = np.random.default_rng(8)
+    R, n, m = 64, 500, 90
+    xp1 = np.sort(rng.uniform(2.0, 1100.0, n))
+    xpr = np.sort(rng.uniform(2.0, 1100.0, (R, n)), axis=1)
+    fp = rng.uniform(180.0, 310.0, (R, n))
+    at = rng.uniform(-50.0, 1200.0, (R, m))
+    at[:, 0] = xp1[5]
+    at[3, 7] = np.nan
+    got = parcel.interp1d_numba(at, xp1, fp)
+    ref = np.stack([np.interp(at[r], xp1, fp[r]) for r in range(R)])
+    assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(got[~np.isnan(ref)], ref[~np.isnan(ref)])
+    got = parcel.interp1d_numba(at, xpr, fp)
+    ref = np.stack([np.interp(at[r], xpr[r], fp[r]) for r in range(R)])
+    assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(got[~np.isnan(ref)], ref[~np.isnan(ref)])
+    g32 = ctx.interp1d(torch.from_numpy(at).float().cuda(), torch.from_numpy(xp1).float().cuda(),
+                       torch.from_numpy(fp).float().cuda())
+    assert g32.dtype == torch.float32 and g32.shape == (R, m)

@@ -88,3 +88,17 @@ def test_find_intersections_against_oracle(log_x, soundings):
     got = hs.find_intersections(P, A, T, log_x=log_x)
     for k in ora:
         _same(got[k], ora[k])
+
+
+def test_interp1d_is_numpy_interp():
+    """interp1d_numba (PF:23-37) == numpy.interp: inside, on the nodes, outside (end values), NaN points, NaN values."""
+    rng = np.random.default_rng(8)
+    xp = np.sort(rng.uniform(2.0, 1100.0, 300))
+    fp = rng.uniform(180.0, 310.0, 300)
+    at = np.concatenate([rng.uniform(-50.0, 1200.0, 2000), xp[::7], [xp[0], xp[-1], np.nan]])
+    got, ref = hs.interp1d(at, xp, fp), np.interp(at, xp, fp)
+    assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(got[~np.isnan(ref)], ref[~np.isnan(ref)])
+    fp[40:43] = np.nan
+    got, ref = hs.interp1d(at, xp, fp), np.interp(at, xp, fp)
+    assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(got[~np.isnan(ref)], ref[~np.isnan(ref)])
+    assert hs.interp1d(np.array([1.0, 5.0, 9.0]), np.array([5.0]), np.array([7.0])).tolist() == [7.0, 7.0, 7.0]

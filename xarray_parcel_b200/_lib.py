@@ -65,7 +65,7 @@ EXPORTS = ["xp_version", "xp_create", "xp_destroy", "xp_last_error", "xp_take_fl
            "xp_dry_lapse", "xp_mixing_ratio", "xp_virtual_temperature", "xp_wet_bulb_temperature",
            "xp_significant_hail_parameter", "xp_storm_proxies", "xp_mixed_layer", "xp_mixed_parcel",
            "xp_layer_bounds", "xp_insert_level", "xp_shift_out_nans", "xp_trapz", "xp_valid_data",
-           "xp_find_intersections"]
+           "xp_find_intersections", "xp_interp1d"]
 
 PROXY_INPUTS = ["mixed_100_cape", "mixed_50_cape", "mu_cape", "shear_magnitude", "mixed_100_lifted_index",
                 "mixed_100_dci", "positive_shear", "mixed_50_cin", "mixed_100_cin", "lapse_rate_700_500",
@@ -186,6 +186,8 @@ def load_library():
         lib.xp_find_intersections.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_int64,
                                               c_int32, c_int64, c_int32, c_int32, ctypes.POINTER(XpIntersectionsOut),
                                               c_void_p]
+        lib.xp_interp1d.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int32, c_int32,
+                                    c_int32, c_void_p]
         lib.xp_launch_count.argtypes = [c_void_p]
         lib.xp_launch_count.restype = ctypes.c_uint64
         lib.xp_last_kernel_ms.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_float)]
@@ -636,6 +638,22 @@ class Context:
                                             ctypes.byref(o), self._stream())
         self._check(st, "xp_find_intersections")
         return outs
+
+    def interp1d(self, at, xp, fp):
+        """interp1d_numba (PF:23-37): numpy.interp along the last axis of ``at`` [..., m] with ``xp`` ([n] or
+        [..., n], increasing) and ``fp`` [..., n]."""
+        dt = fp.dtype
+        lead = torch.broadcast_shapes(at.shape[:-1], fp.shape[:-1])
+        m, n = at.shape[-1], fp.shape[-1]
+        at2 = at.to(dt).expand(*lead, m).reshape(-1, m).contiguous()
+        fp2 = fp.expand(*lead, n).reshape(-1, n).contiguous()
+        x1d = xp.dim() == 1
+        xp2 = xp.to(dt).contiguous() if x1d else xp.to(dt).expand(*lead, n).reshape(-1, n).contiguous()
+        out = torch.empty_like(at2)
+        st = self.lib.xp_interp1d(self.handle, at2.data_ptr(), xp2.data_ptr(), int(x1d), fp2.data_ptr(), out.data_ptr(),
+                                  at2.shape[0], m, n, _dtype_code(fp2), self._stream())
+        self._check(st, "xp_interp1d")
+        return out.reshape(*lead, m)
 
     def valid_data(self, pressure, n_columns):
         """The pressure check of valid_data (PF:2320); the verdict arrives through take_flags()."""

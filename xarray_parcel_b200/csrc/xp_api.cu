@@ -782,6 +782,21 @@ xp_status xp_find_intersections(xp_context *ctx, const void *x, int64_t x_level_
     return check_cuda(ctx, cudaGetLastError(), "find_intersections kernel launch");
 }
 
+xp_status xp_interp1d(xp_context *ctx, const void *at, const void *xp, int32_t xp_is_1d, const void *fp, void *out,
+                      int64_t n_rows, int32_t m, int32_t n, int32_t dtype, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (n_rows == 0 || m == 0) return XP_OK;
+    if (!at || !xp || !fp || !out || n_rows < 0 || m < 0 || n < 1)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad interp1d arguments");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    XP_DISPATCH(dtype,
+                launch_interp1d<float>((const float *)at, (const float *)xp, (const float *)fp, (float *)out, n_rows, m, n, xp_is_1d, st),
+                launch_interp1d<double>((const double *)at, (const double *)xp, (const double *)fp, (double *)out, n_rows, m, n, xp_is_1d, st));
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "interp1d kernel launch");
+}
+
 xp_status xp_valid_data(xp_context *ctx, const void *pressure, int64_t pressure_level_stride, int32_t pressure_is_1d,
                         int32_t n_levels, int64_t n_columns, int32_t dtype, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;

@@ -145,6 +145,10 @@ void launch_trapz(const T *x, int64_t xls, int x1d, const T *const *v, T *const 
 template <typename T>
 void launch_find_intersections(const T *x, int64_t xls, int x1d, const T *a, const T *b, int64_t ls, int64_t ols,
                                int L, int64_t n, int log_x, T *const *out6, cudaStream_t stream);
+// interp1d_numba (PF:23-37) = numpy.interp along the last axis: at/out [rows][m], fp [rows][n], xp [rows][n] or [n].
+template <typename T>
+void launch_interp1d(const T *at, const T *xp, const T *fp, T *out, int64_t rows, int m, int n, int xp1d,
+                     cudaStream_t stream);
 template <typename T>
 void launch_pressure_order(const T *p, int64_t pls, int p1d, int L, int64_t n, uint32_t *flags, cudaStream_t stream);
 

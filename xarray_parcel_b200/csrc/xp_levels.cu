@@ -137,6 +137,21 @@ __global__ void find_intersections_kernel(const __grid_constant__ IntersectParam
     }
 }
 
+// interp1d_numba (PF:23-37): row-major core dimensions, one thread per output point; the threads of a warp work on
+// neighbouring points of one row, so the binary-search probes of xp are shared cache lines.
+template <typename T>
+__global__ void interp1d_kernel(const T *at, const T *xp, const T *fp, T *out, int64_t rows, int m, int n, int xp1d) {
+    const int64_t total = rows * (int64_t)m;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / m;
+        const T *xr = xp1d ? xp : xp + r * (int64_t)n;
+        const T *fr = fp + r * (int64_t)n;
+        auto xp_at = [&](int k) { return (double)xr[k]; };
+        auto fp_at = [&](int k) { return (double)fr[k]; };
+        out[i] = (T)interp1d_point((double)at[i], n, xp_at, fp_at);
+    }
+}
+
 template <typename T>
 __global__ void pressure_order_kernel(const T *p, int64_t pls, int p1d, int L, int64_t n, uint32_t *flags) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -204,6 +219,15 @@ void launch_find_intersections(const T *x, int64_t xls, int x1d, const T *a, con
 }
 
 template <typename T>
+void launch_interp1d(const T *at, const T *xp, const T *fp, T *out, int64_t rows, int m, int n, int xp1d,
+                     cudaStream_t stream) {
+    const int64_t total = rows * (int64_t)m;
+    if (total <= 0 || n < 1) return;
+    const int64_t blocks = (total + 255) / 256;
+    interp1d_kernel<T><<<(unsigned)(blocks < 148 * 64 ? blocks : 148 * 64), 256, 0, stream>>>(at, xp, fp, out, rows, m, n, xp1d);
+}
+
+template <typename T>
 void launch_pressure_order(const T *p, int64_t pls, int p1d, int L, int64_t n, uint32_t *flags, cudaStream_t stream) {
     if (n <= 0) return;
     pressure_order_kernel<T><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(p, pls, p1d, L, n, flags);
@@ -217,6 +241,7 @@ void launch_pressure_order(const T *p, int64_t pls, int p1d, int L, int64_t n, u
     template void launch_trapz<T>(const T *, int64_t, int, const T *const *, T *const *, int, int64_t, int, int64_t, \
                                   const uint8_t *, int64_t, int, cudaStream_t);                                       \
     template void launch_pressure_order<T>(const T *, int64_t, int, int, int64_t, uint32_t *, cudaStream_t);       \
+    template void launch_interp1d<T>(const T *, const T *, const T *, T *, int64_t, int, int, int, cudaStream_t);      \
     template void launch_find_intersections<T>(const T *, int64_t, int, const T *, const T *, int64_t, int64_t, int, \
                                                int64_t, int, T *const *, cudaStream_t);
 XP_INST_LEVELS(float)

@@ -70,6 +70,32 @@ XP_HD void interval_crossing(double x0, double x1, double a0, double a1, double 
     if (log_x) ix = exp(ix);                                  // PF:1053
 }
 
+// interp1d_numba (PF:23-37) = numpy.interp for one point: xp increasing, values outside take the end values, an
+// exact hit returns the node value, NaN in gives NaN out; the NaN fall-backs of numpy's arr_interp are kept.
+template <class XpAt, class FpAt>
+XP_HD double interp1d_point(double x, int n, XpAt xp_at, FpAt fp_at) {
+    if (isnan(x)) return x;
+    if (x < xp_at(0)) return fp_at(0);
+    if (x > xp_at(n - 1)) return fp_at(n - 1);
+    int lo = 0, hi = n - 1;                                  // invariant: xp[lo] <= x, and x < xp[hi] or hi == n - 1
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (x >= xp_at(mid)) lo = mid; else hi = mid;
+    }
+    int j = lo;
+    if (x >= xp_at(hi)) j = hi;                              // only when x == xp[n - 1]
+    const double xj = xp_at(j), fj = fp_at(j);
+    if (j == n - 1 || xj == x) return fj;
+    const double xj1 = xp_at(j + 1), fj1 = fp_at(j + 1);
+    const double slope = (fj1 - fj) / (xj1 - xj);
+    double r = slope * (x - xj) + fj;
+    if (isnan(r)) {
+        r = slope * (x - xj1) + fj1;
+        if (isnan(r) && fj == fj1) r = fj;
+    }
+    return r;
+}
+
 // valid_data (PF:2320): pressure.diff(vert_dim).max() < 0.  Returns bit 0 = a difference >= 0 exists,
 // bit 1 = a non-NaN difference exists (the reference's max skips NaN; with no valid difference it fails).
 template <class PressureAt>

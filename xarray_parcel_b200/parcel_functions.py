@@ -526,6 +526,17 @@ def find_intersections(x, a, b, dim="model_level_number", log_x=False, vert_axis
     return lay.dataset(out)
 
 
+def interp1d_numba(at, xp, fp, device=None):
+    """PF:23-37: ``numpy.interp(at, xp, fp)`` along the last axis, broadcasting over the leading ones like the
+    reference's gufunc ``(m),(n),(n)->(m)`` (here a CUDA kernel, ``xp_interp1d``)."""
+    ctx = _lib.get_context(device)
+    on_gpu = isinstance(fp, torch.Tensor) and fp.is_cuda
+    is_t = isinstance(fp, torch.Tensor)
+    conv = lambda a: (a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a, dtype=np.float64))).cuda()
+    out = ctx.interp1d(conv(at), conv(xp), conv(fp))
+    return out if on_gpu else (out.cpu() if is_t else out.cpu().numpy())
+
+
 def valid_data(dat, vert_dim="model_level_number", vert_axis=0, device=None):
     """PF:2308-2321: True if the vertical index steps by one and the pressures decrease with the level number."""
     if hasattr(dat, "coords") and vert_dim in getattr(dat, "coords", {}):
