@@ -272,6 +272,19 @@ xp_status xp_find_intersections(xp_context *ctx, const void *x, int64_t x_level_
                                 const void *b, int64_t level_stride, int64_t out_level_stride, int32_t n_levels,
                                 int64_t n_columns, int32_t dtype, int32_t log_x, const xp_intersections_out *out,
                                 void *stream);
+/* xp_trap_around_zeros: trap_around_zeros (PF:1200-1289, start = 0): for every interval in which y crosses zero
+ * (find_intersections against 0 over x, ln x with log_x) the two triangles next to the zero.  area / x / dx / x_from /
+ * x_to are [2 n_levels - 1][n_columns] with stride out_level_stride: rows 0 .. n_levels-1 the half-area BEFORE the
+ * zero, labelled by the lower level of the interval (the last row is NaN), rows n_levels .. 2 n_levels-2 the half-area
+ * AFTER it, labelled by the upper level; NaN where there is no zero.  mask [n_levels][n_columns] (contiguous) is 1
+ * where the ordinary trapezoid above a level stays in the integral (PF:1285-1287).  Any output may be NULL. */
+typedef struct xp_zero_areas_out {
+    void *area, *x, *dx, *x_from, *x_to;
+    uint8_t *mask;
+} xp_zero_areas_out;
+xp_status xp_trap_around_zeros(xp_context *ctx, const void *x, int64_t x_level_stride, int32_t x_is_1d, const void *y,
+                               int64_t level_stride, int64_t out_level_stride, int32_t n_levels, int64_t n_columns,
+                               int32_t dtype, int32_t log_x, const xp_zero_areas_out *out, void *stream);
 /* xp_interp1d: interp1d_numba (PF:23-37), the reference's only natively compiled function: numpy.interp along the
  * last (contiguous) axis.  at / out are [n_rows][m], fp is [n_rows][n], xp is [n_rows][n] or, with xp_is_1d, one
  * shared [n]; xp must increase.  Points outside xp take the end values (the caller masks them, PF:598-600). */

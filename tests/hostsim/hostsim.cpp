@@ -372,6 +372,23 @@ extern "C" void hostsim_interp1d(const double *at, const double *xp, const doubl
     for (int64_t i = 0; i < m; ++i) out[i] = xp::interp1d_point(at[i], n, xp_at, fp_at);
 }
 
+extern "C" void hostsim_trap_around_zeros(const double *x, const double *y, int64_t n, int L, int log_x,
+                                          double *out /*[3][2L-1][n]: area, x, dx*/) {
+    const int R = 2 * L - 1;
+    for (int64_t i = 0; i < n; ++i) {
+        for (int q = 0; q < 3; ++q) out[((int64_t)q * R + L - 1) * n + i] = xp::qnan();
+        for (int k = 0; k + 1 < L; ++k) {
+            double before[3], after[3];
+            xp::zero_half_areas(x[(int64_t)k * n + i], x[(int64_t)(k + 1) * n + i], y[(int64_t)k * n + i],
+                                y[(int64_t)(k + 1) * n + i], log_x != 0, before, after);
+            for (int q = 0; q < 3; ++q) {
+                out[((int64_t)q * R + k) * n + i] = before[q];
+                out[((int64_t)q * R + L + k) * n + i] = after[q];
+            }
+        }
+    }
+}
+
 extern "C" int hostsim_pressure_order(const double *p, int64_t n, int L) {
     int r = 0;
     for (int64_t i = 0; i < n; ++i) {

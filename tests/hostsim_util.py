@@ -212,3 +212,14 @@ def interp1d(at, xp, fp):
     out = np.empty_like(at)
     lib().hostsim_interp1d(_vp(at), _vp(xp), _vp(fp), ctypes.c_int64(at.size), int(xp.size), _vp(out))
     return out
+
+
+def trap_around_zeros(x, y, log_x=True):
+    x, y = [np.ascontiguousarray(v, dtype=np.float64) for v in (x, y)]
+    L, N = y.shape
+    out = np.empty((3, 2 * L - 1, N))
+    lib().hostsim_trap_around_zeros(_vp(x), _vp(y), ctypes.c_int64(N), L, int(bool(log_x)), _vp(out))
+    areas = {"area": out[0], "x": out[1], "dx": out[2]}
+    areas["x_from"] = areas["x"] - areas["dx"] / 2
+    areas["x_to"] = areas["x"] + areas["dx"] / 2
+    return areas, np.isnan(out[0][:L])

@@ -179,3 +179,16 @@ def test_interp1d_is_numpy_interp(ctx):
     g32 = ctx.interp1d(torch.from_numpy(at).float().cuda(), torch.from_numpy(xp1).float().cuda(),
                        torch.from_numpy(fp).float().cuda())
     assert g32.dtype == torch.float32 and g32.shape == (R, m)
+
+
+@pytest.mark.parametrize("log_x", [True, False])
+def test_trap_around_zeros_against_oracle(ctx, log_x):
+    P, T, D = _columns(seed=28)
+    Y = 0.6 * (T - D) - 4.0 + 3.0 * np.sin(np.arange(P.shape[0]))[:, None]
+    Y[9, :25] = 0.0
+    ora, omask = op.trap_around_zeros(P, Y, log_x=log_x)
+    got, gmask = parcel.trap_around_zeros(P, Y, log_x=log_x)
+    assert np.array_equal(np.asarray(gmask, dtype=bool), omask)
+    assert set(got.keys()) == set(ora.keys())
+    for k in ora:
+        _same(got[k], ora[k])

@@ -102,3 +102,15 @@ def test_interp1d_is_numpy_interp():
     got, ref = hs.interp1d(at, xp, fp), np.interp(at, xp, fp)
     assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(got[~np.isnan(ref)], ref[~np.isnan(ref)])
     assert hs.interp1d(np.array([1.0, 5.0, 9.0]), np.array([5.0]), np.array([7.0])).tolist() == [7.0, 7.0, 7.0]
+
+
+@pytest.mark.parametrize("log_x", [True, False])
+def test_trap_around_zeros_against_oracle(log_x):
+    P, T, D = _columns(seed=28)
+    Y = 0.6 * (T - D) - 4.0 + 3.0 * np.sin(np.arange(P.shape[0]))[:, None]          # crosses zero several times
+    Y[9, :25] = 0.0                                                                  # exact zeros
+    ora, omask = op.trap_around_zeros(P, Y, log_x=log_x)
+    got, gmask = hs.trap_around_zeros(P, Y, log_x=log_x)
+    assert np.array_equal(gmask, omask)
+    for k in ora:
+        _same(got[k], ora[k])

@@ -65,7 +65,7 @@ EXPORTS = ["xp_version", "xp_create", "xp_destroy", "xp_last_error", "xp_take_fl
            "xp_dry_lapse", "xp_mixing_ratio", "xp_virtual_temperature", "xp_wet_bulb_temperature",
            "xp_significant_hail_parameter", "xp_storm_proxies", "xp_mixed_layer", "xp_mixed_parcel",
            "xp_layer_bounds", "xp_insert_level", "xp_shift_out_nans", "xp_trapz", "xp_valid_data",
-           "xp_find_intersections", "xp_interp1d"]
+           "xp_find_intersections", "xp_interp1d", "xp_trap_around_zeros"]
 
 PROXY_INPUTS = ["mixed_100_cape", "mixed_50_cape", "mu_cape", "shear_magnitude", "mixed_100_lifted_index",
                 "mixed_100_dci", "positive_shear", "mixed_50_cin", "mixed_100_cin", "lapse_rate_700_500",
@@ -87,6 +87,13 @@ INTERSECTION_FIELDS = ["all_intersect_x", "all_intersect_y", "increasing_x", "in
 
 class XpIntersectionsOut(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in INTERSECTION_FIELDS]
+
+
+ZERO_AREA_FIELDS = ["area", "x", "dx", "x_from", "x_to"]
+
+
+class XpZeroAreasOut(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ZERO_AREA_FIELDS] + [("mask", c_void_p)]
 
 
 class XpProxyInputs(ctypes.Structure):
@@ -188,6 +195,8 @@ def load_library():
                                               c_void_p]
         lib.xp_interp1d.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                     c_int32, c_void_p]
+        lib.xp_trap_around_zeros.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int64, c_int32,
+                                             c_int64, c_int32, c_int32, ctypes.POINTER(XpZeroAreasOut), c_void_p]
         lib.xp_launch_count.argtypes = [c_void_p]
         lib.xp_launch_count.restype = ctypes.c_uint64
         lib.xp_last_kernel_ms.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_float)]
@@ -654,6 +663,20 @@ class Context:
                                   at2.shape[0], m, n, _dtype_code(fp2), self._stream())
         self._check(st, "xp_interp1d")
         return out.reshape(*lead, m)
+
+    def trap_around_zeros(self, x, y, log_x=True):
+        """trap_around_zeros (PF:1200-1289): (dict of the five [2L-1, N] area arrays, bool mask [L, N])."""
+        y = y.contiguous()
+        L, N = y.shape
+        x = x.to(y.dtype).contiguous()
+        x1d = x.dim() == 1
+        outs = {n: torch.empty((2 * L - 1, N), dtype=y.dtype, device=y.device) for n in ZERO_AREA_FIELDS}
+        mask = torch.empty((L, N), dtype=torch.uint8, device=y.device)
+        o = XpZeroAreasOut(*([outs[n].data_ptr() for n in ZERO_AREA_FIELDS] + [mask.data_ptr()]))
+        st = self.lib.xp_trap_around_zeros(self.handle, x.data_ptr(), 1 if x1d else N, int(x1d), y.data_ptr(), N, N, L,
+                                           N, _dtype_code(y), int(bool(log_x)), ctypes.byref(o), self._stream())
+        self._check(st, "xp_trap_around_zeros")
+        return outs, mask != 0
 
     def valid_data(self, pressure, n_columns):
         """The pressure check of valid_data (PF:2320); the verdict arrives through take_flags()."""

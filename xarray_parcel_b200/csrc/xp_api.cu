@@ -797,6 +797,23 @@ xp_status xp_interp1d(xp_context *ctx, const void *at, const void *xp, int32_t x
     return check_cuda(ctx, cudaGetLastError(), "interp1d kernel launch");
 }
 
+xp_status xp_trap_around_zeros(xp_context *ctx, const void *x, int64_t x_level_stride, int32_t x_is_1d, const void *y,
+                               int64_t level_stride, int64_t out_level_stride, int32_t n_levels, int64_t n_columns,
+                               int32_t dtype, int32_t log_x, const xp_zero_areas_out *out, void *stream) {
+    if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    if (n_columns == 0) return XP_OK;
+    if (!x || !y || !out || n_levels < 1 || n_columns < 0)
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad trap_around_zeros arguments");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    void *o5[5] = {out->area, out->x, out->dx, out->x_from, out->x_to};
+    XP_DISPATCH(dtype,
+                launch_trap_around_zeros<float>((const float *)x, x_level_stride, x_is_1d, (const float *)y, level_stride, out_level_stride, n_levels, n_columns, log_x, (float *const *)o5, out->mask, st),
+                launch_trap_around_zeros<double>((const double *)x, x_level_stride, x_is_1d, (const double *)y, level_stride, out_level_stride, n_levels, n_columns, log_x, (double *const *)o5, out->mask, st));
+    ctx->launches += 1;
+    return check_cuda(ctx, cudaGetLastError(), "trap_around_zeros kernel launch");
+}
+
 xp_status xp_valid_data(xp_context *ctx, const void *pressure, int64_t pressure_level_stride, int32_t pressure_is_1d,
                         int32_t n_levels, int64_t n_columns, int32_t dtype, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;

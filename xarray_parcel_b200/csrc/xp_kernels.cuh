@@ -149,6 +149,11 @@ void launch_find_intersections(const T *x, int64_t xls, int x1d, const T *a, con
 template <typename T>
 void launch_interp1d(const T *at, const T *xp, const T *fp, T *out, int64_t rows, int m, int n, int xp1d,
                      cudaStream_t stream);
+// trap_around_zeros (PF:1200-1289): out5 = area, x, dx, x_from, x_to, each [2L-1][N] (rows 0..L-1 = the half-areas
+// before a zero, labelled by the lower level; rows L..2L-2 = after it, labelled by the upper level); mask [L][N].
+template <typename T>
+void launch_trap_around_zeros(const T *x, int64_t xls, int x1d, const T *y, int64_t ls, int64_t ols, int L, int64_t n,
+                              int log_x, T *const *out5, uint8_t *mask, cudaStream_t stream);
 template <typename T>
 void launch_pressure_order(const T *p, int64_t pls, int p1d, int L, int64_t n, uint32_t *flags, cudaStream_t stream);
 

@@ -137,6 +137,50 @@ __global__ void find_intersections_kernel(const __grid_constant__ IntersectParam
     }
 }
 
+template <typename T>
+struct ZeroAreasParams {
+    const T *x;                 // [L][N] or shared [L]
+    int64_t xls;
+    int x1d;
+    const T *y;                 // [L][N]
+    int64_t ls, ols;
+    int L;
+    int64_t n;
+    int log_x;
+    T *out[5];                  // area, x, dx, x_from, x_to: [2L-1][N] (rows 0..L-1 before, L..2L-2 after), may be null
+    uint8_t *mask;              // [L][N]: 1 where the ordinary interval above this level stays in the integral
+};
+
+// trap_around_zeros (PF:1200-1289): one thread per column, previous level in registers, every row written once.
+template <typename T>
+__global__ void trap_around_zeros_kernel(const __grid_constant__ ZeroAreasParams<T> prm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= prm.n) return;
+    const T *xc = prm.x1d ? prm.x : prm.x + i;
+    const int L = prm.L;
+    auto put = [&](int row, const double (&v)[3]) {
+        const int64_t o = (int64_t)row * prm.ols + i;
+        if (prm.out[0]) prm.out[0][o] = (T)v[0];
+        if (prm.out[1]) prm.out[1][o] = (T)v[1];
+        if (prm.out[2]) prm.out[2][o] = (T)v[2];
+        if (prm.out[3]) prm.out[3][o] = (T)(v[1] - v[2] / 2);            // PF:1277
+        if (prm.out[4]) prm.out[4][o] = (T)(v[1] + v[2] / 2);            // PF:1278
+    };
+    double x0 = (double)xc[0], y0 = (double)prm.y[i];
+    for (int k = 0; k + 1 < L; ++k) {
+        const double x1 = (double)xc[(int64_t)(k + 1) * prm.xls], y1 = (double)prm.y[(int64_t)(k + 1) * prm.ls + i];
+        double before[3], after[3];
+        zero_half_areas(x0, x1, y0, y1, prm.log_x != 0, before, after);
+        put(k, before);
+        put(L + k, after);
+        if (prm.mask) prm.mask[(int64_t)k * prm.n + i] = isnan(before[0]) ? 1 : 0;      // PF:1285-1287
+        x0 = x1; y0 = y1;
+    }
+    const double nanv[3] = {qnan(), qnan(), qnan()};
+    put(L - 1, nanv);                                                   // the top level has no interval above it
+    if (prm.mask) prm.mask[(int64_t)(L - 1) * prm.n + i] = 1;
+}
+
 // interp1d_numba (PF:23-37): row-major core dimensions, one thread per output point; the threads of a warp work on
 // neighbouring points of one row, so the binary-search probes of xp are shared cache lines.
 template <typename T>
@@ -228,6 +272,17 @@ void launch_interp1d(const T *at, const T *xp, const T *fp, T *out, int64_t rows
 }
 
 template <typename T>
+void launch_trap_around_zeros(const T *x, int64_t xls, int x1d, const T *y, int64_t ls, int64_t ols, int L, int64_t n,
+                              int log_x, T *const *out5, uint8_t *mask, cudaStream_t stream) {
+    if (n <= 0 || L < 1) return;
+    ZeroAreasParams<T> prm;
+    prm.x = x; prm.xls = xls; prm.x1d = x1d; prm.y = y; prm.ls = ls; prm.ols = ols; prm.L = L; prm.n = n;
+    prm.log_x = log_x; prm.mask = mask;
+    for (int f = 0; f < 5; ++f) prm.out[f] = out5[f];
+    trap_around_zeros_kernel<T><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(prm);
+}
+
+template <typename T>
 void launch_pressure_order(const T *p, int64_t pls, int p1d, int L, int64_t n, uint32_t *flags, cudaStream_t stream) {
     if (n <= 0) return;
     pressure_order_kernel<T><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(p, pls, p1d, L, n, flags);
@@ -242,6 +297,8 @@ void launch_pressure_order(const T *p, int64_t pls, int p1d, int L, int64_t n, u
                                   const uint8_t *, int64_t, int, cudaStream_t);                                       \
     template void launch_pressure_order<T>(const T *, int64_t, int, int, int64_t, uint32_t *, cudaStream_t);       \
     template void launch_interp1d<T>(const T *, const T *, const T *, T *, int64_t, int, int, int, cudaStream_t);      \
+    template void launch_trap_around_zeros<T>(const T *, int64_t, int, const T *, int64_t, int64_t, int, int64_t,    \
+                                              int, T *const *, uint8_t *, cudaStream_t);                              \
     template void launch_find_intersections<T>(const T *, int64_t, int, const T *, const T *, int64_t, int64_t, int, \
                                                int64_t, int, T *const *, cudaStream_t);
 XP_INST_LEVELS(float)

@@ -70,6 +70,25 @@ XP_HD void interval_crossing(double x0, double x1, double a0, double a1, double 
     if (log_x) ix = exp(ix);                                  // PF:1053
 }
 
+// trap_around_zeros (PF:1200-1289, start = 0), one interval between two neighbouring levels: where y crosses zero
+// (find_intersections against 0, PF:1225) the two triangles next to the zero -- "before" belongs to the lower
+// level (shift_x = 1, PF:1272), "after" to the upper one (PF:1273); v[0..2] = area, x (centre), dx.  x0 / x1 are the
+// raw coordinates; with log_x everything is in ln x, the zero taking the reference's exp / log round trip (PF:1053, 1232).
+XP_HD void zero_half_areas(double x0, double x1, double y0, double y1, bool log_x, double (&before)[3],
+                           double (&after)[3]) {
+    const double c0 = log_x ? log(x0) : x0, c1 = log_x ? log(x1) : x1;
+    double ix, iy, sc;
+    interval_crossing(c0, c1, y0, y1, 0.0, 0.0, log_x, ix, iy, sc);
+    if (isnan(iy)) {                                         // PF:1237, 1242-1244: no zero in this interval
+        for (int q = 0; q < 3; ++q) before[q] = after[q] = qnan();
+        return;
+    }
+    const double zx = log_x ? log(ix) : ix;
+    const double dxb = c0 - zx, dxa = c1 - zx;               // PF:1258
+    before[0] = (y0 / 2) * fabs(dxb); before[1] = c0 - dxb / 2; before[2] = fabs(dxb);   // PF:1261-1263
+    after[0] = (y1 / 2) * fabs(dxa); after[1] = c1 - dxa / 2; after[2] = fabs(dxa);
+}
+
 // interp1d_numba (PF:23-37) = numpy.interp for one point: xp increasing, values outside take the end values, an
 // exact hit returns the node value, NaN in gives NaN out; the NaN fall-backs of numpy's arr_interp are kept.
 template <class XpAt, class FpAt>

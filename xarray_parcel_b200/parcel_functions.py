@@ -526,6 +526,21 @@ def find_intersections(x, a, b, dim="model_level_number", log_x=False, vert_axis
     return lay.dataset(out)
 
 
+def trap_around_zeros(x, y, dim="model_level_number", log_x=True, start=0, vert_axis=0, device=None):
+    """PF:1200-1289 (``start`` = 0): the half-areas next to every zero of ``y`` along ``x``.  Returns (areas, mask):
+    areas holds area, x, dx, x_from, x_to on 2L - 1 levels (the before-zero parts labelled by the lower level, then
+    the after-zero parts), mask [L] is True where the ordinary trapezoid above a level stays in the integral."""
+    assert start == 0, "only start=0 (the reference's own use) is implemented"
+    ctx = _lib.get_context(device)
+    lay, dtype, on_gpu = _layout_of(y, dim, vert_axis)
+    xb, yb = _blocks(lay, [x, y], dtype)
+    (yb,) = _full_blocks(lay, [yb])
+    res, mask = ctx.trap_around_zeros(xb, yb, log_x=log_x)
+    fin = lambda v: v if on_gpu else v.cpu()
+    areas = lay.dataset({k: lay.wrap_profile(fin(v), k, 2 * lay.L - 1) for k, v in res.items()})
+    return areas, lay.wrap_profile(fin(mask), "mask", lay.L)
+
+
 def interp1d_numba(at, xp, fp, device=None):
     """PF:23-37: ``numpy.interp(at, xp, fp)`` along the last axis, broadcasting over the leading ones like the
     reference's gufunc ``(m),(n),(n)->(m)`` (here a CUDA kernel, ``xp_interp1d``)."""
