@@ -114,3 +114,35 @@ def test_trap_around_zeros_against_oracle(log_x):
     assert np.array_equal(gmask, omask)
     for k in ora:
         _same(got[k], ora[k])
+
+
+def test_size_independent_properties():
+    """Properties that hold whatever the input: trapz is linear in the integrand and additive over the sign split,
+    shift_out_nans is idempotent, insert_level keeps every original level in order and adds exactly one, and a
+    mixed-layer mean of a constant is that constant."""
+    P, T, D = _columns(n=2000, L=45, seed=29)
+    ok = ~np.isnan(P[0])
+    P, T, D = P[:, ok], np.nan_to_num(T[:, ok], nan=250.0), np.nan_to_num(D[:, ok], nan=240.0)
+    V = T - D - 8.0
+    # trapz: linearity, and all = positive + negative parts
+    a, b = hs.trapz(P, T), hs.trapz(P, V)
+    np.testing.assert_allclose(hs.trapz(P, 2.0 * T - 3.0 * V), 2.0 * a - 3.0 * b, rtol=1e-10)
+    np.testing.assert_allclose(hs.trapz(P, V, sign=1) + hs.trapz(P, V, sign=-1), b, rtol=1e-10, atol=1e-9)
+    # shift_out_nans: idempotent, and the shifted column starts with a value
+    lead = np.arange(P.shape[0])[:, None] < np.random.default_rng(3).integers(0, 5, P.shape[1])[None, :]
+    Pn = np.where(lead, np.nan, P)
+    s1, k1 = hs.shift_out_nans(Pn, Pn)
+    s2, k2 = hs.shift_out_nans(s1, s1)
+    assert not np.isnan(s1[0]).any() and (k2 == 0).all() and np.array_equal(np.isnan(s1), np.isnan(s2))
+    assert np.array_equal(s1[~np.isnan(s1)], s2[~np.isnan(s2)])
+    # insert_level: one more level, sorted, the original levels survive in order
+    lev_p = P[0] - np.random.default_rng(4).uniform(1.0, 400.0, P.shape[1])
+    out_p = hs.insert_level(P, P, lev_p, lev_p)
+    out_t = hs.insert_level(P, T, lev_p, np.full(P.shape[1], -1.0))
+    assert out_p.shape[0] == P.shape[0] + 1 and (np.diff(out_p, axis=0) <= 0).all()
+    assert ((out_t == -1.0).sum(axis=0) == 1).all()
+    kept = out_t.T[(out_t != -1.0).T].reshape(P.shape[1], P.shape[0]).T
+    assert np.array_equal(kept, T)
+    # mixed layer of a constant field
+    (m,) = hs.mixed_layer(P, [np.full_like(P, 7.25)], depth=80.0)
+    np.testing.assert_allclose(m, 7.25, rtol=1e-12)
