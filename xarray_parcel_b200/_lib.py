@@ -325,8 +325,18 @@ class Context:
         if t.is_cuda and t.device.index != self.device:
             raise ValueError(f"tensors are on {t.device}, context is on cuda:{self.device}")
         ls = t.stride(0) if L > 1 else N
+        # a broadcast view (stride 0 along the levels, e.g. t.expand(L, N)) would make the kernels read L*N
+        # elements of an N-element allocation: reject it instead of inventing a stride
+        if L > 1 and ls < N:
+            raise ValueError("temperature/dewpoint level stride is smaller than n_columns "
+                             "(broadcast or overlapping view): call .contiguous() first")
+        if not p1d and L > 1 and pls < N:
+            raise ValueError("pressure level stride is smaller than n_columns "
+                             "(broadcast or overlapping view): call .contiguous() first")
+        if p1d and L > 1 and pls < 1:
+            raise ValueError("1-D pressure must not be a broadcast view")
         return XpColumns(p.data_ptr(), t.data_ptr(), td.data_ptr(), N, L, _dtype_code(t),
-                         max(ls, N), max(pls, 1 if p1d else N), int(p1d), mem), L, N
+                         ls, pls, int(p1d), mem), L, N
 
     def _alloc_out(self, like, N, L, profile, pin, fields=None, shift=True):
         """Output block for one parcel kind: scalars [n_fields, N], shift [N], optional profile

@@ -41,8 +41,14 @@ struct xp_context {
     cudaStream_t last_fast_stream = nullptr;
     bool last_was_fast = false;
     int sm_count = 148;
+    // experiment knobs, read from the environment once in xp_create (never in the launch path)
+    int vote_mask = 3;
+    int host_block_mb = 256;
     std::mutex mu;
 };
+
+// at most this many per-stream scratch buffers are kept; beyond it the others are synchronised and freed
+constexpr size_t kMaxScratchStreams = 8;
 
 namespace {
 
@@ -77,7 +83,7 @@ xp_status check_cuda(xp_context *ctx, cudaError_t e, const char *what) {
         if (_st != XP_OK) return _st;                                 \
     } while (0)
 
-Opts to_opts(const xp_options *o) {
+Opts to_opts(const xp_context *ctx, const xp_options *o) {
     xp_options d;
     xp_default_options(&d);
     if (o) d = *o;
@@ -90,12 +96,7 @@ Opts to_opts(const xp_options *o) {
     r.ml_depth = d.mixed_layer_depth;
     r.mu_depth = d.most_unstable_depth;
     r.exact_only = d.exact_only != 0;
-    static int vote_mask = -1;
-    if (vote_mask < 0) {
-        const char *e = getenv("XP_FAST_VOTE_MASK");
-        vote_mask = e ? (atoi(e) & 15) : 3;
-    }
-    r.vote_mask = vote_mask;
+    r.vote_mask = ctx ? ctx->vote_mask : 3;
     return r;
 }
 
@@ -167,6 +168,13 @@ xp_status run_device(xp_context *ctx, const xp_columns *cols, int kind_mask,
     if constexpr (std::is_same<T, float>::value) {
         const ColsArg<float> ca = to_cols<float>(cols);
         if (!o.exact_only && cols->n_columns > 0 && fast_eligible(ca, kind_mask, oa)) {
+            if (!ctx->scratch.count(stream) && ctx->scratch.size() >= kMaxScratchStreams) {
+                // bound the per-stream scratch map: drop the buffers of the other streams (after their work is done)
+                for (auto &kv : ctx->scratch) {
+                    if (kv.second.ptr) { cudaStreamSynchronize(kv.first); cudaFree(kv.second.ptr); }
+                }
+                ctx->scratch.clear();
+            }
             xp_context::Scratch &sc = ctx->scratch[stream];
             const size_t need = fast_scratch_bytes(cols->n_columns);
             if (sc.bytes < need) {
@@ -221,12 +229,7 @@ xp_status run_host(xp_context *ctx, const xp_columns *cols, int kind_mask,
     // block size: ~256 MB per slot (XP_HOST_BLOCK_MB overrides), multiple of 1024 columns.  Measured on the B200
     // box (ERA5 suite, 1.33 GB per call): 256 MB 160.6 M columns/s, 128 MB 155.5, 64 MB 151.3, 32 MB 126.3 --
     // the per-block copies (2 strided H2D, ~40 D2H) cost more than the shorter pipeline fill/drain saves.
-    static int block_mb = -1;
-    if (block_mb < 0) {
-        const char *e = getenv("XP_HOST_BLOCK_MB");
-        block_mb = e ? atoi(e) : 256;
-        if (block_mb < 1 || block_mb > 4096) block_mb = 256;
-    }
+    const int block_mb = ctx->host_block_mb;
     int64_t C = (int64_t)((size_t)block_mb << 20) / (int64_t)per_col;
     C = std::max<int64_t>(1024, (C / 1024) * 1024);
     C = std::min<int64_t>(C, ((N + 1023) / 1024) * 1024);
@@ -244,6 +247,17 @@ xp_status run_host(xp_context *ctx, const xp_columns *cols, int kind_mask,
     for (int s = 0; s < xp_context::kSlots; ++s)
         if (!ctx->slot_stream[s]) XP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->slot_stream[s], cudaStreamNonBlocking));
 
+    if ((kind_mask & kEX) && (!ex || !ex->pressure || !ex->temperature || !ex->dewpoint))
+        return fail(ctx, XP_ERR_INVALID_ARGUMENT, "explicit parcel arrays are required");
+    // Whatever way this function is left, no copy may still be writing the caller's buffers and no kernel may
+    // still be using the slot buffers: drain every slot stream on exit (error paths included).
+    struct DrainSlots {
+        xp_context *c;
+        ~DrainSlots() {
+            for (int s = 0; s < xp_context::kSlots; ++s)
+                if (c->slot_stream[s]) cudaStreamSynchronize(c->slot_stream[s]);
+        }
+    } drain{ctx};
     const char *hp = (const char *)cols->pressure, *ht = (const char *)cols->temperature,
                *htd = (const char *)cols->dewpoint;
     int slot = 0;
@@ -278,8 +292,6 @@ xp_status run_host(xp_context *ctx, const xp_columns *cols, int kind_mask,
         dc.pressure = dP; dc.temperature = dT; dc.dewpoint = dTd;
         xp_parcel_in dex = {nullptr, nullptr, nullptr};
         if (kind_mask & kEX) {
-            if (!ex || !ex->pressure || !ex->temperature || !ex->dewpoint)
-                return fail(ctx, XP_ERR_INVALID_ARGUMENT, "explicit parcel arrays are required");
             const void *src[3] = {ex->pressure, ex->temperature, ex->dewpoint};
             const void **dst[3] = {&dex.pressure, &dex.temperature, &dex.dewpoint};
             for (int i = 0; i < 3; ++i) {
@@ -362,7 +374,7 @@ xp_status run_any(xp_context *ctx, const xp_columns *cols, int kind_mask,
         return fail(ctx, XP_ERR_TABLES_NOT_LOADED, "Call load_moist_adiabat_lookups first.");
     if (cols->n_columns == 0) return XP_OK;
     DeviceGuard guard(ctx->device);
-    const Opts o = to_opts(opts);
+    const Opts o = to_opts(ctx, opts);
     if (cols->mem == XP_MEM_HOST) return run_host(ctx, cols, kind_mask, outs, ex, o);
     if (cols->dtype == XP_F32)
         return run_device<float>(ctx, cols, kind_mask, outs, ex, o, (cudaStream_t)stream, true);
@@ -402,6 +414,11 @@ xp_status xp_create(int device, xp_context **out_ctx) {
     ctx->device = device;
     DeviceGuard guard(device);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (const char *ev = getenv("XP_FAST_VOTE_MASK")) ctx->vote_mask = atoi(ev) & 15;
+    if (const char *ev = getenv("XP_HOST_BLOCK_MB")) {
+        const int mb = atoi(ev);
+        if (mb >= 1 && mb <= 4096) ctx->host_block_mb = mb;
+    }
     if ((e = cudaMalloc(&ctx->d_flags, sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMemset(ctx->d_flags, 0, sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
@@ -435,6 +452,7 @@ const char *xp_last_error(const xp_context *ctx) { return ctx ? ctx->err.c_str()
 
 xp_status xp_take_flags(xp_context *ctx, void *stream, uint32_t *out_flags) {
     if (!ctx || !out_flags) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     DeviceGuard guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     XP_CUDA(ctx, cudaMemcpyAsync(out_flags, ctx->d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -451,6 +469,7 @@ static xp_status ensure_table_memory(xp_context *ctx) {
 
 xp_status xp_tables_build(xp_context *ctx, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     DeviceGuard guard(ctx->device);
     xp_status st = ensure_table_memory(ctx);
     if (st != XP_OK) return st;
@@ -468,6 +487,7 @@ xp_status xp_tables_build(xp_context *ctx, void *stream) {
 
 xp_status xp_tables_set(xp_context *ctx, const uint16_t *index_grid_host, const float *curves_host) {
     if (!ctx || !index_grid_host || !curves_host) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     DeviceGuard guard(ctx->device);
     xp_status st = ensure_table_memory(ctx);
     if (st != XP_OK) return st;
@@ -479,6 +499,7 @@ xp_status xp_tables_set(xp_context *ctx, const uint16_t *index_grid_host, const 
 
 xp_status xp_tables_get(xp_context *ctx, uint16_t *index_grid_host, float *curves_host) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (!ctx->tables) return fail(ctx, XP_ERR_TABLES_NOT_LOADED, "Call load_moist_adiabat_lookups first.");
     DeviceGuard guard(ctx->device);
     if (index_grid_host)
@@ -522,9 +543,10 @@ xp_status xp_lcl(xp_context *ctx, const void *p, const void *t, const void *td, 
                  int32_t dtype, const xp_options *opts, void *lcl_p, void *lcl_t, void *lcl_tv,
                  void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (!p || !t || !td || n < 0) return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad lcl arguments");
     DeviceGuard guard(ctx->device);
-    const Opts o = to_opts(opts);
+    const Opts o = to_opts(ctx, opts);
     cudaStream_t st = (cudaStream_t)stream;
     XP_DISPATCH(dtype,
                 launch_lcl<float>((const float *)p, (const float *)t, (const float *)td, n, o, (float *)lcl_p, (float *)lcl_t, (float *)lcl_tv, st),
@@ -538,6 +560,7 @@ xp_status xp_moist_lapse(xp_context *ctx, const void *pressure, int64_t level_st
                          const void *parcel_temperature, const void *parcel_pressure,
                          void *out_temperature, int64_t out_level_stride, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (!ctx->tables) return fail(ctx, XP_ERR_TABLES_NOT_LOADED, "Call load_moist_adiabat_lookups first.");
     if (!pressure || !parcel_temperature || !parcel_pressure || !out_temperature)
         return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad moist_lapse arguments");
@@ -558,12 +581,13 @@ xp_status xp_parcel_profile(xp_context *ctx, const void *pressure, int64_t level
                             int64_t out_level_stride, void *lcl_pressure, void *lcl_temperature,
                             void *lcl_virtual_temperature, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (!ctx->tables) return fail(ctx, XP_ERR_TABLES_NOT_LOADED, "Call load_moist_adiabat_lookups first.");
     if (!pressure || !parcel || !parcel->pressure || !parcel->temperature || !parcel->dewpoint)
         return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad parcel_profile arguments");
     DeviceGuard guard(ctx->device);
     Tables tb = {ctx->d_index, ctx->d_curves};
-    const Opts o = to_opts(opts);
+    const Opts o = to_opts(ctx, opts);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == XP_F32) {
         ParcelArg<float> pa = {(const float *)parcel->pressure, (const float *)parcel->temperature, (const float *)parcel->dewpoint};
@@ -584,6 +608,7 @@ xp_status xp_lfc_el(xp_context *ctx, const void *pressure, const void *parcel_te
                     const void *lcl_temperature, void *lfc_pressure, void *lfc_temperature,
                     void *el_pressure, void *el_temperature, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (!pressure || !parcel_temperature || !temperature || !lcl_pressure || !lcl_temperature)
         return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad lfc_el arguments");
     DeviceGuard guard(ctx->device);
@@ -601,10 +626,11 @@ xp_status xp_cape_cin_base(xp_context *ctx, const void *pressure, const void *te
                            const void *lfc_pressure, const void *el_pressure,
                            const xp_options *opts, void *cape, void *cin, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (!pressure || !temperature || !parcel_temperature || !lfc_pressure || !el_pressure)
         return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad cape_cin_base arguments");
     DeviceGuard guard(ctx->device);
-    const Opts o = to_opts(opts);
+    const Opts o = to_opts(ctx, opts);
     cudaStream_t st = (cudaStream_t)stream;
     XP_DISPATCH(dtype,
                 launch_cape_cin_base<float>((const float *)pressure, (const float *)temperature, (const float *)parcel_temperature, level_stride, n_levels, n_columns, (const float *)lfc_pressure, (const float *)el_pressure, o, (float *)cape, (float *)cin, st),
@@ -619,6 +645,7 @@ xp_status xp_interp_levels(xp_context *ctx, const void *coords, int64_t coords_l
                            int32_t dtype, const void *at, double at_scalar, int32_t log_coords,
                            void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (n_columns == 0) return XP_OK;
     if (!coords || !fields || !outputs || n_fields < 1 || n_fields > 4 || n_levels < 1 || n_columns < 0)
         return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad interp_levels arguments");
@@ -638,6 +665,7 @@ xp_status xp_level_crossing(xp_context *ctx, const void *coords, int64_t coords_
                             int32_t n_levels, int64_t n_columns, int32_t dtype, double level,
                             void *output, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (n_columns == 0) return XP_OK;
     if (!coords || !field || !output || n_levels < 1 || n_columns < 0)
         return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad level_crossing arguments");
@@ -655,6 +683,7 @@ xp_status xp_mixed_layer(xp_context *ctx, const void *pressure, int64_t pressure
                          int32_t pressure_field, int64_t level_stride, int32_t n_levels, int64_t n_columns,
                          int32_t dtype, double depth, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (n_columns == 0) return XP_OK;
     if (!pressure || !fields || !outputs || n_fields < 1 || n_fields > 4 || pressure_field >= n_fields || n_levels < 1 ||
         n_columns < 0)
@@ -675,6 +704,7 @@ xp_status xp_mixed_parcel(xp_context *ctx, const void *pressure, int64_t pressur
                           int64_t level_stride, int32_t n_levels, int64_t n_columns, int32_t dtype, double depth,
                           const xp_mixed_parcel_out *out, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (n_columns == 0) return XP_OK;
     if (!pressure || !temperature || !dewpoint || !out || n_levels < 1 || n_columns < 0)
         return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad mixed_parcel arguments");
@@ -692,6 +722,7 @@ xp_status xp_layer_bounds(xp_context *ctx, const void *pressure, int64_t pressur
                           int32_t pressure_is_1d, int32_t n_levels, int64_t n_columns, int32_t dtype, double depth,
                           int32_t interpolate, void *bottom_pressure, void *top_pressure, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (n_columns == 0) return XP_OK;
     if (!pressure || (!bottom_pressure && !top_pressure) || n_levels < 1 || n_columns < 0)
         return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad layer_bounds arguments");
@@ -709,6 +740,7 @@ xp_status xp_insert_level(xp_context *ctx, const void *coords, int64_t coords_le
                           void *const *outputs, int32_t n_fields, void *coords_out, int64_t level_stride,
                           int64_t out_level_stride, int32_t n_levels, int64_t n_columns, int32_t dtype, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (n_columns == 0) return XP_OK;
     if (!coords || !level_coord || n_fields < 0 || n_fields > 4 || (n_fields == 0 && !coords_out) ||
         (n_fields > 0 && (!fields || !level_values || !outputs)) || n_levels < 1 || n_columns < 0)
@@ -729,6 +761,7 @@ xp_status xp_shift_out_nans(xp_context *ctx, const void *ref_field, const void *
                             int32_t n_fields, int64_t level_stride, int32_t n_levels, int64_t n_columns,
                             int32_t dtype, int32_t *level_shift, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (n_columns == 0) return XP_OK;
     if (!ref_field || n_fields < 0 || n_fields > 4 || (n_fields == 0 && !level_shift) ||
         (n_fields > 0 && (!fields || !outputs)) || n_levels < 1 || n_columns < 0)
@@ -749,6 +782,7 @@ xp_status xp_trapz(xp_context *ctx, const void *x, int64_t x_level_stride, int32
                    void *const *outputs, int32_t n_fields, int64_t level_stride, int32_t n_levels, int64_t n_columns,
                    int32_t dtype, const uint8_t *mask, int64_t mask_level_stride, int32_t sign, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (n_columns == 0) return XP_OK;
     if (!x || !fields || !outputs || n_fields < 1 || n_fields > 4 || n_levels < 1 || n_columns < 0 || sign < -1 || sign > 1)
         return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad trapz arguments");
@@ -768,6 +802,7 @@ xp_status xp_find_intersections(xp_context *ctx, const void *x, int64_t x_level_
                                 int64_t n_columns, int32_t dtype, int32_t log_x, const xp_intersections_out *out,
                                 void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (n_columns == 0) return XP_OK;
     if (!x || !a || !b || !out || n_levels < 1 || n_columns < 0)
         return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad find_intersections arguments");
@@ -785,6 +820,7 @@ xp_status xp_find_intersections(xp_context *ctx, const void *x, int64_t x_level_
 xp_status xp_interp1d(xp_context *ctx, const void *at, const void *xp, int32_t xp_is_1d, const void *fp, void *out,
                       int64_t n_rows, int32_t m, int32_t n, int32_t dtype, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (n_rows == 0 || m == 0) return XP_OK;
     if (!at || !xp || !fp || !out || n_rows < 0 || m < 0 || n < 1)
         return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad interp1d arguments");
@@ -801,6 +837,7 @@ xp_status xp_trap_around_zeros(xp_context *ctx, const void *x, int64_t x_level_s
                                int64_t level_stride, int64_t out_level_stride, int32_t n_levels, int64_t n_columns,
                                int32_t dtype, int32_t log_x, const xp_zero_areas_out *out, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (n_columns == 0) return XP_OK;
     if (!x || !y || !out || n_levels < 1 || n_columns < 0)
         return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad trap_around_zeros arguments");
@@ -817,6 +854,7 @@ xp_status xp_trap_around_zeros(xp_context *ctx, const void *x, int64_t x_level_s
 xp_status xp_valid_data(xp_context *ctx, const void *pressure, int64_t pressure_level_stride, int32_t pressure_is_1d,
                         int32_t n_levels, int64_t n_columns, int32_t dtype, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (n_columns == 0) return XP_OK;
     if (!pressure || n_levels < 1 || n_columns < 0) return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad valid_data arguments");
     DeviceGuard guard(ctx->device);
@@ -833,6 +871,7 @@ xp_status xp_dewpoint_from_specific_humidity(xp_context *ctx, const void *pressu
                                              const void *specific_humidity, int64_t n, int32_t dtype,
                                              int32_t metpy_compat, void *dewpoint, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (n == 0) return XP_OK;
     if (!pressure || !temperature || !specific_humidity || !dewpoint || n < 0 || (metpy_compat != 141 && metpy_compat != 162))
         return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad dewpoint_from_specific_humidity arguments");
@@ -848,6 +887,7 @@ xp_status xp_dewpoint_from_specific_humidity(xp_context *ctx, const void *pressu
 xp_status xp_saturation_mixing_ratio(xp_context *ctx, const void *pressure, const void *temperature, int64_t n,
                                      int32_t dtype, void *mixing_ratio, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (n == 0) return XP_OK;
     if (!pressure || !temperature || !mixing_ratio || n < 0)
         return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad saturation_mixing_ratio arguments");
@@ -863,6 +903,7 @@ xp_status xp_saturation_mixing_ratio(xp_context *ctx, const void *pressure, cons
 xp_status xp_dry_lapse(xp_context *ctx, const void *pressure, const void *parcel_temperature,
                        const void *parcel_pressure, int64_t n, int32_t dtype, void *temperature, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (n == 0) return XP_OK;
     if (!pressure || !parcel_temperature || !parcel_pressure || !temperature || n < 0)
         return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad dry_lapse arguments");
@@ -878,6 +919,7 @@ xp_status xp_dry_lapse(xp_context *ctx, const void *pressure, const void *parcel
 xp_status xp_mixing_ratio(xp_context *ctx, const void *temperature, const void *dewpoint, const void *pressure,
                           int64_t n, int32_t dtype, int32_t metpy_compat, void *mixing_ratio, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (n == 0) return XP_OK;
     if (!temperature || !dewpoint || !pressure || !mixing_ratio || n < 0 || (metpy_compat != 141 && metpy_compat != 162))
         return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad mixing_ratio arguments");
@@ -893,6 +935,7 @@ xp_status xp_mixing_ratio(xp_context *ctx, const void *temperature, const void *
 xp_status xp_virtual_temperature(xp_context *ctx, const void *temperature, const void *mixing_ratio, int64_t n,
                                  int32_t dtype, double epsilon, void *virtual_temperature, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (n == 0) return XP_OK;
     if (!temperature || !mixing_ratio || !virtual_temperature || n < 0)
         return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad virtual_temperature arguments");
@@ -908,6 +951,7 @@ xp_status xp_virtual_temperature(xp_context *ctx, const void *temperature, const
 xp_status xp_wet_bulb_temperature(xp_context *ctx, const void *pressure, const void *temperature,
                                   const void *dewpoint, int64_t n, int32_t dtype, void *wet_bulb, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (!ctx->tables) return fail(ctx, XP_ERR_TABLES_NOT_LOADED, "Call load_moist_adiabat_lookups first.");
     if (n == 0) return XP_OK;
     if (!pressure || !temperature || !dewpoint || !wet_bulb || n < 0)
@@ -926,6 +970,7 @@ xp_status xp_significant_hail_parameter(xp_context *ctx, const void *mucape, con
                                         const void *lapse, const void *temp_500, const void *shear,
                                         const void *flh, int64_t n, int32_t dtype, void *ship, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (n == 0) return XP_OK;
     if (!mucape || !mixing_ratio || !lapse || !temp_500 || !shear || !flh || !ship || n < 0)
         return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad significant_hail_parameter arguments");
@@ -942,6 +987,7 @@ xp_status xp_significant_hail_parameter(xp_context *ctx, const void *mucape, con
 xp_status xp_storm_proxies(xp_context *ctx, const xp_proxy_inputs *in, int64_t n, int32_t dtype,
                            const xp_proxy_outputs *out, void *stream) {
     if (!ctx) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (n == 0) return XP_OK;
     if (!in || !out || n < 0) return fail(ctx, XP_ERR_INVALID_ARGUMENT, "bad storm_proxies arguments");
     const void *iv[13] = {in->mixed_100_cape, in->mixed_50_cape, in->mu_cape, in->shear_magnitude,
@@ -965,6 +1011,7 @@ uint64_t xp_launch_count(const xp_context *ctx) { return ctx ? ctx->launches : 0
 
 xp_status xp_last_exact_count(xp_context *ctx, int64_t *out_count) {
     if (!ctx || !out_count) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     *out_count = -1;
     if (!ctx->last_was_fast) return XP_OK;
     DeviceGuard guard(ctx->device);
@@ -976,6 +1023,7 @@ xp_status xp_last_exact_count(xp_context *ctx, int64_t *out_count) {
 
 xp_status xp_last_kernel_ms(xp_context *ctx, float *out_ms) {
     if (!ctx || !out_ms) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     if (!ctx->ev_valid) return fail(ctx, XP_ERR_INVALID_ARGUMENT, "no timed launch yet");
     DeviceGuard guard(ctx->device);
     XP_CUDA(ctx, cudaEventSynchronize(ctx->ev1));

@@ -356,6 +356,21 @@ __global__ void __launch_bounds__(kPCol6Threads, 2) suite_fast_pcol6_kernel(cons
 
 }  // namespace
 
+// Build/experiment knobs from the environment, read ONCE per process (thread-safe static initialisation), never
+// in the launch path.
+struct FastKnobs { int pcol6, staged; };
+static const FastKnobs &fast_knobs() {
+    static const FastKnobs k = [] {
+        FastKnobs r;
+        const char *e = getenv("XP_PCOL6");
+        r.pcol6 = e ? atoi(e) : 0;
+        e = getenv("XP_FAST_STAGED");
+        r.staged = e ? atoi(e) : 0;          // default 0: measured fastest
+        return r;
+    }();
+    return k;
+}
+
 size_t fast_scratch_bytes(int64_t n) {
     // Prep | coef table | list counter | list
     return ((sizeof(Prep) + 255) & ~(size_t)255) + (size_t)fast::kMaxLevels * fast::kNI * sizeof(Coef) + 256 +
@@ -411,21 +426,17 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
         // parcel only, 2: every kind).  Measured on the B200 (1 M x 70 SB / 2.8 M x 70 SB+ML, M columns/s): generic
         // sweep 1069 / 693, v6 sweep 938 / 506 -- since the generic sweep reads its pre-pass levels ahead and
         // searches the LCL level in chunks of independent loads it wins everywhere, so it is the default.
-        static int pcol6 = -1;
-        if (pcol6 < 0) { const char *e = getenv("XP_PCOL6"); pcol6 = e ? atoi(e) : 0; }
+        const int pcol6 = fast_knobs().pcol6;
         const uint64_t span = (uint64_t)cols.n + (uint64_t)cols.L * (uint64_t)std::max(cols.ls, cols.pls);
         if (pcol6 && ((kind_mask & 7) == 1 || pcol6 == 2) && mode && !profile && span < ((uint64_t)1 << 32)) {
             const int lv = kPCol6StashLevels;
             const size_t smem6 = (size_t)lv * 3 * sizeof(float) * kPCol6Threads;
             const unsigned g6 = (unsigned)((cols.n + kPCol6Threads - 1) / kPCol6Threads);
-            static bool attr_set[8] = {};
+            // (the shared-memory opt-in is a per-DEVICE attribute: set on every launch, ~1 us, never cached per process)
 #define XP_PCOL6_CASE(K)                                                                                          \
     case K:                                                                                                       \
-        if (!attr_set[K]) {                                                                                       \
-            if (cudaFuncSetAttribute(suite_fast_pcol6_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                     (int)((size_t)kPCol6StashLevels * 3 * sizeof(float) * kPCol6Threads)) != cudaSuccess) return -1; \
-            attr_set[K] = true;                                                                                   \
-        }                                                                                                         \
+        if (cudaFuncSetAttribute(suite_fast_pcol6_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                 (int)((size_t)kPCol6StashLevels * 3 * sizeof(float) * kPCol6Threads)) != cudaSuccess) return -1; \
         suite_fast_pcol6_kernel<K><<<g6, kPCol6Threads, smem6, stream>>>(pp, lv);                                 \
         break;
             switch (kind_mask & 7) {
@@ -472,12 +483,7 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
     // shared memory: Prep | coefficient table | (staged) the environment curve of every thread
     const size_t smem_table = ((sizeof(Prep) + 127) & ~(size_t)127) + (size_t)cols.L * fast::kNI * sizeof(Coef);
     const size_t smem_env = (size_t)cols.L * kFastThreads * sizeof(float);
-    static int staged_ok = -1;
-    if (staged_ok < 0) {
-        const char *e = getenv("XP_FAST_STAGED");
-        staged_ok = e ? atoi(e) : 0;       // default 0: measured fastest
-    }
-    int staged = staged_ok;
+    int staged = fast_knobs().staged;
     if (staged == 1 && smem_table + smem_env + 256 > (size_t)227 * 1024) staged = 0;
     // the v6 sweep addresses T/Td with 32-bit element offsets; larger arrays take the generic sweep (variant 2)
     if (mode == 1 && staged == 0 && (uint64_t)cols.n + (uint64_t)cols.L * (uint64_t)cols.ls >= ((uint64_t)1 << 32)) staged = 2;
@@ -496,15 +502,13 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
     const int threads = kFastThreads;      // one 512-thread CTA per SM (128 registers per thread)
     const int64_t tiles = (cols.n + threads - 1) / threads;
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
-    static size_t smem_set[3][2][1][8] = {};
+    // the dynamic shared-memory opt-in is a per-DEVICE function attribute: set it on every launch (a process may
+    // hold contexts on several GPUs; a process-wide cache would skip the second device)
 #define XP_FAST_LAUNCH(K, M, S)                                                                                  \
     do {                                                                                                         \
-        if (smem > smem_set[S][M][0][K]) {                                                                       \
-            if (cudaFuncSetAttribute(suite_fast_kernel<K, M, kFastThreads, S>,                                   \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)     \
-                return -1;                                                                                       \
-            smem_set[S][M][0][K] = smem;                                                                         \
-        }                                                                                                        \
+        if (cudaFuncSetAttribute(suite_fast_kernel<K, M, kFastThreads, S>,                                       \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)         \
+            return -1;                                                                                           \
         suite_fast_kernel<K, M, kFastThreads, S><<<grid, kFastThreads, smem, stream>>>(fp);                      \
     } while (0)
 #define XP_FAST_CASE(K)                                                                           \

@@ -264,6 +264,13 @@ def _options(kwargs):
     return {k: kwargs[k] for k in known if k in kwargs}
 
 
+def _clear_flags(ctx):
+    """The reference-assert flags live in one word per context that only take_flags() clears: drop whatever an
+    earlier call that never collected them (direct Context use, another function) left behind, so that every
+    function of this module reports its OWN launches only."""
+    ctx.take_flags()
+
+
 def _check_flags(ctx):
     flags = ctx.take_flags()
     assert not (flags & _lib.FLAG_PRESSURES_NOT_UNIQUE), "Vertical pressures are not unique"   # PF:131
@@ -293,6 +300,7 @@ def _profile_levels(kind, res, L):
 def _run(kind, pressure, temperature, dewpoint, vert_dim, vert_axis, device, profile, explicit=None,
          depth=None, **kwargs):
     lay, ctx, p, t, td = _prepare(pressure, temperature, dewpoint, vert_dim, vert_axis, device)
+    _clear_flags(ctx)
     okw = _options(kwargs)
     if depth is not None:
         okw["mixed_layer_depth" if kind == "ml" else "most_unstable_depth"] = depth
@@ -560,6 +568,7 @@ def valid_data(dat, vert_dim="model_level_number", vert_axis=0, device=None):
     lay, dtype, _ = _layout_of(dat["pressure"], vert_dim, vert_axis)
     (pb,) = _blocks(lay, [dat["pressure"]], dtype)
     n = int(np.prod(lay.col_shape)) if lay.col_shape else 1
+    _clear_flags(ctx)
     ctx.valid_data(pb, n)
     flags = ctx.take_flags()
     assert (flags & _lib.FLAG_PRESSURE_ORDER_CHECKED) and not (flags & _lib.FLAG_PRESSURE_NOT_DECREASING), \
@@ -665,6 +674,7 @@ def parcel_suite(pressure, temperature, dewpoint, vert_dim="model_level_number",
     lay, ctx, p, t, td = _prepare(pressure, temperature, dewpoint, vert_dim, vert_axis, device)
     opts = _lib.make_options(mixed_layer_depth=mixed_layer_depth, most_unstable_depth=most_unstable_depth,
                              **_options(kwargs))
+    _clear_flags(ctx)
     res = ctx.cape_cin(p, t, td, kinds=("sb", "ml", "mu"), options=opts, profile=False)
     _check_flags(ctx)
     out = {}
