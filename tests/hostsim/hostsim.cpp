@@ -11,6 +11,7 @@
 
 #include "../../xarray_parcel_b200/csrc/xp_fast_pcol.cuh"
 #include "../../xarray_parcel_b200/csrc/xp_fast6.cuh"
+#include "../../xarray_parcel_b200/csrc/xp_fast7.cuh"
 #include "../../xarray_parcel_b200/csrc/xp_fast_pcol6.cuh"
 #include "../../xarray_parcel_b200/csrc/xp_layers.cuh"
 #include "../../xarray_parcel_b200/csrc/xp_levels.cuh"
@@ -113,6 +114,14 @@ struct HostCoef {
 };
 }  // namespace
 
+// Which sweep the columns 2, 3 mod 4 of hostsim_fast_suite run under the default options (6: xp_fast6.cuh, 7:
+// xp_fast7.cuh) and, for v7, the stand-in for the other lanes' LCL rows (see host_warp_max_floor).
+static int g_fast_sweep = 7;
+extern "C" void hostsim_set_fast_sweep(int version, int ka_floor) {
+    g_fast_sweep = version;
+    xp::fast::host_warp_max_floor() = ka_floor;
+}
+
 extern "C" int hostsim_fast_suite(const float *p, const float *t, const float *td, int64_t n, int L,
                                   const int *iopts, double ml_depth, double mu_depth,
                                   const uint16_t *index_grid, const float *curves, float *out,
@@ -148,10 +157,12 @@ extern "C" int hostsim_fast_suite(const float *p, const float *t, const float *t
             const HostRd6 rd6 = {t, td, (uint32_t)c, (uint32_t)n};
             if ((c & 3) == 2) {
                 HostStash st;
-                redo[c] = xp::fast::suite_column6<7u>(rd6, cf_tv, pr, tb, o, st, r);
+                redo[c] = (g_fast_sweep == 7) ? xp::fast::suite_column7<7u>(rd6, cf_tv, pr, tb, o, st, r)
+                                              : xp::fast::suite_column6<7u>(rd6, cf_tv, pr, tb, o, st, r);
             } else {
                 xp::fast::NoStash st;
-                redo[c] = xp::fast::suite_column6<7u>(rd6, cf_tv, pr, tb, o, st, r);
+                redo[c] = (g_fast_sweep == 7) ? xp::fast::suite_column7<7u>(rd6, cf_tv, pr, tb, o, st, r)
+                                              : xp::fast::suite_column6<7u>(rd6, cf_tv, pr, tb, o, st, r);
             }
         } else if (c & 1) {
             xp::fast::EnvRecompute env;

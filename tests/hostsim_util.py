@@ -21,7 +21,7 @@ KINDS = {"sb": 0, "ml": 1, "mu": 2, "explicit": 3}
 
 
 def build():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("xp_math.cuh", "xp_column.cuh", "xp_parcels.cuh", "xp_fast.cuh", "xp_fast_pcol.cuh", "xp_fast6.cuh", "xp_fast_pcol6.cuh", "xp_layers.cuh", "xp_levels.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("xp_math.cuh", "xp_column.cuh", "xp_parcels.cuh", "xp_fast.cuh", "xp_fast_pcol.cuh", "xp_fast6.cuh", "xp_fast7.cuh", "xp_fast_pcol6.cuh", "xp_layers.cuh", "xp_levels.cuh")]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     os.makedirs(BUILD, exist_ok=True)
@@ -79,6 +79,12 @@ def cape_cin(p, t, td, tables, kind="sb", explicit=None, vtc=True, lcl_interp="l
     if profile:
         res["profile"] = {k: prof[i] for i, k in enumerate(PROFILE)}
     return res
+
+
+def set_fast_sweep(version=7, ka_floor=0):
+    """Select the sweep (6 / 7) that columns 2, 3 mod 4 run under the default options, and for v7 the stand-in for
+    the highest LCL row among the other lanes of the warp."""
+    lib().hostsim_set_fast_sweep(int(version), int(ka_floor))
 
 
 def fast_suite(p, t, td, tables, vtc=True, lcl_interp="log", pos_cape_neg_cin=True, post_zero_cin=False,

@@ -6,6 +6,7 @@
 #include "xp_fast.cuh"
 #include "xp_fast_pcol.cuh"
 #include "xp_fast6.cuh"
+#include "xp_fast7.cuh"
 #include "xp_fast_pcol6.cuh"
 #include "xp_kernels.cuh"
 
@@ -121,7 +122,10 @@ __device__ __forceinline__ void store_fast_all(const OutArg<float> &o, int64_t c
     if (parcel) { o.par_p[col] = r.par_p; o.par_t[col] = r.par_t; o.par_td[col] = r.par_td; }
 }
 
-constexpr int kFastThreads = 512;
+#ifndef XP_FAST_THREADS
+#define XP_FAST_THREADS 640
+#endif
+constexpr int kFastThreads = XP_FAST_THREADS;   // threads of the one persistent CTA per SM
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -145,8 +149,9 @@ struct StashSmem {
     __device__ __forceinline__ void get(int k, float &t, float &td) const { t = base[(2 * k) * stride]; td = base[(2 * k + 1) * stride]; }
 };
 
-// STAGED: 0 = environment recomputed in the sweep; 1 = environment curve staged in shared memory + early
-// termination; 2 = recomputed, with a first pass over all levels for the early-termination bound.
+// STAGED: 0 = environment recomputed in the sweep (default options: the v6 sweep of xp_fast6.cuh); 1 = environment
+// curve staged in shared memory + early termination; 2 = recomputed, with a first pass over all levels for the
+// early-termination bound; 3 = the v7 sweep of xp_fast7.cuh (default options only; shared memory as 0).
 template <unsigned KINDS, int MODE, int THREADS, int STAGED>
 __global__ void __launch_bounds__(THREADS, 1) suite_fast_kernel(const __grid_constant__ FastParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -205,7 +210,11 @@ __global__ void __launch_bounds__(THREADS, 1) suite_fast_kernel(const __grid_con
         const GlobalRd rd{prm.t + col, prm.td + col, prm.ls};
         fast::FResult res[3];
         unsigned redo;
-        if (MODE == 1 && STAGED == 0) {
+        if (MODE == 1 && STAGED == 3) {
+            StashSmem st{s_env + threadIdx.x, (int)blockDim.x, prm.stash_levels};
+            const GlobalRd32 rd32{prm.t, prm.td, (uint32_t)col, (uint32_t)prm.ls};
+            redo = fast::suite_column7<KINDS>(rd32, cf, pr, prm.tb, prm.o, st, res);
+        } else if (MODE == 1 && STAGED == 0) {
             // default options: the v6 sweep on the virtual-temperature table (xp_fast6.cuh); the shared
             // memory left after the table stashes T/Td of the lowest levels of every thread's column
             StashSmem st{s_env + threadIdx.x, (int)blockDim.x, prm.stash_levels};
@@ -358,7 +367,7 @@ __global__ void __launch_bounds__(kPCol6Threads, 2) suite_fast_pcol6_kernel(cons
 
 // Build/experiment knobs from the environment, read ONCE per process (thread-safe static initialisation), never
 // in the launch path.
-struct FastKnobs { int pcol6, staged; };
+struct FastKnobs { int pcol6, staged, sweep; };
 static const FastKnobs &fast_knobs() {
     static const FastKnobs k = [] {
         FastKnobs r;
@@ -366,6 +375,8 @@ static const FastKnobs &fast_knobs() {
         r.pcol6 = e ? atoi(e) : 0;
         e = getenv("XP_FAST_STAGED");
         r.staged = e ? atoi(e) : 0;          // default 0: measured fastest
+        e = getenv("XP_FAST_SWEEP");
+        r.sweep = e ? atoi(e) : 7;           // 7: xp_fast7.cuh (default), 6: xp_fast6.cuh
         return r;
     }();
     return k;
@@ -487,11 +498,13 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
     if (staged == 1 && smem_table + smem_env + 256 > (size_t)227 * 1024) staged = 0;
     // the v6 sweep addresses T/Td with 32-bit element offsets; larger arrays take the generic sweep (variant 2)
     if (mode == 1 && staged == 0 && (uint64_t)cols.n + (uint64_t)cols.L * (uint64_t)cols.ls >= ((uint64_t)1 << 32)) staged = 2;
-    fast_coef_kernel<<<cols.L, fast::kNI, 0, stream>>>(prep, tb.curves, coef, (mode == 1 && staged == 0) ? 1 : 0);
+    const bool v6 = (mode == 1 && staged == 0);
+    if (v6 && fast_knobs().sweep == 7) staged = 3;
+    fast_coef_kernel<<<cols.L, fast::kNI, 0, stream>>>(prep, tb.curves, coef, v6 ? 1 : 0);
     size_t smem = smem_table + (staged == 1 ? smem_env : 0);
     fp.stash_levels = 0;
-    if (mode == 1 && staged == 0) {
-        // v6 sweep: stash as many of the lowest levels as fit (at most 16: the pre-pass depth of real axes)
+    if (v6) {
+        // v6 / v7 sweep: stash as many of the lowest levels as fit (at most 16: the pre-pass depth of real axes)
         const size_t per_level = 2 * sizeof(float) * kFastThreads;
         const size_t room = (size_t)227 * 1024 - 256 - smem_table;
         int lv = (int)(room / per_level);
@@ -499,7 +512,7 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
         fp.stash_levels = lv;
         smem += (size_t)lv * per_level;
     }
-    const int threads = kFastThreads;      // one 512-thread CTA per SM (128 registers per thread)
+    const int threads = kFastThreads;      // one persistent CTA per SM (640 threads x 96 registers: measured best of 512..768)
     const int64_t tiles = (cols.n + threads - 1) / threads;
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
     // the dynamic shared-memory opt-in is a per-DEVICE function attribute: set it on every launch (a process may
@@ -515,6 +528,7 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
     case K:                                                                                       \
         if (staged == 1) { if (mode) XP_FAST_LAUNCH(K, 1, 1); else XP_FAST_LAUNCH(K, 0, 1); }     \
         else if (staged == 2) { if (mode) XP_FAST_LAUNCH(K, 1, 2); else XP_FAST_LAUNCH(K, 0, 2); }\
+        else if (staged == 3) { XP_FAST_LAUNCH(K, 1, 3); }                                        \
         else { if (mode) XP_FAST_LAUNCH(K, 1, 0); else XP_FAST_LAUNCH(K, 0, 0); }                 \
         break;
     switch (kind_mask & 7) {

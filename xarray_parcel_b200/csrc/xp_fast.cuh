@@ -64,7 +64,8 @@ struct Prep {
     double thfac[kMaxLevels];     // (1000/p)^kappa  (potential temperature factor, PF:253)
     double p64[kMaxLevels];
     float p[kMaxLevels], lnp[kMaxLevels], pk[kMaxLevels];   // p, ln p, p^kappa
-    float plk[kMaxLevels][4];                               // the same three, packed per level (one 16-byte load)
+    float plk[kMaxLevels][4];                               // the same three, packed per level (one 16-byte load), +
+                                                            // [3] = 0.5 (ln p[k-1] - ln p[k]): half-width of the interval below level k
 };
 
 // ---- per-call constants of the shared pressure axis ----------------------------------------------------
@@ -96,6 +97,7 @@ XP_HD void compute_prep_axis(int L, const Opts &o, Prep &pr) {
     for (int k = 0; k < L; ++k)
         if (pr.p64[k] >= 2.5) n_table = k + 1;
     pr.n_table = n_table;
+    for (int k = 1; k < L; ++k) pr.plk[k][3] = 0.5f * (pr.lnp[k - 1] - pr.lnp[k]);   // float32, as the sweeps compute it
     pr.p0 = pr.p64[0];
     pr.exner0 = exner(pr.p64[0]);
     // mixed layer: get_layer(interpolate=True) PF:63-100 + trapz(x='pressure') PF:186-198, as weights
