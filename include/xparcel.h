@@ -81,6 +81,14 @@ typedef struct {
     int32_t pressure_is_1d;        /* 1: pressure is one shared axis [n_levels] (ERA5-style
                                       pressure levels); element k at pressure[k*pressure_level_stride] */
     int32_t mem;                   /* xp_memspace, applies to inputs AND outputs of the call */
+    int32_t dewpoint_is_specific_humidity;
+                                   /* 1: `dewpoint` holds SPECIFIC HUMIDITY q [kg/kg] instead; every kernel converts it as
+                                      each level is loaded, Td = metpy.calc.dewpoint_from_specific_humidity(p, T, q) in the
+                                      form of xp_options.metpy_compat (the q -> Td front end of conv_properties,
+                                      PF:1889, 1969; parcel_test.py:432-436) -- model output (p, T, q) is consumed
+                                      directly and the dewpoint array is never materialised.  Parcel dewpoints
+                                      (surface, most-unstable level, mixed-layer mean) are converted in float64. */
+    int32_t reserved_;             /* must be 0 */
 } xp_columns;
 
 /* Function kwargs of the reference that select behaviour (PF:1394-1397, PF:1291-1293). */

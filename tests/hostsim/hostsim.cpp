@@ -18,13 +18,19 @@
 
 namespace {
 
+// != 0 (141 / 162): the dewpoint arrays handed to the entry points hold specific humidity (hostsim_set_qmode)
+static int g_qmode = 0;
+
 struct HostReader {
     const double *p, *t, *td;
     int64_t ls, pls;
     int L;
     double P(int k) const { return p[(int64_t)k * pls]; }
     double Tk(int k) const { return t[(int64_t)k * ls]; }
-    double Td(int k) const { return td[(int64_t)k * ls]; }
+    double Td(int k) const {
+        const double raw = td[(int64_t)k * ls];
+        return g_qmode ? xp::dewpoint_from_q(P(k), Tk(k), raw, g_qmode) : raw;
+    }
 };
 
 struct HostProf {
@@ -116,6 +122,7 @@ struct HostCoef {
 
 // Which sweep the columns 2, 3 mod 4 of hostsim_fast_suite run under the default options (6: xp_fast6.cuh, 7:
 // xp_fast7.cuh) and, for v7, the stand-in for the other lanes' LCL rows (see host_warp_max_floor).
+extern "C" void hostsim_set_qmode(int qmode) { g_qmode = qmode; }
 static int g_fast_sweep = 7;
 extern "C" void hostsim_set_fast_sweep(int version, int ka_floor) {
     g_fast_sweep = version;
@@ -130,6 +137,7 @@ extern "C" int hostsim_fast_suite(const float *p, const float *t, const float *t
     xp::Opts o;
     o.vtc = iopts[0]; o.log_interp = iopts[1]; o.pos_neg = iopts[2]; o.post_zero = iopts[3];
     o.compat = iopts[4]; o.exact_only = 0; o.vote_mask = 0; o.ml_depth = ml_depth; o.mu_depth = mu_depth;
+    o.qmode = g_qmode;
     static xp::fast::Prep pr;
     xp::fast::compute_prep(p, 1, L, o, pr);
     if (!pr.ok) return 0;
@@ -139,6 +147,7 @@ extern "C" int hostsim_fast_suite(const float *p, const float *t, const float *t
     HostCoef cf = {coef.data()};
     // default options: the v6 sweep on the virtual-temperature table (xp_fast6.cuh) -- what the kernel runs
     const bool m1 = o.vtc && o.compat == 141 && o.pos_neg;
+    if (g_qmode && !m1) return 0;          // specific-humidity input: the v7 sweep only (fast_eligible in xp_fast.cu)
     std::vector<xp::fast::Coef> coef_tv;
     if (m1) {
         coef_tv.resize((size_t)L * xp::fast::kNI);
@@ -152,16 +161,16 @@ extern "C" int hostsim_fast_suite(const float *p, const float *t, const float *t
         xp::fast::FResult r[3];
         // default options: v6 sweep on columns 2, 3 mod 4 (the generic sweep keeps 0, 1 mod 4);
         // other options: even columns environment staged + early termination, odd columns recomputed
-        if (m1 && (c & 3) >= 2) {
+        if (m1 && ((c & 3) >= 2 || g_qmode)) {
             // column 2 mod 4: T/Td of the lowest levels stashed by the pre-pass; 3 mod 4: no stash
             const HostRd6 rd6 = {t, td, (uint32_t)c, (uint32_t)n};
             if ((c & 3) == 2) {
                 HostStash st;
-                redo[c] = (g_fast_sweep == 7) ? xp::fast::suite_column7<7u>(rd6, cf_tv, pr, tb, o, st, r)
+                redo[c] = (g_fast_sweep == 7) ? xp::fast::suite_column7<7u, true>(rd6, cf_tv, pr, tb, o, st, r)
                                               : xp::fast::suite_column6<7u>(rd6, cf_tv, pr, tb, o, st, r);
             } else {
                 xp::fast::NoStash st;
-                redo[c] = (g_fast_sweep == 7) ? xp::fast::suite_column7<7u>(rd6, cf_tv, pr, tb, o, st, r)
+                redo[c] = (g_fast_sweep == 7) ? xp::fast::suite_column7<7u, true>(rd6, cf_tv, pr, tb, o, st, r)
                                               : xp::fast::suite_column6<7u>(rd6, cf_tv, pr, tb, o, st, r);
             }
         } else if (c & 1) {
@@ -240,15 +249,16 @@ extern "C" int hostsim_fast_suite_pcol(const float *p, const float *t, const flo
     xp::Opts o;
     o.vtc = iopts[0]; o.log_interp = iopts[1]; o.pos_neg = iopts[2]; o.post_zero = iopts[3];
     o.compat = iopts[4]; o.exact_only = 0; o.vote_mask = 0; o.ml_depth = ml_depth; o.mu_depth = mu_depth;
+    o.qmode = g_qmode;
     for (int64_t c = 0; c < n; ++c) {
         HostRdP rd = {p + c, t + c, td + c, n};
         xp::fast::FResult r[3];
         const bool m1 = o.vtc && o.compat == 141 && o.pos_neg;
         if (prof) {
             HostProfW pw = {prof, n, c, L};
-            redo[c] = m1 ? xp::fast::suite_column_pcol<7u, 1>(rd, L, tb, o, pw, r)
-                         : xp::fast::suite_column_pcol<7u, 0>(rd, L, tb, o, pw, r);
-        } else if (m1 && (c % 3) != 0) {
+            redo[c] = m1 ? xp::fast::suite_column_pcol<7u, 1, true>(rd, L, tb, o, pw, r)
+                         : xp::fast::suite_column_pcol<7u, 0, true>(rd, L, tb, o, pw, r);
+        } else if (m1 && (c % 3) != 0 && !g_qmode) {
             // default options, no profile: the v6 sweep (xp_fast_pcol6.cuh) on two columns out of three, with a
             // stash of 36 levels (the kernel's), of 5 levels (search and sweep cross its end) or none
             const HostRdP6 rd6 = {p, t, td, (uint32_t)c, (uint32_t)n};
@@ -261,8 +271,8 @@ extern "C" int hostsim_fast_suite_pcol(const float *p, const float *t, const flo
             }
         } else {
             xp::fast::NoProfile np;
-            redo[c] = m1 ? xp::fast::suite_column_pcol<7u, 1>(rd, L, tb, o, np, r)
-                         : xp::fast::suite_column_pcol<7u, 0>(rd, L, tb, o, np, r);
+            redo[c] = m1 ? xp::fast::suite_column_pcol<7u, 1, true>(rd, L, tb, o, np, r)
+                         : xp::fast::suite_column_pcol<7u, 0, true>(rd, L, tb, o, np, r);
         }
         for (int q = 0; q < 3; ++q) {
             const float vals[12] = {r[q].cape, r[q].cin, r[q].lcl_p, r[q].lcl_t, r[q].lcl_tv, r[q].lfc_p,

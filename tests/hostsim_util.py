@@ -87,6 +87,12 @@ def set_fast_sweep(version=7, ka_floor=0):
     lib().hostsim_set_fast_sweep(int(version), int(ka_floor))
 
 
+def set_qmode(qmode=0):
+    """0: the dewpoint arguments are dewpoints; 141 / 162: they hold specific humidity, converted on load in that
+    MetPy form (xp_columns.dewpoint_is_specific_humidity)."""
+    lib().hostsim_set_qmode(int(qmode))
+
+
 def fast_suite(p, t, td, tables, vtc=True, lcl_interp="log", pos_cape_neg_cin=True, post_zero_cin=False,
                metpy_compat=141, ml_depth=100.0, mu_depth=300.0, profile=False):
     """Run the host-compiled float32 fast path on a shared pressure axis p [L] (xp_fast.cuh) or

@@ -37,7 +37,8 @@ class XpColumns(ctypes.Structure):
     _fields_ = [("pressure", c_void_p), ("temperature", c_void_p), ("dewpoint", c_void_p),
                 ("n_columns", c_int64), ("n_levels", c_int32), ("dtype", c_int32),
                 ("level_stride", c_int64), ("pressure_level_stride", c_int64),
-                ("pressure_is_1d", c_int32), ("mem", c_int32)]
+                ("pressure_is_1d", c_int32), ("mem", c_int32),
+                ("dewpoint_is_specific_humidity", c_int32), ("reserved_", c_int32)]
 
 
 class XpOptions(ctypes.Structure):
@@ -379,14 +380,18 @@ class Context:
         return n
 
     def cape_cin(self, p, t, td, kinds=("sb",), options=None, profile=False, explicit=None,
-                 pin_outputs=False, out=None):
+                 pin_outputs=False, out=None, specific_humidity=False):
         """Run the fused kernel for the requested parcel kinds on level-major torch tensors.
 
         CUDA tensors: asynchronous on the current stream.  CPU tensors: staged through the
         device by the library (host path of the C ABI).  Returns {kind: {field: tensor}}.
+        ``specific_humidity=True``: ``td`` holds specific humidity [kg/kg]; the kernels convert it to the dewpoint
+        as each level is loaded (metpy.calc.dewpoint_from_specific_humidity in the options' metpy_compat form,
+        PF:1889, 1969) -- no dewpoint array is materialised.
         """
         opts = options if options is not None else make_options()
         cols, L, N = self._columns(p, t, td)
+        cols.dewpoint_is_specific_humidity = int(bool(specific_humidity))
         kinds = tuple(kinds)
         keep = {}
         outs = out if out is not None else self.alloc_outputs(t, kinds, profile, pin_outputs)

@@ -124,8 +124,9 @@ OutArg<T> to_out(const xp_parcel_out *o) {
 }
 
 template <typename T>
-ColsArg<T> to_cols(const xp_columns *c) {
+ColsArg<T> to_cols(const xp_columns *c, const Opts &o) {
     ColsArg<T> r;
+    r.qmode = c->dewpoint_is_specific_humidity ? o.compat : 0;
     r.p = (const T *)c->pressure; r.t = (const T *)c->temperature; r.td = (const T *)c->dewpoint;
     r.n = c->n_columns; r.L = c->n_levels;
     r.ls = c->level_stride; r.pls = c->pressure_level_stride; r.p1d = c->pressure_is_1d != 0;
@@ -166,8 +167,8 @@ xp_status run_device(xp_context *ctx, const xp_columns *cols, int kind_mask,
     Tables tb = {ctx->d_index, ctx->d_curves};
     ctx->last_was_fast = false;
     if constexpr (std::is_same<T, float>::value) {
-        const ColsArg<float> ca = to_cols<float>(cols);
-        if (!o.exact_only && cols->n_columns > 0 && fast_eligible(ca, kind_mask, oa)) {
+        const ColsArg<float> ca = to_cols<float>(cols, o);
+        if (!o.exact_only && cols->n_columns > 0 && fast_eligible(ca, kind_mask, oa, o)) {
             if (!ctx->scratch.count(stream) && ctx->scratch.size() >= kMaxScratchStreams) {
                 // bound the per-stream scratch map: drop the buffers of the other streams (after their work is done)
                 for (auto &kv : ctx->scratch) {
@@ -193,7 +194,7 @@ xp_status run_device(xp_context *ctx, const xp_columns *cols, int kind_mask,
         }
     }
     if (time_it) cudaEventRecord(ctx->ev0, stream);
-    launch_cape_cin<T>(to_cols<T>(cols), tb, o, kind_mask, oa, pa, ctx->d_flags, stream);
+    launch_cape_cin<T>(to_cols<T>(cols, o), tb, o, kind_mask, oa, pa, ctx->d_flags, stream);
     if (time_it) { cudaEventRecord(ctx->ev1, stream); ctx->ev_valid = true; }
     ctx->launches += (cols->n_columns > 0) ? 1 : 0;
     return check_cuda(ctx, cudaGetLastError(), "cape_cin kernel launch");

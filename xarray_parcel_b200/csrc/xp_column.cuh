@@ -30,6 +30,7 @@ struct Opts {
     int exact_only;      // 1: never take the float32 fast path
     int vote_mask;       // fast path: early-termination vote every (vote_mask + 1) iterations (tuning)
     double ml_depth, mu_depth;
+    int qmode = 0;       // fast paths: != 0 (141 / 162 = compat): the dewpoint array holds specific humidity (ColsArg::qmode)
 };
 
 // ---- moist-adiabat lookup (PF:525-607) -------------------------------------------------

@@ -114,17 +114,7 @@ __global__ void level_crossing_kernel(const __grid_constant__ CrossParams<T> prm
 template <typename T>
 __global__ void dewpoint_from_q_kernel(const T *p, const T *t, const T *q, int64_t n, int compat, T *out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double pp = (double)p[i], tt = (double)t[i], qq = (double)q[i];
-        const double w = qq / (1 - qq);                                  // mixing_ratio_from_specific_humidity
-        double e;
-        if (compat == 162) {
-            e = pp * w / (kEps + w);                                     // vapor_pressure(p, w)
-        } else {
-            const double es_t = sat_vapor_pressure(tt);
-            const double rh = w / (kEps * es_t / (pp - es_t));           // relative_humidity_from_mixing_ratio
-            e = rh * es_t;
-        }
-        out[i] = (T)dewpoint_from_e(e);
+        out[i] = (T)dewpoint_from_q((double)p[i], (double)t[i], (double)q[i], compat);
     }
 }
 

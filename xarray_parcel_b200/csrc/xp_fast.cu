@@ -151,7 +151,8 @@ struct StashSmem {
 
 // STAGED: 0 = environment recomputed in the sweep (default options: the v6 sweep of xp_fast6.cuh); 1 = environment
 // curve staged in shared memory + early termination; 2 = recomputed, with a first pass over all levels for the
-// early-termination bound; 3 = the v7 sweep of xp_fast7.cuh (default options only; shared memory as 0).
+// early-termination bound; 3 = the v7 sweep of xp_fast7.cuh (default options only; shared memory as 0); 4 = the v7 sweep
+// with specific humidity in place of the dewpoint, converted in the load stage (xp_columns.dewpoint_is_specific_humidity).
 template <unsigned KINDS, int MODE, int THREADS, int STAGED>
 __global__ void __launch_bounds__(THREADS, 1) suite_fast_kernel(const __grid_constant__ FastParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -210,10 +211,10 @@ __global__ void __launch_bounds__(THREADS, 1) suite_fast_kernel(const __grid_con
         const GlobalRd rd{prm.t + col, prm.td + col, prm.ls};
         fast::FResult res[3];
         unsigned redo;
-        if (MODE == 1 && STAGED == 3) {
+        if (MODE == 1 && (STAGED == 3 || STAGED == 4)) {
             StashSmem st{s_env + threadIdx.x, (int)blockDim.x, prm.stash_levels};
             const GlobalRd32 rd32{prm.t, prm.td, (uint32_t)col, (uint32_t)prm.ls};
-            redo = fast::suite_column7<KINDS>(rd32, cf, pr, prm.tb, prm.o, st, res);
+            redo = fast::suite_column7<KINDS, STAGED == 4>(rd32, cf, pr, prm.tb, prm.o, st, res);
         } else if (MODE == 1 && STAGED == 0) {
             // default options: the v6 sweep on the virtual-temperature table (xp_fast6.cuh); the shared
             // memory left after the table stashes T/Td of the lowest levels of every thread's column
@@ -293,7 +294,7 @@ struct ProfileWriter {
     }
 };
 
-template <unsigned KINDS, int MODE, bool PROFILE>
+template <unsigned KINDS, int MODE, bool PROFILE, bool QIN = false>
 __global__ void __launch_bounds__(kPColThreads, 2) suite_fast_pcol_kernel(const __grid_constant__ PColParams prm) {
     const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= prm.n) return;
@@ -302,10 +303,10 @@ __global__ void __launch_bounds__(kPColThreads, 2) suite_fast_pcol_kernel(const 
     unsigned redo;
     if (PROFILE) {
         ProfileWriter pw{prm.outs, col, prm.L};
-        redo = fast::suite_column_pcol<KINDS, MODE>(rd, prm.L, prm.tb, prm.o, pw, res);
+        redo = fast::suite_column_pcol<KINDS, MODE, QIN>(rd, prm.L, prm.tb, prm.o, pw, res);
     } else {
         fast::NoProfile np;
-        redo = fast::suite_column_pcol<KINDS, MODE>(rd, prm.L, prm.tb, prm.o, np, res);
+        redo = fast::suite_column_pcol<KINDS, MODE, QIN>(rd, prm.L, prm.tb, prm.o, np, res);
     }
     if (KINDS & 1u) store_fast(prm.outs[0], col, res[0]);
     if (KINDS & 2u) store_fast(prm.outs[1], col, res[1]);
@@ -397,8 +398,12 @@ static bool wants_profile(int kind_mask, const OutArg<float> *outs) {
     return false;
 }
 
-bool fast_eligible(const ColsArg<float> &cols, int kind_mask, const OutArg<float> *outs) {
+bool fast_eligible(const ColsArg<float> &cols, int kind_mask, const OutArg<float> *outs, const Opts &o) {
     if (cols.L < 3 || cols.n >= (int64_t)1 << 28) return false;
+    // specific humidity in place of the dewpoint: on a shared axis only the v7 sweep (default options) converts on load
+    // (and that sweep addresses the arrays with 32-bit element offsets)
+    if (cols.qmode && cols.p1d && (!(o.vtc && o.compat == 141 && o.pos_neg) ||
+                                   (uint64_t)cols.n + (uint64_t)cols.L * (uint64_t)cols.ls >= ((uint64_t)1 << 32))) return false;
     if (cols.p1d && cols.L > fast::kMaxLevels) return false;
     if (kind_mask & ~(kSB | kML | kMU)) return false;
     if (cols.p1d && wants_profile(kind_mask, outs)) return false;   // shared-axis kernel: scalars only
@@ -422,6 +427,7 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
     const int mode = (o.vtc && o.compat == 141 && o.pos_neg) ? 1 : 0;
     ListParams lp;
     lp.cols = cols; lp.tb = tb; lp.o = o;
+    lp.o.qmode = cols.qmode;
     for (int q = 0; q < 3; ++q) lp.outs[q] = outs[q];
     lp.list = list; lp.list_count = count; lp.capacity = cols.n; lp.flags = flags;
     if (!cols.p1d) {
@@ -429,6 +435,7 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
         PColParams pp;
         pp.p = cols.p; pp.t = cols.t; pp.td = cols.td; pp.n = cols.n; pp.ls = cols.ls; pp.pls = cols.pls;
         pp.L = cols.L; pp.tb = tb; pp.o = o;
+        pp.o.qmode = cols.qmode;
         for (int q = 0; q < 3; ++q) pp.outs[q] = outs[q];
         pp.list = list; pp.list_count = count;
         const unsigned g = (unsigned)((cols.n + kPColThreads - 1) / kPColThreads);
@@ -439,7 +446,7 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
         // searches the LCL level in chunks of independent loads it wins everywhere, so it is the default.
         const int pcol6 = fast_knobs().pcol6;
         const uint64_t span = (uint64_t)cols.n + (uint64_t)cols.L * (uint64_t)std::max(cols.ls, cols.pls);
-        if (pcol6 && ((kind_mask & 7) == 1 || pcol6 == 2) && mode && !profile && span < ((uint64_t)1 << 32)) {
+        if (pcol6 && !cols.qmode && ((kind_mask & 7) == 1 || pcol6 == 2) && mode && !profile && span < ((uint64_t)1 << 32)) {
             const int lv = kPCol6StashLevels;
             const size_t smem6 = (size_t)lv * 3 * sizeof(float) * kPCol6Threads;
             const unsigned g6 = (unsigned)((cols.n + kPCol6Threads - 1) / kPCol6Threads);
@@ -460,7 +467,10 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
         }
 #define XP_PCOL_CASE(K)                                                                          \
     case K:                                                                                      \
-        if (profile) {                                                                           \
+        if (cols.qmode) {   /* specific-humidity input: the run-time-option kernels */           \
+            if (profile) suite_fast_pcol_kernel<K, 0, true, true><<<g, kPColThreads, 0, stream>>>(pp);   \
+            else suite_fast_pcol_kernel<K, 0, false, true><<<g, kPColThreads, 0, stream>>>(pp);  \
+        } else if (profile) {                                                                           \
             if (mode) suite_fast_pcol_kernel<K, 1, true><<<g, kPColThreads, 0, stream>>>(pp);    \
             else suite_fast_pcol_kernel<K, 0, true><<<g, kPColThreads, 0, stream>>>(pp);         \
         } else {                                                                                 \
@@ -481,6 +491,7 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
     FastParams fp;
     fp.t = cols.t; fp.td = cols.td; fp.n = cols.n; fp.ls = cols.ls;
     fp.prep = prep; fp.coef = coef; fp.tb = tb; fp.o = o; fp.kinds = (unsigned)kind_mask;
+    fp.o.qmode = cols.qmode;
     for (int q = 0; q < 3; ++q) fp.outs[q] = outs[q];
     fp.list = list; fp.list_count = count;
     fp.dense_out = 1;
@@ -494,12 +505,13 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
     // shared memory: Prep | coefficient table | (staged) the environment curve of every thread
     const size_t smem_table = ((sizeof(Prep) + 127) & ~(size_t)127) + (size_t)cols.L * fast::kNI * sizeof(Coef);
     const size_t smem_env = (size_t)cols.L * kFastThreads * sizeof(float);
-    int staged = fast_knobs().staged;
+    int staged = cols.qmode ? 0 : fast_knobs().staged;      // specific-humidity input: the v7 sweep only
     if (staged == 1 && smem_table + smem_env + 256 > (size_t)227 * 1024) staged = 0;
     // the v6 sweep addresses T/Td with 32-bit element offsets; larger arrays take the generic sweep (variant 2)
     if (mode == 1 && staged == 0 && (uint64_t)cols.n + (uint64_t)cols.L * (uint64_t)cols.ls >= ((uint64_t)1 << 32)) staged = 2;
     const bool v6 = (mode == 1 && staged == 0);
-    if (v6 && fast_knobs().sweep == 7) staged = 3;
+    if (v6 && (fast_knobs().sweep == 7 || cols.qmode)) staged = cols.qmode ? 4 : 3;
+    if (cols.qmode && staged != 4) return -1;               // (fast_eligible keeps such calls away)
     fast_coef_kernel<<<cols.L, fast::kNI, 0, stream>>>(prep, tb.curves, coef, v6 ? 1 : 0);
     size_t smem = smem_table + (staged == 1 ? smem_env : 0);
     fp.stash_levels = 0;
@@ -529,6 +541,7 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
         if (staged == 1) { if (mode) XP_FAST_LAUNCH(K, 1, 1); else XP_FAST_LAUNCH(K, 0, 1); }     \
         else if (staged == 2) { if (mode) XP_FAST_LAUNCH(K, 1, 2); else XP_FAST_LAUNCH(K, 0, 2); }\
         else if (staged == 3) { XP_FAST_LAUNCH(K, 1, 3); }                                        \
+        else if (staged == 4) { XP_FAST_LAUNCH(K, 1, 4); }                                        \
         else { if (mode) XP_FAST_LAUNCH(K, 1, 0); else XP_FAST_LAUNCH(K, 0, 0); }                 \
         break;
     switch (kind_mask & 7) {

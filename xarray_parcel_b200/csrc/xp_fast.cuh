@@ -306,6 +306,28 @@ XP_HD double exp64_fast(double x) {
 }
 
 
+// ---- specific humidity -> dewpoint on load (xp_columns.dewpoint_is_specific_humidity; PF:1889, 1969) -------------------
+// metpy.calc.dewpoint_from_specific_humidity in the form of MetPy `compat` (see dewpoint_from_q in xp_math.cuh).
+// float32 for the levels of the sweep (|error| ~1e-5 K, far inside the decision margins: d Tv / d Td ~ 2e-4) ...
+XP_HD float f_td_from_q(float p, float t, float q, int compat) {
+    const float w = q * f_rcp(1.0f - q);
+    const float e = (compat == 162) ? p * w * f_rcp(kEpsF + w) : w * (p - f_es(t)) * (1.0f / kEpsF);
+    const float v = kLn2 * f_lg2(e * (1.0f / 6.112f));
+    return f_fma(243.5f * v, f_rcp(17.67f - v), 273.15f);
+}
+// ... float64 (branch-free helpers, ~3 ulp) for what the table cell of a parcel's LCL hangs on: the vapour pressure of
+// a level (mixed-layer mean) and the dewpoint of a parcel level.
+XP_HD double e64_from_q_fast(double p, double t, double q, int compat) {
+    const double w = q * rcp64(1.0 - q);
+    if (compat == 162) return p * w * rcp64(kEps + w);
+    const double es_t = kSat0 * exp64_fast(17.67 * (t - 273.15) * rcp64(t - 29.65));
+    return w * (p - es_t) * (1.0 / kEps);
+}
+XP_HD double td64_from_q_fast(double p, double t, double q, int compat) {
+    const double val = log64_fast(e64_from_q_fast(p, t, q, compat) * (1.0 / kSat0));
+    return 243.5 * val * rcp64(17.67 - val) + kZeroC;
+}
+
 // ---- LCL (metpy.calc.lcl fixed point, PF:644), cheaper float64 polish -------------------------------------------
 // Same scheme as lcl_fast (xp_fast.cuh): float32 Newton on F(q) = q - (tdp(v0 + ln q)/T)^3.5, then ONE float64
 // Newton step.  Here only the RESIDUAL F is evaluated in float64 (one log, reciprocals and a square root by

@@ -198,7 +198,7 @@ XP_HD void next_level7(const Rd &rd, Sweep6 &s, const Stash &stash, bool from_st
 // Mixed-phase iterations [it0, it1) for the parcels in KACT.
 template <unsigned KACT, bool GUARD_MU, class Rd, class CoefRow, class Stash>
 XP_HD void sweep_mixed7(const Rd &rd, Sweep7 &w, CoefRow &crow, const Stash &stash, bool from_stash, int it0, int it1, int nt,
-                        FParcel &sb, FParcel &ml, FParcel &mu) {
+                        int qmode, FParcel &sb, FParcel &ml, FParcel &mu) {
     Sweep6 &s = w.s;
     for (int it = it0; it < it1; ++it) {
         float t, td;
@@ -206,6 +206,7 @@ XP_HD void sweep_mixed7(const Rd &rd, Sweep7 &w, CoefRow &crow, const Stash &sta
         const float p_cur = s.lp[0], x_cur = s.lp[1], pk_cur = s.lp[2];
         w.h_prv = s.lp[3];
         s.lp += 4;
+        if (qmode && !from_stash) td = f_td_from_q(p_cur, t, td, qmode);              // the stash holds dewpoints already
         const float b_cur = f_env_tv7(t, td, p_cur);                                  // PF:839-843
         if (KACT & 1u) step7_mixed<false>(sb, it, w.itf, cubic_at(crow.at(sb.m), sb.f) - s.b_prv, f_fma(sb.c_dryv, pk_cur, -b_cur), x_cur, s.x_prv);
         if (KACT & 2u) step7_mixed<false>(ml, it, w.itf, cubic_at(crow.at(ml.m), ml.f) - s.b_prv, f_fma(ml.c_dryv, pk_cur, -b_cur), x_cur, s.x_prv);
@@ -220,7 +221,7 @@ XP_HD void sweep_mixed7(const Rd &rd, Sweep7 &w, CoefRow &crow, const Stash &sta
 // TOP the warp checks after every iteration whether it can stop (see sweep_top6); returns true if it did.
 template <unsigned KINDS, bool TOP, class Rd, class CoefRow>
 XP_HD bool sweep_above7(const Rd &rd, Sweep7 &w, CoefRow &crow, int it0, int it1, int nt, float stop_below,
-                        FParcel &sb, FParcel &ml, FParcel &mu) {
+                        int qmode, FParcel &sb, FParcel &ml, FParcel &mu) {
     Sweep6 &s = w.s;
     NoStash ns;
     for (int it = it0; it < it1; ++it) {
@@ -228,6 +229,7 @@ XP_HD bool sweep_above7(const Rd &rd, Sweep7 &w, CoefRow &crow, int it0, int it1
         next_level7(rd, s, ns, false, it, nt, t, td);
         const float p_cur = s.lp[0], h_cur = s.lp[3];
         s.lp += 4;
+        if (qmode) td = f_td_from_q(p_cur, t, td, qmode);
         const float b_cur = f_env_tv7(t, td, p_cur);                                  // PF:839-843
         const float h = w.h_prv, b = s.b_prv;
         if (KINDS & 1u) step7_above(sb, w.itf, cubic_at(crow.at(sb.m), sb.f) - b, h);
@@ -250,7 +252,8 @@ XP_HD bool sweep_above7(const Rd &rd, Sweep7 &w, CoefRow &crow, int it0, int it1
 
 // The whole suite for one column, default options.  Interfaces as suite_column6; `pr.plk[k][3]` must hold the
 // half-width 0.5 (ln p[k-1] - ln p[k]) of the interval below level k.
-template <unsigned KINDS, class Rd, class Cf, class Stash>
+// QIN: the dewpoint array may hold specific humidity (o.qmode says in which MetPy form); false compiles the conversion away.
+template <unsigned KINDS, bool QIN, class Rd, class Cf, class Stash>
 XP_HD unsigned suite_column7(const Rd &rd, const Cf &cf, const Prep &pr, const Tables &tb, const Opts &o,
                              Stash &stash, FResult res[3]) {
     unsigned redo = 0;
@@ -259,6 +262,9 @@ XP_HD unsigned suite_column7(const Rd &rd, const Cf &cf, const Prep &pr, const T
     const int n_low = max(1, max((KINDS & 4u) ? pr.K_mu : 0, (KINDS & 2u) ? pr.n_ml_w : 0));
     const uint32_t ls = rd.ls();
     const int n_stash = (stash.capacity() >= n_low) ? n_low : 0;
+    // != 0: the dewpoint array holds specific humidity (xp_columns.dewpoint_is_specific_humidity): every level is
+    // converted as it is loaded (float32), the parcels' dewpoints and the mixed-layer vapour pressures in float64
+    const int qm = QIN ? o.qmode : 0;
     Sweep7 w;
     Sweep6 &s = w.s;
     {
@@ -278,23 +284,25 @@ XP_HD unsigned suite_column7(const Rd &rd, const Cf &cf, const Prep &pr, const T
     int k_mu = 0;
     uint32_t off0 = rd.off0();
     for (int k = 1; k < n_low; ++k) rd.prefetch(off0 + (uint32_t)k * ls);
-    const float t_sfc = rd.ldT(off0), td_sfc = rd.ldTd(off0);
-    float t_nx = t_sfc, td_nx = td_sfc;
+    const float t_sfc = rd.ldT(off0), raw_sfc = rd.ldTd(off0);
+    float t_nx = t_sfc, td_nx = raw_sfc, mu_raw = raw_sfc;
 #pragma unroll(kPrepassUnroll)
     for (int k = 0; k < n_low; ++k) {
-        const float t = t_nx, td = td_nx;
+        const float t = t_nx, raw = td_nx;
         off0 += ls;
         if (k + 1 < n_low) { t_nx = rd.ldT(off0); td_nx = rd.ldTd(off0); }
+        const float p = pr.p[k];
+        const float td = qm ? f_td_from_q(p, t, raw, qm) : raw;
         if (k < n_stash) stash.put(k, t, td);
         nanacc = f_fma(t, 0.0f, f_fma(td, 0.0f, nanacc));
-        const float p = pr.p[k];
         const float e = f_es7(td);
         const float ipe = f_rcp(p - e);
         const float r = kEpsF * e * ipe;                 // saturation mixing ratio of the dewpoint (PF:258)
         if ((KINDS & 2u) && k < pr.n_ml_w) {
             // mixed_parcel PF:253-258 in float64 (see suite_column)
             const double tdd = (double)td;
-            const double e64 = kSat0 * exp64_fast(17.67 * (tdd - 273.15) * rcp64(tdd - 29.65));
+            const double e64 = qm ? e64_from_q_fast(pr.p64[k], (double)t, (double)raw, qm)
+                                  : kSat0 * exp64_fast(17.67 * (tdd - 273.15) * rcp64(tdd - 29.65));
             sum_th += pr.mlw[k] * ((double)t * pr.thfac[k]);
             sum_w += pr.mlw[k] * (kEps * e64 * rcp64(pr.p64[k] - e64));
         }
@@ -308,9 +316,18 @@ XP_HD unsigned suite_column7(const Rd &rd, const Cf &cf, const Prep &pr, const T
             v = f_fma(0.28f * r * kLn2, l2t - f_lg2(t_l), v);                       // + 0.28 r ln(T/t_l)
             v = f_fma(r * f_fma(0.448f, r, 1.0f), f_fma(3036.0f, it_l, -1.78f), v);
             nanacc = f_fma(v, 0.0f, nanacc);
-            if (v > best) { second = best; best = v; k_mu = k; mu_t = t; mu_td = td; }   // ties: larger p (PF:128)
+            if (v > best) { second = best; best = v; k_mu = k; mu_t = t; mu_td = td; mu_raw = raw; }   // ties: larger p (PF:128)
             else if (v > second) second = v;
         }
+    }
+    // the surface dewpoint (pre-pass level 0) and the parcels' dewpoints in float64
+    double td_sfc64, mu_td64;
+    float td_sfc;
+    if (qm) {
+        td_sfc64 = td64_from_q_fast(pr.p0, (double)t_sfc, (double)raw_sfc, qm);
+        td_sfc = (float)td_sfc64;
+    } else {
+        td_sfc = raw_sfc; td_sfc64 = (double)raw_sfc;
     }
     // the top of the column: coldest environment temperature above kTopCheckHpa (see suite_column6)
     float tmin_top = 1e30f, tmax_top = -1e30f;
@@ -334,10 +351,13 @@ XP_HD unsigned suite_column7(const Rd &rd, const Cf &cf, const Prep &pr, const T
     Setup6 u_sb, u_ml, u_mu;
     auto lev = [&](int k, float &t, float &td) {
         if (k < n_stash) stash.get(k, t, td);
-        else { const uint32_t o_ = rd.off0() + (uint32_t)k * ls; t = rd.ldT(o_); td = rd.ldTd(o_); }
+        else {
+            const uint32_t o_ = rd.off0() + (uint32_t)k * ls; t = rd.ldT(o_); td = rd.ldTd(o_);
+            if (qm) td = f_td_from_q(pr.p[k], t, td, qm);
+        }
     };
     double mp_t = 0.0, mp_td = 0.0;
-    if (KINDS & 1u) setup6_a(pr.p0, (double)t_sfc, (double)td_sfc, sb, u_sb);
+    if (KINDS & 1u) setup6_a(pr.p0, (double)t_sfc, td_sfc64, sb, u_sb);
     if (KINDS & 2u) {
         mp_t = sum_th * pr.exner0;                                               // PF:268-269
         {
@@ -348,7 +368,9 @@ XP_HD unsigned suite_column7(const Rd &rd, const Cf &cf, const Prep &pr, const T
     }
     if (KINDS & 4u) {
         if (!(best - second >= kThetaEMargin)) redo |= 4u;                       // argmax within float32 error
-        setup6_a(pr.p64[k_mu], (double)mu_t, (double)mu_td, mu, u_mu);
+        mu_td64 = qm ? td64_from_q_fast(pr.p64[k_mu], (double)mu_t, (double)mu_raw, qm) : (double)mu_td;
+        if (qm) mu_td = (float)mu_td64;
+        setup6_a(pr.p64[k_mu], (double)mu_t, mu_td64, mu, u_mu);
     }
     if (KINDS & 1u) setup6_b(lev, pr, tb, 1, sb, u_sb);
     if (KINDS & 2u) setup6_b(lev, pr, tb, pr.K_ml, ml, u_ml);
@@ -387,14 +409,14 @@ XP_HD unsigned suite_column7(const Rd &rd, const Cf &cf, const Prep &pr, const T
     const bool fs = n_stash > 0;
     const int it_c = fs ? max(it_b, min(n_stash, nt)) : it_b;     // guards and the stash end here
     const int it_abv = min(max(it_c, ka_max + 2), nt + 1);        // mixed phase: [1, it_abv), above phase: [it_abv, nt]
-    sweep_mixed7<KINDS & 5u, true>(rd, w, crow, stash, fs, 1, it_a, nt, sb, ml, mu);
-    sweep_mixed7<KINDS, true>(rd, w, crow, stash, fs, it_a, it_c, nt, sb, ml, mu);
-    sweep_mixed7<KINDS, false>(rd, w, crow, stash, false, it_c, min(it_abv, nt), nt, sb, ml, mu);
+    sweep_mixed7<KINDS & 5u, true>(rd, w, crow, stash, fs, 1, it_a, nt, qm, sb, ml, mu);
+    sweep_mixed7<KINDS, true>(rd, w, crow, stash, fs, it_a, it_c, nt, qm, sb, ml, mu);
+    sweep_mixed7<KINDS, false>(rd, w, crow, stash, false, it_c, min(it_abv, nt), nt, qm, sb, ml, mu);
     const int it_d = max(it_abv, min(pr.k_top + 1, nt));
     bool stopped = false;
     if (it_abv <= nt) {
-        sweep_above7<KINDS, false>(rd, w, crow, it_abv, min(it_d, nt), nt, 0.0f, sb, ml, mu);
-        stopped = sweep_above7<KINDS, true>(rd, w, crow, max(it_d, it_abv), nt, nt, tmin_top - kStopMargin, sb, ml, mu);
+        sweep_above7<KINDS, false>(rd, w, crow, it_abv, min(it_d, nt), nt, 0.0f, qm, sb, ml, mu);
+        stopped = sweep_above7<KINDS, true>(rd, w, crow, max(it_d, it_abv), nt, nt, tmin_top - kStopMargin, qm, sb, ml, mu);
     }
     // last iteration (it == nt): there is no level nt; every parcel not bound for the exact path is above its LCL
     if (!stopped) {

@@ -28,9 +28,10 @@ struct PColParcel : FParcel {
 };
 
 // Per-parcel set-up for per-column pressure.  Rd: float P(k), T(k), Td(k).
+// qm != 0: the dewpoint array holds specific humidity in that MetPy form (levels converted as they are read).
 template <class Rd>
 XP_HD void setup_parcel_pcol(const Rd &rd, int L, const Tables &tb, const Opts &o, double p0, double t0,
-                             double td0, float x_start, int knext, PColParcel &pc) {
+                             double td0, float x_start, int knext, PColParcel &pc, int qm = 0) {
     pc.bad = false;
     pc.kfirst = knext;
     if (!(t0 - td0 >= kSaturationMargin) || !(p0 > 0.0)) { pc.bad = true; t0 = 280.0; td0 = 270.0; p0 = 1000.0; }
@@ -94,8 +95,10 @@ XP_HD void setup_parcel_pcol(const Rd &rd, int L, const Tables &tb, const Opts &
     if (ka >= L || pkb == lp) { pc.bad = true; pc.ka = L; return; }            // LCL above the top / on a level
     float tb_, tdb;
     if (before_is_start) { tb_ = t0f; tdb = td0f; }
-    else { tb_ = rd.T(ka - 1); tdb = rd.Td(ka - 1); }
-    const float ta = rd.T(ka), tda = rd.Td(ka);
+    else { tb_ = rd.T(ka - 1); tdb = rd.Td(ka - 1); if (qm) tdb = f_td_from_q((float)pkb, tb_, tdb, qm); }
+    const float ta = rd.T(ka);
+    float tda = rd.Td(ka);
+    if (qm) tda = f_td_from_q((float)pka, ta, tda, qm);                // the array holds specific humidity
     const float x_l = kLn2 * f_lg2(lpf);
     float xb, xa, at;
     if (o.log_interp) { xb = kLn2 * f_lg2((float)pkb); xa = kLn2 * f_lg2((float)pka); at = x_l; }
@@ -142,14 +145,20 @@ XP_HD void parcel_iteration_pcol(PColParcel &c, int it, bool last, int j_cur, fl
 }
 
 // The suite for one column with its own pressure profile.  Returns the redo mask (see suite_column).
-template <unsigned KINDS, int MODE, class Rd, class Prof>
+// QIN: the dewpoint array may hold specific humidity (o.qmode); false compiles the conversion away.
+template <unsigned KINDS, int MODE, bool QIN, class Rd, class Prof>
 XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Opts &o, Prof &prof, FResult res[3]) {
     unsigned redo = 0, rows_exact = 0;       // rows_exact: kinds whose profile rows the exact path must rewrite too
     float nanacc = 0.0f;
     bool bad_axis = false;                 // pressure not finite / not strictly decreasing / outside the table
-    const float p_sfc = rd.P(0), t_sfc = rd.T(0), td_sfc = rd.Td(0);
-    nanacc = f_fma(p_sfc, 0.0f, f_fma(t_sfc, 0.0f, f_fma(td_sfc, 0.0f, nanacc)));
+    // qm != 0: the dewpoint array holds specific humidity (xp_columns.dewpoint_is_specific_humidity): levels are
+    // converted as they are loaded (float32), parcel dewpoints and mixed-layer vapour pressures in float64
+    const int qm = QIN ? o.qmode : 0;
+    const float p_sfc = rd.P(0), t_sfc = rd.T(0), raw_sfc = rd.Td(0);
     const double bottom = (double)p_sfc;                                         // PF:80 (pressure decreases upward)
+    const double td_sfc64 = qm ? td64_from_q_fast(bottom, (double)t_sfc, (double)raw_sfc, qm) : (double)raw_sfc;
+    const float td_sfc = (float)td_sfc64;
+    nanacc = f_fma(p_sfc, 0.0f, f_fma(t_sfc, 0.0f, f_fma(td_sfc, 0.0f, nanacc)));
     if (!(p_sfc <= 1100.0f)) bad_axis = true;
     // ---- pre-pass: mixed-layer means (float64) and most-unstable argmax over the lowest levels ------------
     const double top_ml = bottom - o.ml_depth;                                   // PF:84, PF:1636
@@ -157,13 +166,14 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
     double sum_th = 0.0, sum_w = 0.0, pp = bottom, thp = 0.0, wp = 0.0;
     int K_ml = L;
     bool ml_done = !(KINDS & 2u), mu_done = !(KINDS & 4u);
-    float best = -1e30f, second = -1e30f, mu_t = 0.0f, mu_td = 0.0f, mu_p = p_sfc;
+    float best = -1e30f, second = -1e30f, mu_t = 0.0f, mu_td = 0.0f, mu_p = p_sfc, mu_raw = raw_sfc;
     int k_mu = 0;
-    float p_n1 = p_sfc, t_n1 = t_sfc, td_n1 = td_sfc, p_n2 = 0.0f, t_n2 = 0.0f, td_n2 = 0.0f;
+    float p_n1 = p_sfc, t_n1 = t_sfc, td_n1 = raw_sfc, p_n2 = 0.0f, t_n2 = 0.0f, td_n2 = 0.0f;
     if (1 < L) { p_n2 = rd.P(1); t_n2 = rd.T(1); td_n2 = rd.Td(1); }
     for (int k = 0; k < L && !(ml_done && mu_done); ++k) {
         // levels are read two iterations ahead (this loop's float64 body hides one memory round trip, not two)
-        const float pf = p_n1, t = t_n1, td = td_n1;
+        const float pf = p_n1, t = t_n1, raw = td_n1;
+        const float td = qm ? f_td_from_q(pf, t, raw, qm) : raw;
         p_n1 = p_n2; t_n1 = t_n2; td_n1 = td_n2;
         if (k + 2 < L) { p_n2 = rd.P(k + 2); t_n2 = rd.T(k + 2); td_n2 = rd.Td(k + 2); }
         nanacc = f_fma(pf, 0.0f, f_fma(t, 0.0f, f_fma(td, 0.0f, nanacc)));
@@ -174,7 +184,8 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
             // (branch-free float64 exp / log and Newton reciprocals of xp_fast.cuh: ~3 ulp, a third of the
             //  instructions of the libm calls)
             const double tdd = (double)td;
-            const double e = kSat0 * exp64_fast(17.67 * (tdd - 273.15) * rcp64(tdd - 29.65));
+            const double e = qm ? e64_from_q_fast(p, (double)t, (double)raw, qm)
+                                : kSat0 * exp64_fast(17.67 * (tdd - 273.15) * rcp64(tdd - 29.65));
             const double th = (double)t * exp64_fast(-kKappa * log64_fast(p * 1e-3));   // PF:253
             const double w = kEps * e * rcp64(p - e);                            // PF:258
             if (p >= top_ml) {
@@ -213,7 +224,7 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
                 v = f_fma(0.28f * r * kLn2, l2t - f_lg2(t_l), v);
                 v = f_fma(r * f_fma(0.448f, r, 1.0f), f_fma(3036.0f, it_l, -1.78f), v);
                 nanacc = f_fma(v, 0.0f, nanacc);
-                if (v > best) { second = best; best = v; k_mu = k; mu_t = t; mu_td = td; mu_p = pf; }
+                if (v > best) { second = best; best = v; k_mu = k; mu_t = t; mu_td = td; mu_p = pf; mu_raw = raw; }
                 else if (v > second) second = v;
             }
         }
@@ -223,7 +234,7 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
     PColParcel sb, ml, mu;
     const float x_sfc = kLn2 * f_lg2(p_sfc);
     if (KINDS & 1u) {
-        setup_parcel_pcol(rd, L, tb, o, bottom, (double)t_sfc, (double)td_sfc, x_sfc, 1, sb);
+        setup_parcel_pcol(rd, L, tb, o, bottom, (double)t_sfc, td_sfc64, x_sfc, 1, sb, qm);
         res[0].par_p = p_sfc; res[0].par_t = t_sfc; res[0].par_td = td_sfc; res[0].shift = 0;
     }
     if (KINDS & 2u) {
@@ -231,12 +242,14 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
         double mp_t, mp_td;
         mixed_parcel_t_td(bottom, (1. / depth) * sum_th, (1. / depth) * sum_w, mp_t, mp_td);   // PF:161, 268-282
         if (!ml_done || K_ml < 1) { redo |= 2u; rows_exact |= 2u; K_ml = max(K_ml, 1); }   // no level above / NaN layer: exact path
-        setup_parcel_pcol(rd, L, tb, o, bottom, mp_t, mp_td, x_sfc, K_ml, ml);
+        setup_parcel_pcol(rd, L, tb, o, bottom, mp_t, mp_td, x_sfc, K_ml, ml, qm);
         res[1].par_p = p_sfc; res[1].par_t = (float)mp_t; res[1].par_td = (float)mp_td; res[1].shift = K_ml;
     }
     if (KINDS & 4u) {
         if (!(best - second >= kThetaEMargin)) { redo |= 4u; rows_exact |= 4u; }
-        setup_parcel_pcol(rd, L, tb, o, (double)mu_p, (double)mu_t, (double)mu_td, kLn2 * f_lg2(mu_p), k_mu + 1, mu);
+        const double mu_td64 = qm ? td64_from_q_fast((double)mu_p, (double)mu_t, (double)mu_raw, qm) : (double)mu_td;
+        if (qm) mu_td = (float)mu_td64;
+        setup_parcel_pcol(rd, L, tb, o, (double)mu_p, (double)mu_t, mu_td64, kLn2 * f_lg2(mu_p), k_mu + 1, mu, qm);
         res[2].par_p = mu_p; res[2].par_t = mu_t; res[2].par_td = mu_td; res[2].shift = k_mu;
     }
     // ---- the sweep ----------------------------------------------------------------------------------------
@@ -266,7 +279,10 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
     }
     const int Lq = L - shift;                         // levels from the first swept one's predecessor up
     float p_s = p_sfc, t_s = t_sfc, td_s = td_sfc;
-    if (shift > 0) { p_s = rd.P(shift); t_s = rd.T(shift); td_s = rd.Td(shift); }
+    if (shift > 0) {
+        p_s = rd.P(shift); t_s = rd.T(shift); td_s = rd.Td(shift);
+        if (qm) td_s = f_td_from_q(p_s, t_s, td_s, qm);
+    }
     EnvLevel e_prv = {p_s, t_s, td_s, 0.0f};
     float b_prv = 0.0f, x_prv = (shift > 0) ? kLn2 * f_lg2(p_s) : x_sfc, p_prv = p_s;
     float w_prv;
@@ -284,7 +300,9 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
     float p_nxt = Rd::ld(ppp), t_nxt = Rd::ld(tp), td_nxt = Rd::ld(tdp);
     for (int it = 1; it <= Lq; ++it) {
         const bool last = (it == Lq);
-        const float p_cur0 = p_nxt, t = t_nxt, td = td_nxt;
+        const float p_cur0 = p_nxt, t = t_nxt;
+        float td = td_nxt;
+        if (qm && !last) td = f_td_from_q(p_cur0, t, td, qm);
         ppp += pls; tp += ls; tdp += ls;
         if (it + 1 < Lq) { p_nxt = Rd::ld(ppp); t_nxt = Rd::ld(tp); td_nxt = Rd::ld(tdp); }
         float b_cur = 0.0f, x_cur = x_prv, pk_cur = 0.0f, p_cur = p_prv, w_cur = w_prv;

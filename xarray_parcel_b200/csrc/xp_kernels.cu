@@ -13,9 +13,13 @@ struct GlobalReader {
     const T *p, *t, *td;
     int64_t ls, pls;
     int L;
+    int qmode;          // != 0: td holds specific humidity (ColsArg::qmode): converted as the level is loaded, in float64
     __device__ __forceinline__ double P(int k) const { return (double)__ldg(p + (int64_t)k * pls); }
     __device__ __forceinline__ double Tk(int k) const { return (double)__ldg(t + (int64_t)k * ls); }
-    __device__ __forceinline__ double Td(int k) const { return (double)__ldg(td + (int64_t)k * ls); }
+    __device__ __forceinline__ double Td(int k) const {
+        const double raw = (double)__ldg(td + (int64_t)k * ls);
+        return qmode ? dewpoint_from_q(P(k), Tk(k), raw, qmode) : raw;          // PF:1889, 1969
+    }
 };
 
 template <typename T>
@@ -27,6 +31,7 @@ __device__ __forceinline__ GlobalReader<T> make_reader(const ColsArg<T> &c, int6
     r.ls = c.ls;
     r.pls = c.pls;
     r.L = c.L;
+    r.qmode = c.qmode;
     return r;
 }
 
@@ -144,9 +149,13 @@ struct StagedReader {
     const float *p, *t, *td;
     int ps, s;                  // element strides between levels (p: 1 for the shared axis)
     int L;
+    int qmode;                  // as GlobalReader
     __device__ __forceinline__ double P(int k) const { return (double)p[k * ps]; }
     __device__ __forceinline__ double Tk(int k) const { return (double)t[k * s]; }
-    __device__ __forceinline__ double Td(int k) const { return (double)td[k * s]; }
+    __device__ __forceinline__ double Td(int k) const {
+        const double raw = (double)td[k * s];
+        return qmode ? dewpoint_from_q(P(k), Tk(k), raw, qmode) : raw;
+    }
 };
 
 // One thread per (column, parcel kind) item.  STAGED: dynamic shared memory holds blockDim.x columns.
@@ -183,7 +192,7 @@ __global__ void __launch_bounds__(128, 3) suite_list_kernel(const __grid_constan
             }
             StagedReader sr;
             sr.p = prm.cols.p1d ? s_p : s_p + threadIdx.x; sr.ps = prm.cols.p1d ? 1 : nt;
-            sr.t = s_t + threadIdx.x; sr.td = s_td + threadIdx.x; sr.s = nt; sr.L = L;
+            sr.t = s_t + threadIdx.x; sr.td = s_td + threadIdx.x; sr.s = nt; sr.L = L; sr.qmode = prm.cols.qmode;
             run_column(sr, kind, prm.tb, prm.o, qnan(), qnan(), qnan(), r, p0, t0, td0, shift, np);
         } else {
             run_column(rd, kind, prm.tb, prm.o, qnan(), qnan(), qnan(), r, p0, t0, td0, shift, np);

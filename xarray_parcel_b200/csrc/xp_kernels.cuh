@@ -16,6 +16,7 @@ struct ColsArg {
     int64_t ls;         // level stride of t/td
     int64_t pls;        // level stride of p
     int p1d;            // pressure is a shared 1-D axis
+    int qmode;          // 0: td holds dewpoint; 141 / 162: td holds specific humidity, converted on load in that MetPy form
 };
 
 // Outputs of one parcel kind (any pointer may be null).
@@ -97,7 +98,7 @@ void launch_suite_list(const ListParams &lp, int sm_count, cudaStream_t stream);
 // Float32 fast path of the suite on a shared pressure axis (xp_fast.cu / xp_fast.cuh): prep +
 // coefficient + fast kernel + exact fix-up over the uncertain-column list, all on `stream`.
 // `scratch` must hold fast_scratch_bytes(n) bytes and must not be shared by launches in flight.
-bool fast_eligible(const ColsArg<float> &cols, int kind_mask, const OutArg<float> *outs);
+bool fast_eligible(const ColsArg<float> &cols, int kind_mask, const OutArg<float> *outs, const Opts &o);
 size_t fast_scratch_bytes(int64_t n);
 int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &o, int kind_mask,
                       const OutArg<float> *outs, void *scratch, uint32_t *flags, int sm_count,

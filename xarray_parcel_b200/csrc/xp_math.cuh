@@ -71,6 +71,23 @@ XP_HD double sat_mixing_ratio(double p, double t) {
 // metpy.calc.vapor_pressure(p, w) [PF:275]
 XP_HD double vapor_pressure(double p, double w) { return p * w / (kEps + w); }
 
+// metpy.calc.dewpoint_from_specific_humidity(p, T, q) as the reference calls it [PF:1889, 1969; parcel_test.py:
+// 432-436]: MetPy 1.4.1 goes through the relative humidity, MetPy >= 1.6 through the vapour pressure
+// (environment_changes_eval.ipynb:278).  Used by the pointwise kernel and by every column reader when the
+// dewpoint array of a call holds specific humidity (xp_columns.dewpoint_is_specific_humidity).
+XP_HD double dewpoint_from_q(double p, double t, double q, int compat) {
+    const double w = q / (1 - q);                                        // mixing_ratio_from_specific_humidity
+    double e;
+    if (compat == 162) {
+        e = p * w / (kEps + w);                                          // vapor_pressure(p, w)
+    } else {
+        const double es_t = sat_vapor_pressure(t);
+        const double rh = w / (kEps * es_t / (p - es_t));                // relative_humidity_from_mixing_ratio
+        e = rh * es_t;
+    }
+    return dewpoint_from_e(e);
+}
+
 // PF:684-710 mixing_ratio(T, Td, p): RH from dewpoint, then w from RH.
 XP_HD double mixing_ratio_t_td(double t, double td, double p, int compat) {
     double es_t = sat_vapor_pressure(t);

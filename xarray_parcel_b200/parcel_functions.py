@@ -298,7 +298,7 @@ def _profile_levels(kind, res, L):
 
 
 def _run(kind, pressure, temperature, dewpoint, vert_dim, vert_axis, device, profile, explicit=None,
-         depth=None, **kwargs):
+         depth=None, specific_humidity=False, **kwargs):
     lay, ctx, p, t, td = _prepare(pressure, temperature, dewpoint, vert_dim, vert_axis, device)
     _clear_flags(ctx)
     okw = _options(kwargs)
@@ -308,7 +308,8 @@ def _run(kind, pressure, temperature, dewpoint, vert_dim, vert_axis, device, pro
     ex = None
     if explicit is not None:
         ex = [lay.scalar_to_block(e, t.dtype).to(t.device) for e in explicit]
-    res = ctx.cape_cin(p, t, td, kinds=(kind,), options=opts, profile=profile, explicit=ex)[kind]
+    res = ctx.cape_cin(p, t, td, kinds=(kind,), options=opts, profile=profile, explicit=ex,
+                       specific_humidity=specific_humidity)[kind]
     _check_flags(ctx)
     cc = lay.dataset({"cape": lay.wrap_scalar(res["cape"], "cape"),
                       "cin": lay.wrap_scalar(res["cin"], "cin")})
@@ -667,15 +668,18 @@ def from_most_unstable_parcel(pressure, temperature, dewpoint, vert_dim="model_l
 
 
 def parcel_suite(pressure, temperature, dewpoint, vert_dim="model_level_number", vert_axis=0,
-                 device=None, mixed_layer_depth=100, most_unstable_depth=300, **kwargs):
+                 device=None, mixed_layer_depth=100, most_unstable_depth=300, specific_humidity=False, **kwargs):
     """Surface-based + mixed-layer + most-unstable CAPE/CIN/LCL/LFC/EL in ONE pass over the columns
     (the hot-path part of parcel_test.py:416-547 ``conv_properties_xarray``; no profile output).
-    Returns a Dataset with the reference's prefixed names: surface_*, mixed_100_*, max_*."""
+    Returns a Dataset with the reference's prefixed names: surface_*, mixed_100_*, max_*.
+    ``specific_humidity=True``: ``dewpoint`` holds specific humidity [kg/kg] -- model output (p, T, q) is consumed
+    directly, converted in the kernels' load stage (parcel_test.py:432-436 computes the dewpoint first)."""
     lay, ctx, p, t, td = _prepare(pressure, temperature, dewpoint, vert_dim, vert_axis, device)
     opts = _lib.make_options(mixed_layer_depth=mixed_layer_depth, most_unstable_depth=most_unstable_depth,
                              **_options(kwargs))
     _clear_flags(ctx)
-    res = ctx.cape_cin(p, t, td, kinds=("sb", "ml", "mu"), options=opts, profile=False)
+    res = ctx.cape_cin(p, t, td, kinds=("sb", "ml", "mu"), options=opts, profile=False,
+                       specific_humidity=specific_humidity)
     _check_flags(ctx)
     out = {}
     prefixes = {"sb": "surface", "ml": f"mixed_{int(mixed_layer_depth)}", "mu": "max"}
@@ -1104,6 +1108,10 @@ def _conv(dat, vert_dim, vert_axis, device, min_set, ignore_nans, metpy_compat):
         pass
     kw = dict(vert_dim=vert_dim, vert_axis=vert_axis, device=device)
     out = {}
+    # the lifting kernels read (p, T, q) themselves and convert q in their load stage (xp_columns.
+    # dewpoint_is_specific_humidity); `td` above is only what the reference hands back / what the indices need
+    q = dat["specific_humidity"]
+    lift = dict(kw, metpy_compat=metpy_compat, specific_humidity=True)
 
     def merge(ds):
         for k in ds:
@@ -1118,14 +1126,14 @@ def _conv(dat, vert_dim, vert_axis, device, min_set, ignore_nans, metpy_compat):
                                         description="Deep convective index using " + desc, **kw))
 
     if not min_set:
-        cc, prof, mu_parcel = most_unstable_cape_cin(p, t, td, depth=250, prefix="mu", metpy_compat=metpy_compat, **kw)
+        cc, prof, mu_parcel = most_unstable_cape_cin(p, t, q, depth=250, prefix="mu", **lift)
         parcel_block("mu", cc, prof, "most-unstable parcel in lowest 250 hPa.")
         out["mu_mixing_ratio"] = _pointwise("saturation_mixing_ratio", [mu_parcel["pressure"], mu_parcel["dewpoint"]],
                                             name="mu_mixing_ratio", device=device)   # PF:2047-2053
-    cc, prof, _ = mixed_layer_cape_cin(p, t, td, depth=100, prefix="mixed_100", metpy_compat=metpy_compat, **kw)
+    cc, prof, _ = mixed_layer_cape_cin(p, t, q, depth=100, prefix="mixed_100", **lift)
     parcel_block("mixed_100", cc, prof, "fully-mixed lowest 100 hPa parcel.")
     if not min_set:
-        cc, prof, _ = mixed_layer_cape_cin(p, t, td, depth=50, prefix="mixed_50", metpy_compat=metpy_compat, **kw)
+        cc, prof, _ = mixed_layer_cape_cin(p, t, q, depth=50, prefix="mixed_50", **lift)
         parcel_block("mixed_50", cc, prof, "fully-mixed lowest 50 hPa parcel.")
     out["lapse_rate_700_500"] = lapse_rate(p, t, dat["height_asl"], **kw)
     out["temp_500"] = isobar_temperature(p, t, 500, **kw)
