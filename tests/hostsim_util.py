@@ -8,7 +8,10 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "hostsim", "hostsim.cpp")
-BUILD = os.path.join(HERE, "hostsim", "_build")
+# XP_HOSTSIM_SANITIZE=1: AddressSanitizer + UndefinedBehaviorSanitizer build of the same per-column code (run the
+# CPU tests under LD_PRELOAD=$(gcc -print-file-name=libasan.so); tools/run_sanitizers.sh does it)
+SANITIZE = os.environ.get("XP_HOSTSIM_SANITIZE", "") not in ("", "0")
+BUILD = os.path.join(HERE, "hostsim", "_build_asan" if SANITIZE else "_build")
 LIB = os.path.join(BUILD, "libhostsim.so")
 CSRC = os.path.join(os.path.dirname(HERE), "xarray_parcel_b200", "csrc")
 
@@ -28,6 +31,8 @@ def build():
     # -ffp-contract=off: keep host arithmetic un-fused, like NumPy's
     cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++", SRC,
            "-o", LIB]
+    if SANITIZE:
+        cmd[1:2] = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-fno-sanitize-recover=undefined"]
     subprocess.run(cmd, check=True)
     return LIB
 

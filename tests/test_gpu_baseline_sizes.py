@@ -1,0 +1,148 @@
+"""GPU parity at the FULL sizes of the BASELINE.json configurations that test_gpu_parity.py only covered scaled down:
+
+* configs[2]  Aus400-shaped hourly step, 2.8 M columns x 70 model levels, surface-based + mixed-layer (100 hPa);
+* configs[4]  most-unstable parcel (lowest 300 hPa) with the full parcel_profile_with_lcl output, 10 M x 90
+              (the output-bound stress case: 6 profile arrays of 91 x 10 M float32 = 21.8 GB).
+
+At these sizes the oracle cannot see every column, so each test combines size-independent properties over ALL
+columns (bitwise determinism, sign constraints, LFC above the LCL, the NaN padding of the profile rows, row 0 == the
+parcel itself) with the oracle on a random sample of >= 20 000 of the SAME columns -- scalars and, for configs[4],
+every profile row.  Short columns entirely inside the mixed layer (L = 1..3) are compared too."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import parcel as op
+from xarray_parcel_b200 import _lib, synth
+from test_gpu_parity import FIELDS, _check, _np64, _oracle_suite, ctx, gpu_tables  # noqa: F401  (fixtures)
+
+pytestmark = pytest.mark.gpu
+SAMPLE = 20000
+PROFILE = ["pressure", "temperature", "virtual_temperature", "environment_temperature",
+           "environment_virtual_temperature", "environment_dewpoint"]
+
+
+def _bits(x):
+    return x.view(torch.int32)
+
+
+def _not_knife_edge(ora, prefix, t0=None, td0=None):
+    """Columns whose parcel is NOT saturated to the last bit.  For a parcel with T == Td the LCL is the parcel level
+    itself and the reference's LFC hinges on whether exp(log(p)) comes out one ulp below p in ITS libm (the crossing
+    at the duplicated LCL pressure counts as "above the LCL" only then, PF:1127-1132) -- rounding noise of the
+    platform, not something a different libm can reproduce ("knife-edge set"; the first run of
+    this test found such a column: CAPE 4203 vs 4284 J/kg, both the float32 and the float64 kernel on the
+    mathematically consistent side).  They are left out of the oracle comparison here; their number is bounded by the
+    generator's saturated fraction (3 %)."""
+    pt = ora[prefix + "parcel_temperature"] if t0 is None else t0
+    pd_ = ora[prefix + "parcel_dewpoint"] if td0 is None else td0
+    keep = ~(pt == pd_)
+    assert (~keep).mean() < 0.05
+    return keep
+
+
+def _sub(d, keep):
+    return {k: v[keep] for k, v in d.items()}
+
+
+def test_config2_aus400_step_sb_ml_full_size(ctx, gpu_tables):
+    n = 2_800_000
+    p, t, td = synth.model_level_columns(n, 70, seed=202, device="cuda")
+    r1 = ctx.cape_cin(p, t, td, kinds=("sb", "ml"))
+    r2 = ctx.cape_cin(p, t, td, kinds=("sb", "ml"))
+    for kind in ("sb", "ml"):
+        for f in FIELDS:
+            assert torch.equal(_bits(r1[kind][f]), _bits(r2[kind][f])), (kind, f, "not deterministic")
+        cape, cin = r1[kind]["cape"], r1[kind]["cin"]
+        fin = ~torch.isnan(cape)
+        assert bool((cape[fin] >= 0).all()) and bool((cin[~torch.isnan(cin)] <= 0).all())
+        lcl, lfc = r1[kind]["lcl_pressure"], r1[kind]["lfc_pressure"]
+        ok = ~torch.isnan(lfc)
+        assert bool((lfc[ok] <= lcl[ok]).all())
+        assert float((cape > 0).float().mean()) > 0.05
+    sel = torch.randperm(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))[:SAMPLE]
+    ora = _oracle_suite(p[:, sel], t[:, sel], td[:, sel], gpu_tables)
+    t0, td0 = _np64(t[0, sel], td[0, sel])
+    for kind in ("sb", "ml"):
+        keep = _not_knife_edge(ora, kind + "_", *((t0, td0) if kind == "sb" else (None, None)))
+        kt = torch.from_numpy(keep).cuda()
+        _check({f: r1[kind][f][sel][kt] for f in FIELDS}, _sub(ora, keep), kind + "_", "fast", what="configs[2] sample: ")
+    # number of levels inside the mixed layer (an integer output): bit-exact; a column without a surface has none
+    P = _np64(p[:, sel])[0]
+    with np.errstate(invalid="ignore"):
+        k_ml = np.where(np.isnan(P[0]), P.shape[0], (P >= (P[0] - 100.0)[None, :]).sum(0))
+    assert np.array_equal(r1["ml"]["level_shift"][sel].cpu().numpy(), k_ml)
+
+
+def test_config4_most_unstable_with_profile_rows_full_size(ctx, gpu_tables):
+    n, L = 10_000_000, 90
+    p, t, td = synth.model_level_columns(n, L, seed=404, device="cuda")
+    out = ctx.alloc_outputs(t, ("mu",), True, False)
+    r1 = ctx.cape_cin(p, t, td, kinds=("mu",), profile=True, out=out)["mu"]
+    torch.cuda.synchronize()
+    # checksums of the first run (per array: the sum of the float32 bit patterns as int64), then the same buffers again
+    names = FIELDS + ["profile_" + k for k in PROFILE]
+    sums = {k: int(_bits(r1[k]).long().sum()) for k in names}
+    shift1 = r1["level_shift"].clone()
+    r2 = ctx.cape_cin(p, t, td, kinds=("mu",), profile=True, out=out)["mu"]
+    torch.cuda.synchronize()
+    for k in names:
+        assert int(_bits(r2[k]).long().sum()) == sums[k], (k, "not deterministic")
+    assert torch.equal(shift1, r2["level_shift"])
+    # properties over all columns: row 0 is the parcel itself, rows past the lifted column are NaN padding
+    shift = r2["level_shift"].long()                                   # level of the most-unstable parcel
+    assert bool((shift >= 0).all()) and bool((shift <= L).all())               # L: no parcel (all-NaN column)
+    row0 = r2["profile_pressure"][0]
+    par = r2["parcel_pressure"]
+    same = (row0 == par) | (torch.isnan(row0) & torch.isnan(par))
+    assert bool(same.all())
+    n_rows = (L - shift) + 1                                           # levels from the parcel up + the LCL row
+    last = r2["profile_pressure"].gather(0, (n_rows - 1).clamp(max=L)[None, :])[0]
+    valid = ~torch.isnan(par)
+    assert bool((~torch.isnan(last[valid])).all()), "the top row of a lifted column is missing"
+    pad = torch.arange(L + 1, device="cuda")[:, None] >= n_rows[None, :]
+    for k in PROFILE:
+        assert bool(torch.isnan(r2["profile_" + k][pad]).all()), (k, "padding rows are not NaN")
+    del pad
+    # the oracle on a sample of the same columns: scalars and every profile row
+    sel = torch.randperm(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))[:SAMPLE]
+    P, T, D = _np64(p[:, sel], t[:, sel], td[:, sel])
+    opts = op.Options(op.MoistLapseLUT(gpu_tables), lcl_mode="converged")
+    cc, prof, ul = op.most_unstable_cape_cin(P, T, D, opts)
+    ora = {"mu_" + f: (cc[f] if f in cc else prof[f]) for f in FIELDS}
+    keep = _not_knife_edge(ora, "mu_", ul["temperature"], ul["dewpoint"])
+    kt = torch.from_numpy(keep).cuda()
+    _check({f: r2[f][sel][kt] for f in FIELDS}, _sub(ora, keep), "mu_", "fast", what="configs[4] sample: ")
+    nrow = prof["pressure"].shape[0]
+    for k in PROFILE:
+        a = r2["profile_" + k][:, sel].double().cpu().numpy()[:, keep]
+        b = prof[k][:, keep]
+        assert np.array_equal(np.isnan(a[:nrow]), np.isnan(b)), (k, "NaN pattern of the rows differs from the oracle")
+        assert np.isnan(a[nrow:]).all(), k
+        ok = ~np.isnan(b)
+        assert np.allclose(a[:nrow][ok], b[ok], rtol=3e-6, atol=0), (k, float(np.abs(a[:nrow][ok] - b[ok]).max()))
+
+
+def test_mixed_layer_on_columns_shorter_than_the_layer(ctx, gpu_tables):
+    """L = 1..3: the whole column lies inside the lowest 100 hPa.  The reference then averages over a few hPa and
+    divides by the 100 hPa depth (PF:158-161): a mixed parcel of ~0-40 K whose LCL 'fixed point' is ~1e6-1e9 hPa.
+    Meaningless, but it is what the reference computes -- parcel, LCL and CAPE/CIN must still agree with the oracle."""
+    p, t, td = synth.model_level_columns(512, 30, seed=3, nan_columns=0.0, allnan_columns=0.0)
+    p, t, td = p.double(), t.double(), td.double()
+    for L in (1, 2, 3):
+        ps, ts, tds = p[:L].contiguous(), t[:L].contiguous(), td[:L].contiguous()
+        ora = _oracle_suite(ps, ts, tds, gpu_tables)
+        res = ctx.cape_cin(ps.cuda(), ts.cuda(), tds.cuda(), kinds=("ml",))["ml"]
+        for f, key in (("parcel_temperature", "ml_parcel_temperature"), ("parcel_dewpoint", "ml_parcel_dewpoint"),
+                       ("cape", "ml_cape"), ("cin", "ml_cin")):
+            a, b = res[f].cpu().numpy(), ora[key]
+            assert np.array_equal(np.isnan(a), np.isnan(b)), (L, f)
+            ok = ~np.isnan(b)
+            assert np.allclose(a[ok], b[ok], rtol=1e-9, atol=1e-9), (L, f)
+        if L >= 2:
+            assert float(np.nanmax(ora["ml_parcel_temperature"])) < 100.0        # the documented nonsense parcel
+            # its LCL iteration has no fixed point: both sides end somewhere absurd (1e6 .. 1e10 hPa, or NaN when
+            # an iterate overflows) -- the one output that is not comparable for these columns
+            for v in (res["lcl_pressure"].cpu().numpy(), ora["ml_lcl_pressure"]):
+                assert np.all(np.isnan(v) | (v > 1e5)), L

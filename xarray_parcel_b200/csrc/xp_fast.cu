@@ -75,10 +75,11 @@ struct GlobalRd {
 struct GlobalRd32 {
     const float *t, *td;
     uint32_t col, lstride;
+    uint64_t limit;                       // elements addressable from the bases (XP_BOUNDS_CHECK builds only)
     __device__ __forceinline__ uint32_t off0() const { return col; }
     __device__ __forceinline__ uint32_t ls() const { return lstride; }
-    __device__ __forceinline__ float ldT(uint32_t off) const { return __ldg(t + off); }
-    __device__ __forceinline__ float ldTd(uint32_t off) const { return __ldg(td + off); }
+    __device__ __forceinline__ float ldT(uint32_t off) const { XP_CHECK(off < limit); return __ldg(t + off); }
+    __device__ __forceinline__ float ldTd(uint32_t off) const { XP_CHECK(off < limit); return __ldg(td + off); }
     __device__ __forceinline__ void prefetch(uint32_t off) const {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(t + off));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(td + off));
@@ -87,15 +88,28 @@ struct GlobalRd32 {
 
 struct SmemCoefRow {
     const Coef *row;
+#ifdef XP_BOUNDS_CHECK
+    const Coef *lo, *hi;                  // the table in shared memory
+#endif
     __device__ __forceinline__ void advance() { row += fast::kNI; }
     __device__ __forceinline__ Coef at(int m) const {
+#ifdef XP_BOUNDS_CHECK
+        XP_CHECK(m >= 0 && m < fast::kNI && row + m >= lo && row + m < hi);
+#endif
         const float4 v = *reinterpret_cast<const float4 *>(row + m);
         return Coef{v.x, v.y, v.z, v.w};
     }
 };
 struct SmemCoef {
     const Coef *base;
-    __device__ __forceinline__ SmemCoefRow row(int k) const { return SmemCoefRow{base + k * fast::kNI}; }
+    int rows;                             // levels held
+    __device__ __forceinline__ SmemCoefRow row(int k) const {
+#ifdef XP_BOUNDS_CHECK
+        return SmemCoefRow{base + k * fast::kNI, base, base + (size_t)rows * fast::kNI};
+#else
+        return SmemCoefRow{base + k * fast::kNI};
+#endif
+    }
 };
 
 __device__ __forceinline__ void store_fast(const OutArg<float> &o, int64_t col, const fast::FResult &r) {
@@ -145,8 +159,14 @@ struct StashSmem {
     float *base;
     int stride, cap;
     __device__ __forceinline__ int capacity() const { return cap; }
-    __device__ __forceinline__ void put(int k, float t, float td) { base[(2 * k) * stride] = t; base[(2 * k + 1) * stride] = td; }
-    __device__ __forceinline__ void get(int k, float &t, float &td) const { t = base[(2 * k) * stride]; td = base[(2 * k + 1) * stride]; }
+    __device__ __forceinline__ void put(int k, float t, float td) {
+        XP_CHECK(k >= 0 && k < cap);
+        base[(2 * k) * stride] = t; base[(2 * k + 1) * stride] = td;
+    }
+    __device__ __forceinline__ void get(int k, float &t, float &td) const {
+        XP_CHECK(k >= 0 && k < cap);
+        t = base[(2 * k) * stride]; td = base[(2 * k + 1) * stride];
+    }
 };
 
 // STAGED: 0 = environment recomputed in the sweep (default options: the v6 sweep of xp_fast6.cuh); 1 = environment
@@ -202,7 +222,7 @@ __global__ void __launch_bounds__(THREADS, 1) suite_fast_kernel(const __grid_con
                 : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0u) : "memory");
         }
     }
-    const SmemCoef cf{s_coef};
+    const SmemCoef cf{s_coef, pr.n_table};
     float *s_env = reinterpret_cast<float *>(s_coef + (size_t)pr.n_table * fast::kNI);
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < prm.n; base += (int64_t)gridDim.x * blockDim.x) {
         // lanes past the end redo the last column (warp-uniform votes need every lane) and do not store
@@ -213,13 +233,13 @@ __global__ void __launch_bounds__(THREADS, 1) suite_fast_kernel(const __grid_con
         unsigned redo;
         if (MODE == 1 && (STAGED == 3 || STAGED == 4)) {
             StashSmem st{s_env + threadIdx.x, (int)blockDim.x, prm.stash_levels};
-            const GlobalRd32 rd32{prm.t, prm.td, (uint32_t)col, (uint32_t)prm.ls};
+            const GlobalRd32 rd32{prm.t, prm.td, (uint32_t)col, (uint32_t)prm.ls, (uint64_t)prm.n + (uint64_t)(pr.L - 1) * (uint64_t)prm.ls};
             redo = fast::suite_column7<KINDS, STAGED == 4>(rd32, cf, pr, prm.tb, prm.o, st, res);
         } else if (MODE == 1 && STAGED == 0) {
             // default options: the v6 sweep on the virtual-temperature table (xp_fast6.cuh); the shared
             // memory left after the table stashes T/Td of the lowest levels of every thread's column
             StashSmem st{s_env + threadIdx.x, (int)blockDim.x, prm.stash_levels};
-            const GlobalRd32 rd32{prm.t, prm.td, (uint32_t)col, (uint32_t)prm.ls};
+            const GlobalRd32 rd32{prm.t, prm.td, (uint32_t)col, (uint32_t)prm.ls, (uint64_t)prm.n + (uint64_t)(pr.L - 1) * (uint64_t)prm.ls};
             redo = fast::suite_column6<KINDS>(rd32, cf, pr, prm.tb, prm.o, st, res);
         } else if (STAGED == 1) {
             EnvSmem env{s_env + threadIdx.x, (int)blockDim.x};

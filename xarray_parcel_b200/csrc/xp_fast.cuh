@@ -295,11 +295,13 @@ XP_HD double exp64_fast(double x) {
     for (int i = 1; i < 12; ++i) p = fma(p, r, kExpC[i]);
     p = fma(p, r, 1.0); p = fma(p, r, 1.0);
 #if defined(__CUDACC__)
-    const long long ni = (long long)__double2int_rn(n);
-    return __longlong_as_double(__double_as_longlong(p) + (ni << 52));
+    // (the exponent is added as an UNSIGNED shift: shifting a negative signed value left is undefined behaviour in
+    //  C++17 -- UBSan flags it in the host build of this code -- while the two's-complement sum is what is wanted)
+    const unsigned long long ni = (unsigned long long)(long long)__double2int_rn(n);
+    return __longlong_as_double((long long)((unsigned long long)__double_as_longlong(p) + (ni << 52)));
 #else
-    long long pb; std::memcpy(&pb, &p, 8);
-    pb += ((long long)n) << 52;
+    unsigned long long pb; std::memcpy(&pb, &p, 8);
+    pb += ((unsigned long long)(long long)n) << 52;
     double out; std::memcpy(&out, &pb, 8);
     return out;
 #endif

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "xp_column.cuh"
 
@@ -85,12 +86,42 @@ struct ListParams {
 constexpr unsigned kListMuIsSb = 8u;
 constexpr unsigned kListRowsOk = 1u;         // entry >> 28: the float32 profile rows of this item stand (scalars only)
 
+// -DXP_BOUNDS_CHECK (the libxparcel_check.so variant that __graft_entry__.build() also produces; compute-sanitizer is
+// closed on the B200 pool): every computed index into the shared-memory stash / coefficient table, the uncertain-column
+// list and the T/Td arrays of the fast kernels is checked on the device; a violation prints its site and traps, which
+// the host sees as a failed launch (tests/test_gpu_bounds_check.py).
+#ifdef XP_BOUNDS_CHECK
+#define XP_CHECK(cond)                                                                                     \
+    do {                                                                                                   \
+        if (!(cond)) {                                                                                     \
+            printf("XP_BOUNDS_CHECK failed: %s at %s:%d (block %d thread %d)\n", #cond, __FILE__, __LINE__, \
+                   (int)blockIdx.x, (int)threadIdx.x);                                                     \
+            __trap();                                                                                      \
+        }                                                                                                  \
+    } while (0)
+#else
+#define XP_CHECK(cond) ((void)0)
+#endif
+
 // Append the items of one column (redo: bits 0-2 kinds, bit 3 = kListMuIsSb, bits 4-6 = rows-ok per kind).
 __device__ __forceinline__ void push_redo(uint32_t *list, uint32_t *count, int64_t capacity, int64_t col,
                                           unsigned redo) {
-    if (redo & 1u) list[atomicAdd(count + 0, 1u)] = (uint32_t)col | ((redo & kListMuIsSb) << 28) | (((redo >> 4) & 1u) << 28);
-    if (redo & 2u) list[capacity + atomicAdd(count + 1, 1u)] = (uint32_t)col | (((redo >> 5) & 1u) << 28);
-    if (redo & 4u) list[2 * capacity + atomicAdd(count + 2, 1u)] = (uint32_t)col | (((redo >> 6) & 1u) << 28);
+    XP_CHECK(col >= 0 && col < capacity);
+    if (redo & 1u) {
+        const uint32_t i = atomicAdd(count + 0, 1u);
+        XP_CHECK((int64_t)i < capacity);
+        list[i] = (uint32_t)col | ((redo & kListMuIsSb) << 28) | (((redo >> 4) & 1u) << 28);
+    }
+    if (redo & 2u) {
+        const uint32_t i = atomicAdd(count + 1, 1u);
+        XP_CHECK((int64_t)i < capacity);
+        list[capacity + i] = (uint32_t)col | (((redo >> 5) & 1u) << 28);
+    }
+    if (redo & 4u) {
+        const uint32_t i = atomicAdd(count + 2, 1u);
+        XP_CHECK((int64_t)i < capacity);
+        list[2 * capacity + i] = (uint32_t)col | (((redo >> 6) & 1u) << 28);
+    }
     atomicAdd(count + 3, 1u);
 }
 void launch_suite_list(const ListParams &lp, int sm_count, cudaStream_t stream);
