@@ -56,6 +56,8 @@ def parse_args():
                     help="columns of the workload timed on the CPU oracle (0 = skip)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--ref-columns", type=int, default=0, help="--impl reference: columns per step")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra lines of the default run (other BASELINE configs, float64 I/O, pageable e2e)")
     return ap.parse_args()
 
 
@@ -91,6 +93,18 @@ def algorithmic_bytes(spec, elt=4):
     if spec["profile"]:
         per_col_out += 6 * (L + 1) * elt * len(spec["kinds"])
     return b_in, per_col_out * N
+
+
+def config_dict(spec):
+    """The `config` of the JSON line -- identical in the B200 arm and in --impl reference (same workload; the
+    reference arm times a bounded SAMPLE of it per step and says so in cpu_baseline.sample)."""
+    b_in, _ = algorithmic_bytes(spec)
+    return {"workload": spec["name"], "columns_per_gpu": spec["N"], "levels": spec["L"],
+            "parcels": list(spec["kinds"]), "io_dtype": "f32",
+            "pressure": "shared 1-D axis" if spec["p1d"] else "per column",
+            "profile_rows": bool(spec["profile"]),
+            "l2": f"inputs {b_in / 1e6:.0f} MB per step > 126 MB L2, no flush needed",
+            "sharding": "column blocks, one per GPU, no collective"}
 
 
 # ------------------------------------------------------------------------------- clocks
@@ -238,8 +252,8 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": spec["name"], "columns_per_step": n_cols, "levels": spec["L"],
-                       "parcels": list(spec["kinds"])},
+            "config": config_dict(spec),
+            "sample_columns_per_step": n_cols,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -337,6 +351,11 @@ def run_b200(args):
     e2e_check = float(torch.nan_to_num(r[first]["cape"]).double().sum())
     dev_check = float(torch.nan_to_num(outs[first][1][0]).double().sum())
 
+    # ---- extras of the default single-GPU run: the other BASELINE configs, float64 I/O, pageable e2e ------------
+    extras = None
+    if rank == 0 and world == 1 and args.workload == "era5_suite" and not args.no_extras:
+        extras = run_extras(args, ctx, spec, p, t, td, opts, hp, ht, htd, houts)
+
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and args.cpu_sample > 0:
@@ -369,15 +388,10 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if n_exact >= 0 else "f64",
             "data": "synthetic",
-            "config": {"workload": spec["name"], "columns_per_gpu": spec["N"], "levels": spec["L"],
-                       "arithmetic": ("float32 sweep + float64 LCL/mixed-layer means; columns with a decision "
-                                      "inside the float32 margin recomputed in float64" if n_exact >= 0
-                                      else "float64"),
-                       "parcels": list(kinds), "io_dtype": "f32",
-                       "pressure": "shared 1-D axis" if spec["p1d"] else "per column",
-                       "l2": f"inputs {b_in / 1e6:.0f} MB per step > 126 MB L2, no flush needed",
-                       "sharding": "column blocks, one per GPU, no collective",
-                       "host_cpus_rank0": (f"{len(cpus)} cores next to the GPU (NVML affinity)" if cpus else "inherited")},
+            "config": config_dict(spec),
+            "arithmetic": ("float32 sweep + float64 LCL/mixed-layer means; columns with a decision "
+                           "inside the float32 margin recomputed in float64" if n_exact >= 0 else "float64"),
+            "host_cpus_rank0": (f"{len(cpus)} cores next to the GPU (NVML affinity)" if cpus else "inherited"),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "timer": "host wall clock around xp_suite(mem=HOST), max over ranks",
                     "checksum_matches_device_run": abs(e2e_check - dev_check) <= 1e-6 * max(1.0, abs(dev_check))},
@@ -394,9 +408,90 @@ def run_b200(args):
             "reference_assert_flags": flags,
             "exact_path_columns": n_exact,
         }
+        if extras:
+            line["extras"] = extras
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _time_device(fn, steps, warmup):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def run_extras(args, ctx, spec, p, t, td, opts, hp, ht, htd, houts):
+    """Extra measurements of the default run (rank 0, one GPU; every one a few seconds):
+      other_configs  the model-level BASELINE configs ([1] 1 M x 70 SB, [2] 2.8 M x 70 SB+ML, [4] 10 M x 90 MU + profile
+                     rows): columns/s with inputs resident in HBM and the fraction of their own HBM roofline;
+      f64_io         the same ERA5 suite with float64 inputs and outputs (the reference's dtype): exact float64 kernel;
+      e2e_pageable   the suite through the reference-facing Python function (parcel_functions.parcel_suite) from
+                     PAGEABLE NumPy arrays -- what an xarray user holds -- result Dataset on the host."""
+    import numpy as np
+    import torch
+    out = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak = float(json.load(f)["hbm_gbs"])
+    except Exception:
+        peak = 6650.0
+    others = {}
+    for wl in ("model70_sb", "model70_sb_ml", "model90_mu_profile"):
+        a2 = argparse.Namespace(**vars(args))
+        a2.workload, a2.columns = wl, 0
+        sp = workload_spec(a2)
+        try:
+            q = make_inputs(sp, 1234, p.device)
+            o2 = ctx.alloc_outputs(q[1], sp["kinds"], profile=sp["profile"], fields=BENCH_FIELDS, shift=False)
+            ms = _time_device(lambda: ctx.cape_cin(*q, kinds=sp["kinds"], options=opts, out=o2), 10, 3)
+            bi, bo = algorithmic_bytes(sp)
+            others[wl] = {"config": config_dict(sp), "value": sp["N"] / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                          "roofline_frac": (bi + bo) / (ms * 1e-3) / 1e9 / peak,
+                          "bytes_per_column": (bi + bo) / sp["N"], "exact_path_columns": ctx.last_exact_count()}
+            del q, o2
+        except Exception as e:
+            others[wl] = {"error": repr(e)}
+        torch.cuda.empty_cache()
+    out["other_configs"] = others
+    try:                                      # float64 I/O: 1/4 of the columns (the exact kernel is ~30x slower)
+        n64 = max(1, spec["N"] // 4)
+        p64 = p.double() if p.dim() == 1 else p[:, :n64].double().contiguous()
+        t64, td64 = t[:, :n64].double().contiguous(), td[:, :n64].double().contiguous()
+        o64 = ctx.alloc_outputs(t64, spec["kinds"], profile=False, fields=BENCH_FIELDS, shift=False)
+        ms = _time_device(lambda: ctx.cape_cin(p64, t64, td64, kinds=spec["kinds"], options=opts, out=o64), 3, 1)
+        bi, bo = algorithmic_bytes(dict(spec, N=n64), elt=8)
+        out["f64_io"] = {"columns": n64, "value": n64 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                         "roofline_frac": (bi + bo) / (ms * 1e-3) / 1e9 / peak,
+                         "kernel": "xp::cape_cin_kernel<double> (float64 exact path)"}
+        del p64, t64, td64, o64
+    except Exception as e:
+        out["f64_io"] = {"error": repr(e)}
+    try:                                      # pageable NumPy in, host Dataset out, through the public function
+        import xarray_parcel_b200.parcel_functions as pf
+        P, T, D = [np.array(x.numpy()) for x in (hp, ht, htd)]          # fresh pageable copies
+        pf.parcel_suite(P, T, D, vert_axis=0)
+        t0 = time.perf_counter()
+        n_rep = 3
+        for _ in range(n_rep):
+            ds = pf.parcel_suite(P, T, D, vert_axis=0)
+        dt = (time.perf_counter() - t0) / n_rep
+        out["e2e_pageable"] = {"value": spec["N"] / dt, "unit": UNIT, "seconds_per_call": dt,
+                               "api": "parcel_functions.parcel_suite(numpy float32 arrays, pageable) -> Dataset of "
+                                      "NumPy arrays; includes the driver's staging of pageable memory and the "
+                                      "allocation of the result arrays",
+                               "variables": len(ds)}
+    except Exception as e:
+        out["e2e_pageable"] = {"error": repr(e)}
+    return out
 
 
 _JSON_OUT = None

@@ -21,9 +21,13 @@
  *    Decision-critical arithmetic is float64 inside the kernels either way.
  *  - mem = XP_MEM_DEVICE: pointers are device pointers on the context's device and the
  *    call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default).
- *    mem = XP_MEM_HOST: pointers are host pointers; the library stages column blocks
- *    through pinned buffers (H2D, kernel, D2H overlapped) and returns when outputs are
- *    complete.
+ *    mem = XP_MEM_HOST: pointers are host pointers; the library streams column blocks
+ *    through three device slots on three streams (H2D, kernel, D2H of different blocks
+ *    overlap) and returns when the outputs are complete.  The copies are issued straight
+ *    from / to the caller's buffers: page-locked (pinned, cudaHostAlloc / cudaHostRegister)
+ *    buffers copy asynchronously at PCIe speed; pageable buffers work too, but the driver
+ *    then stages every copy through its own bounce buffers, synchronously (measured:
+ *    bench.py extras.e2e_pageable vs e2e).
  *  - Reference `assert`s that depend on data (PF:131 'Vertical pressures are not unique',
  *    PF:1149 'Top temperature is NaN.') are reported through xp_take_flags().
  */

@@ -8,6 +8,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -35,6 +36,11 @@ struct xp_context {
     cudaStream_t slot_stream[kSlots] = {nullptr, nullptr, nullptr};
     void *slot_buf[kSlots] = {nullptr, nullptr, nullptr};
     size_t slot_bytes = 0;
+    // page-locked mirrors of the slots: bounce buffers for callers whose host arrays are PAGEABLE (what NumPy /
+    // xarray users hold).  Allocated on the first such call.
+    void *slot_pin[kSlots] = {nullptr, nullptr, nullptr};
+    size_t slot_pin_bytes = 0;
+    int host_threads = 8;
     // fast-path scratch (prep, coefficient table, uncertain-column list), one per stream in use
     struct Scratch { void *ptr = nullptr; size_t bytes = 0; };
     std::map<cudaStream_t, Scratch> scratch;
@@ -202,6 +208,42 @@ xp_status run_device(xp_context *ctx, const xp_columns *cols, int kind_mask,
 
 size_t elt_size(int dtype) { return dtype == XP_F64 ? 8 : 4; }
 
+// ---- pageable host memory ------------------------------------------------------------------------------------
+// A copy engine can only read page-locked memory.  Given a pageable pointer the driver stages the copy through its
+// own small bounce buffer, synchronously (measured on the B200 box: 13.7 GB/s instead of 55 GB/s, and no overlap
+// with the kernels).  run_host therefore stages such arrays itself: host threads copy each column block between the
+// caller's arrays and a page-locked mirror of the device slot (46 GB/s measured), the DMA runs from / to the
+// mirror, and the host copy of one block overlaps the transfers and kernels of the others.
+bool is_pageable(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+struct RowCopy { char *dst; const char *src; size_t width, dpitch, spitch; int rows; };
+
+// memcpy of row sets on `nthreads` host threads (rows are cut into <= 4 MB pieces dealt round-robin)
+void parallel_copy(const std::vector<RowCopy> &jobs, int nthreads) {
+    struct Piece { char *d; const char *s; size_t n; };
+    std::vector<Piece> pieces;
+    const size_t kPiece = (size_t)4 << 20;
+    for (const RowCopy &j : jobs)
+        for (int r = 0; r < j.rows; ++r)
+            for (size_t o = 0; o < j.width; o += kPiece)
+                pieces.push_back({j.dst + (size_t)r * j.dpitch + o, j.src + (size_t)r * j.spitch + o,
+                                  std::min(kPiece, j.width - o)});
+    if (pieces.empty()) return;
+    nthreads = std::max(1, std::min<int>(nthreads, (int)pieces.size()));
+    auto work = [&](int t) {
+        for (size_t i = t; i < pieces.size(); i += nthreads) std::memcpy(pieces[i].d, pieces[i].s, pieces[i].n);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+}
+
 // Host-resident columns: stream column blocks through the device (H2D, kernel, D2H on
 // kSlots streams so copies of one block overlap the kernel of another).
 xp_status run_host(xp_context *ctx, const xp_columns *cols, int kind_mask,
@@ -247,6 +289,34 @@ xp_status run_host(xp_context *ctx, const xp_columns *cols, int kind_mask,
     }
     for (int s = 0; s < xp_context::kSlots; ++s)
         if (!ctx->slot_stream[s]) XP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->slot_stream[s], cudaStreamNonBlocking));
+    // pageable caller arrays are staged through page-locked mirrors of the slots (see is_pageable above)
+    bool stage_in = is_pageable(cols->temperature) || is_pageable(cols->dewpoint) || is_pageable(cols->pressure);
+    if ((kind_mask & kEX) && ex) stage_in = stage_in || is_pageable(ex->temperature);
+    bool stage_out = false;
+    for (int k = 0; k < 4; ++k) {
+        if (!((kind_mask >> k) & 1) || !outs[k]) continue;
+        const xp_parcel_out *q = outs[k];
+        const void *any[] = {q->cape, q->cin, q->lcl_pressure, q->lfc_pressure, q->el_pressure, q->parcel_pressure,
+                             q->level_shift, q->profile_pressure, q->profile_temperature};
+        for (const void *ptr : any)
+            if (ptr) { stage_out = stage_out || is_pageable(ptr); break; }
+    }
+    if ((stage_in || stage_out) && need > ctx->slot_pin_bytes) {
+        for (int s = 0; s < xp_context::kSlots; ++s) {
+            if (ctx->slot_pin[s]) { cudaFreeHost(ctx->slot_pin[s]); ctx->slot_pin[s] = nullptr; }
+        }
+        ctx->slot_pin_bytes = 0;
+        for (int s = 0; s < xp_context::kSlots; ++s) XP_CUDA(ctx, cudaHostAlloc(&ctx->slot_pin[s], need, cudaHostAllocDefault));
+        ctx->slot_pin_bytes = need;
+    }
+    // outputs of a block that wait in the page-locked mirror of its slot until the slot's stream has drained
+    std::vector<RowCopy> pending_out[xp_context::kSlots];
+    auto retire = [&](int s) -> xp_status {
+        if (!stage_in && !stage_out) return XP_OK;
+        XP_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));       // the mirror is free again / its outputs are in
+        if (!pending_out[s].empty()) { parallel_copy(pending_out[s], ctx->host_threads); pending_out[s].clear(); }
+        return XP_OK;
+    };
 
     if ((kind_mask & kEX) && (!ex || !ex->pressure || !ex->temperature || !ex->dewpoint))
         return fail(ctx, XP_ERR_INVALID_ARGUMENT, "explicit parcel arrays are required");
@@ -266,6 +336,9 @@ xp_status run_host(xp_context *ctx, const xp_columns *cols, int kind_mask,
         const int64_t n = std::min<int64_t>(C, N - c0);
         cudaStream_t st = ctx->slot_stream[slot];
         char *base = (char *)ctx->slot_buf[slot];
+        char *pin = (char *)ctx->slot_pin[slot];
+        { const xp_status rs = retire(slot); if (rs != XP_OK) return rs; }
+        std::vector<RowCopy> in_jobs;
         size_t off = 0;
         auto carve = [&](size_t bytes) { char *p = base + off; off += (bytes + 255) & ~(size_t)255; return p; };
         // the slot's previous block must be fully drained (its D2H copies are on the same stream,
@@ -275,19 +348,18 @@ xp_status run_host(xp_context *ctx, const xp_columns *cols, int kind_mask,
         dc.n_columns = n;
         dc.level_stride = n;
         char *dT = carve((size_t)L * n * es), *dTd = carve((size_t)L * n * es), *dP;
-        XP_CUDA(ctx, cudaMemcpy2DAsync(dT, n * es, ht + c0 * es, cols->level_stride * es, n * es, L,
-                                       cudaMemcpyHostToDevice, st));
-        XP_CUDA(ctx, cudaMemcpy2DAsync(dTd, n * es, htd + c0 * es, cols->level_stride * es, n * es, L,
-                                       cudaMemcpyHostToDevice, st));
+        // a host array [rows][width] with pitch `spitch` -> the device carve `d` (contiguous rows)
+        struct H2D { char *d; const char *h; size_t width, spitch; int rows; };
+        std::vector<H2D> h2d;
+        h2d.push_back({dT, ht + c0 * es, (size_t)n * es, (size_t)cols->level_stride * es, L});
+        h2d.push_back({dTd, htd + c0 * es, (size_t)n * es, (size_t)cols->level_stride * es, L});
         if (cols->pressure_is_1d) {
             dP = carve((size_t)L * es);
-            XP_CUDA(ctx, cudaMemcpy2DAsync(dP, es, hp, cols->pressure_level_stride * es, es, L,
-                                           cudaMemcpyHostToDevice, st));
+            h2d.push_back({dP, hp, es, (size_t)cols->pressure_level_stride * es, L});
             dc.pressure_level_stride = 1;
         } else {
             dP = carve((size_t)L * n * es);
-            XP_CUDA(ctx, cudaMemcpy2DAsync(dP, n * es, hp + c0 * es, cols->pressure_level_stride * es,
-                                           n * es, L, cudaMemcpyHostToDevice, st));
+            h2d.push_back({dP, hp + c0 * es, (size_t)n * es, (size_t)cols->pressure_level_stride * es, L});
             dc.pressure_level_stride = n;
         }
         dc.pressure = dP; dc.temperature = dT; dc.dewpoint = dTd;
@@ -297,8 +369,22 @@ xp_status run_host(xp_context *ctx, const xp_columns *cols, int kind_mask,
             const void **dst[3] = {&dex.pressure, &dex.temperature, &dex.dewpoint};
             for (int i = 0; i < 3; ++i) {
                 char *d = carve((size_t)n * es);
-                XP_CUDA(ctx, cudaMemcpyAsync(d, (const char *)src[i] + c0 * es, n * es, cudaMemcpyHostToDevice, st));
+                h2d.push_back({d, (const char *)src[i] + c0 * es, (size_t)n * es, 0, 1});
                 *dst[i] = d;
+            }
+        }
+        if (stage_in) {
+            // caller -> page-locked mirror (host threads), then ONE contiguous DMA per array
+            for (const H2D &c : h2d) in_jobs.push_back({pin + (c.d - base), c.h, c.width, c.width, c.spitch, c.rows});
+            parallel_copy(in_jobs, ctx->host_threads);
+            for (const H2D &c : h2d)
+                XP_CUDA(ctx, cudaMemcpyAsync(c.d, pin + (c.d - base), c.width * c.rows, cudaMemcpyHostToDevice, st));
+        } else {
+            for (const H2D &c : h2d) {
+                if (c.rows == 1)
+                    XP_CUDA(ctx, cudaMemcpyAsync(c.d, c.h, c.width, cudaMemcpyHostToDevice, st));
+                else
+                    XP_CUDA(ctx, cudaMemcpy2DAsync(c.d, c.width, c.h, c.spitch, c.width, c.rows, cudaMemcpyHostToDevice, st));
             }
         }
         // device-side outputs mirror the host layout per block
@@ -353,14 +439,24 @@ xp_status run_host(xp_context *ctx, const xp_columns *cols, int kind_mask,
                             : run_device<double>(ctx, &dc, kind_mask, douts, &dex, o, st, false);
         if (stt != XP_OK) return stt;
         for (const Copy &c : copies) {
-            if (c.rows == 1)
+            if (stage_out) {
+                // device -> page-locked mirror now; mirror -> caller when the slot is retired
+                XP_CUDA(ctx, cudaMemcpyAsync(pin + (c.d - base), c.d, c.width * c.rows, cudaMemcpyDeviceToHost, st));
+                pending_out[slot].push_back({c.h, pin + (c.d - base), c.width, c.rows == 1 ? c.width : c.hpitch, c.width, c.rows});
+            } else if (c.rows == 1) {
                 XP_CUDA(ctx, cudaMemcpyAsync(c.h, c.d, c.width, cudaMemcpyDeviceToHost, st));
-            else
+            } else {
                 XP_CUDA(ctx, cudaMemcpy2DAsync(c.h, c.hpitch, c.d, c.width, c.width, c.rows,
                                                cudaMemcpyDeviceToHost, st));
+            }
         }
     }
-    for (int s = 0; s < xp_context::kSlots; ++s) XP_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
+    // drain in block order: the slot after the last one used holds the oldest block in flight
+    for (int i = 0; i < xp_context::kSlots; ++i) {
+        const int s = (slot + i) % xp_context::kSlots;
+        XP_CUDA(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
+        if (!pending_out[s].empty()) { parallel_copy(pending_out[s], ctx->host_threads); pending_out[s].clear(); }
+    }
     return XP_OK;
 }
 
@@ -416,6 +512,11 @@ xp_status xp_create(int device, xp_context **out_ctx) {
     DeviceGuard guard(device);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (const char *ev = getenv("XP_FAST_VOTE_MASK")) ctx->vote_mask = atoi(ev) & 15;
+    {
+        const unsigned hc = std::thread::hardware_concurrency();
+        ctx->host_threads = (int)std::max(1u, std::min(8u, hc ? hc : 1u));
+        if (const char *ev = getenv("XP_HOST_THREADS")) ctx->host_threads = std::max(1, std::min(64, atoi(ev)));
+    }
     if (const char *ev = getenv("XP_HOST_BLOCK_MB")) {
         const int mb = atoi(ev);
         if (mb >= 1 && mb <= 4096) ctx->host_block_mb = mb;
@@ -440,6 +541,7 @@ void xp_destroy(xp_context *ctx) {
         cudaFree(ctx->d_flags);
         for (int s = 0; s < xp_context::kSlots; ++s) {
             if (ctx->slot_buf[s]) cudaFree(ctx->slot_buf[s]);
+            if (ctx->slot_pin[s]) cudaFreeHost(ctx->slot_pin[s]);
             if (ctx->slot_stream[s]) cudaStreamDestroy(ctx->slot_stream[s]);
         }
         for (auto &kv : ctx->scratch) cudaFree(kv.second.ptr);
