@@ -177,19 +177,23 @@ XP_HD void sweep_finish7(const FParcel &s, const Cf &cf, const Prep &pr, const O
 
 // Shared per-level state of the v7 sweep (the T/Td pipeline of Sweep6 plus the half-width of the last interval).
 struct Sweep7 {
-    Sweep6 s;
+    Sweep6 s;                             // t_n1 / td_n1: the next global level; off / k_pf: the level after t_n2
+    float t_n2, td_n2;                    // the level after that (two levels in flight: the r2a profile had 30 % of
+                                          // the above-phase loop waiting on a one-level-ahead load)
     float h_prv;                          // half-width of the interval (it-2, it-1)
     float itf;                            // float(it)
 };
 
 // One level of T/Td: from the stash or from the global prefetch pipeline (as sweep_segment6).
 template <class Rd, class Stash>
-XP_HD void next_level7(const Rd &rd, Sweep6 &s, const Stash &stash, bool from_stash, int it, int nt, float &t, float &td) {
+XP_HD void next_level7(const Rd &rd, Sweep7 &w, const Stash &stash, bool from_stash, int it, int nt, float &t, float &td) {
+    Sweep6 &s = w.s;
     if (from_stash) {
         stash.get(it, t, td);
     } else {
         t = s.t_n1; td = s.td_n1;
-        if (s.k_pf < nt) { s.t_n1 = rd.ldT(s.off); s.td_n1 = rd.ldTd(s.off); }    // one level ahead
+        s.t_n1 = w.t_n2; s.td_n1 = w.td_n2;
+        if (s.k_pf < nt) { w.t_n2 = rd.ldT(s.off); w.td_n2 = rd.ldTd(s.off); }    // two levels ahead
         if (s.k_pf + kL2Ahead < nt) rd.prefetch(s.off + kL2Ahead * s.ls);
         s.off += s.ls; ++s.k_pf;
     }
@@ -202,7 +206,7 @@ XP_HD void sweep_mixed7(const Rd &rd, Sweep7 &w, CoefRow &crow, const Stash &sta
     Sweep6 &s = w.s;
     for (int it = it0; it < it1; ++it) {
         float t, td;
-        next_level7(rd, s, stash, from_stash, it, nt, t, td);
+        next_level7(rd, w, stash, from_stash, it, nt, t, td);
         const float p_cur = s.lp[0], x_cur = s.lp[1], pk_cur = s.lp[2];
         w.h_prv = s.lp[3];
         s.lp += 4;
@@ -224,9 +228,11 @@ XP_HD bool sweep_above7(const Rd &rd, Sweep7 &w, CoefRow &crow, int it0, int it1
                         int qmode, FParcel &sb, FParcel &ml, FParcel &mu) {
     Sweep6 &s = w.s;
     NoStash ns;
+    // (unrolling this loop by two -- so that the load pipeline rotates through registers without moves -- was
+    //  measured slower: 1.352 vs 1.277 ms per step)
     for (int it = it0; it < it1; ++it) {
         float t, td;
-        next_level7(rd, s, ns, false, it, nt, t, td);
+        next_level7(rd, w, ns, false, it, nt, t, td);
         const float p_cur = s.lp[0], h_cur = s.lp[3];
         s.lp += 4;
         if (qmode) td = f_td_from_q(p_cur, t, td, qmode);
@@ -270,12 +276,13 @@ XP_HD unsigned suite_column7(const Rd &rd, const Cf &cf, const Prep &pr, const T
     {
         const int k0 = (n_stash > 0) ? n_stash : 1;          // first level the sweep reads from global memory
         s.off = rd.off0() + (uint32_t)k0 * ls; s.ls = ls;
-        s.t_n1 = s.td_n1 = 0.0f;
+        s.t_n1 = s.td_n1 = w.t_n2 = w.td_n2 = 0.0f;
         if (k0 < nt) { s.t_n1 = rd.ldT(s.off); s.td_n1 = rd.ldTd(s.off); }
+        if (k0 + 1 < nt) { w.t_n2 = rd.ldT(s.off + ls); w.td_n2 = rd.ldTd(s.off + ls); }
 #pragma unroll
-        for (int j = 1; j <= kL2Ahead; ++j)
+        for (int j = 2; j <= kL2Ahead + 1; ++j)
             if (k0 + j < nt) rd.prefetch(s.off + (uint32_t)j * ls);
-        s.off += ls; s.k_pf = k0 + 1;
+        s.off += 2 * ls; s.k_pf = k0 + 2;
     }
     for (int k = pr.k_top; k < nt; ++k) rd.prefetch(rd.off0() + (uint32_t)k * ls);
     // ---- pre-pass over the lowest levels: mixed-layer means (float64) and most-unstable argmax (as v6) ----
@@ -286,11 +293,15 @@ XP_HD unsigned suite_column7(const Rd &rd, const Cf &cf, const Prep &pr, const T
     for (int k = 1; k < n_low; ++k) rd.prefetch(off0 + (uint32_t)k * ls);
     const float t_sfc = rd.ldT(off0), raw_sfc = rd.ldTd(off0);
     float t_nx = t_sfc, td_nx = raw_sfc, mu_raw = raw_sfc;
+    float t_n2 = 0.0f, td_n2 = 0.0f;                         // levels are read two iterations ahead
+    off0 += ls;
+    if (1 < n_low) { t_n2 = rd.ldT(off0); td_n2 = rd.ldTd(off0); }
 #pragma unroll(kPrepassUnroll)
     for (int k = 0; k < n_low; ++k) {
         const float t = t_nx, raw = td_nx;
+        t_nx = t_n2; td_nx = td_n2;
         off0 += ls;
-        if (k + 1 < n_low) { t_nx = rd.ldT(off0); td_nx = rd.ldTd(off0); }
+        if (k + 2 < n_low) { t_n2 = rd.ldT(off0); td_n2 = rd.ldTd(off0); }
         const float p = pr.p[k];
         const float td = qm ? f_td_from_q(p, t, raw, qm) : raw;
         if (k < n_stash) stash.put(k, t, td);
@@ -331,12 +342,19 @@ XP_HD unsigned suite_column7(const Rd &rd, const Cf &cf, const Prep &pr, const T
     }
     // the top of the column: coldest environment temperature above kTopCheckHpa (see suite_column6)
     float tmin_top = 1e30f, tmax_top = -1e30f;
-    for (int k = pr.k_top; k < nt; ++k) {
-        const uint32_t o_ = rd.off0() + (uint32_t)k * ls;
-        const float t = rd.ldT(o_), td = rd.ldTd(o_);
-        nanacc = f_fma(t, 0.0f, f_fma(td, 0.0f, nanacc));
-        tmin_top = fminf(tmin_top, t);
-        tmax_top = fmaxf(tmax_top, t);
+    for (int k = pr.k_top; k < nt; k += 4) {               // four levels (eight loads) in flight per round trip
+        float tq[4], dq[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t o_ = rd.off0() + (uint32_t)min(k + j, nt - 1) * ls;
+            tq[j] = rd.ldT(o_); dq[j] = rd.ldTd(o_);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            nanacc = f_fma(tq[j], 0.0f, f_fma(dq[j], 0.0f, nanacc));
+            tmin_top = fminf(tmin_top, tq[j]);
+            tmax_top = fmaxf(tmax_top, tq[j]);
+        }
     }
     bool singular = false;
     if (nt > pr.k_top && !(f_es(tmax_top) < 0.5f * pr.p[nt - 1])) {
