@@ -129,7 +129,7 @@ struct Sweep {
 
     // Feed the next profile level (pressure p, parcel curve a, environment curve b).
     XP_HD void emit(double p, double a, double b, bool is_lcl_level) {
-        const double x = log(p);
+        const double x = xp_log(p);
         // bookkeeping that is per level, not per interval
         if (!isnan(p) && !(p >= min_p)) min_p = p;                      // PF:1329 pressure.min()
         if (!isnan(b)) any_b = true;
@@ -150,10 +150,10 @@ struct Sweep {
                 const double ix = (d1 * xp_ - d0 * x) / (d1 - d0);
                 const double frac = (ix - xp_) / (x - xp_);
                 const double iy = frac * (a - ap_) + ap_;
-                const double px = exp(ix);
+                const double px = xp_exp(ix);
                 // the same crossing seen by trap_around_zeros on y = A - B vs 0: PF:1225-1237
                 const double zy = frac * (d1 - d0) + d0;
-                const double zx = log(px);
+                const double zx = xp_log(px);
                 double area_lo = qnan(), area_hi = qnan();
                 if (!isnan(zy)) {                                       // PF:1241-1244 masks
                     area_lo = (d0 / 2) * fabs(xp_ - zx);                // PF:1256-1261 (before zero)
@@ -234,7 +234,7 @@ XP_HD void env_at_lcl(bool have_before, double pb, double tb_, double tdb,
                                            double &tv) {
     if (!have_before || !have_after) { t = td = tv = qnan(); return; }
     double cb, ca, at;
-    if (o.log_interp) { cb = log(pb); ca = log(pa); at = log(lcl_p); }
+    if (o.log_interp) { cb = xp_log(pb); ca = xp_log(pa); at = xp_log(lcl_p); }
     else { cb = pb; ca = pa; at = lcl_p; }
     t = interp_bracket(tb_, ta, cb, ca, at);
     td = interp_bracket(tdb, tda, cb, ca, at);

@@ -225,88 +225,12 @@ XP_HD float f_mixing_ratio(float es_t, float es_td, float p, int compat) {
 }
 XP_HD float f_tv(float t, float w) { return t * f_fma(0.608f, w, 1.0f); }
 
-// ---- float64 helpers without IEEE division / libm slow paths (fast paths only) ------------------------------------
-// Reciprocal and square root by float32-seeded Newton steps (~1e-16 relative), branch-free log / exp below.
-XP_HD double rcp64(double y) {
-    double r = (double)f_rcp((float)y);
-    r = fma(fma(-y, r, 1.0), r, r);
-    return fma(fma(-y, r, 1.0), r, r);
-}
-XP_HD double sqrt64(double y) {               // y ~ 1
-#if defined(__CUDACC__)
-    double r = (double)rsqrtf((float)y);
-#else
-    double r = 1.0 / sqrt(y);
-#endif
-    r = r * fma(-0.5 * y, r * r, 1.5);
-    r = r * fma(-0.5 * y, r * r, 1.5);
-    return y * r;
-}
-// Branch-free float64 log / exp for the arguments of this path (no special cases: x finite, log: x in
-// (1e-300, 1e300), exp: |x| < 700).  ~3 ulp -- the path needs 1e-12 relative -- in a third of the instructions
-// of the libm versions and, having no slow-path branches, they let the compiler interleave the three parcels.
-// Polynomial coefficients live in constant memory on the device: a DFMA takes a constant-bank operand directly,
-// whereas a float64 literal costs two uniform moves per use.
-#if defined(__CUDACC__)
-#define XP_CONST_TABLE static __constant__ double
-#else
-#define XP_CONST_TABLE static const double
-#endif
-XP_CONST_TABLE kLogC[11] = {1.0 / 23.0, 1.0 / 21.0, 1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0,
-                            1.0 / 9.0, 1.0 / 7.0, 1.0 / 5.0, 1.0 / 3.0};
-XP_CONST_TABLE kExpC[12] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
-                            1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
-XP_CONST_TABLE kLn2Split[2] = {6.93147180369123816490e-01, 1.90821492927058770002e-10};
-
-XP_HD double log64_fast(double x) {
-#if defined(__CUDACC__)
-    long long bits = __double_as_longlong(x);
-#else
-    long long bits; std::memcpy(&bits, &x, 8);
-#endif
-    int e = (int)(bits >> 52) - 1023;
-    long long mb = (bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL;        // mantissa in [1, 2)
-    const bool hi = (bits & 0x000fffffffffffffLL) > 0x0006a09e667f3bcdLL;       // > sqrt(2): use m/2, e+1
-    mb = hi ? (mb - 0x0010000000000000LL) : mb;
-    e = hi ? e + 1 : e;
-#if defined(__CUDACC__)
-    const double m = __longlong_as_double(mb);
-#else
-    double m; std::memcpy(&m, &mb, 8);
-#endif
-    const double f = m - 1.0;                                                   // [-0.293, 0.414]
-    const double s = f * rcp64(2.0 + f);                                        // |s| <= 0.172
-    const double z = s * s;
-    double p = kLogC[0];
-#pragma unroll
-    for (int i = 1; i < 11; ++i) p = fma(p, z, kLogC[i]);
-    const double lm = fma(2.0 * s * z, p, 2.0 * s);                             // ln m = 2 atanh(s)
-    const double ed = (double)e;
-    return fma(ed, kLn2Split[0], fma(ed, kLn2Split[1], lm));                    // + e ln2 (hi + lo)
-}
-XP_HD double exp64_fast(double x) {
-    const double kMagic = 6755399441055744.0;                                   // 1.5 * 2^52: rint by addition
-    const double tn = fma(x, 1.4426950408889634, kMagic);
-    const double n = tn - kMagic;
-    double r = fma(-n, kLn2Split[0], x);
-    r = fma(-n, kLn2Split[1], r);                                               // |r| <= 0.3466
-    double p = kExpC[0];                                                        // 1/13! ... 1/2!
-#pragma unroll
-    for (int i = 1; i < 12; ++i) p = fma(p, r, kExpC[i]);
-    p = fma(p, r, 1.0); p = fma(p, r, 1.0);
-#if defined(__CUDACC__)
-    // (the exponent is added as an UNSIGNED shift: shifting a negative signed value left is undefined behaviour in
-    //  C++17 -- UBSan flags it in the host build of this code -- while the two's-complement sum is what is wanted)
-    const unsigned long long ni = (unsigned long long)(long long)__double2int_rn(n);
-    return __longlong_as_double((long long)((unsigned long long)__double_as_longlong(p) + (ni << 52)));
-#else
-    unsigned long long pb; std::memcpy(&pb, &p, 8);
-    pb += ((unsigned long long)(long long)n) << 52;
-    double out; std::memcpy(&out, &pb, 8);
-    return out;
-#endif
-}
-
+// (rcp64 / sqrt64 / log64_fast / exp64_fast -- the branch-free float64 helpers -- live in xp_math.cuh: the exact
+//  fix-up over the uncertain-column list uses them too)
+using xp::exp64_fast;
+using xp::log64_fast;
+using xp::rcp64;
+using xp::sqrt64;
 
 // ---- specific humidity -> dewpoint on load (xp_columns.dewpoint_is_specific_humidity; PF:1889, 1969) -------------------
 // metpy.calc.dewpoint_from_specific_humidity in the form of MetPy `compat` (see dewpoint_from_q in xp_math.cuh).

@@ -4,86 +4,9 @@
 
 #include "xp_kernels.cuh"
 #include "xp_parcels.cuh"
+#include "xp_kernels_common.cuh"
 
 namespace xp {
-
-// ---- column readers --------------------------------------------------------------------
-template <typename T>
-struct GlobalReader {
-    const T *p, *t, *td;
-    int64_t ls, pls;
-    int L;
-    int qmode;          // != 0: td holds specific humidity (ColsArg::qmode): converted as the level is loaded, in float64
-    __device__ __forceinline__ double P(int k) const { return (double)__ldg(p + (int64_t)k * pls); }
-    __device__ __forceinline__ double Tk(int k) const { return (double)__ldg(t + (int64_t)k * ls); }
-    __device__ __forceinline__ double Td(int k) const {
-        const double raw = (double)__ldg(td + (int64_t)k * ls);
-        return qmode ? dewpoint_from_q(P(k), Tk(k), raw, qmode) : raw;          // PF:1889, 1969
-    }
-};
-
-template <typename T>
-__device__ __forceinline__ GlobalReader<T> make_reader(const ColsArg<T> &c, int64_t col) {
-    GlobalReader<T> r;
-    r.p = c.p1d ? c.p : c.p + col;
-    r.t = c.t + col;
-    r.td = c.td + col;
-    r.ls = c.ls;
-    r.pls = c.pls;
-    r.L = c.L;
-    r.qmode = c.qmode;
-    return r;
-}
-
-// ---- profile writer ------------------------------------------------------------------------
-template <typename T>
-struct ProfWriter {
-    T *p, *t, *tv, *et, *etv, *etd;
-    int64_t ls;
-    bool any;
-    __device__ __forceinline__ void put(int v, const ProfileRow &r) const {
-        if (!any) return;
-        const int64_t o = (int64_t)v * ls;
-        if (p) p[o] = (T)r.p;
-        if (t) t[o] = (T)r.t;
-        if (tv) tv[o] = (T)r.tv;
-        if (et) et[o] = (T)r.env_t;
-        if (etv) etv[o] = (T)r.env_tv;
-        if (etd) etd[o] = (T)r.env_td;
-    }
-};
-
-template <typename T>
-__device__ __forceinline__ ProfWriter<T> make_writer(const OutArg<T> &o, int64_t col) {
-    ProfWriter<T> w;
-    w.p = o.prof_p ? o.prof_p + col : nullptr;
-    w.t = o.prof_t ? o.prof_t + col : nullptr;
-    w.tv = o.prof_tv ? o.prof_tv + col : nullptr;
-    w.et = o.prof_et ? o.prof_et + col : nullptr;
-    w.etv = o.prof_etv ? o.prof_etv + col : nullptr;
-    w.etd = o.prof_etd ? o.prof_etd + col : nullptr;
-    w.ls = o.prof_ls;
-    w.any = w.p || w.t || w.tv || w.et || w.etv || w.etd;
-    return w;
-}
-
-template <typename T>
-__device__ __forceinline__ void store_result(const OutArg<T> &o, int64_t col, const ParcelResult &r,
-                                             double pp, double pt, double ptd, int shift) {
-    if (o.cape) o.cape[col] = (T)r.cape;
-    if (o.cin) o.cin[col] = (T)r.cin;
-    if (o.lcl_p) o.lcl_p[col] = (T)r.lcl_p;
-    if (o.lcl_t) o.lcl_t[col] = (T)r.lcl_t;
-    if (o.lcl_tv) o.lcl_tv[col] = (T)r.lcl_tv;
-    if (o.lfc_p) o.lfc_p[col] = (T)r.lfc_p;
-    if (o.lfc_t) o.lfc_t[col] = (T)r.lfc_t;
-    if (o.el_p) o.el_p[col] = (T)r.el_p;
-    if (o.el_t) o.el_t[col] = (T)r.el_t;
-    if (o.par_p) o.par_p[col] = (T)pp;
-    if (o.par_t) o.par_t[col] = (T)pt;
-    if (o.par_td) o.par_td[col] = (T)ptd;
-    if (o.shift) o.shift[col] = shift;
-}
 
 // ---- the fused kernel: parcel selection + lift, for every requested parcel kind ---------
 template <typename T>
@@ -134,92 +57,6 @@ void launch_cape_cin(const ColsArg<T> &cols, const Tables &tb, const Opts &o, in
     const int block = 128;
     const int64_t grid = (cols.n + block - 1) / block;
     cape_cin_kernel<T><<<(unsigned)grid, block, 0, stream>>>(prm);
-}
-
-// ---- exact fix-up over the list of columns handed over by the float32 fast paths -----------------------------
-struct NoProf {
-    __device__ __forceinline__ void put(int, const ProfileRow &) const {}
-};
-
-// A column staged once in shared memory ([level][thread], conflict-free): the exact path makes ~8 passes over a
-// column (layer bounds, theta-e search, LCL bracket, lift, ...), each of which would otherwise fetch the item's
-// scattered 32-byte sectors from DRAM again (ncu, 10 M x 90 most-unstable + profile rows: 27.5 GB read for
-// 375 k items = 73 KB per item against 1 KB of input).  A shared 1-D pressure axis is staged once per CTA.
-struct StagedReader {
-    const float *p, *t, *td;
-    int ps, s;                  // element strides between levels (p: 1 for the shared axis)
-    int L;
-    int qmode;                  // as GlobalReader
-    __device__ __forceinline__ double P(int k) const { return (double)p[k * ps]; }
-    __device__ __forceinline__ double Tk(int k) const { return (double)t[k * s]; }
-    __device__ __forceinline__ double Td(int k) const {
-        const double raw = (double)td[k * s];
-        return qmode ? dewpoint_from_q(P(k), Tk(k), raw, qmode) : raw;
-    }
-};
-
-// One thread per (column, parcel kind) item.  STAGED: dynamic shared memory holds blockDim.x columns.
-template <bool STAGED>
-__global__ void __launch_bounds__(128, 3) suite_list_kernel(const __grid_constant__ ListParams prm) {
-    extern __shared__ float s_cols[];
-    const uint32_t c0 = prm.list_count[0], c1 = prm.list_count[1], c2 = prm.list_count[2];
-    const uint64_t total = (uint64_t)c0 + c1 + c2;
-    const int L = prm.cols.L, nt = (int)blockDim.x;
-    float *s_t = s_cols, *s_td = s_cols + (size_t)L * nt, *s_p = s_cols + (size_t)2 * L * nt;
-    if (STAGED && prm.cols.p1d) {
-        for (int k = threadIdx.x; k < L; k += nt) s_p[k] = __ldg(prm.cols.p + (int64_t)k * prm.cols.pls);
-        __syncthreads();
-    }
-    for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
-         it += (uint64_t)gridDim.x * blockDim.x) {
-        const int kind = it < c0 ? 0 : (it < (uint64_t)c0 + c1 ? 1 : 2);
-        const uint64_t idx = it - (kind == 0 ? 0 : (kind == 1 ? c0 : (uint64_t)c0 + c1));
-        const uint32_t e = prm.list[(uint64_t)kind * prm.capacity + idx];
-        const bool also_mu = kind == 0 && ((e >> 28) & kListMuIsSb);
-        const int64_t col = (int64_t)(e & 0x0fffffffu);
-        const GlobalReader<float> rd = make_reader(prm.cols, col);
-        ParcelResult r;
-        double p0, t0, td0;
-        int shift;
-        ProfWriter<float> np = make_writer(prm.outs[kind], col);       // profile rows too, where requested ...
-        if ((e >> 28) & kListRowsOk) np.any = false;                   // ... unless the float32 rows stand
-        if (STAGED) {
-            // independent loads, all in flight at once; only this thread reads its slots back: no barrier needed
-            for (int k = 0; k < L; ++k) {
-                s_t[k * nt + threadIdx.x] = __ldg(rd.t + (int64_t)k * rd.ls);
-                s_td[k * nt + threadIdx.x] = __ldg(rd.td + (int64_t)k * rd.ls);
-                if (!prm.cols.p1d) s_p[k * nt + threadIdx.x] = __ldg(rd.p + (int64_t)k * rd.pls);
-            }
-            StagedReader sr;
-            sr.p = prm.cols.p1d ? s_p : s_p + threadIdx.x; sr.ps = prm.cols.p1d ? 1 : nt;
-            sr.t = s_t + threadIdx.x; sr.td = s_td + threadIdx.x; sr.s = nt; sr.L = L; sr.qmode = prm.cols.qmode;
-            run_column(sr, kind, prm.tb, prm.o, qnan(), qnan(), qnan(), r, p0, t0, td0, shift, np);
-        } else {
-            run_column(rd, kind, prm.tb, prm.o, qnan(), qnan(), qnan(), r, p0, t0, td0, shift, np);
-        }
-        for (int w = 0; w < (also_mu ? 2 : 1); ++w) store_result(prm.outs[w == 0 ? kind : 2], col, r, p0, t0, td0, shift);
-        if (r.flags && prm.flags) atomicOr(prm.flags, r.flags);
-    }
-}
-
-void launch_suite_list(const ListParams &lp, int sm_count, cudaStream_t stream) {
-    // staged variant when 3 CTAs per SM fit (the register budget allows no more): 128 threads, else 64
-    const size_t per_thread = (size_t)lp.cols.L * (lp.cols.p1d ? 2 : 3) * sizeof(float);
-    const size_t axis = lp.cols.p1d ? (size_t)lp.cols.L * sizeof(float) : 0;
-    const size_t budget = 72 * 1024;
-    static const bool staged = getenv("XP_LIST_STAGED") && atoi(getenv("XP_LIST_STAGED")) == 1;   // A/B knob, off by default until measured
-    int threads = 0;
-    if (!staged) threads = 0;
-    else if (per_thread * 128 + axis <= budget) threads = 128;
-    else if (per_thread * 64 + axis <= budget) threads = 64;
-    if (threads) {
-        const size_t smem = per_thread * threads + axis;
-        // per device, so set on every launch (a host-side call of about a microsecond)
-        cudaFuncSetAttribute(suite_list_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
-        suite_list_kernel<true><<<sm_count * 8 * (128 / threads), threads, smem, stream>>>(lp);
-    } else {
-        suite_list_kernel<false><<<sm_count * 8, 128, 0, stream>>>(lp);
-    }
 }
 
 // ---- individually exposed steps -------------------------------------------------------------

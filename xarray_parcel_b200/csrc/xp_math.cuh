@@ -53,13 +53,121 @@ XP_HD double qnan() {
 #endif
 }
 
+// ---- branch-free float64 helpers (no IEEE division, no libm slow paths) --------------------------------------------
+// Used by the float32 fast paths (float64 LCL polish, mixed-layer means) and, with XP_F64_FAST_MATH, by the exact
+// fix-up over the uncertain-column list (xp_list.cu), whose run time is the latency of ONE item's float64 chain.
+#if defined(__CUDACC__)
+XP_HD float xp_rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#else
+XP_HD float xp_rcp_approx(float x) { return 1.0f / x; }
+#endif
+// Reciprocal and square root by float32-seeded Newton steps (~1e-16 relative), branch-free log / exp below.
+XP_HD double rcp64(double y) {
+    double r = (double)xp_rcp_approx((float)y);
+    r = fma(fma(-y, r, 1.0), r, r);
+    return fma(fma(-y, r, 1.0), r, r);
+}
+XP_HD double sqrt64(double y) {               // y ~ 1
+#if defined(__CUDACC__)
+    double r = (double)rsqrtf((float)y);
+#else
+    double r = 1.0 / sqrt(y);
+#endif
+    r = r * fma(-0.5 * y, r * r, 1.5);
+    r = r * fma(-0.5 * y, r * r, 1.5);
+    return y * r;
+}
+// Branch-free float64 log / exp for the arguments of this path (no special cases: x finite, log: x in
+// (1e-300, 1e300), exp: |x| < 700).  ~3 ulp -- the path needs 1e-12 relative -- in a third of the instructions
+// of the libm versions and, having no slow-path branches, they let the compiler interleave the three parcels.
+// Polynomial coefficients live in constant memory on the device: a DFMA takes a constant-bank operand directly,
+// whereas a float64 literal costs two uniform moves per use.
+#if defined(__CUDACC__)
+#define XP_CONST_TABLE static __constant__ double
+#else
+#define XP_CONST_TABLE static const double
+#endif
+XP_CONST_TABLE kLogC[11] = {1.0 / 23.0, 1.0 / 21.0, 1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0,
+                            1.0 / 9.0, 1.0 / 7.0, 1.0 / 5.0, 1.0 / 3.0};
+XP_CONST_TABLE kExpC[12] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
+                            1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+XP_CONST_TABLE kLn2Split[2] = {6.93147180369123816490e-01, 1.90821492927058770002e-10};
+
+XP_HD double log64_fast(double x) {
+#if defined(__CUDACC__)
+    long long bits = __double_as_longlong(x);
+#else
+    long long bits; std::memcpy(&bits, &x, 8);
+#endif
+    int e = (int)(bits >> 52) - 1023;
+    long long mb = (bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL;        // mantissa in [1, 2)
+    const bool hi = (bits & 0x000fffffffffffffLL) > 0x0006a09e667f3bcdLL;       // > sqrt(2): use m/2, e+1
+    mb = hi ? (mb - 0x0010000000000000LL) : mb;
+    e = hi ? e + 1 : e;
+#if defined(__CUDACC__)
+    const double m = __longlong_as_double(mb);
+#else
+    double m; std::memcpy(&m, &mb, 8);
+#endif
+    const double f = m - 1.0;                                                   // [-0.293, 0.414]
+    const double s = f * rcp64(2.0 + f);                                        // |s| <= 0.172
+    const double z = s * s;
+    double p = kLogC[0];
+#pragma unroll
+    for (int i = 1; i < 11; ++i) p = fma(p, z, kLogC[i]);
+    const double lm = fma(2.0 * s * z, p, 2.0 * s);                             // ln m = 2 atanh(s)
+    const double ed = (double)e;
+    return fma(ed, kLn2Split[0], fma(ed, kLn2Split[1], lm));                    // + e ln2 (hi + lo)
+}
+XP_HD double exp64_fast(double x) {
+    const double kMagic = 6755399441055744.0;                                   // 1.5 * 2^52: rint by addition
+    const double tn = fma(x, 1.4426950408889634, kMagic);
+    const double n = tn - kMagic;
+    double r = fma(-n, kLn2Split[0], x);
+    r = fma(-n, kLn2Split[1], r);                                               // |r| <= 0.3466
+    double p = kExpC[0];                                                        // 1/13! ... 1/2!
+#pragma unroll
+    for (int i = 1; i < 12; ++i) p = fma(p, r, kExpC[i]);
+    p = fma(p, r, 1.0); p = fma(p, r, 1.0);
+#if defined(__CUDACC__)
+    // (the exponent is added as an UNSIGNED shift: shifting a negative signed value left is undefined behaviour in
+    //  C++17 -- UBSan flags it in the host build of this code -- while the two's-complement sum is what is wanted)
+    const unsigned long long ni = (unsigned long long)(long long)__double2int_rn(n);
+    return __longlong_as_double((long long)((unsigned long long)__double_as_longlong(p) + (ni << 52)));
+#else
+    unsigned long long pb; std::memcpy(&pb, &p, 8);
+    pb += ((unsigned long long)(long long)n) << 52;
+    double out; std::memcpy(&out, &pb, 8);
+    return out;
+#endif
+}
+
+
+
+// exp / log / pow of the exact column code.  Default: libm, rounding like NumPy's to the last bits.  With
+// XP_F64_FAST_MATH (xp_list.cu only): the branch-free versions above (~3 ulp) for ordinary arguments, libm for the
+// special ones (NaN, zero, negative, overflow), so that NaN propagation and the reference's asserts behave the same.
+#if defined(XP_F64_FAST_MATH)
+XP_HD double xp_exp(double x) { return (fabs(x) < 700.0) ? exp64_fast(x) : exp(x); }
+XP_HD double xp_log(double x) { return (x > 1e-300 && x < 1e300) ? log64_fast(x) : log(x); }
+XP_HD double xp_pow(double x, double y) {
+    if (!(x > 1e-300 && x < 1e300)) return pow(x, y);
+    const double l = y * log64_fast(x);
+    return (fabs(l) < 700.0) ? exp64_fast(l) : pow(x, y);
+}
+#else
+XP_HD double xp_exp(double x) { return exp(x); }
+XP_HD double xp_log(double x) { return log(x); }
+XP_HD double xp_pow(double x, double y) { return pow(x, y); }
+#endif
+
 // Bolton (1980): metpy.calc.saturation_vapor_pressure [PF:258, 698, 760]
 XP_HD double sat_vapor_pressure(double t) {
-    return kSat0 * exp(17.67 * (t - 273.15) / (t - 29.65));
+    return kSat0 * xp_exp(17.67 * (t - 273.15) / (t - 29.65));
 }
 // metpy.calc.dewpoint, degC -> K [PF:280-281, inside metpy.calc.lcl PF:644]
 XP_HD double dewpoint_from_e(double e) {
-    double val = log(e / kSat0);
+    double val = xp_log(e / kSat0);
     return 243.5 * val / (17.67 - val) + kZeroC;
 }
 // metpy.calc.mixing_ratio(e, p)
@@ -101,21 +209,21 @@ XP_HD double mixing_ratio_t_td(double t, double td, double p, int compat) {
 XP_HD double virtual_temperature(double t, double w) {
     return t * (1 + kVtEps * w);
 }
-XP_HD double exner(double p) { return pow(p / 1000.0, kKappa); }   // [PF:269]
+XP_HD double exner(double p) { return xp_pow(p / 1000.0, kKappa); }   // [PF:269]
 XP_HD double potential_temperature(double p, double t) {           // [PF:253]
     return t / exner(p);
 }
 // PF:291-316
 XP_HD double dry_lapse(double p, double t0, double p0) {
-    return t0 * pow(p / p0, kKappa);
+    return t0 * xp_pow(p / p0, kKappa);
 }
 // metpy.calc.equivalent_potential_temperature, Bolton (1980) eq. 39 [PF:123]
 XP_HD double theta_e(double p, double t, double td) {
     double r = sat_mixing_ratio(p, td);
     double e = sat_vapor_pressure(td);
-    double t_l = 56 + 1. / (1. / (td - 56) + log(t / td) / 800.);
-    double th_l = potential_temperature(p - e, t) * pow(t / t_l, 0.28 * r);
-    return th_l * exp(r * (1 + 0.448 * r) * (3036. / t_l - 1.78));
+    double t_l = 56 + 1. / (1. / (td - 56) + xp_log(t / td) / 800.);
+    double th_l = potential_temperature(p - e, t) * xp_pow(t / t_l, 0.28 * r);
+    return th_l * xp_exp(r * (1 + 0.448 * r) * (3036. / t_l - 1.78));
 }
 // dT/dp of the pseudo-adiabat (metpy.calc.moist_lapse) [PF:480]
 XP_HD double moist_lapse_rhs(double p, double t) {
@@ -132,7 +240,7 @@ XP_HD void lcl_solve(double p0, double t, double td, double &lcl_p,
     const double w = mixing_ratio_ep(sat_vapor_pressure(td), p0);
     auto g = [&](double p) {
         double tdp = dewpoint_from_e(vapor_pressure(p, w));
-        return p0 * pow(tdp / t, kInvKappa);
+        return p0 * xp_pow(tdp / t, kInvKappa);
     };
     double p = p0;
     bool bad = false;

@@ -66,7 +66,7 @@ XP_HD void mixed_parcel(const Reader &rd, double depth, double &mp_p, double &mp
             if (have_prev) {
                 double tha = th, wa = w, pa = p;
                 if (pp == top) { tha = thp; wa = wp; pa = pp; }
-                const double cb = log(pp), ca = log(pa), at = log(top);
+                const double cb = xp_log(pp), ca = xp_log(pa), at = xp_log(top);
                 const double th_top = interp_bracket(thp, tha, cb, ca, at);
                 const double w_top = interp_bracket(wp, wa, cb, ca, at);
                 const double dx = fabs(top - pp);
