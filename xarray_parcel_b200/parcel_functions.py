@@ -33,7 +33,7 @@ __all__ = ["load_moist_adiabat_lookups", "lookup_tables_loaded", "moist_adiabat_
            "parcel_profile_with_lcl", "lfc_el", "cape_cin_base", "cape_cin",
            "surface_based_cape_cin", "mixed_layer_cape_cin", "most_unstable_cape_cin",
            "mixed_parcel", "most_unstable_parcel", "mix_layer", "from_most_unstable_parcel",
-           "parcel_suite", "Dataset", "linear_interp", "log_interp", "lifted_index",
+           "parcel_suite", "parcel_suite_chunks", "Dataset", "linear_interp", "log_interp", "lifted_index",
            "deep_convective_index", "isobar_temperature", "lapse_rate", "freezing_level_height",
            "melting_level_height", "wet_bulb_temperature_fast", "wind_shear",
            "dewpoint_from_specific_humidity", "conv_properties", "min_conv_properties"]
@@ -690,6 +690,31 @@ def parcel_suite(pressure, temperature, dewpoint, vert_dim="model_level_number",
             for name in ("pressure", "temperature", "dewpoint"):
                 out[f"{pre}_parcel_{name}"] = lay.wrap_scalar(res[kind]["parcel_" + name], name)
     return lay.dataset(out)
+
+
+def parcel_suite_chunks(blocks, mixed_layer_depth=100, most_unstable_depth=300, workers=2, device=None,
+                        specific_humidity=False, **kwargs):
+    """``parcel_suite`` over a CHUNKED source: ``blocks`` is an iterable of (pressure, temperature, dewpoint) column
+    blocks, level-major [L, n_i] -- NumPy / memmap / zarr / dask arrays or anything with ``.compute()`` /
+    ``__array__`` (``streaming.iter_column_blocks`` cuts big lazy arrays into such blocks without reading them).
+    Yields one ``Dataset`` of host arrays per block, in order, with the names of ``parcel_suite``.  Blocks are read,
+    uploaded, lifted and downloaded concurrently (xarray_parcel_b200/streaming.py) -- the stand-in for the
+    reference's dask ``map_blocks`` execution (PF:585-592, 667)."""
+    from . import streaming
+    opts = _lib.make_options(mixed_layer_depth=mixed_layer_depth, most_unstable_depth=most_unstable_depth,
+                             **_options(kwargs))
+    prefixes = {"sb": "surface", "ml": f"mixed_{int(mixed_layer_depth)}", "mu": "max"}
+    for res in streaming.suite_blocks(blocks, kinds=("sb", "ml", "mu"), workers=workers, device=device,
+                                      options=opts, specific_humidity=specific_humidity):
+        out = Dataset()
+        for kind, pre in prefixes.items():
+            for name in ["cape", "cin"] + _SCALAR_VARS:
+                out[f"{pre}_{name}"] = res[kind][name].numpy()
+            if kind != "sb":
+                for name in ("pressure", "temperature", "dewpoint"):
+                    out[f"{pre}_parcel_{name}"] = res[kind]["parcel_" + name].numpy()
+        out.var_attrs = {k: dict(_ATTRS.get(k.split("_", 1)[-1], {})) for k in out}
+        yield out
 
 
 # ---- individually exposed steps ---------------------------------------------------------------
