@@ -462,16 +462,20 @@ def run_extras(args, ctx, spec, p, t, td, opts, hp, ht, htd, houts):
             others[wl] = {"error": repr(e)}
         torch.cuda.empty_cache()
     out["other_configs"] = others
-    try:                                      # float64 I/O: 1/4 of the columns (the exact kernel is ~30x slower)
-        n64 = max(1, spec["N"] // 4)
-        p64 = p.double() if p.dim() == 1 else p[:, :n64].double().contiguous()
-        t64, td64 = t[:, :n64].double().contiguous(), td[:, :n64].double().contiguous()
+    try:                                      # float64 I/O (the reference's dtype), same columns
+        n64 = spec["N"]
+        p64 = p.double() if p.dim() == 1 else p.double().contiguous()
+        t64, td64 = t.double().contiguous(), td.double().contiguous()
         o64 = ctx.alloc_outputs(t64, spec["kinds"], profile=False, fields=BENCH_FIELDS, shift=False)
-        ms = _time_device(lambda: ctx.cape_cin(p64, t64, td64, kinds=spec["kinds"], options=opts, out=o64), 3, 1)
+        ms = _time_device(lambda: ctx.cape_cin(p64, t64, td64, kinds=spec["kinds"], options=opts, out=o64), 10, 3)
+        fast64 = ctx.last_exact_count() >= 0
         bi, bo = algorithmic_bytes(dict(spec, N=n64), elt=8)
         out["f64_io"] = {"columns": n64, "value": n64 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
-                         "roofline_frac": (bi + bo) / (ms * 1e-3) / 1e9 / peak,
-                         "kernel": "xp::cape_cin_kernel<double> (float64 exact path)"}
+                         "roofline_frac": (bi + bo) / (ms * 1e-3) / 1e9 / peak, "bytes_per_column": (bi + bo) / n64,
+                         "kernel": ("xp::suite_fast_kernel<..., double> (float32 sweep of float64 columns, float64 "
+                                    "parcels) + suite_list_kernel<double>" if fast64
+                                    else "xp::cape_cin_kernel<double> (float64 exact path)"),
+                         "exact_path_columns": ctx.last_exact_count()}
         del p64, t64, td64, o64
     except Exception as e:
         out["f64_io"] = {"error": repr(e)}

@@ -89,6 +89,9 @@ struct HostRdF {
     static void prefetch(const float *) {}
 };
 struct HostRd6 {                       // v6 sweep: 32-bit element offsets from the array bases
+    static constexpr bool kDouble = false;
+    double ldT64(uint32_t off) const { return (double)t[off]; }
+    double ldTd64(uint32_t off) const { return (double)td[off]; }
     const float *t, *td;
     uint32_t col, lstride;
     uint32_t off0() const { return col; }

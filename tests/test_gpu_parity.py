@@ -166,7 +166,11 @@ def test_suite_matches_oracle(ctx, gpu_tables, o, shape, dtype):
     res = ctx.cape_cin(p.cuda(), t.cuda(), td.cuda(), kinds=("sb", "ml", "mu"), options=opts)
     assert ctx.take_flags() == 0
     rtol = 1e-9 if dtype == torch.float64 else 3e-7
-    fast = dtype == torch.float32                               # float32 columns -> the fast paths
+    # float32 columns -> the fast paths; float64 columns take the fast kernel too on a shared pressure axis with the
+    # reference's default options (float32 sweep of float64 columns, float64 parcels: launch_suite_fast_f64)
+    default_opts = (o.get("virtual_temperature_correction", True) and o.get("pos_cape_neg_cin", True)
+                    and o.get("metpy_compat", "1.4.1") == "1.4.1")
+    fast = dtype == torch.float32 or (shape == "era5" and default_opts)
     assert (ctx.last_exact_count() >= 0) == fast
     if fast:
         assert ctx.last_exact_count() < 0.08 * t.shape[1]
@@ -180,6 +184,34 @@ def test_suite_matches_oracle(ctx, gpu_tables, o, shape, dtype):
                 assert np.array_equal(np.isnan(a), np.isnan(b))
                 ok = ~np.isnan(b)
                 assert np.allclose(a[ok], b[ok], rtol=3e-7 if fast else rtol, atol=0)
+
+
+def test_float64_columns_take_the_fast_kernel(ctx, gpu_tables):
+    """float64 inputs (the reference's dtype) on a shared axis: same kernel as float32 columns, parcels read in
+    float64, float64 outputs; against the oracle on the float64 values, against the float64 exact kernel, and the
+    float32 rounding of the inputs must not move any integer output."""
+    g = torch.Generator().manual_seed(5)
+    p, t, td = synth.era5_columns(60_000, seed=91, nan_columns=0.01)
+    t64 = t.double() + 1e-6 * torch.rand(t.shape, generator=g, dtype=torch.float64)      # not float32-representable
+    td64 = torch.minimum(td.double() - 1e-6 * torch.rand(t.shape, generator=g, dtype=torch.float64), t64)
+    p64 = p.double()
+    res = ctx.cape_cin(p64.cuda(), t64.cuda(), td64.cuda(), kinds=("sb", "ml", "mu"))
+    n_exact = ctx.last_exact_count()
+    assert 0 <= n_exact < 0.05 * t.shape[1], n_exact                                     # the fast kernel ran
+    assert res["sb"]["cape"].dtype == torch.float64
+    exact = ctx.cape_cin(p64.cuda(), t64.cuda(), td64.cuda(), kinds=("sb", "ml", "mu"),
+                         options=_lib.make_options(exact_only=True))
+    assert ctx.last_exact_count() == -1
+    ora = _oracle_suite(p64, t64, td64, gpu_tables)
+    for kind in ("sb", "ml", "mu"):
+        _check(res[kind], ora, kind + "_", "fast", what="float64 fast vs oracle: ")
+        ex = {kind + "_" + f: exact[kind][f].cpu().numpy() for f in FIELDS}
+        _check(res[kind], ex, kind + "_", "fast", what="float64 fast vs exact: ")
+        assert torch.equal(res[kind]["level_shift"], exact[kind]["level_shift"])
+    # single kinds and the non-dense output set go through the same kernel
+    one = ctx.cape_cin(p64.cuda(), t64.cuda(), td64.cuda(), kinds=("mu",))["mu"]
+    for f in FIELDS:
+        assert torch.equal(one[f].view(torch.int64), res["mu"][f].view(torch.int64)), f
 
 
 def test_fast_path_vs_exact_path(ctx, gpu_tables):

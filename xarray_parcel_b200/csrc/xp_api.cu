@@ -199,6 +199,35 @@ xp_status run_device(xp_context *ctx, const xp_columns *cols, int kind_mask,
             return check_cuda(ctx, cudaGetLastError(), "fast suite launch");
         }
     }
+    if constexpr (std::is_same<T, double>::value) {
+        // float64 columns on a shared pressure axis, default options: the same fast kernel (launch_suite_fast_f64)
+        if (!o.exact_only && cols->n_columns > 0 && cols->pressure_is_1d && !(kind_mask & kEX)) {
+            if (!ctx->scratch.count(stream) && ctx->scratch.size() >= kMaxScratchStreams) {
+                for (auto &kv : ctx->scratch) {
+                    if (kv.second.ptr) { cudaStreamSynchronize(kv.first); cudaFree(kv.second.ptr); }
+                }
+                ctx->scratch.clear();
+            }
+            xp_context::Scratch &sc = ctx->scratch[stream];
+            const size_t need = fast_scratch_bytes(cols->n_columns);
+            if (sc.bytes < need) {
+                if (sc.ptr) { cudaStreamSynchronize(stream); cudaFree(sc.ptr); sc.ptr = nullptr; sc.bytes = 0; }
+                XP_CUDA(ctx, cudaMalloc(&sc.ptr, need));
+                sc.bytes = need;
+            }
+            if (time_it) cudaEventRecord(ctx->ev0, stream);
+            const int nl = launch_suite_fast_f64(to_cols<double>(cols, o), tb, o, kind_mask, oa, sc.ptr, ctx->d_flags,
+                                                 ctx->sm_count, stream);
+            if (nl == -1) return check_cuda(ctx, cudaGetLastError(), "fast suite shared-memory attribute");
+            if (nl >= 0) {
+                ctx->launches += nl;
+                if (time_it) { cudaEventRecord(ctx->ev1, stream); ctx->ev_valid = true; }
+                ctx->last_was_fast = true;
+                ctx->last_fast_stream = stream;
+                return check_cuda(ctx, cudaGetLastError(), "fast suite launch (float64 columns)");
+            }
+        }
+    }
     if (time_it) cudaEventRecord(ctx->ev0, stream);
     launch_cape_cin<T>(to_cols<T>(cols, o), tb, o, kind_mask, oa, pa, ctx->d_flags, stream);
     if (time_it) { cudaEventRecord(ctx->ev1, stream); ctx->ev_valid = true; }

@@ -29,7 +29,8 @@ using fast::Prep;
 namespace {
 
 // ---- prep kernels: axis constants (one thread) and the cubic coefficient table -----------------------
-__global__ void fast_prep_kernel(const float *__restrict__ p, int64_t pls, int L, Opts o, Prep *out) {
+template <typename TP>
+__global__ void fast_prep_kernel(const TP *__restrict__ p, int64_t pls, int L, Opts o, Prep *out) {
     if (threadIdx.x < L && threadIdx.x < fast::kMaxLevels) fast::compute_prep_level(p, pls, threadIdx.x, *out);
     __syncthreads();
     if (threadIdx.x == 0) fast::compute_prep_axis(L, o, *out);
@@ -44,20 +45,22 @@ __global__ void fast_coef_kernel(const Prep *__restrict__ prep, const float *__r
 }
 
 // ---- the fast suite kernel ---------------------------------------------------------------------------------------
-struct FastParams {
-    const float *t, *td;
+template <typename T>
+struct FastParamsT {
+    const T *t, *td;
     int64_t n, ls;
     const Prep *prep;
     const Coef *coef;
     Tables tb;
     Opts o;
     unsigned kinds;
-    OutArg<float> outs[3];
+    OutArg<T> outs[3];
     uint32_t *list;          // 3 regions of n entries (see ListParams)
     uint32_t *list_count;
     int stash_levels;        // levels of T/Td per thread that fit in shared memory after the table (v6 sweep)
     int dense_out;           // the requested outputs are exactly the 9 scalars per kind + parcel p/T/Td of ML, MU
 };
+using FastParams = FastParamsT<float>;
 
 struct GlobalRd {
     const float *t, *td;
@@ -72,19 +75,26 @@ struct GlobalRd {
 };
 
 // v6 sweep: 32-bit element offsets from the array bases (see Sweep6 in xp_fast6.cuh)
-struct GlobalRd32 {
-    const float *t, *td;
+// T = double: float64 columns.  The sweep consumes them rounded to float32; the parcel levels are re-read in float64
+// (ldT64 / ldTd64) by suite_column7.
+template <typename T>
+struct GlobalRd32T {
+    static constexpr bool kDouble = sizeof(T) == 8;
+    const T *t, *td;
     uint32_t col, lstride;
     uint64_t limit;                       // elements addressable from the bases (XP_BOUNDS_CHECK builds only)
     __device__ __forceinline__ uint32_t off0() const { return col; }
     __device__ __forceinline__ uint32_t ls() const { return lstride; }
-    __device__ __forceinline__ float ldT(uint32_t off) const { XP_CHECK(off < limit); return __ldg(t + off); }
-    __device__ __forceinline__ float ldTd(uint32_t off) const { XP_CHECK(off < limit); return __ldg(td + off); }
+    __device__ __forceinline__ float ldT(uint32_t off) const { XP_CHECK(off < limit); return (float)__ldg(t + off); }
+    __device__ __forceinline__ float ldTd(uint32_t off) const { XP_CHECK(off < limit); return (float)__ldg(td + off); }
+    __device__ __forceinline__ double ldT64(uint32_t off) const { XP_CHECK(off < limit); return (double)__ldg(t + off); }
+    __device__ __forceinline__ double ldTd64(uint32_t off) const { XP_CHECK(off < limit); return (double)__ldg(td + off); }
     __device__ __forceinline__ void prefetch(uint32_t off) const {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(t + off));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(td + off));
     }
 };
+using GlobalRd32 = GlobalRd32T<float>;
 
 struct SmemCoefRow {
     const Coef *row;
@@ -112,28 +122,30 @@ struct SmemCoef {
     }
 };
 
-__device__ __forceinline__ void store_fast(const OutArg<float> &o, int64_t col, const fast::FResult &r) {
-    if (o.cape) o.cape[col] = r.cape;
-    if (o.cin) o.cin[col] = r.cin;
-    if (o.lcl_p) o.lcl_p[col] = r.lcl_p;
-    if (o.lcl_t) o.lcl_t[col] = r.lcl_t;
-    if (o.lcl_tv) o.lcl_tv[col] = r.lcl_tv;
-    if (o.lfc_p) o.lfc_p[col] = r.lfc_p;
-    if (o.lfc_t) o.lfc_t[col] = r.lfc_t;
-    if (o.el_p) o.el_p[col] = r.el_p;
-    if (o.el_t) o.el_t[col] = r.el_t;
-    if (o.par_p) o.par_p[col] = r.par_p;
-    if (o.par_t) o.par_t[col] = r.par_t;
-    if (o.par_td) o.par_td[col] = r.par_td;
+template <typename T>
+__device__ __forceinline__ void store_fast(const OutArg<T> &o, int64_t col, const fast::FResult &r) {
+    if (o.cape) o.cape[col] = (T)r.cape;
+    if (o.cin) o.cin[col] = (T)r.cin;
+    if (o.lcl_p) o.lcl_p[col] = (T)r.lcl_p;
+    if (o.lcl_t) o.lcl_t[col] = (T)r.lcl_t;
+    if (o.lcl_tv) o.lcl_tv[col] = (T)r.lcl_tv;
+    if (o.lfc_p) o.lfc_p[col] = (T)r.lfc_p;
+    if (o.lfc_t) o.lfc_t[col] = (T)r.lfc_t;
+    if (o.el_p) o.el_p[col] = (T)r.el_p;
+    if (o.el_t) o.el_t[col] = (T)r.el_t;
+    if (o.par_p) o.par_p[col] = (T)r.par_p;
+    if (o.par_t) o.par_t[col] = (T)r.par_t;
+    if (o.par_td) o.par_td[col] = (T)r.par_td;
     if (o.shift) o.shift[col] = r.shift;
 }
 
 // Every scalar output of the kind is requested (the usual case): no pointer checks.
-__device__ __forceinline__ void store_fast_all(const OutArg<float> &o, int64_t col, const fast::FResult &r, bool parcel) {
-    o.cape[col] = r.cape; o.cin[col] = r.cin;
-    o.lcl_p[col] = r.lcl_p; o.lcl_t[col] = r.lcl_t; o.lcl_tv[col] = r.lcl_tv;
-    o.lfc_p[col] = r.lfc_p; o.lfc_t[col] = r.lfc_t; o.el_p[col] = r.el_p; o.el_t[col] = r.el_t;
-    if (parcel) { o.par_p[col] = r.par_p; o.par_t[col] = r.par_t; o.par_td[col] = r.par_td; }
+template <typename T>
+__device__ __forceinline__ void store_fast_all(const OutArg<T> &o, int64_t col, const fast::FResult &r, bool parcel) {
+    o.cape[col] = (T)r.cape; o.cin[col] = (T)r.cin;
+    o.lcl_p[col] = (T)r.lcl_p; o.lcl_t[col] = (T)r.lcl_t; o.lcl_tv[col] = (T)r.lcl_tv;
+    o.lfc_p[col] = (T)r.lfc_p; o.lfc_t[col] = (T)r.lfc_t; o.el_p[col] = (T)r.el_p; o.el_t[col] = (T)r.el_t;
+    if (parcel) { o.par_p[col] = (T)r.par_p; o.par_t[col] = (T)r.par_t; o.par_td[col] = (T)r.par_td; }
 }
 
 #ifndef XP_FAST_THREADS
@@ -173,8 +185,9 @@ struct StashSmem {
 // curve staged in shared memory + early termination; 2 = recomputed, with a first pass over all levels for the
 // early-termination bound; 3 = the v7 sweep of xp_fast7.cuh (default options only; shared memory as 0); 4 = the v7 sweep
 // with specific humidity in place of the dewpoint, converted in the load stage (xp_columns.dewpoint_is_specific_humidity).
-template <unsigned KINDS, int MODE, int THREADS, int STAGED>
-__global__ void __launch_bounds__(THREADS, 1) suite_fast_kernel(const __grid_constant__ FastParams prm) {
+// T: element type of the columns and of the outputs (double only with the v7 sweep, STAGED 3).
+template <unsigned KINDS, int MODE, int THREADS, int STAGED, typename T = float>
+__global__ void __launch_bounds__(THREADS, 1) suite_fast_kernel(const __grid_constant__ FastParamsT<T> prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
     Prep *s_prep = reinterpret_cast<Prep *>(smem_raw);
@@ -228,26 +241,28 @@ __global__ void __launch_bounds__(THREADS, 1) suite_fast_kernel(const __grid_con
         // lanes past the end redo the last column (warp-uniform votes need every lane) and do not store
         const bool valid = base + threadIdx.x < prm.n;
         const int64_t col = valid ? base + threadIdx.x : prm.n - 1;
-        const GlobalRd rd{prm.t + col, prm.td + col, prm.ls};
         fast::FResult res[3];
         unsigned redo;
-        if (MODE == 1 && (STAGED == 3 || STAGED == 4)) {
+        if constexpr (MODE == 1 && (STAGED == 3 || STAGED == 4)) {
             StashSmem st{s_env + threadIdx.x, (int)blockDim.x, prm.stash_levels};
-            const GlobalRd32 rd32{prm.t, prm.td, (uint32_t)col, (uint32_t)prm.ls, (uint64_t)prm.n + (uint64_t)(pr.L - 1) * (uint64_t)prm.ls};
+            const GlobalRd32T<T> rd32{prm.t, prm.td, (uint32_t)col, (uint32_t)prm.ls, (uint64_t)prm.n + (uint64_t)(pr.L - 1) * (uint64_t)prm.ls};
             redo = fast::suite_column7<KINDS, STAGED == 4>(rd32, cf, pr, prm.tb, prm.o, st, res);
-        } else if (MODE == 1 && STAGED == 0) {
+        } else if constexpr (MODE == 1 && STAGED == 0) {
             // default options: the v6 sweep on the virtual-temperature table (xp_fast6.cuh); the shared
             // memory left after the table stashes T/Td of the lowest levels of every thread's column
             StashSmem st{s_env + threadIdx.x, (int)blockDim.x, prm.stash_levels};
             const GlobalRd32 rd32{prm.t, prm.td, (uint32_t)col, (uint32_t)prm.ls, (uint64_t)prm.n + (uint64_t)(pr.L - 1) * (uint64_t)prm.ls};
             redo = fast::suite_column6<KINDS>(rd32, cf, pr, prm.tb, prm.o, st, res);
-        } else if (STAGED == 1) {
+        } else if constexpr (STAGED == 1) {
+            const GlobalRd rd{prm.t + col, prm.td + col, prm.ls};
             EnvSmem env{s_env + threadIdx.x, (int)blockDim.x};
             redo = fast::suite_column<KINDS, MODE>(rd, cf, pr, prm.tb, prm.o, env, res);
-        } else if (STAGED == 2) {
+        } else if constexpr (STAGED == 2) {
+            const GlobalRd rd{prm.t + col, prm.td + col, prm.ls};
             fast::EnvMinOnly env;
             redo = fast::suite_column<KINDS, MODE>(rd, cf, pr, prm.tb, prm.o, env, res);
         } else {
+            const GlobalRd rd{prm.t + col, prm.td + col, prm.ls};
             fast::EnvRecompute env;
             redo = fast::suite_column<KINDS, MODE>(rd, cf, pr, prm.tb, prm.o, env, res);
         }
@@ -571,6 +586,78 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
 #undef XP_FAST_LAUNCH
 #undef XP_FAST_CASE
 
+    launch_suite_list(lp, sm_count, stream);
+    return 4;
+}
+
+// ---- float64 columns ---------------------------------------------------------------------------------------------
+// The reference computes in float64 (MetPy / pint); callers that hand float64 arrays over get the same v7 kernel: the
+// sweep consumes every level rounded to float32 (its decisions keep their margins: the rounding is 1.5e-5 K against
+// kDecisionEps = 6e-4 K), the parcels' own T / Td and the mixed-layer sums are read in float64, the outputs are
+// written as float64, and the fix-up list is recomputed by the float64 exact code on the float64 columns.
+int launch_suite_fast_f64(const ColsArg<double> &cols, const Tables &tb, const Opts &o, int kind_mask,
+                          const OutArg<double> *outs, void *scratch, uint32_t *flags, int sm_count,
+                          cudaStream_t stream) {
+    if (cols.n <= 0) return 0;
+    const bool mode1 = o.vtc && o.compat == 141 && o.pos_neg;
+    if (!cols.p1d || !mode1 || cols.qmode || cols.L < 3 || cols.L > fast::kMaxLevels || cols.n >= ((int64_t)1 << 28)) return -2;
+    if (kind_mask & ~(kSB | kML | kMU)) return -2;
+    if ((uint64_t)cols.n + (uint64_t)cols.L * (uint64_t)cols.ls >= ((uint64_t)1 << 32)) return -2;
+    for (int q = 0; q < 3; ++q) {
+        if (!((kind_mask >> q) & 1)) continue;
+        const OutArg<double> &oq = outs[q];
+        if (oq.prof_p || oq.prof_t || oq.prof_tv || oq.prof_et || oq.prof_etv || oq.prof_etd) return -2;
+    }
+    unsigned char *base = static_cast<unsigned char *>(scratch);
+    Prep *prep = reinterpret_cast<Prep *>(base);
+    size_t off = (sizeof(Prep) + 255) & ~(size_t)255;
+    Coef *coef = reinterpret_cast<Coef *>(base + off);
+    off += (size_t)fast::kMaxLevels * fast::kNI * sizeof(Coef);
+    uint32_t *count = reinterpret_cast<uint32_t *>(base + off);
+    off += 256;
+    uint32_t *list = reinterpret_cast<uint32_t *>(base + off);
+    cudaMemsetAsync(count, 0, 4 * sizeof(uint32_t), stream);
+    ListParamsT<double> lp;
+    lp.cols = cols; lp.tb = tb; lp.o = o;
+    for (int q = 0; q < 3; ++q) lp.outs[q] = outs[q];
+    lp.list = list; lp.list_count = count; lp.capacity = cols.n; lp.flags = flags;
+    fast_prep_kernel<<<1, 64, 0, stream>>>(cols.p, cols.pls, cols.L, o, prep);
+    fast_coef_kernel<<<cols.L, fast::kNI, 0, stream>>>(prep, tb.curves, coef, 1);
+    FastParamsT<double> fp;
+    fp.t = cols.t; fp.td = cols.td; fp.n = cols.n; fp.ls = cols.ls;
+    fp.prep = prep; fp.coef = coef; fp.tb = tb; fp.o = o; fp.kinds = (unsigned)kind_mask;
+    fp.o.qmode = 0;
+    for (int q = 0; q < 3; ++q) fp.outs[q] = outs[q];
+    fp.list = list; fp.list_count = count;
+    fp.dense_out = 1;
+    for (int q = 0; q < 3; ++q) {
+        if (!((kind_mask >> q) & 1)) continue;
+        const OutArg<double> &oq = outs[q];
+        const bool nine = oq.cape && oq.cin && oq.lcl_p && oq.lcl_t && oq.lcl_tv && oq.lfc_p && oq.lfc_t && oq.el_p && oq.el_t;
+        const bool par = oq.par_p && oq.par_t && oq.par_td, no_par = !oq.par_p && !oq.par_t && !oq.par_td;
+        if (!nine || oq.shift || (q == 0 ? !no_par : !par)) fp.dense_out = 0;
+    }
+    const size_t smem_table = ((sizeof(Prep) + 127) & ~(size_t)127) + (size_t)cols.L * fast::kNI * sizeof(Coef);
+    const size_t per_level = 2 * sizeof(float) * kFastThreads;
+    const size_t room = (size_t)227 * 1024 - 256 - smem_table;
+    int lv = (int)(room / per_level);
+    lv = lv > 16 ? 16 : lv;
+    fp.stash_levels = lv;
+    const size_t smem = smem_table + (size_t)lv * per_level;
+    const int64_t tiles = (cols.n + kFastThreads - 1) / kFastThreads;
+    const int grid = (int)(tiles < sm_count ? tiles : sm_count);
+#define XP_FAST64_CASE(K)                                                                                         \
+    case K:                                                                                                       \
+        if (cudaFuncSetAttribute(suite_fast_kernel<K, 1, kFastThreads, 3, double>,                                \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)          \
+            return -1;                                                                                            \
+        suite_fast_kernel<K, 1, kFastThreads, 3, double><<<grid, kFastThreads, smem, stream>>>(fp);               \
+        break;
+    switch (kind_mask & 7) {
+        XP_FAST64_CASE(1) XP_FAST64_CASE(2) XP_FAST64_CASE(3) XP_FAST64_CASE(4) XP_FAST64_CASE(5) XP_FAST64_CASE(6) XP_FAST64_CASE(7)
+        default: return -1;
+    }
+#undef XP_FAST64_CASE
     launch_suite_list(lp, sm_count, stream);
     return 4;
 }

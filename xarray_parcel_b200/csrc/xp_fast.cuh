@@ -70,7 +70,8 @@ struct Prep {
 
 // ---- per-call constants of the shared pressure axis ----------------------------------------------------
 // Level part (independent per level; the prep kernel runs it with one thread per level).
-XP_HD void compute_prep_level(const float *p, int64_t pls, int k, Prep &pr) {
+template <typename TP>
+XP_HD void compute_prep_level(const TP *p, int64_t pls, int k, Prep &pr) {
     const double pk = (double)p[(int64_t)k * pls];
     pr.p64[k] = pk;
     pr.p[k] = (float)pk;
@@ -143,7 +144,8 @@ XP_HD void compute_prep_axis(int L, const Opts &o, Prep &pr) {
     pr.ok = ok ? 1 : 0;
 }
 
-XP_HD void compute_prep(const float *p, int64_t pls, int L, const Opts &o, Prep &pr) {
+template <typename TP>
+XP_HD void compute_prep(const TP *p, int64_t pls, int L, const Opts &o, Prep &pr) {
     for (int k = 0; k < L && k < kMaxLevels; ++k) compute_prep_level(p, pls, k, pr);
     compute_prep_axis(L, o, pr);
 }

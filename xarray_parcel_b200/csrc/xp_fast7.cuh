@@ -292,6 +292,11 @@ XP_HD unsigned suite_column7(const Rd &rd, const Cf &cf, const Prep &pr, const T
     uint32_t off0 = rd.off0();
     for (int k = 1; k < n_low; ++k) rd.prefetch(off0 + (uint32_t)k * ls);
     const float t_sfc = rd.ldT(off0), raw_sfc = rd.ldTd(off0);
+    // float64 columns (Rd::kDouble): the SWEEP runs on the values rounded to float32 (1.5e-5 K, inside the decision
+    // margins), but everything the table cell of a parcel's LCL hangs on -- the parcel's own T / Td and the
+    // mixed-layer sums -- is read in float64, exactly as for float32 columns (whose values ARE their float64 values)
+    double t_sfc64 = (double)t_sfc, raw_sfc64 = (double)raw_sfc;
+    if (Rd::kDouble) { t_sfc64 = rd.ldT64(off0); raw_sfc64 = rd.ldTd64(off0); }
     float t_nx = t_sfc, td_nx = raw_sfc, mu_raw = raw_sfc;
     float t_n2 = 0.0f, td_n2 = 0.0f;                         // levels are read two iterations ahead
     off0 += ls;
@@ -311,10 +316,12 @@ XP_HD unsigned suite_column7(const Rd &rd, const Cf &cf, const Prep &pr, const T
         const float r = kEpsF * e * ipe;                 // saturation mixing ratio of the dewpoint (PF:258)
         if ((KINDS & 2u) && k < pr.n_ml_w) {
             // mixed_parcel PF:253-258 in float64 (see suite_column)
-            const double tdd = (double)td;
-            const double e64 = qm ? e64_from_q_fast(pr.p64[k], (double)t, (double)raw, qm)
+            double t64 = (double)t, raw64 = (double)raw;
+            if (Rd::kDouble) { const uint32_t ok_ = rd.off0() + (uint32_t)k * ls; t64 = rd.ldT64(ok_); raw64 = rd.ldTd64(ok_); }
+            const double tdd = qm ? (double)td : raw64;
+            const double e64 = qm ? e64_from_q_fast(pr.p64[k], t64, raw64, qm)
                                   : kSat0 * exp64_fast(17.67 * (tdd - 273.15) * rcp64(tdd - 29.65));
-            sum_th += pr.mlw[k] * ((double)t * pr.thfac[k]);
+            sum_th += pr.mlw[k] * (t64 * pr.thfac[k]);
             sum_w += pr.mlw[k] * (kEps * e64 * rcp64(pr.p64[k] - e64));
         }
         if ((KINDS & 4u) && k < pr.K_mu) {
@@ -335,10 +342,10 @@ XP_HD unsigned suite_column7(const Rd &rd, const Cf &cf, const Prep &pr, const T
     double td_sfc64, mu_td64;
     float td_sfc;
     if (qm) {
-        td_sfc64 = td64_from_q_fast(pr.p0, (double)t_sfc, (double)raw_sfc, qm);
+        td_sfc64 = td64_from_q_fast(pr.p0, t_sfc64, raw_sfc64, qm);
         td_sfc = (float)td_sfc64;
     } else {
-        td_sfc = raw_sfc; td_sfc64 = (double)raw_sfc;
+        td_sfc = raw_sfc; td_sfc64 = raw_sfc64;
     }
     // the top of the column: coldest environment temperature above kTopCheckHpa (see suite_column6)
     float tmin_top = 1e30f, tmax_top = -1e30f;
@@ -375,7 +382,7 @@ XP_HD unsigned suite_column7(const Rd &rd, const Cf &cf, const Prep &pr, const T
         }
     };
     double mp_t = 0.0, mp_td = 0.0;
-    if (KINDS & 1u) setup6_a(pr.p0, (double)t_sfc, td_sfc64, sb, u_sb);
+    if (KINDS & 1u) setup6_a(pr.p0, t_sfc64, td_sfc64, sb, u_sb);
     if (KINDS & 2u) {
         mp_t = sum_th * pr.exner0;                                               // PF:268-269
         {
@@ -386,9 +393,11 @@ XP_HD unsigned suite_column7(const Rd &rd, const Cf &cf, const Prep &pr, const T
     }
     if (KINDS & 4u) {
         if (!(best - second >= kThetaEMargin)) redo |= 4u;                       // argmax within float32 error
-        mu_td64 = qm ? td64_from_q_fast(pr.p64[k_mu], (double)mu_t, (double)mu_raw, qm) : (double)mu_td;
+        double mu_t64 = (double)mu_t, mu_raw64 = (double)mu_raw;
+        if (Rd::kDouble) { const uint32_t om_ = rd.off0() + (uint32_t)k_mu * ls; mu_t64 = rd.ldT64(om_); mu_raw64 = rd.ldTd64(om_); }
+        mu_td64 = qm ? td64_from_q_fast(pr.p64[k_mu], mu_t64, mu_raw64, qm) : mu_raw64;
         if (qm) mu_td = (float)mu_td64;
-        setup6_a(pr.p64[k_mu], (double)mu_t, mu_td64, mu, u_mu);
+        setup6_a(pr.p64[k_mu], mu_t64, mu_td64, mu, u_mu);
     }
     if (KINDS & 1u) setup6_b(lev, pr, tb, 1, sb, u_sb);
     if (KINDS & 2u) setup6_b(lev, pr, tb, pr.K_ml, ml, u_ml);

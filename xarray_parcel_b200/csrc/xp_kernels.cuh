@@ -73,16 +73,18 @@ void launch_cape_cin_base(const T *pressure, const T *env_t, const T *parcel_t, 
 // `list_count[0..2]` = entries per kind, `list_count[3]` = columns with at least one entry (device
 // memory).  Dense per-kind regions keep every lane of the fix-up kernel busy and its warps kind-uniform.
 // Lives in xp_kernels.cu because that file is compiled without FMA contraction.
-struct ListParams {
-    ColsArg<float> cols;
+template <typename T>
+struct ListParamsT {
+    ColsArg<T> cols;
     Tables tb;
     Opts o;
-    OutArg<float> outs[3];
+    OutArg<T> outs[3];
     const uint32_t *list;
     const uint32_t *list_count;
     int64_t capacity;
     uint32_t *flags;
 };
+using ListParams = ListParamsT<float>;
 constexpr unsigned kListMuIsSb = 8u;
 constexpr unsigned kListRowsOk = 1u;         // entry >> 28: the float32 profile rows of this item stand (scalars only)
 
@@ -125,6 +127,7 @@ __device__ __forceinline__ void push_redo(uint32_t *list, uint32_t *count, int64
     atomicAdd(count + 3, 1u);
 }
 void launch_suite_list(const ListParams &lp, int sm_count, cudaStream_t stream);
+void launch_suite_list(const ListParamsT<double> &lp, int sm_count, cudaStream_t stream);   // float64 columns (never staged)
 
 // Float32 fast path of the suite on a shared pressure axis (xp_fast.cu / xp_fast.cuh): prep +
 // coefficient + fast kernel + exact fix-up over the uncertain-column list, all on `stream`.
@@ -135,6 +138,12 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
                       const OutArg<float> *outs, void *scratch, uint32_t *flags, int sm_count,
                       cudaStream_t stream);
 uint32_t fast_last_list_count(void *scratch, cudaStream_t stream);
+// The same fast path for float64 columns and outputs on a shared pressure axis with the reference's default options
+// (the v7 sweep: float32 per level, float64 parcels; the fix-up list runs on the float64 columns).  Returns the
+// number of launches, or -2 when the call does not qualify (the caller then runs the float64 exact kernel).
+int launch_suite_fast_f64(const ColsArg<double> &cols, const Tables &tb, const Opts &o, int kind_mask,
+                          const OutArg<double> *outs, void *scratch, uint32_t *flags, int sm_count,
+                          cudaStream_t stream);
 
 // Derived-index helpers (xp_derived.cu): linear/log interpolation of up to 4 fields at one coordinate
 // value per column (PF:1758-1828) and the lowest crossing of a field with a constant (PF:992-1064).

@@ -34,8 +34,8 @@ struct StagedReader {
 };
 
 // One thread per (column, parcel kind) item.  STAGED: dynamic shared memory holds blockDim.x columns.
-template <bool STAGED>
-__global__ void __launch_bounds__(128, 3) suite_list_kernel(const __grid_constant__ ListParams prm) {
+template <bool STAGED, typename T = float>
+__global__ void __launch_bounds__(128, 3) suite_list_kernel(const __grid_constant__ ListParamsT<T> prm) {
     extern __shared__ float s_cols[];
     const uint32_t c0 = prm.list_count[0], c1 = prm.list_count[1], c2 = prm.list_count[2];
     const uint64_t total = (uint64_t)c0 + c1 + c2;
@@ -52,13 +52,13 @@ __global__ void __launch_bounds__(128, 3) suite_list_kernel(const __grid_constan
         const uint32_t e = prm.list[(uint64_t)kind * prm.capacity + idx];
         const bool also_mu = kind == 0 && ((e >> 28) & kListMuIsSb);
         const int64_t col = (int64_t)(e & 0x0fffffffu);
-        const GlobalReader<float> rd = make_reader(prm.cols, col);
+        const GlobalReader<T> rd = make_reader(prm.cols, col);
         ParcelResult r;
         double p0, t0, td0;
         int shift;
-        ProfWriter<float> np = make_writer(prm.outs[kind], col);       // profile rows too, where requested ...
+        ProfWriter<T> np = make_writer(prm.outs[kind], col);       // profile rows too, where requested ...
         if ((e >> 28) & kListRowsOk) np.any = false;                   // ... unless the float32 rows stand
-        if (STAGED) {
+        if constexpr (STAGED) {
             // independent loads, all in flight at once; only this thread reads its slots back: no barrier needed
             for (int k = 0; k < L; ++k) {
                 s_t[k * nt + threadIdx.x] = __ldg(rd.t + (int64_t)k * rd.ls);
@@ -95,6 +95,10 @@ void launch_suite_list(const ListParams &lp, int sm_count, cudaStream_t stream) 
     } else {
         suite_list_kernel<false><<<sm_count * 8, 128, 0, stream>>>(lp);
     }
+}
+
+void launch_suite_list(const ListParamsT<double> &lp, int sm_count, cudaStream_t stream) {
+    suite_list_kernel<false, double><<<sm_count * 8, 128, 0, stream>>>(lp);
 }
 
 }  // namespace xp
