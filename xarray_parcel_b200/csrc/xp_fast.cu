@@ -307,7 +307,16 @@ struct PColParams {
     uint32_t *list_count;
 };
 
-constexpr int kPColThreads = 256;
+#ifndef XP_PCOL_THREADS
+#define XP_PCOL_THREADS 256
+#endif
+constexpr int kPColThreads = XP_PCOL_THREADS;
+// CTAs per SM the per-column-pressure kernel is compiled for: a single parcel kind without profile rows fits 85
+// registers (three 256-thread CTAs: measured 1.09 vs 0.95 G columns/s on 1 M x 70 surface-based); two or three kinds
+// spill there (SB+ML: 0.48 vs 0.70 G) and stay at two CTAs x 128 registers.
+constexpr int pcol_ctas(unsigned kinds, bool profile) {
+    return (!profile && (kinds == 1u || kinds == 2u || kinds == 4u)) ? 3 : 2;
+}
 
 // parcel_profile_with_lcl rows (PF:806-931) of the fast path: [L+1][N] arrays per kind, NULL = not wanted
 struct ProfileWriter {
@@ -330,7 +339,7 @@ struct ProfileWriter {
 };
 
 template <unsigned KINDS, int MODE, bool PROFILE, bool QIN = false>
-__global__ void __launch_bounds__(kPColThreads, 2) suite_fast_pcol_kernel(const __grid_constant__ PColParams prm) {
+__global__ void __launch_bounds__(kPColThreads, pcol_ctas(KINDS, PROFILE)) suite_fast_pcol_kernel(const __grid_constant__ PColParams prm) {
     const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= prm.n) return;
     const PColRd rd{prm.p + col, prm.t + col, prm.td + col, prm.ls, prm.pls};

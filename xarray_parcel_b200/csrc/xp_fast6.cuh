@@ -23,10 +23,6 @@
 #define XP_PREPASS_UNROLL 1
 #endif
 
-#ifndef XP_PREPASS_UNROLL
-#define XP_PREPASS_UNROLL 1
-#endif
-
 namespace xp {
 namespace fast {
 
