@@ -244,6 +244,21 @@ struct HostProfW {
 };
 }  // namespace
 
+// 0: all three kinds at once (KINDS = 7); 2 / 4: ONE lifted kind (mixed layer / most unstable) with profile rows -- the
+// re-based sweep -- read through a per-thread ring of `g_pcol_ring` levels (0: direct loads).
+static int g_pcol_kind = 0, g_pcol_ring = 0;
+extern "C" void hostsim_set_pcol_kind(int kind, int ring_levels) { g_pcol_kind = kind; g_pcol_ring = ring_levels; }
+namespace {
+struct HostRing {
+    static constexpr bool kEnabled = true;
+    int cap;
+    float p[64], t[64], td[64];
+    int capacity() const { return cap; }
+    void put(int s, float a, float b, float c) { if (s < 0 || s >= cap) __builtin_trap(); p[s] = a; t[s] = b; td[s] = c; }
+    void get(int s, float &a, float &b, float &c) const { if (s < 0 || s >= cap) __builtin_trap(); a = p[s]; b = t[s]; c = td[s]; }
+};
+}  // namespace
+
 extern "C" int hostsim_fast_suite_pcol(const float *p, const float *t, const float *td, int64_t n, int L,
                                        const int *iopts, double ml_depth, double mu_depth,
                                        const uint16_t *index_grid, const float *curves, float *out,
@@ -257,10 +272,21 @@ extern "C" int hostsim_fast_suite_pcol(const float *p, const float *t, const flo
         HostRdP rd = {p + c, t + c, td + c, n};
         xp::fast::FResult r[3];
         const bool m1 = o.vtc && o.compat == 141 && o.pos_neg;
-        if (prof) {
+        xp::fast::NoRing nr;
+        if (prof && (g_pcol_kind == 2 || g_pcol_kind == 4)) {
             HostProfW pw = {prof, n, c, L};
-            redo[c] = m1 ? xp::fast::suite_column_pcol<7u, 1, true>(rd, L, tb, o, pw, r)
-                         : xp::fast::suite_column_pcol<7u, 0, true>(rd, L, tb, o, pw, r);
+            HostRing ring; ring.cap = g_pcol_ring;
+            for (int q = 0; q < 3; ++q) r[q] = xp::fast::FResult();
+            if (g_pcol_kind == 2)
+                redo[c] = g_pcol_ring ? xp::fast::suite_column_pcol<2u, 1, true>(rd, L, tb, o, pw, ring, r)
+                                      : xp::fast::suite_column_pcol<2u, 1, true>(rd, L, tb, o, pw, nr, r);
+            else
+                redo[c] = g_pcol_ring ? xp::fast::suite_column_pcol<4u, 1, true>(rd, L, tb, o, pw, ring, r)
+                                      : xp::fast::suite_column_pcol<4u, 1, true>(rd, L, tb, o, pw, nr, r);
+        } else if (prof) {
+            HostProfW pw = {prof, n, c, L};
+            redo[c] = m1 ? xp::fast::suite_column_pcol<7u, 1, true>(rd, L, tb, o, pw, nr, r)
+                         : xp::fast::suite_column_pcol<7u, 0, true>(rd, L, tb, o, pw, nr, r);
         } else if (m1 && (c % 3) != 0 && !g_qmode) {
             // default options, no profile: the v6 sweep (xp_fast_pcol6.cuh) on two columns out of three, with a
             // stash of 36 levels (the kernel's), of 5 levels (search and sweep cross its end) or none
@@ -274,8 +300,8 @@ extern "C" int hostsim_fast_suite_pcol(const float *p, const float *t, const flo
             }
         } else {
             xp::fast::NoProfile np;
-            redo[c] = m1 ? xp::fast::suite_column_pcol<7u, 1, true>(rd, L, tb, o, np, r)
-                         : xp::fast::suite_column_pcol<7u, 0, true>(rd, L, tb, o, np, r);
+            redo[c] = m1 ? xp::fast::suite_column_pcol<7u, 1, true>(rd, L, tb, o, np, nr, r)
+                         : xp::fast::suite_column_pcol<7u, 0, true>(rd, L, tb, o, np, nr, r);
         }
         for (int q = 0; q < 3; ++q) {
             const float vals[12] = {r[q].cape, r[q].cin, r[q].lcl_p, r[q].lcl_t, r[q].lcl_tv, r[q].lfc_p,

@@ -92,6 +92,12 @@ def set_fast_sweep(version=7, ka_floor=0):
     lib().hostsim_set_fast_sweep(int(version), int(ka_floor))
 
 
+def set_pcol_kind(kind=0, ring_levels=0):
+    """hostsim_fast_suite_pcol: 0 = all three kinds at once; 2 / 4 = ONE lifted kind (mixed layer / most unstable) with
+    profile rows (the re-based sweep), read through a per-thread ring of ``ring_levels`` levels (0: direct loads)."""
+    lib().hostsim_set_pcol_kind(int(kind), int(ring_levels))
+
+
 def set_qmode(qmode=0):
     """0: the dewpoint arguments are dewpoints; 141 / 162: they hold specific humidity, converted on load in that
     MetPy form (xp_columns.dewpoint_is_specific_humidity)."""

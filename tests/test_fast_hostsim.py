@@ -137,6 +137,46 @@ def test_fast_profile_rows_per_column_pressure(oracle_tables, vtc):
     assert seen_rows_ok[0] > 0                   # the case is exercised
 
 
+@pytest.mark.parametrize("kind,code", [("ml", 2), ("mu", 4)])
+def test_rebased_profile_sweep_through_the_ring(oracle_tables, kind, code):
+    """ONE lifted kind with profile rows (BASELINE configs[4]): the sweep is re-based per lane (row r at iteration
+    r) and reads its levels through a per-thread ring that every lane of a warp fills level-synchronously.  The
+    rows must be the oracle's and must not depend on the ring (capacity 48 / too small to be used / none) nor on how
+    far the other lanes of the warp lag (the host stand-in for the warp maximum)."""
+    p, t, td = synth.model_level_columns(400, 90, seed=21)
+    P, T, D = [x.numpy().astype(np.float64) for x in (p, t, td)]
+    opts = op.Options(op.MoistLapseLUT(oracle_tables), lcl_mode="converged")
+    fn = {"ml": op.mixed_layer_cape_cin, "mu": op.most_unstable_cape_cin}[kind]
+    prof = fn(P, T, D, opts)[1]
+    n = prof["pressure"].shape[0]
+    runs = {}
+    try:
+        for ring, floor in ((0, 0), (48, 0), (48, 30), (8, 0), (64, 45)):
+            hs.set_pcol_kind(code, ring)
+            hs.set_fast_sweep(7, floor)
+            runs[(ring, floor)] = hs.fast_suite(p.numpy(), t.numpy(), td.numpy(), oracle_tables, profile=True)
+    finally:
+        hs.set_pcol_kind(0, 0)
+        hs.set_fast_sweep(7, 0)
+    res0, redo0 = runs[(0, 0)]
+    keep = (redo0 & 7) == 0
+    assert keep.mean() > 0.8
+    for k in ("pressure", "temperature", "virtual_temperature", "environment_temperature",
+              "environment_virtual_temperature", "environment_dewpoint"):
+        a = res0[kind]["profile"][k].astype(np.float64)[:, keep]
+        b = prof[k][:, keep]
+        assert np.array_equal(np.isnan(a[:n]), np.isnan(b)), k
+        ok = ~np.isnan(b)
+        assert np.allclose(a[:n][ok], b[ok], rtol=3e-6, atol=0), k
+    for key, (res, redo) in runs.items():
+        assert np.array_equal(redo, redo0), key
+        for k, v in res0[kind]["profile"].items():
+            w = res[kind]["profile"][k]
+            assert np.array_equal(v.view(np.int32), w.view(np.int32)), (key, k)
+        for f in ("cape", "cin", "lfc_pressure", "el_pressure"):
+            assert np.array_equal(res0[kind][f].view(np.int32), res[kind][f].view(np.int32)), (key, f)
+
+
 def test_fast_suite_per_column_pressure_depths_and_90_levels(oracle_tables):
     p, t, td = synth.model_level_columns(3000, 90, seed=22, nan_columns=0, allnan_columns=0, saturated=0)
     P, T, D = [a.numpy().astype(np.float64) for a in (p, t, td)]

@@ -338,19 +338,48 @@ struct ProfileWriter {
     }
 };
 
-template <unsigned KINDS, int MODE, bool PROFILE, bool QIN = false>
-__global__ void __launch_bounds__(kPColThreads, pcol_ctas(KINDS, PROFILE)) suite_fast_pcol_kernel(const __grid_constant__ PColParams prm) {
+// Per-thread ring of (p, T, Td) levels in dynamic shared memory for the re-based profile sweep (fast::NoRing in
+// xp_fast_pcol.cuh): element (slot, which, thread) at base[(3 slot + which) * blockDim.x + thread] -- conflict-free.
+constexpr int kPColRingLevels = 48;        // covers a most-unstable search over 43 levels (300 hPa of a 90-level grid)
+constexpr int kPColRingThreads = 128;      // 48 x 3 x 4 B x 128 = 72 KB per CTA: three CTAs per SM
+struct RingSmem {
+    static constexpr bool kEnabled = true;
+    float *base;
+    int stride;
+    __device__ __forceinline__ int capacity() const { return kPColRingLevels; }
+    __device__ __forceinline__ void put(int s, float p, float t, float td) {
+        XP_CHECK(s >= 0 && s < kPColRingLevels);
+        base[(3 * s) * stride] = p; base[(3 * s + 1) * stride] = t; base[(3 * s + 2) * stride] = td;
+    }
+    __device__ __forceinline__ void get(int s, float &p, float &t, float &td) const {
+        XP_CHECK(s >= 0 && s < kPColRingLevels);
+        p = base[(3 * s) * stride]; t = base[(3 * s + 1) * stride]; td = base[(3 * s + 2) * stride];
+    }
+};
+
+// RING: one lifted kind with profile rows -- the re-based sweep reads its levels through the shared-memory ring
+// (kPColRingThreads threads per CTA); everything else reads directly (kPColThreads).
+template <unsigned KINDS, int MODE, bool PROFILE, bool QIN = false, bool RING = false>
+__global__ void __launch_bounds__(RING ? kPColRingThreads : kPColThreads, RING ? 3 : pcol_ctas(KINDS, PROFILE))
+suite_fast_pcol_kernel(const __grid_constant__ PColParams prm) {
+    extern __shared__ __align__(16) float s_ring[];
     const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= prm.n) return;
     const PColRd rd{prm.p + col, prm.t + col, prm.td + col, prm.ls, prm.pls};
     fast::FResult res[3];
     unsigned redo;
-    if (PROFILE) {
+    if constexpr (PROFILE && RING) {
         ProfileWriter pw{prm.outs, col, prm.L};
-        redo = fast::suite_column_pcol<KINDS, MODE, QIN>(rd, prm.L, prm.tb, prm.o, pw, res);
+        RingSmem ring{s_ring + threadIdx.x, (int)blockDim.x};
+        redo = fast::suite_column_pcol<KINDS, MODE, QIN>(rd, prm.L, prm.tb, prm.o, pw, ring, res);
+    } else if constexpr (PROFILE) {
+        ProfileWriter pw{prm.outs, col, prm.L};
+        fast::NoRing ring;
+        redo = fast::suite_column_pcol<KINDS, MODE, QIN>(rd, prm.L, prm.tb, prm.o, pw, ring, res);
     } else {
         fast::NoProfile np;
-        redo = fast::suite_column_pcol<KINDS, MODE, QIN>(rd, prm.L, prm.tb, prm.o, np, res);
+        fast::NoRing ring;
+        redo = fast::suite_column_pcol<KINDS, MODE, QIN>(rd, prm.L, prm.tb, prm.o, np, ring, res);
     }
     if (KINDS & 1u) store_fast(prm.outs[0], col, res[0]);
     if (KINDS & 2u) store_fast(prm.outs[1], col, res[1]);
@@ -412,7 +441,7 @@ __global__ void __launch_bounds__(kPCol6Threads, 2) suite_fast_pcol6_kernel(cons
 
 // Build/experiment knobs from the environment, read ONCE per process (thread-safe static initialisation), never
 // in the launch path.
-struct FastKnobs { int pcol6, staged, sweep; };
+struct FastKnobs { int pcol6, staged, sweep, ring; };
 static const FastKnobs &fast_knobs() {
     static const FastKnobs k = [] {
         FastKnobs r;
@@ -420,6 +449,11 @@ static const FastKnobs &fast_knobs() {
         r.pcol6 = e ? atoi(e) : 0;
         e = getenv("XP_FAST_STAGED");
         r.staged = e ? atoi(e) : 0;          // default 0: measured fastest
+        e = getenv("XP_PCOL_RING");
+        // 1: re-based profile sweeps read through the shared-memory ring.  Default 0 -- measured on 10 M x 90
+        // most-unstable + profile rows: DRAM reads 38.6 -> 24.5 GB, writes 30.5 -> 26.7 GB, but the kernel takes 39.1
+        // instead of 33.2 ms (12 instead of 16 warps per SM; it is latency-bound, not DRAM-bound: 2.1 TB/s).
+        r.ring = e ? atoi(e) : 0;
         e = getenv("XP_FAST_SWEEP");
         r.sweep = e ? atoi(e) : 7;           // 7: xp_fast7.cuh (default), 6: xp_fast6.cuh
         return r;
@@ -506,6 +540,25 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
                 default: return -1;
             }
 #undef XP_PCOL6_CASE
+            launch_suite_list(lp, sm_count, stream);
+            return 2;
+        }
+        // one LIFTED kind (mixed layer / most unstable) with profile rows: the re-based sweep through the ring
+        if (profile && ((kind_mask & 7) == 2 || (kind_mask & 7) == 4) && fast_knobs().ring) {
+            const size_t rsm = (size_t)kPColRingLevels * 3 * sizeof(float) * kPColRingThreads;
+            const unsigned gr = (unsigned)((cols.n + kPColRingThreads - 1) / kPColRingThreads);
+#define XP_PCOL_RING(K, M, Q)                                                                                          \
+    do {                                                                                                               \
+        if (cudaFuncSetAttribute(suite_fast_pcol_kernel<K, M, true, Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)rsm) != cudaSuccess) return -1;                                                  \
+        suite_fast_pcol_kernel<K, M, true, Q, true><<<gr, kPColRingThreads, rsm, stream>>>(pp);                        \
+    } while (0)
+            if ((kind_mask & 7) == 2) {
+                if (cols.qmode) XP_PCOL_RING(2, 0, true); else if (mode) XP_PCOL_RING(2, 1, false); else XP_PCOL_RING(2, 0, false);
+            } else {
+                if (cols.qmode) XP_PCOL_RING(4, 0, true); else if (mode) XP_PCOL_RING(4, 1, false); else XP_PCOL_RING(4, 0, false);
+            }
+#undef XP_PCOL_RING
             launch_suite_list(lp, sm_count, stream);
             return 2;
         }

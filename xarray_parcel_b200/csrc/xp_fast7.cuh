@@ -21,18 +21,13 @@
 //   * Bolton's es with the constant 6.112 folded into the exponent (one multiply less, twice per level).
 #pragma once
 #include "xp_fast6.cuh"
+#include "xp_fast_pcol.cuh"
 
 namespace xp {
 namespace fast {
 
-#if defined(__CUDACC__)
-#define XP_WARP_MAX_INT(x) __reduce_max_sync(0xffffffffu, (x))
-#else
-// The host simulation runs one column at a time; tests/hostsim sets this floor to stand in for the other lanes of a
-// warp (a larger value keeps the column in the mixed phase longer: the results must not depend on it).
-inline int &host_warp_max_floor() { static int v = 0; return v; }
-#define XP_WARP_MAX_INT(x) ((x) > xp::fast::host_warp_max_floor() ? (x) : xp::fast::host_warp_max_floor())
-#endif
+// XP_WARP_MAX_INT (warp-wide integer maximum; on the host a settable floor that stands in for the other lanes of a
+// warp -- tests/hostsim) is defined in xp_fast_pcol.cuh.
 
 // es(T) = 6.112 * 2^(kEsC (1 - 243.5/(T - 29.65))) = 2^(kEsA - kEsB/(T - 29.65))
 constexpr float kEsA = 17.67f * 1.4426950408889634f + 2.611644f;   // + log2(6.112) = 2.6116443...

@@ -12,6 +12,15 @@
 #pragma once
 #include "xp_fast.cuh"
 
+#ifndef XP_WARP_MAX_INT
+#if defined(__CUDACC__)
+#define XP_WARP_MAX_INT(x) __reduce_max_sync(__activemask(), (x))
+#else
+namespace xp { namespace fast { inline int &host_warp_max_floor() { static int v = 0; return v; } } }
+#define XP_WARP_MAX_INT(x) ((x) > xp::fast::host_warp_max_floor() ? (x) : xp::fast::host_warp_max_floor())
+#endif
+#endif
+
 namespace xp {
 namespace fast {
 
@@ -113,6 +122,20 @@ XP_HD void setup_parcel_pcol(const Rd &rd, int L, const Tables &tb, const Opts &
     if (!(te == te) || !(tde == tde)) pc.bad = true;
 }
 
+// Per-thread ring of (p, T, Td) levels for the RE-BASED profile sweep (one lifted kind + profile rows, see
+// suite_column_pcol): there iteration `it` of a lane consumes level it + shift with a per-lane shift, so direct loads
+// put the 32 lanes of a warp on up to 32 different lines (ncu, 10 M x 90 most-unstable + rows: 38.6 GB read for
+// 10.8 GB of input).  With a ring every lane loads the SAME level at the same time -- one coalesced line per array --
+// into its own slots and consumes it `wmax - shift` iterations later; only the thread that wrote a slot reads it, so
+// there is nothing to synchronise.  kRingLead levels are fetched beyond the furthest lane to cover the load latency.
+constexpr int kRingLead = 4;
+struct NoRing {
+    static constexpr bool kEnabled = false;
+    XP_HD int capacity() const { return 0; }
+    XP_HD void put(int, float, float, float) const {}
+    XP_HD void get(int, float &p, float &t, float &td) const { p = t = td = 0.0f; }
+};
+
 // Environment of a level as the profile rows need it.
 struct EnvLevel { float p, t, td, tv; };
 
@@ -146,8 +169,8 @@ XP_HD void parcel_iteration_pcol(PColParcel &c, int it, bool last, int j_cur, fl
 
 // The suite for one column with its own pressure profile.  Returns the redo mask (see suite_column).
 // QIN: the dewpoint array may hold specific humidity (o.qmode); false compiles the conversion away.
-template <unsigned KINDS, int MODE, bool QIN, class Rd, class Prof>
-XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Opts &o, Prof &prof, FResult res[3]) {
+template <unsigned KINDS, int MODE, bool QIN, class Rd, class Prof, class Ring>
+XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Opts &o, Prof &prof, Ring &ring, FResult res[3]) {
     unsigned redo = 0, rows_exact = 0;       // rows_exact: kinds whose profile rows the exact path must rewrite too
     float nanacc = 0.0f;
     bool bad_axis = false;                 // pressure not finite / not strictly decreasing / outside the table
@@ -297,14 +320,28 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
     const int k1 = min(1 + shift, L - 1);
     const float *ppp = rd.pptr(k1), *tp = rd.tptr(k1), *tdp = rd.tdptr(k1);
     const int64_t ls = rd.stride(), pls = rd.pstride();
-    float p_nxt = Rd::ld(ppp), t_nxt = Rd::ld(tp), td_nxt = Rd::ld(tdp);
+    // re-based sweep through the ring (see NoRing): warp-uniform window of levels [it + wmin, it + wmax + lead]
+    bool use_ring = false;
+    int wmax = 0, g_next = 0;
+    if (Ring::kEnabled && Prof::kEnabled && (KINDS == 2u || KINDS == 4u)) {
+        wmax = XP_WARP_MAX_INT(shift);
+        const int wmin = max(0, -(XP_WARP_MAX_INT(-shift)));
+        use_ring = (wmax - wmin + 1 + kRingLead) <= ring.capacity();
+        g_next = wmin + 1;
+    }
+    float p_nxt = 0.0f, t_nxt = 0.0f, td_nxt = 0.0f;
+    if (!use_ring) { p_nxt = Rd::ld(ppp); t_nxt = Rd::ld(tp); td_nxt = Rd::ld(tdp); }
     for (int it = 1; it <= Lq; ++it) {
         const bool last = (it == Lq);
-        const float p_cur0 = p_nxt, t = t_nxt;
-        float td = td_nxt;
+        float p_cur0 = p_nxt, t = t_nxt, td = td_nxt;
+        if (use_ring) {
+            const int need = min(it + wmax + kRingLead, L - 1);       // the same for every lane still in the loop
+            for (; g_next <= need; ++g_next) ring.put(g_next % ring.capacity(), rd.P(g_next), rd.T(g_next), rd.Td(g_next));
+            if (!last) ring.get((it + shift) % ring.capacity(), p_cur0, t, td);
+        }
         if (qm && !last) td = f_td_from_q(p_cur0, t, td, qm);
         ppp += pls; tp += ls; tdp += ls;
-        if (it + 1 < Lq) { p_nxt = Rd::ld(ppp); t_nxt = Rd::ld(tp); td_nxt = Rd::ld(tdp); }
+        if (!use_ring && it + 1 < Lq) { p_nxt = Rd::ld(ppp); t_nxt = Rd::ld(tp); td_nxt = Rd::ld(tdp); }
         float b_cur = 0.0f, x_cur = x_prv, pk_cur = 0.0f, p_cur = p_prv, w_cur = w_prv;
         EnvLevel e_cur = e_prv;
         int j_cur = 0;
