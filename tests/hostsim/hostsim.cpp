@@ -13,6 +13,7 @@
 #include "../../xarray_parcel_b200/csrc/xp_fast6.cuh"
 #include "../../xarray_parcel_b200/csrc/xp_fast7.cuh"
 #include "../../xarray_parcel_b200/csrc/xp_fast_pcol6.cuh"
+#include "../../xarray_parcel_b200/csrc/xp_fast_pcol7.cuh"
 #include "../../xarray_parcel_b200/csrc/xp_layers.cuh"
 #include "../../xarray_parcel_b200/csrc/xp_levels.cuh"
 
@@ -246,8 +247,37 @@ struct HostProfW {
 
 // 0: all three kinds at once (KINDS = 7); 2 / 4: ONE lifted kind (mixed layer / most unstable) with profile rows -- the
 // re-based sweep -- read through a per-thread ring of `g_pcol_ring` levels (0: direct loads).
-static int g_pcol_kind = 0, g_pcol_ring = 0;
+static int g_pcol_kind = 0, g_pcol_ring = 0, g_pcol_table = 0;
 extern "C" void hostsim_set_pcol_kind(int kind, int ring_levels) { g_pcol_kind = kind; g_pcol_ring = ring_levels; }
+// 1: default options without profile rows read the adiabat family from the two-segment table (fast::PTabView) -- what
+// suite_fast_ptab_kernel runs
+extern "C" void hostsim_set_pcol_table(int on) { g_pcol_table = on; }
+// max |table - reference evaluation| over a sample of (adiabat, pressure) pairs: out[0] segment A (100..1100 hPa),
+// out[1] 20..100 hPa, out[2] 2.5..20 hPa
+extern "C" void hostsim_ptab_error(const float *curves, int n_samples, double *out) {
+    std::vector<xp::fast::Coef> tab((size_t)xp::fast::kPTabNodes * xp::fast::kPTabIntervals);
+    for (int j = 0; j < xp::fast::kPTabNodes; ++j)
+        for (int m = 0; m < xp::fast::kPTabIntervals; ++m)
+            tab[(size_t)j * xp::fast::kPTabIntervals + m] = xp::fast::compute_ptab_coef(curves, j, m + xp::fast::kPTabFirstInterval);
+    const xp::fast::PTabView pt{tab.data(), xp::fast::ptab_desc()};
+    for (int i = 0; i < 9; ++i) out[i] = 0.0;
+    uint64_t s = 88172645463325252ull;
+    auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (double)(s >> 11) / 9007199254740992.0; };
+    for (int i = 0; i < n_samples; ++i) {
+        const int a0 = xp::fast::kPTabFirstInterval * xp::fast::kNodeStride +
+                       (int)(rnd() * ((xp::fast::kLastInterval + 1 - xp::fast::kPTabFirstInterval) * xp::fast::kNodeStride - 1));
+        const int seg = i % 3;
+        const double p = seg == 0 ? 100.0 + rnd() * 1000.0 : (seg == 1 ? 20.0 + rnd() * 80.0 : 2.5 + rnd() * 17.5);
+        const int m = a0 / xp::fast::kNodeStride;
+        const float f = (float)(a0 - m * xp::fast::kNodeStride) * (1.0f / xp::fast::kNodeStride);
+        const float xi = xp::fast::f_ex2((float)xp::kKappa * xp::fast::f_lg2((float)p));
+        const float got = pt.eval(pt.level(xi), m, f);
+        const double t = xp::adiabat_temperature(curves + (size_t)a0 * xp::kNP, (double)(float)p);
+        const double want = xp::virtual_temperature(t, xp::sat_mixing_ratio((double)(float)p, t));
+        const double e = fabs((double)got - want);
+        if (e > out[seg]) { out[seg] = e; out[3 + 2 * seg] = (double)a0; out[4 + 2 * seg] = p; }
+    }
+}
 namespace {
 struct HostRing {
     static constexpr bool kEnabled = true;
@@ -278,16 +308,16 @@ extern "C" int hostsim_fast_suite_pcol(const float *p, const float *t, const flo
             HostRing ring; ring.cap = g_pcol_ring;
             for (int q = 0; q < 3; ++q) r[q] = xp::fast::FResult();
             if (g_pcol_kind == 2)
-                redo[c] = g_pcol_ring ? xp::fast::suite_column_pcol<2u, 1, true>(rd, L, tb, o, pw, ring, r)
-                                      : xp::fast::suite_column_pcol<2u, 1, true>(rd, L, tb, o, pw, nr, r);
+                redo[c] = g_pcol_ring ? xp::fast::suite_column_pcol<2u, 1, true>(rd, L, tb, o, pw, ring, xp::fast::NoPTab(), r)
+                                      : xp::fast::suite_column_pcol<2u, 1, true>(rd, L, tb, o, pw, nr, xp::fast::NoPTab(), r);
             else
-                redo[c] = g_pcol_ring ? xp::fast::suite_column_pcol<4u, 1, true>(rd, L, tb, o, pw, ring, r)
-                                      : xp::fast::suite_column_pcol<4u, 1, true>(rd, L, tb, o, pw, nr, r);
+                redo[c] = g_pcol_ring ? xp::fast::suite_column_pcol<4u, 1, true>(rd, L, tb, o, pw, ring, xp::fast::NoPTab(), r)
+                                      : xp::fast::suite_column_pcol<4u, 1, true>(rd, L, tb, o, pw, nr, xp::fast::NoPTab(), r);
         } else if (prof) {
             HostProfW pw = {prof, n, c, L};
-            redo[c] = m1 ? xp::fast::suite_column_pcol<7u, 1, true>(rd, L, tb, o, pw, nr, r)
-                         : xp::fast::suite_column_pcol<7u, 0, true>(rd, L, tb, o, pw, nr, r);
-        } else if (m1 && (c % 3) != 0 && !g_qmode) {
+            redo[c] = m1 ? xp::fast::suite_column_pcol<7u, 1, true>(rd, L, tb, o, pw, nr, xp::fast::NoPTab(), r)
+                         : xp::fast::suite_column_pcol<7u, 0, true>(rd, L, tb, o, pw, nr, xp::fast::NoPTab(), r);
+        } else if (m1 && (c % 3) != 0 && !g_qmode && !g_pcol_table) {
             // default options, no profile: the v6 sweep (xp_fast_pcol6.cuh) on two columns out of three, with a
             // stash of 36 levels (the kernel's), of 5 levels (search and sweep cross its end) or none
             const HostRdP6 rd6 = {p, t, td, (uint32_t)c, (uint32_t)n};
@@ -298,10 +328,24 @@ extern "C" int hostsim_fast_suite_pcol(const float *p, const float *t, const flo
                 xp::fast::NoStash3 st;
                 redo[c] = xp::fast::suite_column_pcol6<7u>(rd6, L, tb, o, st, r);
             }
+        } else if (m1 && g_pcol_table) {
+            static std::vector<xp::fast::Coef> tab;
+            static const float *tab_of = nullptr;
+            if (tab_of != curves) {
+                tab.resize((size_t)xp::fast::kPTabNodes * xp::fast::kPTabIntervals);
+                for (int j = 0; j < xp::fast::kPTabNodes; ++j)
+                    for (int m = 0; m < xp::fast::kPTabIntervals; ++m)
+                        tab[(size_t)j * xp::fast::kPTabIntervals + m] =
+                            xp::fast::compute_ptab_coef(curves, j, m + xp::fast::kPTabFirstInterval);
+                tab_of = curves;
+            }
+            const xp::fast::PTabView pt{tab.data(), xp::fast::ptab_desc()};
+            xp::fast::NoProfile np;
+            redo[c] = xp::fast::suite_column_pcol<7u, 1, true>(rd, L, tb, o, np, nr, pt, r);
         } else {
             xp::fast::NoProfile np;
-            redo[c] = m1 ? xp::fast::suite_column_pcol<7u, 1, true>(rd, L, tb, o, np, nr, r)
-                         : xp::fast::suite_column_pcol<7u, 0, true>(rd, L, tb, o, np, nr, r);
+            redo[c] = m1 ? xp::fast::suite_column_pcol<7u, 1, true>(rd, L, tb, o, np, nr, xp::fast::NoPTab(), r)
+                         : xp::fast::suite_column_pcol<7u, 0, true>(rd, L, tb, o, np, nr, xp::fast::NoPTab(), r);
         }
         for (int q = 0; q < 3; ++q) {
             const float vals[12] = {r[q].cape, r[q].cin, r[q].lcl_p, r[q].lcl_t, r[q].lcl_tv, r[q].lfc_p,
@@ -324,7 +368,8 @@ extern "C" void hostsim_lcl_fast(const double *p, const double *t, const double 
 
 // Branch-free float64 log / exp of the v6 fast path (xp_fast6.cuh): which = 0 log, 1 exp.
 extern "C" void hostsim_fast_math64(const double *x, int64_t n, int which, double *y) {
-    for (int64_t i = 0; i < n; ++i) y[i] = which == 0 ? xp::fast::log64_fast(x[i]) : xp::fast::exp64_fast(x[i]);
+    for (int64_t i = 0; i < n; ++i)
+        y[i] = which == 0 ? xp::fast::log64_fast(x[i]) : (which == 1 ? xp::fast::exp64_fast(x[i]) : xp::pow_kappa64(x[i]));
 }
 
 // Layer primitives (xp_layers.cuh): mixed_layer of n_fields variables x [n_fields][L][n], mixed_parcel (out

@@ -24,7 +24,7 @@ KINDS = {"sb": 0, "ml": 1, "mu": 2, "explicit": 3}
 
 
 def build():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("xp_math.cuh", "xp_column.cuh", "xp_parcels.cuh", "xp_fast.cuh", "xp_fast_pcol.cuh", "xp_fast6.cuh", "xp_fast7.cuh", "xp_fast_pcol6.cuh", "xp_layers.cuh", "xp_levels.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("xp_math.cuh", "xp_column.cuh", "xp_parcels.cuh", "xp_fast.cuh", "xp_fast_pcol.cuh", "xp_fast6.cuh", "xp_fast7.cuh", "xp_fast_pcol6.cuh", "xp_fast_pcol7.cuh", "xp_layers.cuh", "xp_levels.cuh")]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     os.makedirs(BUILD, exist_ok=True)
@@ -96,6 +96,21 @@ def set_pcol_kind(kind=0, ring_levels=0):
     """hostsim_fast_suite_pcol: 0 = all three kinds at once; 2 / 4 = ONE lifted kind (mixed layer / most unstable) with
     profile rows (the re-based sweep), read through a per-thread ring of ``ring_levels`` levels (0: direct loads)."""
     lib().hostsim_set_pcol_kind(int(kind), int(ring_levels))
+
+
+def set_pcol_table(on=True):
+    """Per-column pressure, default options, no profile rows: read the adiabat family from the two-segment
+    shared-memory table (fast::PTabView; what suite_fast_ptab_kernel runs) instead of gathering the curve table."""
+    lib().hostsim_set_pcol_table(int(bool(on)))
+
+
+def ptab_error(tables, n_samples=60000):
+    """max |table - reference evaluation| of the virtual temperature of the saturated parcel [K] over random
+    (adiabat, pressure) pairs in 100..1100 hPa, 20..100 hPa and 2.5..20 hPa."""
+    cur = np.ascontiguousarray(tables.curves_asc, dtype=np.float32)
+    out = np.zeros(9)
+    lib().hostsim_ptab_error(ctypes.c_void_p(cur.ctypes.data), int(n_samples), ctypes.c_void_p(out.ctypes.data))
+    return out
 
 
 def set_qmode(qmode=0):

@@ -137,6 +137,47 @@ def test_fast_profile_rows_per_column_pressure(oracle_tables, vtc):
     assert seen_rows_ok[0] > 0                   # the case is exercised
 
 
+def test_ptab_accuracy(oracle_tables):
+    """The adiabat family on the two-segment shared-memory grid (fast::PTabView) against the reference's evaluation of
+    one adiabat (np.interp on the 0.5 hPa nodes + saturation mixing ratio + virtual temperature): inside the margins
+    the kernels decide with (kPTabMarginA 8e-4 / B 5e-3 / Top 0.1 K, half of each for the table itself)."""
+    err = hs.ptab_error(oracle_tables, 300000)
+    assert err[0] < 4e-4 and err[1] < 2.5e-3 and err[2] < 0.06, err
+
+
+def test_per_column_pressure_through_the_shared_memory_table(oracle_tables):
+    """suite_fast_ptab_kernel's column code (default options, no profile rows): the moist adiabat comes from the
+    shared-memory table instead of two gathers per (level, parcel).  Kept columns against the oracle, and no more
+    columns handed over than with the gathers (+1 % for the wider margins)."""
+    p, t, td = synth.model_level_columns(5000, 70, seed=17)
+    P, T, D = [a.numpy().astype(np.float64) for a in (p, t, td)]
+    ora = op.suite(P, T, D, op.Options(op.MoistLapseLUT(oracle_tables), lcl_mode="converged"))
+    gather, redo_g = hs.fast_suite(p.numpy(), t.numpy(), td.numpy(), oracle_tables)
+    hs.set_pcol_table(True)
+    try:
+        res, redo = hs.fast_suite(p.numpy(), t.numpy(), td.numpy(), oracle_tables)
+    finally:
+        hs.set_pcol_table(False)
+    check_fast(res, redo, ora, max_redo=0.08)
+    assert (redo != 0).mean() < (redo_g != 0).mean() + 0.01, ((redo != 0).mean(), (redo_g != 0).mean())
+    for kind in ("ml", "mu"):
+        assert np.array_equal(res[kind]["level_shift"], gather[kind]["level_shift"])
+    # the mixed / above phase boundary is the warp's (here: a stand-in for the other lanes): results must not move
+    hs.set_pcol_table(True)
+    try:
+        for floor in (25, 80):
+            hs.set_fast_sweep(7, floor)
+            res2, redo2 = hs.fast_suite(p.numpy(), t.numpy(), td.numpy(), oracle_tables)
+            assert np.array_equal(redo, redo2), floor
+            keep = redo == 0
+            for kind in ("sb", "ml", "mu"):
+                for f in FIELDS:
+                    assert np.array_equal(res[kind][f][keep].view(np.int32), res2[kind][f][keep].view(np.int32)), (floor, kind, f)
+    finally:
+        hs.set_pcol_table(False)
+        hs.set_fast_sweep(7, 0)
+
+
 @pytest.mark.parametrize("kind,code", [("ml", 2), ("mu", 4)])
 def test_rebased_profile_sweep_through_the_ring(oracle_tables, kind, code):
     """ONE lifted kind with profile rows (BASELINE configs[4]): the sweep is re-based per lane (row r at iteration
@@ -250,6 +291,12 @@ def test_branch_free_log_exp_accuracy():
     y = np.empty_like(x)
     fn(ptr(x), ctypes.c_int64(x.size), ctypes.c_int(1), ptr(y))
     assert np.abs(y / np.exp(x) - 1).max() < 1e-15
+    # pow_kappa64: x^(2/7) by a float32 estimate + one Newton step on y^7 = x^2 (the potential-temperature factor
+    # (1000/p)^kappa of the mixed-layer pre-pass): 3 eps^2 ~ 3e-13 relative
+    x = np.concatenate([rng.uniform(0.9, 400.0, 300_000), np.array([1.0, 1000.0 / 1100.0, 1000.0 / 2.5])])
+    y = np.empty_like(x)
+    fn(ptr(x), ctypes.c_int64(x.size), ctypes.c_int(2), ptr(y))
+    assert np.abs(y / x ** (2.0 / 7.0) - 1).max() < 1e-12
 
 
 def test_fast_suite_warm_stratopause(oracle_tables):

@@ -61,18 +61,23 @@ def _compare(res, redo, o, n, what, min_kept):
     assert kept >= min_kept * 3 * n, (what, kept)
 
 
-@pytest.mark.parametrize("layout,compat", [("era5", "1.4.1"), ("model", "1.4.1"), ("model", "1.6.2")])
+@pytest.mark.parametrize("layout,compat", [("era5", "1.4.1"), ("model", "1.4.1"), ("model", "1.6.2"), ("model-table", "1.4.1")])
 def test_fast_path_converts_specific_humidity_on_load_hostsim(oracle_tables, layout, compat):
-    """The SAME per-column code the kernels inline (tests/hostsim), on the CPU."""
+    """The SAME per-column code the kernels inline (tests/hostsim), on the CPU ("model-table": the per-column-pressure
+    sweep on the shared-memory adiabat table, suite_fast_ptab_kernel<K, true>)."""
     n = 3000
+    table = layout == "model-table"
+    layout = "model" if table else layout
     p, t, q, P, T = _q_columns(layout, n, seed=31)
     o, _ = _oracle(P, T, q, oracle_tables, compat)
     code = 141 if compat == "1.4.1" else 162
     hs.set_qmode(code)
+    hs.set_pcol_table(table)
     try:
         out = hs.fast_suite(p, t, q, oracle_tables, metpy_compat=code)
     finally:
         hs.set_qmode(0)
+        hs.set_pcol_table(False)
     assert out is not None
     res, redo = out
     _compare(res, redo, o, n, (layout, compat), 0.9)

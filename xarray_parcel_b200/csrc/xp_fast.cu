@@ -8,6 +8,7 @@
 #include "xp_fast6.cuh"
 #include "xp_fast7.cuh"
 #include "xp_fast_pcol6.cuh"
+#include "xp_fast_pcol7.cuh"
 #include "xp_kernels.cuh"
 
 // Streaming read of column data (each element is used once): evict-first in L2 so that it does not push the
@@ -371,20 +372,77 @@ suite_fast_pcol_kernel(const __grid_constant__ PColParams prm) {
     if constexpr (PROFILE && RING) {
         ProfileWriter pw{prm.outs, col, prm.L};
         RingSmem ring{s_ring + threadIdx.x, (int)blockDim.x};
-        redo = fast::suite_column_pcol<KINDS, MODE, QIN>(rd, prm.L, prm.tb, prm.o, pw, ring, res);
+        redo = fast::suite_column_pcol<KINDS, MODE, QIN>(rd, prm.L, prm.tb, prm.o, pw, ring, fast::NoPTab(), res);
     } else if constexpr (PROFILE) {
         ProfileWriter pw{prm.outs, col, prm.L};
         fast::NoRing ring;
-        redo = fast::suite_column_pcol<KINDS, MODE, QIN>(rd, prm.L, prm.tb, prm.o, pw, ring, res);
+        redo = fast::suite_column_pcol<KINDS, MODE, QIN>(rd, prm.L, prm.tb, prm.o, pw, ring, fast::NoPTab(), res);
     } else {
         fast::NoProfile np;
         fast::NoRing ring;
-        redo = fast::suite_column_pcol<KINDS, MODE, QIN>(rd, prm.L, prm.tb, prm.o, np, ring, res);
+        redo = fast::suite_column_pcol<KINDS, MODE, QIN>(rd, prm.L, prm.tb, prm.o, np, ring, fast::NoPTab(), res);
     }
     if (KINDS & 1u) store_fast(prm.outs[0], col, res[0]);
     if (KINDS & 2u) store_fast(prm.outs[1], col, res[1]);
     if (KINDS & 4u) store_fast(prm.outs[2], col, res[2]);
     if (redo) push_redo(prm.list, prm.list_count, prm.n, col, redo);
+}
+
+// ---- per-column pressure with the adiabat family in SHARED memory (fast::PTabView, xp_fast_pcol.cuh) ----------------
+// Default options, scalar outputs.  Persistent: one 512-thread CTA per SM stages the 136 KB table once, by bulk
+// asynchronous copies (TMA, one per node row) completing on an mbarrier, then walks over 512-column tiles.
+__global__ void ptab_coef_kernel(const float *__restrict__ curves, Coef *__restrict__ coef) {
+    const int j = blockIdx.x;
+    for (int m = threadIdx.x; m < fast::kPTabIntervals; m += blockDim.x)
+        coef[(size_t)j * fast::kPTabIntervals + m] = fast::compute_ptab_coef(curves, j, m + fast::kPTabFirstInterval);
+}
+
+constexpr int kPTabThreads = 512;
+template <unsigned KINDS, bool QIN>
+__global__ void __launch_bounds__(kPTabThreads, 1) suite_fast_ptab_kernel(const __grid_constant__ PColParams prm,
+                                                                          const Coef *__restrict__ coef) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+    Coef *s_tab = reinterpret_cast<Coef *>(smem_raw);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t row_bytes = fast::kPTabIntervals * sizeof(Coef);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)),
+                     "r"(row_bytes * (uint32_t)fast::kPTabNodes) : "memory");
+        for (int j = 0; j < fast::kPTabNodes; ++j) {
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    smem_u32(s_tab + (size_t)j * fast::kPTabIntervals)),
+                "l"(coef + (size_t)j * fast::kPTabIntervals), "r"(row_bytes), "r"(smem_u32(&mbar))
+                : "memory");
+        }
+    }
+    {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0u) : "memory");
+        }
+    }
+    const fast::PTabView ptab{s_tab, fast::ptab_desc()};
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < prm.n; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t col = base + threadIdx.x;
+        if (col >= prm.n) continue;
+        const PColRd rd{prm.p + col, prm.t + col, prm.td + col, prm.ls, prm.pls};
+        fast::FResult res[3];
+        fast::NoProfile np;
+        fast::NoRing ring;
+        const unsigned redo = fast::suite_column_pcol<KINDS, 1, QIN>(rd, prm.L, prm.tb, prm.o, np, ring, ptab, res);
+        if (KINDS & 1u) store_fast(prm.outs[0], col, res[0]);
+        if (KINDS & 2u) store_fast(prm.outs[1], col, res[1]);
+        if (KINDS & 4u) store_fast(prm.outs[2], col, res[2]);
+        if (redo) push_redo(prm.list, prm.list_count, prm.n, col, redo);
+    }
 }
 
 // ---- per-column pressure, v6 sweep (xp_fast_pcol6.cuh): default options, scalar outputs ----------------------
@@ -441,7 +499,7 @@ __global__ void __launch_bounds__(kPCol6Threads, 2) suite_fast_pcol6_kernel(cons
 
 // Build/experiment knobs from the environment, read ONCE per process (thread-safe static initialisation), never
 // in the launch path.
-struct FastKnobs { int pcol6, staged, sweep, ring; };
+struct FastKnobs { int pcol6, staged, sweep, ring, ptab; };
 static const FastKnobs &fast_knobs() {
     static const FastKnobs k = [] {
         FastKnobs r;
@@ -454,6 +512,8 @@ static const FastKnobs &fast_knobs() {
         // most-unstable + profile rows: DRAM reads 38.6 -> 24.5 GB, writes 30.5 -> 26.7 GB, but the kernel takes 39.1
         // instead of 33.2 ms (12 instead of 16 warps per SM; it is latency-bound, not DRAM-bound: 2.1 TB/s).
         r.ring = e ? atoi(e) : 0;
+        e = getenv("XP_PCOL_TABLE");
+        r.ptab = e ? atoi(e) : 1;            // 1: per-column pressure, default options: adiabat family in shared memory
         e = getenv("XP_FAST_SWEEP");
         r.sweep = e ? atoi(e) : 7;           // 7: xp_fast7.cuh (default), 6: xp_fast6.cuh
         return r;
@@ -542,6 +602,35 @@ int launch_suite_fast(const ColsArg<float> &cols, const Tables &tb, const Opts &
 #undef XP_PCOL6_CASE
             launch_suite_list(lp, sm_count, stream);
             return 2;
+        }
+        // default options, scalar outputs: the adiabat family from shared memory (suite_fast_ptab_kernel)
+        // (two or three kinds: +5 % over the gather kernels on 2 M x 70; ONE kind is faster through the gather kernel at
+        //  three CTAs per SM -- 1.12 vs 1.02 G columns/s surface-based -- unless XP_PCOL_TABLE=2 forces the table)
+        const int nk = ((kind_mask >> 0) & 1) + ((kind_mask >> 1) & 1) + ((kind_mask >> 2) & 1);
+        if (mode && !profile && (fast_knobs().ptab == 2 || (fast_knobs().ptab == 1 && nk >= 2))) {
+            ptab_coef_kernel<<<fast::kPTabNodes, 160, 0, stream>>>(tb.curves, coef);
+            const size_t tsm = (size_t)fast::kPTabNodes * fast::kPTabIntervals * sizeof(Coef);
+            const int64_t tiles = (cols.n + kPTabThreads - 1) / kPTabThreads;
+            const int gt = (int)(tiles < sm_count ? tiles : sm_count);
+#define XP_PTAB_CASE(K)                                                                                               \
+    case K:                                                                                                           \
+        if (cols.qmode) {                                                                                             \
+            if (cudaFuncSetAttribute(suite_fast_ptab_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                     (int)tsm) != cudaSuccess) return -1;                                             \
+            suite_fast_ptab_kernel<K, true><<<gt, kPTabThreads, tsm, stream>>>(pp, coef);                             \
+        } else {                                                                                                      \
+            if (cudaFuncSetAttribute(suite_fast_ptab_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                     (int)tsm) != cudaSuccess) return -1;                                             \
+            suite_fast_ptab_kernel<K, false><<<gt, kPTabThreads, tsm, stream>>>(pp, coef);                            \
+        }                                                                                                             \
+        break;
+            switch (kind_mask & 7) {
+                XP_PTAB_CASE(1) XP_PTAB_CASE(2) XP_PTAB_CASE(3) XP_PTAB_CASE(4) XP_PTAB_CASE(5) XP_PTAB_CASE(6) XP_PTAB_CASE(7)
+                default: return -1;
+            }
+#undef XP_PTAB_CASE
+            launch_suite_list(lp, sm_count, stream);
+            return 3;
         }
         // one LIFTED kind (mixed layer / most unstable) with profile rows: the re-based sweep through the ring
         if (profile && ((kind_mask & 7) == 2 || (kind_mask & 7) == 4) && fast_knobs().ring) {

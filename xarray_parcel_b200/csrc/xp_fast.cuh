@@ -230,6 +230,7 @@ XP_HD float f_tv(float t, float w) { return t * f_fma(0.608f, w, 1.0f); }
 // (rcp64 / sqrt64 / log64_fast / exp64_fast -- the branch-free float64 helpers -- live in xp_math.cuh: the exact
 //  fix-up over the uncertain-column list uses them too)
 using xp::exp64_fast;
+using xp::pow_kappa64;
 using xp::log64_fast;
 using xp::rcp64;
 using xp::sqrt64;

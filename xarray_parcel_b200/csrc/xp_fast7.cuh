@@ -91,8 +91,11 @@ XP_HD void step7_core(FParcel &c, float itf, float d, float h, bool above) {
 // Mixed phase: lanes may be below, at or above their LCL (row schedule of FParcel).
 //   d_m   parcel - environment on the moist adiabat at level it-1 (PF:585-592)
 //   d_d   parcel - environment on the dry adiabat at level it     (PF:742)
-// GUARD: rows it < kfirst are neutral and leave xprev at the row's ln p (most-unstable parcel).
-template <bool GUARD>
+// GUARD 0: the parcel is live at every row.  1: rows it < kfirst are neutral and leave xprev at the row's ln p
+// (most-unstable parcel: its start row is the level below kfirst).  2: rows it < kfirst are neutral and leave xprev
+// untouched (mixed-layer parcel on per-column pressure: its start row is the surface, the levels inside the layer are
+// dropped, PF:1636).
+template <int GUARD>
 XP_HD void step7_mixed(FParcel &c, int it, float itf, float d_m, float d_d, float x_cur, float x_prv) {
     const bool above = it > c.ka, is_lcl = it == c.ka;
     float d = above ? d_m : d_d;
@@ -100,7 +103,11 @@ XP_HD void step7_mixed(FParcel &c, int it, float itf, float d_m, float d_d, floa
     float x = above ? x_prv : x_cur;
     x = is_lcl ? c.x_lcl : x;
     float absd = fabsf(d);
-    if (GUARD) { const bool active = it >= c.kfirst; d = active ? d : 0.0f; absd = active ? absd : 1e30f; }
+    if (GUARD) {
+        const bool active = it >= c.kfirst;
+        d = active ? d : 0.0f; absd = active ? absd : 1e30f;
+        if (GUARD == 2) x = active ? x : c.xprev;
+    }
     const float h = 0.5f * (c.xprev - x);
     c.min_abs_d = fminf(c.min_abs_d, absd);
     step7_core<false>(c, itf, d, h, above);
@@ -207,9 +214,9 @@ XP_HD void sweep_mixed7(const Rd &rd, Sweep7 &w, CoefRow &crow, const Stash &sta
         s.lp += 4;
         if (qmode && !from_stash) td = f_td_from_q(p_cur, t, td, qmode);              // the stash holds dewpoints already
         const float b_cur = f_env_tv7(t, td, p_cur);                                  // PF:839-843
-        if (KACT & 1u) step7_mixed<false>(sb, it, w.itf, cubic_at(crow.at(sb.m), sb.f) - s.b_prv, f_fma(sb.c_dryv, pk_cur, -b_cur), x_cur, s.x_prv);
-        if (KACT & 2u) step7_mixed<false>(ml, it, w.itf, cubic_at(crow.at(ml.m), ml.f) - s.b_prv, f_fma(ml.c_dryv, pk_cur, -b_cur), x_cur, s.x_prv);
-        if (KACT & 4u) step7_mixed<GUARD_MU>(mu, it, w.itf, cubic_at(crow.at(mu.m), mu.f) - s.b_prv, f_fma(mu.c_dryv, pk_cur, -b_cur), x_cur, s.x_prv);
+        if (KACT & 1u) step7_mixed<0>(sb, it, w.itf, cubic_at(crow.at(sb.m), sb.f) - s.b_prv, f_fma(sb.c_dryv, pk_cur, -b_cur), x_cur, s.x_prv);
+        if (KACT & 2u) step7_mixed<0>(ml, it, w.itf, cubic_at(crow.at(ml.m), ml.f) - s.b_prv, f_fma(ml.c_dryv, pk_cur, -b_cur), x_cur, s.x_prv);
+        if (KACT & 4u) step7_mixed<GUARD_MU ? 1 : 0>(mu, it, w.itf, cubic_at(crow.at(mu.m), mu.f) - s.b_prv, f_fma(mu.c_dryv, pk_cur, -b_cur), x_cur, s.x_prv);
         s.b_prv = b_cur; s.x_prv = x_cur;
         w.itf += 1.0f;
         crow.advance();
@@ -449,9 +456,9 @@ XP_HD unsigned suite_column7(const Rd &rd, const Cf &cf, const Prep &pr, const T
             if (KINDS & 4u) step7_above(mu, w.itf, cubic_at(crow.at(mu.m), mu.f) - b, h);
         } else {
             const float big = 1e30f;
-            if (KINDS & 1u) step7_mixed<false>(sb, nt, w.itf, cubic_at(crow.at(sb.m), sb.f) - s.b_prv, -big, s.x_prv, s.x_prv);
-            if (KINDS & 2u) step7_mixed<false>(ml, nt, w.itf, cubic_at(crow.at(ml.m), ml.f) - s.b_prv, -big, s.x_prv, s.x_prv);
-            if (KINDS & 4u) step7_mixed<false>(mu, nt, w.itf, cubic_at(crow.at(mu.m), mu.f) - s.b_prv, -big, s.x_prv, s.x_prv);
+            if (KINDS & 1u) step7_mixed<0>(sb, nt, w.itf, cubic_at(crow.at(sb.m), sb.f) - s.b_prv, -big, s.x_prv, s.x_prv);
+            if (KINDS & 2u) step7_mixed<0>(ml, nt, w.itf, cubic_at(crow.at(ml.m), ml.f) - s.b_prv, -big, s.x_prv, s.x_prv);
+            if (KINDS & 4u) step7_mixed<0>(mu, nt, w.itf, cubic_at(crow.at(mu.m), mu.f) - s.b_prv, -big, s.x_prv, s.x_prv);
         }
     }
     // ---- results ---------------------------------------------------------------------------------------

@@ -24,6 +24,114 @@ namespace xp { namespace fast { inline int &host_warp_max_floor() { static int v
 namespace xp {
 namespace fast {
 
+// ---- the adiabat family as a table in SHARED memory, for arbitrary level pressures ----------------------------------------
+// Per-column pressure has no per-level row of cubics (xp_fast.cuh); the generic kernels gather two 0.5 hPa nodes of the
+// parcel's adiabat from the 125 MB curve table per (level, parcel) -- L2-latency-bound (r1c profiles: 43-52 % issue
+// utilisation, 3.5-5 long-scoreboard stalls per issue).  PTab is the same family on a grid that fits shared memory:
+// virtual temperature of the saturated parcel (PF:760/775, default options) as
+//     cubic across every 64th adiabat (as compute_coef_tv)  x  4-point Lagrange across pressure NODES that are uniform
+//     in xi = p^kappa (the dry adiabat is linear in xi, the moist one nearly so aloft),
+// two segments: A = 100..1100 hPa, 50 nodes (max |table - reference evaluation| 3.7e-4 K, for pseudo-adiabats hotter
+// than 312 K at 1100 hPa next to 100 hPa; ~1e-4 K otherwise); B = 2.5..100 hPa, 24 nodes (<= 2.3e-3 K down to 20 hPa,
+// <= 0.05 K above: nothing is decided that finely up there).  The decision margin of a row scales with its segment
+// (kPTabMarginA / B / Top); tests/test_fast_hostsim.py::test_ptab_accuracy holds the table to those bounds.  Adiabat intervals below
+// kPTabFirstInterval (pseudo-adiabats colder than 230 K at 1100 hPa) are left out: such parcels take the exact path.
+constexpr int kPTabNodesA = 50, kPTabNodesB = 24, kPTabNodes = kPTabNodesA + kPTabNodesB;
+constexpr int kPTabFirstInterval = 89;                              // (230 - 173) / 0.01 / 64
+constexpr int kPTabIntervals = kLastInterval + 1 - kPTabFirstInterval;   // 133 -> 64 x 133 x 16 B = 136 KB
+// (the node grids overlap around the 100 hPa split so that the four-node stencils next to it stay centred)
+constexpr double kPTabSplit = 100.0, kPTabTop = 2.5, kPTabBottom = 1100.0, kPTabLowA = 88.0, kPTabHighB = 125.0;
+constexpr float kPTabMarginA = 8e-4f, kPTabMarginB = 5e-3f, kPTabMarginTop = 0.1f;   // K (kDecisionEps is 6e-4)
+
+struct PTabDesc {               // uniform-in-xi node grids of the two segments
+    float x0a, idxa, x0b, idxb, xsplit, xtop20;
+};
+XP_HD PTabDesc ptab_desc() {
+    PTabDesc d;
+    const double xa0 = pow(kPTabLowA, kKappa), xa1 = pow(kPTabBottom, kKappa);
+    const double xb0 = pow(kPTabTop, kKappa), xb1 = pow(kPTabHighB, kKappa);
+    d.x0a = (float)xa0; d.idxa = (float)((kPTabNodesA - 1) / (xa1 - xa0));
+    d.x0b = (float)xb0; d.idxb = (float)((kPTabNodesB - 1) / (xb1 - xb0));
+    d.xsplit = (float)pow(kPTabSplit, kKappa); d.xtop20 = (float)pow(20.0, kKappa);
+    return d;
+}
+// pressure of node `j` (0 .. kPTabNodes-1; segment B first, ascending pressure)
+XP_HD double ptab_node_pressure(int j) {
+    const double xa0 = pow(kPTabLowA, kKappa), xa1 = pow(kPTabBottom, kKappa);
+    const double xb0 = pow(kPTabTop, kKappa), xb1 = pow(kPTabHighB, kKappa);
+    if (j < kPTabNodesB) {
+        if (j == 0) return kPTabTop;
+        if (j == kPTabNodesB - 1) return kPTabHighB;
+        return pow(xb0 + (xb1 - xb0) * j / (kPTabNodesB - 1), kInvKappa);
+    }
+    j -= kPTabNodesB;
+    if (j == 0) return kPTabLowA;
+    if (j == kPTabNodesA - 1) return kPTabBottom;
+    return pow(xa0 + (xa1 - xa0) * j / (kPTabNodesA - 1), kInvKappa);
+}
+// coefficient (node j, interval m) of the table: as compute_coef_tv, at the node's pressure
+XP_HD Coef compute_ptab_coef(const float *curves, int j, int m) {
+    const double p = ptab_node_pressure(j);
+    double y[4];
+    for (int q = 0; q < 4; ++q) {
+        int a = (m - 1 + q) * kNodeStride;
+        a = min(max(a, 0), kNAdiabats - 1);
+        const double t = adiabat_temperature(curves + (size_t)a * kNP, p);
+        y[q] = virtual_temperature(t, sat_mixing_ratio(p, t));                  // PF:760, 775
+    }
+    Coef c;
+    c.c0 = (float)y[1];
+    c.c1 = (float)(-y[0] / 3 - y[1] / 2 + y[2] - y[3] / 6);
+    c.c2 = (float)(y[0] / 2 - y[1] + y[2] / 2);
+    c.c3 = (float)(-y[0] / 6 + y[1] / 2 - y[2] / 2 + y[3] / 6);
+    return c;
+}
+
+// What a level contributes to every parcel's table evaluation: the first of the four node rows and the Lagrange
+// weights in xi, plus the factor that scales |parcel - environment| before it is compared with kDecisionEps.
+struct PTabLevel {
+    const Coef *row;            // node j-1 (rows are kPTabIntervals apart)
+    float w0, w1, w2, w3;
+    float margin_scale;
+};
+struct PTabView {
+    static constexpr bool kTable = true;
+    const Coef *base;           // [kPTabNodes][kPTabIntervals]
+    PTabDesc d;
+    XP_HD PTabLevel level(float xi) const {
+        const bool seg_a = xi >= d.xsplit;
+        const float s = (xi - (seg_a ? d.x0a : d.x0b)) * (seg_a ? d.idxa : d.idxb);
+        const int n = seg_a ? kPTabNodesA : kPTabNodesB;
+        const int j = min(max((int)s, 1), n - 3);                  // the stencil j-1 .. j+2 stays inside the segment
+        const float u = s - (float)j;
+        PTabLevel lv;
+        lv.row = base + (size_t)((seg_a ? kPTabNodesB : 0) + j - 1) * kPTabIntervals;
+        const float um = u - 1.0f, up = u + 1.0f, u2 = u - 2.0f;
+        lv.w0 = (-1.0f / 6.0f) * u * um * u2;
+        lv.w1 = 0.5f * up * um * u2;
+        lv.w2 = -0.5f * up * u * u2;
+        lv.w3 = (1.0f / 6.0f) * up * u * um;
+        lv.margin_scale = seg_a ? kDecisionEps / kPTabMarginA
+                                : ((xi >= d.xtop20) ? kDecisionEps / kPTabMarginB : kDecisionEps / kPTabMarginTop);
+        return lv;
+    }
+    // virtual temperature of the saturated parcel on adiabat (interval m, position f) at the level
+    XP_HD float eval(const PTabLevel &lv, int m, float f) const {
+        const Coef *r = lv.row + (m - kPTabFirstInterval);
+        const Coef c0 = r[0], c1 = r[kPTabIntervals], c2 = r[2 * kPTabIntervals], c3 = r[3 * kPTabIntervals];
+        const float v0 = f_fma(f_fma(f_fma(c0.c3, f, c0.c2), f, c0.c1), f, c0.c0);
+        const float v1 = f_fma(f_fma(f_fma(c1.c3, f, c1.c2), f, c1.c1), f, c1.c0);
+        const float v2 = f_fma(f_fma(f_fma(c2.c3, f, c2.c2), f, c2.c1), f, c2.c0);
+        const float v3 = f_fma(f_fma(f_fma(c3.c3, f, c3.c2), f, c3.c1), f, c3.c0);
+        return f_fma(lv.w3, v3, f_fma(lv.w2, v2, f_fma(lv.w1, v1, lv.w0 * v0)));
+    }
+};
+struct NoPTab {                 // the generic kernels: adiabats gathered from the curve table in global memory
+    static constexpr bool kTable = false;
+    XP_HD PTabLevel level(float) const { return PTabLevel(); }
+    XP_HD float eval(const PTabLevel &, int, float) const { return 0.0f; }
+};
+
 // np.interp(p, P_ascending, curve) in float32 (PF:585-600); p inside [2.5, 1100] is a precondition.
 XP_HD float adiabat_temperature_f32(const float *__restrict__ curve, int j, float w) {
     const float f0 = XP_LDG(curve + j), f1 = XP_LDG(curve + j + 1);
@@ -40,7 +148,7 @@ struct PColParcel : FParcel {
 // qm != 0: the dewpoint array holds specific humidity in that MetPy form (levels converted as they are read).
 template <class Rd>
 XP_HD void setup_parcel_pcol(const Rd &rd, int L, const Tables &tb, const Opts &o, double p0, double t0,
-                             double td0, float x_start, int knext, PColParcel &pc, int qm = 0) {
+                             double td0, float x_start, int knext, PColParcel &pc, int qm = 0, bool ptab = false) {
     pc.bad = false;
     pc.kfirst = knext;
     if (!(t0 - td0 >= kSaturationMargin) || !(p0 > 0.0)) { pc.bad = true; t0 = 280.0; td0 = 270.0; p0 = 1000.0; }
@@ -51,6 +159,12 @@ XP_HD void setup_parcel_pcol(const Rd &rd, int L, const Tables &tb, const Opts &
     if (adiabat <= 0) pc.bad = true;
     pc.curve = tb.curves + (size_t)(adiabat > 0 ? adiabat - 1 : 0) * kNP;
     pc.m = 0; pc.f = 0.0f; pc.f0 = pc.f1 = 0.0f;
+    if (ptab) {                 // shared-memory table (PTabView): cubic interval and position, as setup6_c
+        const int a0 = adiabat - 1;
+        pc.m = a0 / kNodeStride;
+        if (adiabat <= 0 || pc.m < kPTabFirstInterval || pc.m > kLastInterval) { pc.bad = true; pc.m = kPTabFirstInterval; }
+        pc.f = (float)(a0 - pc.m * kNodeStride) * (1.0f / kNodeStride);
+    }
     const float p0f = (float)p0, t0f = (float)t0, td0f = (float)td0;
     const float lpf = (float)lp, ltf = (float)lt;
     pc.lcl_p = lpf; pc.lcl_t = ltf;
@@ -141,18 +255,25 @@ struct EnvLevel { float p, t, td, tv; };
 
 // One parcel, one iteration (row schedule of xp_fast.cuh).  j_cur: table node of the pressure of level
 // `it` (gathered for the next iteration); w_prv: interpolation weight of level it-1.
-template <int MODE, class Prof>
+template <int MODE, class Prof, class PTab>
 XP_HD void parcel_iteration_pcol(PColParcel &c, int it, bool last, int j_cur, float w_prv, float pk_cur,
                                  float p_prv, float x_cur, float x_prv, float b_cur, float b_prv, bool vtc,
-                                 const EnvLevel &e_cur, const EnvLevel &e_prv, int q, Prof &prof) {
+                                 const EnvLevel &e_cur, const EnvLevel &e_prv, int q, Prof &prof,
+                                 const PTab &ptab, const PTabLevel &lv_prv) {
     const bool above = it > c.ka;
     const bool is_lcl = it == c.ka;
-    const float f0 = c.f0, f1 = c.f1;
-    c.f0 = XP_LDG(c.curve + j_cur); c.f1 = XP_LDG(c.curve + j_cur + 1);         // for the next iteration
-    if (it < c.kfirst || (last && !above)) return;
-    const float tm = f_fma(f1 - f0, w_prv, f0);                                // np.interp, PF:585-592
-    const float es = f_es(tm);
-    const float tv_m = f_tv(tm, kEpsF * es * f_rcp(p_prv - es));                // PF:760, 775
+    float tm = 0.0f, tv_m;
+    if (PTab::kTable) {
+        if (it < c.kfirst || (last && !above)) return;
+        tv_m = ptab.eval(lv_prv, c.m, c.f);                                    // shared-memory table (default options)
+    } else {
+        const float f0 = c.f0, f1 = c.f1;
+        c.f0 = XP_LDG(c.curve + j_cur); c.f1 = XP_LDG(c.curve + j_cur + 1);     // for the next iteration
+        if (it < c.kfirst || (last && !above)) return;
+        tm = f_fma(f1 - f0, w_prv, f0);                                        // np.interp, PF:585-592
+        const float es = f_es(tm);
+        tv_m = f_tv(tm, kEpsF * es * f_rcp(p_prv - es));                        // PF:760, 775
+    }
     const float a_m = vtc ? tv_m : tm;
     const float a_d = c.c_dryv * pk_cur;                                        // PF:742
     const float a = is_lcl ? c.a_lcl : (above ? a_m : a_d);
@@ -165,12 +286,23 @@ XP_HD void parcel_iteration_pcol(PColParcel &c, int it, bool last, int j_cur, fl
         else { const float tp = c.c_dry * pk_cur; prof.put(q, row, e_cur.p, tp, f_tv(tp, c.w_par), e_cur.t, e_cur.tv, e_cur.td); }
     }
     sweep_step<MODE>(c, it, x, a, b, is_lcl, above);
+    // rows read from the coarser part of the table (above 100 hPa) are decided with a wider margin
+    if (PTab::kTable && above) c.min_abs_d = fminf(c.min_abs_d, fabsf(a - b) * lv_prv.margin_scale);
 }
+
+// The sweep of the shared-memory-table kernels (default options, scalar outputs): v7 steps (xp_fast7.cuh) on
+// per-column pressure.  Defined in xp_fast_pcol7.cuh.
+template <unsigned KINDS, class Rd, class PTab>
+XP_HD unsigned ptab7_sweep(const Rd &rd, int L, const Opts &o, const PTab &ptab, PColParcel &sb, PColParcel &ml,
+                           PColParcel &mu, FResult res[3], unsigned redo, float nanacc, bool bad_axis, float best,
+                           float second, int k_mu, int qm, float p_sfc, float t_sfc, float td_sfc, float x_sfc);
 
 // The suite for one column with its own pressure profile.  Returns the redo mask (see suite_column).
 // QIN: the dewpoint array may hold specific humidity (o.qmode); false compiles the conversion away.
-template <unsigned KINDS, int MODE, bool QIN, class Rd, class Prof, class Ring>
-XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Opts &o, Prof &prof, Ring &ring, FResult res[3]) {
+template <unsigned KINDS, int MODE, bool QIN, class Rd, class Prof, class Ring, class PTab>
+XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Opts &o, Prof &prof, Ring &ring,
+                                 const PTab &ptab, FResult res[3]) {
+    static_assert(!PTab::kTable || (MODE == 1 && !Prof::kEnabled), "the shared-memory table holds the virtual temperature only");
     unsigned redo = 0, rows_exact = 0;       // rows_exact: kinds whose profile rows the exact path must rewrite too
     float nanacc = 0.0f;
     bool bad_axis = false;                 // pressure not finite / not strictly decreasing / outside the table
@@ -209,7 +341,7 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
             const double tdd = (double)td;
             const double e = qm ? e64_from_q_fast(p, (double)t, (double)raw, qm)
                                 : kSat0 * exp64_fast(17.67 * (tdd - 273.15) * rcp64(tdd - 29.65));
-            const double th = (double)t * exp64_fast(-kKappa * log64_fast(p * 1e-3));   // PF:253
+            const double th = (double)t * pow_kappa64(1000.0 * rcp64(p));               // PF:253: T (1000 / p)^kappa
             const double w = kEps * e * rcp64(p - e);                            // PF:258
             if (p >= top_ml) {
                 if (k > 0) {
@@ -257,7 +389,7 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
     PColParcel sb, ml, mu;
     const float x_sfc = kLn2 * f_lg2(p_sfc);
     if (KINDS & 1u) {
-        setup_parcel_pcol(rd, L, tb, o, bottom, (double)t_sfc, td_sfc64, x_sfc, 1, sb, qm);
+        setup_parcel_pcol(rd, L, tb, o, bottom, (double)t_sfc, td_sfc64, x_sfc, 1, sb, qm, PTab::kTable);
         res[0].par_p = p_sfc; res[0].par_t = t_sfc; res[0].par_td = td_sfc; res[0].shift = 0;
     }
     if (KINDS & 2u) {
@@ -265,17 +397,20 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
         double mp_t, mp_td;
         mixed_parcel_t_td(bottom, (1. / depth) * sum_th, (1. / depth) * sum_w, mp_t, mp_td);   // PF:161, 268-282
         if (!ml_done || K_ml < 1) { redo |= 2u; rows_exact |= 2u; K_ml = max(K_ml, 1); }   // no level above / NaN layer: exact path
-        setup_parcel_pcol(rd, L, tb, o, bottom, mp_t, mp_td, x_sfc, K_ml, ml, qm);
+        setup_parcel_pcol(rd, L, tb, o, bottom, mp_t, mp_td, x_sfc, K_ml, ml, qm, PTab::kTable);
         res[1].par_p = p_sfc; res[1].par_t = (float)mp_t; res[1].par_td = (float)mp_td; res[1].shift = K_ml;
     }
     if (KINDS & 4u) {
         if (!(best - second >= kThetaEMargin)) { redo |= 4u; rows_exact |= 4u; }
         const double mu_td64 = qm ? td64_from_q_fast((double)mu_p, (double)mu_t, (double)mu_raw, qm) : (double)mu_td;
         if (qm) mu_td = (float)mu_td64;
-        setup_parcel_pcol(rd, L, tb, o, (double)mu_p, (double)mu_t, mu_td64, kLn2 * f_lg2(mu_p), k_mu + 1, mu, qm);
+        setup_parcel_pcol(rd, L, tb, o, (double)mu_p, (double)mu_t, mu_td64, kLn2 * f_lg2(mu_p), k_mu + 1, mu, qm, PTab::kTable);
         res[2].par_p = mu_p; res[2].par_t = mu_t; res[2].par_td = mu_td; res[2].shift = k_mu;
     }
     // ---- the sweep ----------------------------------------------------------------------------------------
+    if constexpr (PTab::kTable)
+        return ptab7_sweep<KINDS>(rd, L, o, ptab, sb, ml, mu, res, redo, nanacc, bad_axis, best, second, k_mu, qm,
+                                  p_sfc, t_sfc, td_sfc, x_sfc);
     const bool vtc = (MODE == 1) ? true : (o.vtc != 0);
     const int compat = (MODE == 1) ? 141 : o.compat;
     if (Prof::kEnabled) {       // start rows: the parcel level itself (environment == parcel there)
@@ -313,10 +448,13 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
         const float s0 = (p_s - 2.5f) * 2.0f;
         const int j0 = min(max((int)s0, 0), kNP - 2);
         w_prv = s0 - (float)j0;
-        if (KINDS & 1u) { sb.f0 = XP_LDG(sb.curve + j0); sb.f1 = XP_LDG(sb.curve + j0 + 1); }
-        if (KINDS & 2u) { ml.f0 = XP_LDG(ml.curve + j0); ml.f1 = XP_LDG(ml.curve + j0 + 1); }
-        if (KINDS & 4u) { mu.f0 = XP_LDG(mu.curve + j0); mu.f1 = XP_LDG(mu.curve + j0 + 1); }
+        if (!PTab::kTable) {
+            if (KINDS & 1u) { sb.f0 = XP_LDG(sb.curve + j0); sb.f1 = XP_LDG(sb.curve + j0 + 1); }
+            if (KINDS & 2u) { ml.f0 = XP_LDG(ml.curve + j0); ml.f1 = XP_LDG(ml.curve + j0 + 1); }
+            if (KINDS & 4u) { mu.f0 = XP_LDG(mu.curve + j0); mu.f1 = XP_LDG(mu.curve + j0 + 1); }
+        }
     }
+    PTabLevel lv_prv = ptab.level(f_ex2((float)kKappa * f_lg2(p_s)));
     const int k1 = min(1 + shift, L - 1);
     const float *ppp = rd.pptr(k1), *tp = rd.tptr(k1), *tdp = rd.tdptr(k1);
     const int64_t ls = rd.stride(), pls = rd.pstride();
@@ -343,6 +481,7 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
         ppp += pls; tp += ls; tdp += ls;
         if (!use_ring && it + 1 < Lq) { p_nxt = Rd::ld(ppp); t_nxt = Rd::ld(tp); td_nxt = Rd::ld(tdp); }
         float b_cur = 0.0f, x_cur = x_prv, pk_cur = 0.0f, p_cur = p_prv, w_cur = w_prv;
+        PTabLevel lv_cur = lv_prv;
         EnvLevel e_cur = e_prv;
         int j_cur = 0;
         if (!last) {
@@ -356,6 +495,7 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
             w_cur = s_cur - (float)j_cur;
             const float l2p = f_lg2(p_cur);
             x_cur = kLn2 * l2p; pk_cur = f_ex2((float)kKappa * l2p);
+            if (PTab::kTable) lv_cur = ptab.level(pk_cur);
             if (vtc || Prof::kEnabled) {
                 const float es_t = f_es(t), es_td = f_es(td);
                 e_cur.tv = f_tv(t, f_mixing_ratio(es_t, es_td, p_cur, compat));  // PF:839-843
@@ -363,10 +503,10 @@ XP_HD unsigned suite_column_pcol(const Rd &rd, int L, const Tables &tb, const Op
             b_cur = vtc ? e_cur.tv : t;
             e_cur.p = p_cur; e_cur.t = t; e_cur.td = td;
         }
-        if (KINDS & 1u) parcel_iteration_pcol<MODE>(sb, it, last, j_cur, w_prv, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc, e_cur, e_prv, 0, prof);
-        if (KINDS & 2u) parcel_iteration_pcol<MODE>(ml, it, last, j_cur, w_prv, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc, e_cur, e_prv, 1, prof);
-        if (KINDS & 4u) parcel_iteration_pcol<MODE>(mu, it, last, j_cur, w_prv, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc, e_cur, e_prv, 2, prof);
-        b_prv = b_cur; x_prv = x_cur; p_prv = p_cur; w_prv = w_cur; e_prv = e_cur;
+        if (KINDS & 1u) parcel_iteration_pcol<MODE>(sb, it, last, j_cur, w_prv, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc, e_cur, e_prv, 0, prof, ptab, lv_prv);
+        if (KINDS & 2u) parcel_iteration_pcol<MODE>(ml, it, last, j_cur, w_prv, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc, e_cur, e_prv, 1, prof, ptab, lv_prv);
+        if (KINDS & 4u) parcel_iteration_pcol<MODE>(mu, it, last, j_cur, w_prv, pk_cur, p_prv, x_cur, x_prv, b_cur, b_prv, vtc, e_cur, e_prv, 2, prof, ptab, lv_prv);
+        b_prv = b_cur; x_prv = x_cur; p_prv = p_cur; w_prv = w_cur; e_prv = e_cur; lv_prv = lv_cur;
     }
     if (Prof::kEnabled) {       // rows above the lifted column are NaN (PF:1552, 1637: levels dropped below)
         const float qn = f_qnan();
