@@ -47,7 +47,8 @@ def build(force=False, verbose=False, extra_flags=(), lib_out=None):
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
-        obj = os.path.join(objdir, src.replace(".cu", f".{os.getpid()}.o"))
+        tag = f"{os.getpid()}.{abs(hash((tuple(extra_flags), lib_out))) % 100000}"     # concurrent builds do not collide
+        obj = os.path.join(objdir, src.replace(".cu", f".{tag}.o"))
         cmd = [nvcc] + NVCC_COMMON + PER_FILE_FLAGS.get(src, []) + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
         cmd += ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))

@@ -118,6 +118,13 @@ struct PTabView {
     // virtual temperature of the saturated parcel on adiabat (interval m, position f) at the level
     XP_HD float eval(const PTabLevel &lv, int m, float f) const {
         const Coef *r = lv.row + (m - kPTabFirstInterval);
+#if defined(XP_BOUNDS_CHECK) && defined(__CUDA_ARCH__)
+        if (m < kPTabFirstInterval || m > kLastInterval || r < base ||
+            r + 3 * kPTabIntervals >= base + (size_t)kPTabNodes * kPTabIntervals) {
+            printf("XP_BOUNDS_CHECK failed: PTabView::eval m=%d row offset %ld\n", m, (long)(lv.row - base));
+            __trap();
+        }
+#endif
         const Coef c0 = r[0], c1 = r[kPTabIntervals], c2 = r[2 * kPTabIntervals], c3 = r[3 * kPTabIntervals];
         const float v0 = f_fma(f_fma(f_fma(c0.c3, f, c0.c2), f, c0.c1), f, c0.c0);
         const float v1 = f_fma(f_fma(f_fma(c1.c3, f, c1.c2), f, c1.c1), f, c1.c0);
