@@ -12,10 +12,14 @@ materialising the whole field on the host or on the device:
 * results come back in source order, one ``Dataset`` of host arrays per block.
 
 The column slices handed to the library are strided VIEWS of the caller's arrays (level stride = full row length): no
-host-side re-packing.  There is no netCDF/HDF5 reader in the build image (no HDF5 library), so ``test_data.nc`` itself
-cannot be opened here; ``numpy.memmap`` / ``.npy`` files are the file-backed source that is tested.
+host-side re-packing.  File-backed sources that are tested: ``numpy.memmap`` / ``.npy`` files and netCDF CLASSIC /
+64-bit-offset files (``iter_netcdf3_blocks``: memory-mapped through ``scipy.io.netcdf_file``, packed int16 variables
+with ``scale_factor`` / ``add_offset`` / ``_FillValue`` unpacked block by block -- the form of ERA5 downloads and of
+``nccopy -k nc6`` output).  netCDF-4 files such as the reference's ``test_data.nc`` are HDF5 containers: there is no HDF5
+library in the build image, so those have to be converted (``nccopy -k nc6 in.nc out.nc``) first.
 """
 
+import os
 import threading
 from collections import deque
 from concurrent.futures import ThreadPoolExecutor
@@ -25,7 +29,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["iter_column_blocks", "suite_blocks"]
+__all__ = ["iter_column_blocks", "iter_netcdf3_blocks", "suite_blocks"]
 
 
 def _materialise(x):
@@ -51,6 +55,91 @@ def iter_column_blocks(pressure, temperature, dewpoint, block_columns):
         e = min(n, s + int(block_columns))
         p = pressure if getattr(pressure, "ndim", len(getattr(pressure, "shape", ()))) == 1 else pressure[:, s:e]
         yield p, temperature[:, s:e], dewpoint[:, s:e]
+
+
+_OPEN_NETCDF = {}
+
+
+class _Unpacked:
+    """A netCDF variable sliced lazily: ``_materialise`` reads (and unpacks: scale_factor / add_offset, missing -> NaN)
+    only the block it is asked for."""
+
+    def __init__(self, var, index, shape, dtype):
+        self.var, self.index, self.shape, self.ndim, self.dtype = var, index, tuple(shape), len(shape), dtype
+
+    def __getitem__(self, idx):
+        assert isinstance(idx, tuple) and len(idx) == 2 and idx[0] == slice(None), "column blocks only: x[:, a:b]"
+        return _Unpacked(self.var, self.index, self.shape, self.dtype).narrow(idx[1])
+
+    def narrow(self, cols):
+        self.cols = cols
+        a, b, _ = cols.indices(self.shape[1])
+        self.shape = (self.shape[0], max(0, b - a))
+        return self
+
+    def compute(self):
+        raw = self.var[self.index]
+        raw = raw.reshape(raw.shape[0], -1)                     # [L, columns]: trailing dimensions are contiguous
+        cols = getattr(self, "cols", slice(None))
+        raw = raw[:, cols]
+        att = self.var._attributes
+        out = np.array(raw, dtype=self.dtype)
+        fill = [att[k] for k in ("_FillValue", "missing_value") if k in att]
+        if "scale_factor" in att or "add_offset" in att:
+            out = out * self.dtype(att.get("scale_factor", 1.0)) + self.dtype(att.get("add_offset", 0.0))
+        for f in fill:
+            out[np.asarray(raw) == np.asarray(f).reshape(-1)[0]] = np.nan
+        return out
+
+
+def iter_netcdf3_blocks(path, block_columns, vert_dim="model_level_number", names=None, dtype=np.float32,
+                        surface_first=True):
+    """Column blocks of a netCDF classic / 64-bit-offset file (memory-mapped, nothing is read until a block is
+    materialised by ``suite_blocks``).  ``names`` maps 'pressure' / 'temperature' / 'dewpoint' to variable names of the
+    file (default: those names; the reference's Datasets use them, PF:263).  Temperature and dewpoint must have the
+    dimensions (..., vert_dim, y, x) or (..., vert_dim, column): the dimensions after ``vert_dim`` are flattened to
+    columns and every index of the leading ones (time steps) is a field of its own; pressure may be the 1-D coordinate
+    of ``vert_dim`` or have the shape of the temperature.  ``surface_first=False``: the vertical axis of the file runs
+    from the model top to the surface (ERA5 pressure-level files) and is reversed on read.  Yields
+    ``(pressure, temperature, dewpoint)`` like ``iter_column_blocks``, in file order (leading index major, column
+    minor)."""
+    from scipy.io import netcdf_file
+    nm = {"pressure": "pressure", "temperature": "temperature", "dewpoint": "dewpoint"}
+    nm.update(names or {})
+    f = _OPEN_NETCDF.get(os.path.abspath(path))
+    if f is None:
+        # memory-mapped; kept open for the life of the process: blocks are read lazily by pool threads, possibly after
+        # this generator is exhausted, and scipy cannot close a mapped file while views of it exist
+        f = _OPEN_NETCDF[os.path.abspath(path)] = netcdf_file(path, "r", mmap=True, maskandscale=False)
+    t_var, d_var, p_var = (f.variables[nm[k]] for k in ("temperature", "dewpoint", "pressure"))
+    dims = list(t_var.dimensions)
+    assert vert_dim in dims, f"{vert_dim!r} is not a dimension of {nm['temperature']!r} {tuple(dims)}"
+    assert tuple(d_var.dimensions) == tuple(dims), "temperature and dewpoint must share their dimensions"
+    iv = dims.index(vert_dim)
+    lead = t_var.shape[:iv]
+    L = t_var.shape[iv]
+    n = int(np.prod(t_var.shape[iv + 1:], dtype=np.int64))
+    p_is_1d = tuple(p_var.dimensions) == (vert_dim,)
+    assert p_is_1d or tuple(p_var.dimensions) == tuple(dims), "pressure: the vertical coordinate or a full field"
+    flip = (slice(None, None, -1),) if not surface_first else (slice(None),)
+
+    class _Var:                                 # a variable with the leading index applied and the vertical axis oriented
+        def __init__(self, var):
+            self._attributes = var._attributes
+            self.var = var
+
+        def __getitem__(self, index):
+            return self.var[(index or ()) + flip]
+
+    p1 = None
+    if p_is_1d:
+        p1 = _Unpacked(_Var(p_var), None, (L, 1), np.float64).compute().reshape(L).astype(dtype)
+    for index in np.ndindex(*lead):
+        for s in range(0, n, int(block_columns)):
+            cols = slice(s, min(n, s + int(block_columns)))
+            blk = [_Unpacked(_Var(v), tuple(index), (L, n), dtype).narrow(cols) for v in (t_var, d_var)]
+            pb = p1 if p_is_1d else _Unpacked(_Var(p_var), tuple(index), (L, n), dtype).narrow(cols)
+            yield pb, blk[0], blk[1]
 
 
 def _to_tensor(a):
