@@ -82,10 +82,12 @@ def _write_netcdf3(path, p, T, D, packed):
     v = f.createVariable("pressure", "f4", ("level",)); v[:] = p
     v = f.createVariable("t", "f4", ("time", "level", "lat", "lon")); v[:] = T
     if packed:
-        sc, off = 0.002, 250.0
+        sc, off = 0.004, 250.0                       # int16 covers 119 .. 381 K
         v = f.createVariable("d2", "i2", ("time", "level", "lat", "lon"))
         v.scale_factor, v.add_offset, v._FillValue = sc, off, np.int16(-32767)
-        q = np.round((D - off) / sc).astype(np.int16)
+        q = np.round((D - off) / sc)
+        assert np.abs(q).max() < 32767
+        q = q.astype(np.int16)
         q[0, 3, 2, 1] = -32767
         v[:] = q
         D = q.astype(np.float32) * np.float32(sc) + np.float32(off)

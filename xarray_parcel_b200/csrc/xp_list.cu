@@ -2,9 +2,9 @@
 // hand over because a decision fell inside their error margin.
 //
 // One thread per item runs the SAME column code as cape_cin_kernel (xp_column.cuh / xp_parcels.cuh), with libm
-// exp / log / pow, no FMA contraction (like xp_kernels.cu).  Measured and dropped: building this file with
-// XP_F64_FAST_MATH (branch-free ~3-ulp exp / log / pow of xp_math.cuh) -- the kernel's duration did not move
-// (0.205 vs 0.194 ms for the 31 k items of the ERA5 bench step): its time is not in the libm calls.
+// exp / log / pow, no FMA contraction (like xp_kernels.cu).  The kernel lasts as long as one item's dependent float64
+// chain; what was measured against that (branch-free math, rows batched or spread over 2 / 4 / 8 lanes, compact code,
+// register budgets) is in profiles/r2_list_kernel.md -- none of it is in the tree.
 #include <cstdlib>
 
 #include "xp_kernels_common.cuh"
@@ -16,35 +16,34 @@ struct NoProf {
     __device__ __forceinline__ void put(int, const ProfileRow &) const {}
 };
 
-// A column staged once in shared memory ([level][thread], conflict-free): the exact path makes ~8 passes over a
-// column (layer bounds, theta-e search, LCL bracket, lift, ...), each of which would otherwise fetch the item's
-// scattered 32-byte sectors from DRAM again (ncu, 10 M x 90 most-unstable + profile rows: 27.5 GB read for
-// 375 k items = 73 KB per item against 1 KB of input).  A shared 1-D pressure axis is staged once per CTA.
-struct StagedReader {
-    const float *p, *t, *td;
-    int ps, s;                  // element strides between levels (p: 1 for the shared axis)
-    int L;
-    int qmode;                  // as GlobalReader
-    __device__ __forceinline__ double P(int k) const { return (double)p[k * ps]; }
-    __device__ __forceinline__ double Tk(int k) const { return (double)t[k * s]; }
+// The item's PRESSURE column staged once in shared memory ([level][thread], conflict-free) when pressure is per
+// column: the float64 column code reads it in up to five passes (column maximum, layer bound, theta-e search, unique
+// count, lift), each of which otherwise fetches the item's scattered 32-byte sectors again -- ncu, 10 M x 90
+// most-unstable + profile rows: the pressure loads alone are 24 % of the kernel's stall samples and it reads 73 KB per
+// item for 8.6 KB of sectors.  Temperature and dewpoint are read in one to two passes and stay in global memory (staging
+// all three -- round 1, 138 KB per 128 items at 90 levels -- halved the resident items and gained nothing).  A shared
+// 1-D axis is L1-resident and is not staged.
+template <typename T>
+struct PStagedReader {
+    GlobalReader<T> g;
+    const float *sp;            // this thread's slots: sp[k * nt]
+    int nt, L, qmode;
+    __device__ __forceinline__ double P(int k) const { return (double)sp[k * nt]; }
+    __device__ __forceinline__ double Tk(int k) const { return g.Tk(k); }
     __device__ __forceinline__ double Td(int k) const {
-        const double raw = (double)td[k * s];
+        const double raw = (double)__ldg(g.td + (int64_t)k * g.ls);
         return qmode ? dewpoint_from_q(P(k), Tk(k), raw, qmode) : raw;
     }
 };
 
-// One thread per (column, parcel kind) item.  STAGED: dynamic shared memory holds blockDim.x columns.
+// One thread per (column, parcel kind) item.  STAGED (float columns with their own pressure): dynamic shared memory
+// holds blockDim.x pressure columns.
 template <bool STAGED, typename T = float>
 __global__ void __launch_bounds__(128, 3) suite_list_kernel(const __grid_constant__ ListParamsT<T> prm) {
-    extern __shared__ float s_cols[];
+    extern __shared__ float s_p[];
     const uint32_t c0 = prm.list_count[0], c1 = prm.list_count[1], c2 = prm.list_count[2];
     const uint64_t total = (uint64_t)c0 + c1 + c2;
     const int L = prm.cols.L, nt = (int)blockDim.x;
-    float *s_t = s_cols, *s_td = s_cols + (size_t)L * nt, *s_p = s_cols + (size_t)2 * L * nt;
-    if (STAGED && prm.cols.p1d) {
-        for (int k = threadIdx.x; k < L; k += nt) s_p[k] = __ldg(prm.cols.p + (int64_t)k * prm.cols.pls);
-        __syncthreads();
-    }
     for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
          it += (uint64_t)gridDim.x * blockDim.x) {
         const int kind = it < c0 ? 0 : (it < (uint64_t)c0 + c1 ? 1 : 2);
@@ -60,14 +59,9 @@ __global__ void __launch_bounds__(128, 3) suite_list_kernel(const __grid_constan
         if ((e >> 28) & kListRowsOk) np.any = false;                   // ... unless the float32 rows stand
         if constexpr (STAGED) {
             // independent loads, all in flight at once; only this thread reads its slots back: no barrier needed
-            for (int k = 0; k < L; ++k) {
-                s_t[k * nt + threadIdx.x] = __ldg(rd.t + (int64_t)k * rd.ls);
-                s_td[k * nt + threadIdx.x] = __ldg(rd.td + (int64_t)k * rd.ls);
-                if (!prm.cols.p1d) s_p[k * nt + threadIdx.x] = __ldg(rd.p + (int64_t)k * rd.pls);
-            }
-            StagedReader sr;
-            sr.p = prm.cols.p1d ? s_p : s_p + threadIdx.x; sr.ps = prm.cols.p1d ? 1 : nt;
-            sr.t = s_t + threadIdx.x; sr.td = s_td + threadIdx.x; sr.s = nt; sr.L = L; sr.qmode = prm.cols.qmode;
+            for (int k = 0; k < L; ++k) s_p[k * nt + threadIdx.x] = (float)__ldg(rd.p + (int64_t)k * rd.pls);
+            PStagedReader<T> sr;
+            sr.g = rd; sr.sp = s_p + threadIdx.x; sr.nt = nt; sr.L = L; sr.qmode = prm.cols.qmode;
             run_column(sr, kind, prm.tb, prm.o, qnan(), qnan(), qnan(), r, p0, t0, td0, shift, np);
         } else {
             run_column(rd, kind, prm.tb, prm.o, qnan(), qnan(), qnan(), r, p0, t0, td0, shift, np);
@@ -78,20 +72,13 @@ __global__ void __launch_bounds__(128, 3) suite_list_kernel(const __grid_constan
 }
 
 void launch_suite_list(const ListParams &lp, int sm_count, cudaStream_t stream) {
-    // staged variant when 3 CTAs per SM fit (the register budget allows no more): 128 threads, else 64
-    const size_t per_thread = (size_t)lp.cols.L * (lp.cols.p1d ? 2 : 3) * sizeof(float);
-    const size_t axis = lp.cols.p1d ? (size_t)lp.cols.L * sizeof(float) : 0;
-    const size_t budget = 72 * 1024;
-    static const bool staged = getenv("XP_LIST_STAGED") && atoi(getenv("XP_LIST_STAGED")) == 1;   // A/B knob, off by default until measured
-    int threads = 0;
-    if (!staged) threads = 0;
-    else if (per_thread * 128 + axis <= budget) threads = 128;
-    else if (per_thread * 64 + axis <= budget) threads = 64;
-    if (threads) {
-        const size_t smem = per_thread * threads + axis;
+    // per-column pressure: staged when three CTAs of 128 items fit one SM (L <= 147 levels)
+    const size_t smem = (size_t)lp.cols.L * 128 * sizeof(float);
+    static const bool off = getenv("XP_LIST_STAGED") && atoi(getenv("XP_LIST_STAGED")) == 0;      // A/B knob
+    if (!lp.cols.p1d && !off && smem <= 75 * 1024) {
         // per device, so set on every launch (a host-side call of about a microsecond)
-        cudaFuncSetAttribute(suite_list_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
-        suite_list_kernel<true><<<sm_count * 8 * (128 / threads), threads, smem, stream>>>(lp);
+        cudaFuncSetAttribute(suite_list_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 75 * 1024);
+        suite_list_kernel<true><<<sm_count * 8, 128, smem, stream>>>(lp);
     } else {
         suite_list_kernel<false><<<sm_count * 8, 128, 0, stream>>>(lp);
     }
