@@ -363,6 +363,10 @@ xp_status xp_last_exact_count(xp_context *ctx, int64_t *out_count);
 /* Device time (ms) of the most recent xp_cape_cin/xp_suite kernel launch with
  * mem = XP_MEM_DEVICE, measured with CUDA events on the launch stream; syncs the stream. */
 xp_status xp_last_kernel_ms(xp_context *ctx, float *out_ms);
+/* The same interval split at the launch of the float64 fix-up kernel, for a call that took the float32 fast path:
+ * out_sweep_ms = axis preparation + coefficient + sweep kernels, out_fixup_ms = the fix-up over the hand-over list
+ * (XP_ERR_INVALID_ARGUMENT if the most recent timed call did not take the fast path). */
+xp_status xp_last_kernel_split_ms(xp_context *ctx, float *out_sweep_ms, float *out_fixup_ms);
 
 #ifdef __cplusplus
 }

@@ -652,3 +652,5 @@ def test_launch_count_and_timer(ctx):
     # fast path, per-column pressure: [table coefficients +] sweep + exact fix-up
     assert ctx.launch_count() in (n0 + 3, n0 + 4)
     assert ctx.last_kernel_ms() > 0
+    sweep_ms, fixup_ms = ctx.last_kernel_split_ms()                   # the same interval, split at the fix-up launch
+    assert sweep_ms > 0 and fixup_ms > 0 and abs(sweep_ms + fixup_ms - ctx.last_kernel_ms()) < 0.05

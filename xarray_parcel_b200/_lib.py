@@ -61,7 +61,7 @@ EXPORTS = ["xp_version", "xp_create", "xp_destroy", "xp_last_error", "xp_take_fl
            "xp_default_options", "xp_tables_build", "xp_tables_set", "xp_tables_get",
            "xp_tables_loaded", "xp_cape_cin", "xp_suite", "xp_lcl", "xp_moist_lapse",
            "xp_parcel_profile", "xp_lfc_el", "xp_cape_cin_base", "xp_launch_count",
-           "xp_last_kernel_ms", "xp_last_exact_count", "xp_interp_levels",
+           "xp_last_kernel_ms", "xp_last_kernel_split_ms", "xp_last_exact_count", "xp_interp_levels",
            "xp_level_crossing", "xp_dewpoint_from_specific_humidity", "xp_saturation_mixing_ratio",
            "xp_dry_lapse", "xp_mixing_ratio", "xp_virtual_temperature", "xp_wet_bulb_temperature",
            "xp_significant_hail_parameter", "xp_storm_proxies", "xp_mixed_layer", "xp_mixed_parcel",
@@ -201,6 +201,7 @@ def load_library():
         lib.xp_launch_count.argtypes = [c_void_p]
         lib.xp_launch_count.restype = ctypes.c_uint64
         lib.xp_last_kernel_ms.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_float)]
+        lib.xp_last_kernel_split_ms.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
         lib.xp_last_exact_count.argtypes = [c_void_p, ctypes.POINTER(c_int64)]
         _lib = lib
         return lib
@@ -299,6 +300,13 @@ class Context:
         ms = ctypes.c_float(0)
         self._check(self.lib.xp_last_kernel_ms(self.handle, ctypes.byref(ms)), "xp_last_kernel_ms")
         return ms.value
+
+    def last_kernel_split_ms(self):
+        """(sweep ms, fix-up ms) of the most recent timed fast-path call (xp_last_kernel_split_ms)."""
+        a, b = ctypes.c_float(0), ctypes.c_float(0)
+        self._check(self.lib.xp_last_kernel_split_ms(self.handle, ctypes.byref(a), ctypes.byref(b)),
+                    "xp_last_kernel_split_ms")
+        return a.value, b.value
 
     # ---- fused path -----------------------------------------------------------------------
     def _columns(self, p, t, td):

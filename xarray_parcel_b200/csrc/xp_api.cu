@@ -29,8 +29,8 @@ struct xp_context {
     uint32_t *d_flags = nullptr;
     std::string err;
     uint64_t launches = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool ev_valid = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;     // ev_mid: just before the fix-up kernel of a fast call
+    bool ev_valid = false, ev_split = false;
     // host-staging pipeline (mem = XP_MEM_HOST)
     static constexpr int kSlots = 3;
     cudaStream_t slot_stream[kSlots] = {nullptr, nullptr, nullptr};
@@ -189,11 +189,12 @@ xp_status run_device(xp_context *ctx, const xp_columns *cols, int kind_mask,
                 XP_CUDA(ctx, cudaMalloc(&sc.ptr, need));
                 sc.bytes = need;
             }
-            if (time_it) cudaEventRecord(ctx->ev0, stream);
+            if (time_it) { cudaEventRecord(ctx->ev0, stream); g_event_before_list = ctx->ev_mid; }
             const int nl = launch_suite_fast(ca, tb, o, kind_mask, oa, sc.ptr, ctx->d_flags, ctx->sm_count, stream);
+            g_event_before_list = nullptr;
             if (nl < 0) return check_cuda(ctx, cudaGetLastError(), "fast suite shared-memory attribute");
             ctx->launches += nl;
-            if (time_it) { cudaEventRecord(ctx->ev1, stream); ctx->ev_valid = true; }
+            if (time_it) { cudaEventRecord(ctx->ev1, stream); ctx->ev_valid = true; ctx->ev_split = nl > 0; }
             ctx->last_was_fast = true;
             ctx->last_fast_stream = stream;
             return check_cuda(ctx, cudaGetLastError(), "fast suite launch");
@@ -215,20 +216,21 @@ xp_status run_device(xp_context *ctx, const xp_columns *cols, int kind_mask,
                 XP_CUDA(ctx, cudaMalloc(&sc.ptr, need));
                 sc.bytes = need;
             }
-            if (time_it) cudaEventRecord(ctx->ev0, stream);
+            if (time_it) { cudaEventRecord(ctx->ev0, stream); g_event_before_list = ctx->ev_mid; }
             const int nl = launch_suite_fast_f64(to_cols<double>(cols, o), tb, o, kind_mask, oa, sc.ptr, ctx->d_flags,
                                                  ctx->sm_count, stream);
+            g_event_before_list = nullptr;
             if (nl == -1) return check_cuda(ctx, cudaGetLastError(), "fast suite shared-memory attribute");
             if (nl >= 0) {
                 ctx->launches += nl;
-                if (time_it) { cudaEventRecord(ctx->ev1, stream); ctx->ev_valid = true; }
+                if (time_it) { cudaEventRecord(ctx->ev1, stream); ctx->ev_valid = true; ctx->ev_split = nl > 0; }
                 ctx->last_was_fast = true;
                 ctx->last_fast_stream = stream;
                 return check_cuda(ctx, cudaGetLastError(), "fast suite launch (float64 columns)");
             }
         }
     }
-    if (time_it) cudaEventRecord(ctx->ev0, stream);
+    if (time_it) { cudaEventRecord(ctx->ev0, stream); ctx->ev_split = false; }
     launch_cape_cin<T>(to_cols<T>(cols, o), tb, o, kind_mask, oa, pa, ctx->d_flags, stream);
     if (time_it) { cudaEventRecord(ctx->ev1, stream); ctx->ev_valid = true; }
     ctx->launches += (cols->n_columns > 0) ? 1 : 0;
@@ -552,7 +554,8 @@ xp_status xp_create(int device, xp_context **out_ctx) {
     }
     if ((e = cudaMalloc(&ctx->d_flags, sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMemset(ctx->d_flags, 0, sizeof(uint32_t))) != cudaSuccess ||
-        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev_mid)) != cudaSuccess) {
         g_create_error = std::string("xp_create: ") + cudaGetErrorString(e);
         delete ctx;
         return XP_ERR_CUDA;
@@ -576,6 +579,7 @@ void xp_destroy(xp_context *ctx) {
         for (auto &kv : ctx->scratch) cudaFree(kv.second.ptr);
         if (ctx->ev0) cudaEventDestroy(ctx->ev0);
         if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+        if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
     }
     delete ctx;
 }
@@ -1160,6 +1164,17 @@ xp_status xp_last_kernel_ms(xp_context *ctx, float *out_ms) {
     DeviceGuard guard(ctx->device);
     XP_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
     XP_CUDA(ctx, cudaEventElapsedTime(out_ms, ctx->ev0, ctx->ev1));
+    return XP_OK;
+}
+
+xp_status xp_last_kernel_split_ms(xp_context *ctx, float *out_sweep_ms, float *out_fixup_ms) {
+    if (!ctx || !out_sweep_ms || !out_fixup_ms) return XP_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!ctx->ev_valid || !ctx->ev_split) return fail(ctx, XP_ERR_INVALID_ARGUMENT, "no timed fast-path launch yet");
+    DeviceGuard guard(ctx->device);
+    XP_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    XP_CUDA(ctx, cudaEventElapsedTime(out_sweep_ms, ctx->ev0, ctx->ev_mid));
+    XP_CUDA(ctx, cudaEventElapsedTime(out_fixup_ms, ctx->ev_mid, ctx->ev1));
     return XP_OK;
 }
 

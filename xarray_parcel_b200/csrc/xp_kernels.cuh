@@ -126,6 +126,10 @@ __device__ __forceinline__ void push_redo(uint32_t *list, uint32_t *count, int64
     }
     atomicAdd(count + 3, 1u);
 }
+// Instrumentation: when set (by run_device around a timed device call, under the context's mutex), launch_suite_list
+// records this event on the stream just before the fix-up kernel -- it splits the call's device time into the float32
+// sweep (prep + coefficient + sweep kernels) and the float64 fix-up (xp_last_kernel_split_ms).
+extern thread_local cudaEvent_t g_event_before_list;
 void launch_suite_list(const ListParams &lp, int sm_count, cudaStream_t stream);
 void launch_suite_list(const ListParamsT<double> &lp, int sm_count, cudaStream_t stream);   // float64 columns (never staged)
 

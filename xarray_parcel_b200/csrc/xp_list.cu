@@ -71,7 +71,10 @@ __global__ void __launch_bounds__(128, 3) suite_list_kernel(const __grid_constan
     }
 }
 
+thread_local cudaEvent_t g_event_before_list = nullptr;
+
 void launch_suite_list(const ListParams &lp, int sm_count, cudaStream_t stream) {
+    if (g_event_before_list) cudaEventRecord(g_event_before_list, stream);
     // per-column pressure: staged when three CTAs of 128 items fit one SM (L <= 147 levels)
     const size_t smem = (size_t)lp.cols.L * 128 * sizeof(float);
     static const bool off = getenv("XP_LIST_STAGED") && atoi(getenv("XP_LIST_STAGED")) == 0;      // A/B knob
@@ -85,6 +88,7 @@ void launch_suite_list(const ListParams &lp, int sm_count, cudaStream_t stream) 
 }
 
 void launch_suite_list(const ListParamsT<double> &lp, int sm_count, cudaStream_t stream) {
+    if (g_event_before_list) cudaEventRecord(g_event_before_list, stream);
     suite_list_kernel<false, double><<<sm_count * 8, 128, 0, stream>>>(lp);
 }
 
