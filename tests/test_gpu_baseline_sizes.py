@@ -146,3 +146,77 @@ def test_mixed_layer_on_columns_shorter_than_the_layer(ctx, gpu_tables):
             # an iterate overflows) -- the one output that is not comparable for these columns
             for v in (res["lcl_pressure"].cpu().numpy(), ora["ml_lcl_pressure"]):
                 assert np.all(np.isnan(v) | (v > 1e5)), L
+
+
+def test_arrays_of_more_than_2_pow_32_elements(ctx, gpu_tables):
+    """Maximum sizes: 117 M ERA5-shaped columns in ONE call -- 4.33e9 elements per array, past what the default
+    shared-axis sweep addresses with its 32-bit element offsets, so the launcher must route the call to the sweep
+    with 64-bit addressing (xp_fast.cu, `staged = 2`), and the hand-over list holds column numbers up to 1.17e8.
+    The field is a 1 M-column block repeated 117 times (2^32 is not a multiple of 10^6: an offset that wrapped would
+    land in a DIFFERENT column of the block), which gives a size-independent property over all columns -- every
+    repetition bit-identical to the first -- on top of the oracle on the last columns of the array."""
+    base_n, reps = 1_000_000, 117
+    p, tb, tdb = synth.era5_columns(base_n, seed=77, device="cuda")
+    L, n = tb.shape[0], base_n * reps
+    assert L * n >= 2 ** 32
+    t = torch.empty((L, n), dtype=torch.float32, device="cuda")
+    td = torch.empty_like(t)
+    t.view(L, reps, base_n).copy_(tb[:, None, :])
+    td.view(L, reps, base_n).copy_(tdb[:, None, :])
+    kinds, fields = ("sb", "ml", "mu"), ["cape", "cin", "lfc_pressure", "el_pressure"]
+    outs = ctx.alloc_outputs(t, kinds, fields=fields, shift=False)
+    r = ctx.cape_cin(p, t, td, kinds=kinds, out=outs)
+    assert ctx.last_exact_count() > 0                                   # the float32 path ran and handed columns over
+    for kind in kinds:
+        for f in fields:
+            x = _bits(r[kind][f]).view(reps, base_n)
+            assert bool((x == x[0:1]).all()), (kind, f, "repetitions differ")
+    tail = slice(n - 3000, n)
+    ora = _oracle_suite(p.cpu(), tb[:, base_n - 3000:].cpu(), tdb[:, base_n - 3000:].cpu(), gpu_tables)
+    for kind, pre in (("sb", "sb_"), ("ml", "ml_"), ("mu", "mu_")):
+        got = {f: r[kind][f][tail].cpu().numpy().astype(np.float64) for f in fields}
+        for f in ("cape", "cin"):
+            o = ora[pre + f]
+            assert np.allclose(got[f], o, rtol=1e-3, atol=1.0, equal_nan=True), (kind, f)
+        for f in ("lfc_pressure", "el_pressure"):
+            o = ora[pre + f]
+            both = ~np.isnan(o) & ~np.isnan(got[f])
+            assert (np.isnan(o) == np.isnan(got[f])).mean() > 0.999, (kind, f)
+            assert np.allclose(got[f][both], o[both], rtol=1e-3), (kind, f)
+    del t, td, outs, r
+    torch.cuda.empty_cache()
+
+
+def test_per_column_pressure_arrays_of_more_than_2_pow_32_elements(ctx, gpu_tables):
+    """The same for per-column pressure: 62 M model-level columns x 70 levels (4.34e9 elements in each of the three
+    arrays, 52 GB of input) in one call, surface-based + mixed-layer parcels (the shared-memory adiabat-family kernel
+    and its fix-up list, both with 64-bit element offsets)."""
+    base_n, reps, L = 1_000_000, 62, 70
+    pb, tb, tdb = synth.model_level_columns(base_n, L, seed=78, device="cuda")
+    n = base_n * reps
+    assert L * n >= 2 ** 32
+    arrays = []
+    for b in (pb, tb, tdb):
+        a = torch.empty((L, n), dtype=torch.float32, device="cuda")
+        a.view(L, reps, base_n).copy_(b[:, None, :])
+        arrays.append(a)
+    p, t, td = arrays
+    kinds, fields = ("sb", "ml"), ["cape", "cin", "lfc_pressure", "el_pressure"]
+    outs = ctx.alloc_outputs(t, kinds, fields=fields, shift=False)
+    r = ctx.cape_cin(p, t, td, kinds=kinds, out=outs)
+    assert ctx.last_exact_count() > 0
+    for kind in kinds:
+        for f in fields:
+            x = _bits(r[kind][f]).view(reps, base_n)
+            assert bool((x == x[0:1]).all()), (kind, f, "repetitions differ")
+    tail = slice(n - 3000, n)
+    lo = base_n - 3000
+    ora = _oracle_suite(pb[:, lo:].cpu(), tb[:, lo:].cpu(), tdb[:, lo:].cpu(), gpu_tables)
+    for kind, pre in (("sb", "sb_"), ("ml", "ml_")):
+        keep = _not_knife_edge(ora, pre, t0=ora.get(pre + "parcel_temperature", _np64(tb[0, lo:].cpu())[0]),
+                               td0=ora.get(pre + "parcel_dewpoint", _np64(tdb[0, lo:].cpu())[0]))
+        for f in ("cape", "cin"):
+            got = r[kind][f][tail].cpu().numpy().astype(np.float64)
+            assert np.allclose(got[keep], ora[pre + f][keep], rtol=1e-3, atol=1.0, equal_nan=True), (kind, f)
+    del arrays, p, t, td, outs, r
+    torch.cuda.empty_cache()
