@@ -220,3 +220,29 @@ def test_per_column_pressure_arrays_of_more_than_2_pow_32_elements(ctx, gpu_tabl
             assert np.allclose(got[keep], ora[pre + f][keep], rtol=1e-3, atol=1.0, equal_nan=True), (kind, f)
     del arrays, p, t, td, outs, r
     torch.cuda.empty_cache()
+
+
+def test_more_columns_than_the_fix_up_list_can_number(ctx, gpu_tables):
+    """2^28 columns and more: an entry of the hand-over list holds the column number in 28 bits, so such a call must
+    not take the float32 path at all (fast_eligible) -- it runs on the float64-arithmetic kernel, 64-bit indexed.
+    269 M three-level columns, a 1 M-column block repeated."""
+    base_n, reps, L = 1_000_000, 269, 3
+    pb, tb, tdb = synth.model_level_columns(base_n, L, seed=79, device="cuda")
+    n = base_n * reps
+    assert n >= 2 ** 28
+    arrays = []
+    for b in (pb, tb, tdb):
+        a = torch.empty((L, n), dtype=torch.float32, device="cuda")
+        a.view(L, reps, base_n).copy_(b[:, None, :])
+        arrays.append(a)
+    p, t, td = arrays
+    fields = ["cape", "cin", "lcl_pressure"]
+    outs = ctx.alloc_outputs(t, ("sb",), fields=fields, shift=False)
+    r = ctx.cape_cin(p, t, td, kinds=("sb",), out=outs)
+    assert ctx.last_exact_count() == -1                                 # not the fast path
+    small = ctx.cape_cin(pb, tb, tdb, kinds=("sb",), options=_lib.make_options(exact_only=True))
+    for f in fields:
+        x = _bits(r["sb"][f]).view(reps, base_n)
+        assert bool((x == _bits(small["sb"][f])[None, :]).all()), (f, "differs from the 1 M-column call")
+    del arrays, p, t, td, outs, r
+    torch.cuda.empty_cache()
