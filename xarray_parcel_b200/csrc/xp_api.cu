@@ -32,7 +32,7 @@ struct xp_context {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;     // ev_mid: just before the fix-up kernel of a fast call
     bool ev_valid = false, ev_split = false;
     // host-staging pipeline (mem = XP_MEM_HOST)
-    static constexpr int kSlots = 3;
+    static constexpr int kSlots = 3;     // 4 and 6 slots measured: no change (the path is PCIe-bound)
     cudaStream_t slot_stream[kSlots] = {nullptr, nullptr, nullptr};
     void *slot_buf[kSlots] = {nullptr, nullptr, nullptr};
     size_t slot_bytes = 0;
@@ -49,7 +49,7 @@ struct xp_context {
     int sm_count = 148;
     // experiment knobs, read from the environment once in xp_create (never in the launch path)
     int vote_mask = 3;
-    int host_block_mb = 256;
+    int host_block_mb = 192;     // column blocks of XP_MEM_HOST calls: 96-192 MB 166 M columns/s on the ERA5 suite, 256 MB 161 M, 64 MB 151 M
     std::mutex mu;
 };
 
