@@ -128,8 +128,9 @@ struct Sweep {
     }
 
     // Feed the next profile level (pressure p, parcel curve a, environment curve b).
-    XP_HD void emit(double p, double a, double b, bool is_lcl_level) {
-        const double x = xp_log(p);
+    XP_HD void emit(double p, double a, double b, bool is_lcl_level) { emit_x(p, xp_log(p), a, b, is_lcl_level); }
+    // The same with x = ln p supplied by the caller (a reader that tabulates the logarithms of a shared pressure axis).
+    XP_HD void emit_x(double p, double x, double a, double b, bool is_lcl_level) {
         // bookkeeping that is per level, not per interval
         if (!isnan(p) && !(p >= min_p)) min_p = p;                      // PF:1329 pressure.min()
         if (!isnan(b)) any_b = true;
@@ -295,10 +296,11 @@ XP_HD void lift_parcel(const Levels &lv, double p0, double t0, double td0, const
 
     // Row evaluation (independent of the sweep state) is issued one level ahead of its use so that its
     // long dependent chains (exp / pow / table gathers) overlap the sweep of the previous row.
-    struct RowEval { double p, t, td, env_tv, tp, tvp; };
+    struct RowEval { double p, x, t, td, env_tv, tp, tvp; };
     auto eval_row = [&](int v) {
         RowEval e;
         lv.get(v, e.p, e.t, e.td);
+        e.x = lv.lnp(v, e.p);                                                   // ln p (PF:1019: crossings in ln p)
         // environment (PF:839-843)
         e.env_tv = virtual_temperature(e.t, mixing_ratio_t_td(e.t, e.td, e.p, o.compat));
         // parcel (PF:742-777)
@@ -309,7 +311,7 @@ XP_HD void lift_parcel(const Levels &lv, double p0, double t0, double td0, const
         e.tvp = virtual_temperature(e.tp, wp);
         return e;
     };
-    RowEval cur = {qnan(), qnan(), qnan(), qnan(), qnan(), qnan()};
+    RowEval cur = {qnan(), qnan(), qnan(), qnan(), qnan(), qnan(), qnan()};
     if (n > 0) cur = eval_row(0);
     for (int v = 0; v < n; ++v) {
         RowEval nxt = cur;
@@ -320,7 +322,7 @@ XP_HD void lift_parcel(const Levels &lv, double p0, double t0, double td0, const
         ProfileRow row = {p, cur.tp, cur.tvp, t, cur.env_tv, td};
         if (isnan(p)) row = {qnan(), qnan(), qnan(), qnan(), qnan(), qnan()};
         prof.put(row_idx++, row);
-        sw.emit(row.p, o.vtc ? row.tv : row.t, o.vtc ? row.env_tv : row.env_t, false);
+        sw.emit_x(row.p, cur.x, o.vtc ? row.tv : row.t, o.vtc ? row.env_tv : row.env_t, false);
         if (!isnan(p)) { have_prev = true; pb = p; tb_ = t; tdb = td; }
         cur = nxt;
     }

@@ -36,11 +36,26 @@ struct PStagedReader {
     }
 };
 
-// One thread per (column, parcel kind) item.  STAGED (float columns with their own pressure): dynamic shared memory
-// holds blockDim.x pressure columns.
-template <bool STAGED, typename T = float>
+// A shared pressure axis: ln p of its levels, tabulated once per CTA in shared memory by the same log() that the
+// column code would call per (item, level) -- 8 % of an item's instructions (37 x 86 of 40.7 k per warp, ncu).
+template <typename T>
+struct AxisLnReader : GlobalReader<T> {
+    const double *ln_axis;
+    __device__ __forceinline__ double LnP(int k) const { return ln_axis[k]; }
+};
+
+// One thread per (column, parcel kind) item.  MODE 0: columns read as they are (per-column pressure, float64 or
+// unstaged); 1: float columns with their own pressure, dynamic shared memory holds blockDim.x pressure columns; 2: a
+// shared pressure axis, dynamic shared memory holds ln p of its levels.
+template <int MODE, typename T = float>
 __global__ void __launch_bounds__(128, 3) suite_list_kernel(const __grid_constant__ ListParamsT<T> prm) {
-    extern __shared__ float s_p[];
+    extern __shared__ __align__(8) float s_p[];
+    double *s_ln = reinterpret_cast<double *>(s_p);
+    if (MODE == 2) {
+        for (int k = threadIdx.x; k < prm.cols.L; k += blockDim.x)
+            s_ln[k] = xp_log((double)__ldg(prm.cols.p + (int64_t)k * prm.cols.pls));
+        __syncthreads();
+    }
     const uint32_t c0 = prm.list_count[0], c1 = prm.list_count[1], c2 = prm.list_count[2];
     const uint64_t total = (uint64_t)c0 + c1 + c2;
     const int L = prm.cols.L, nt = (int)blockDim.x;
@@ -57,12 +72,17 @@ __global__ void __launch_bounds__(128, 3) suite_list_kernel(const __grid_constan
         int shift;
         ProfWriter<T> np = make_writer(prm.outs[kind], col);       // profile rows too, where requested ...
         if ((e >> 28) & kListRowsOk) np.any = false;                   // ... unless the float32 rows stand
-        if constexpr (STAGED) {
+        if constexpr (MODE == 1) {
             // independent loads, all in flight at once; only this thread reads its slots back: no barrier needed
             for (int k = 0; k < L; ++k) s_p[k * nt + threadIdx.x] = (float)__ldg(rd.p + (int64_t)k * rd.pls);
             PStagedReader<T> sr;
             sr.g = rd; sr.sp = s_p + threadIdx.x; sr.nt = nt; sr.L = L; sr.qmode = prm.cols.qmode;
             run_column(sr, kind, prm.tb, prm.o, qnan(), qnan(), qnan(), r, p0, t0, td0, shift, np);
+        } else if constexpr (MODE == 2) {
+            AxisLnReader<T> ar;
+            static_cast<GlobalReader<T> &>(ar) = rd;
+            ar.ln_axis = s_ln;
+            run_column(ar, kind, prm.tb, prm.o, qnan(), qnan(), qnan(), r, p0, t0, td0, shift, np);
         } else {
             run_column(rd, kind, prm.tb, prm.o, qnan(), qnan(), qnan(), r, p0, t0, td0, shift, np);
         }
@@ -80,16 +100,19 @@ void launch_suite_list(const ListParams &lp, int sm_count, cudaStream_t stream) 
     static const bool off = getenv("XP_LIST_STAGED") && atoi(getenv("XP_LIST_STAGED")) == 0;      // A/B knob
     if (!lp.cols.p1d && !off && smem <= 75 * 1024) {
         // per device, so set on every launch (a host-side call of about a microsecond)
-        cudaFuncSetAttribute(suite_list_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 75 * 1024);
-        suite_list_kernel<true><<<sm_count * 8, 128, smem, stream>>>(lp);
+        cudaFuncSetAttribute(suite_list_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 75 * 1024);
+        suite_list_kernel<1><<<sm_count * 8, 128, smem, stream>>>(lp);
+    } else if (lp.cols.p1d) {
+        suite_list_kernel<2><<<sm_count * 8, 128, (size_t)lp.cols.L * sizeof(double), stream>>>(lp);
     } else {
-        suite_list_kernel<false><<<sm_count * 8, 128, 0, stream>>>(lp);
+        suite_list_kernel<0><<<sm_count * 8, 128, 0, stream>>>(lp);
     }
 }
 
 void launch_suite_list(const ListParamsT<double> &lp, int sm_count, cudaStream_t stream) {
     if (g_event_before_list) cudaEventRecord(g_event_before_list, stream);
-    suite_list_kernel<false, double><<<sm_count * 8, 128, 0, stream>>>(lp);
+    if (lp.cols.p1d) suite_list_kernel<2, double><<<sm_count * 8, 128, (size_t)lp.cols.L * sizeof(double), stream>>>(lp);
+    else suite_list_kernel<0, double><<<sm_count * 8, 128, 0, stream>>>(lp);
 }
 
 }  // namespace xp

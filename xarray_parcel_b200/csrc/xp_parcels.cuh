@@ -5,6 +5,17 @@
 
 namespace xp {
 
+// ln P(k): readers may tabulate it (`double LnP(int k) const`: xp_list.cu on a shared pressure axis); the others
+// evaluate the logarithm.  Same function, same argument: the bits are the same either way.
+template <class R, class = void>
+struct ReaderLnP {
+    static XP_HD double get(const R &, int, double p) { return xp_log(p); }
+};
+template <class R>
+struct ReaderLnP<R, decltype((void)&R::LnP)> {
+    static XP_HD double get(const R &r, int k, double) { return r.LnP(k); }
+};
+
 // Levels of the lifted column (see lift_parcel).  `Reader` gives P(k), Tk(k), Td(k), L.
 template <class Reader>
 struct LiftedLevels {
@@ -21,6 +32,11 @@ struct LiftedLevels {
         p = rd.P(k); t = rd.Tk(k); td = rd.Td(k);
         bool keep = (mode == 0) || (mode == 1 ? (p <= thresh) : (p < thresh));
         if (!keep) { p = t = td = qnan(); }
+    }
+    // ln of the pressure `p` that get(v, ...) returned
+    XP_HD double lnp(int v, double p) const {
+        if ((pre && v == 0) || isnan(p)) return xp_log(p);          // the prepended parcel level / a masked level (NaN)
+        return ReaderLnP<Reader>::get(rd, k0 + v - pre, p);
     }
 };
 
