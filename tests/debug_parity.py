@@ -1,9 +1,9 @@
-"""Debug helper (GPU box): compare the CUDA kernel with the host-compiled kernel code (tests/hostsim)
+"""Debug helper (GPU box; test infrastructure -- it uses the oracle, so it lives under tests/): compare the CUDA kernel with the host-compiled kernel code (tests/hostsim)
 and the oracle on one configuration; dump the worst columns to gpurun_out/ for offline replay."""
 import os, sys, json
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))       # run as: python tests/debug_parity.py
 import hostsim_util as hs
 from xarray_parcel_b200 import _lib, synth
 from oracle import tables as otab
