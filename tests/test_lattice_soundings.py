@@ -150,3 +150,22 @@ def test_lattice_soundings_on_a_shared_axis(L, dp):
             rel, ab = FAST_BOUND[f]
             over = np.abs(a[ok] - b[ok]) > rel * np.abs(b[ok]) + ab
             assert not over.any(), f"{kind} {f}: {int(over.sum())} columns outside the float32 bound"
+
+
+@pytest.mark.parametrize("kind", ["sb", "ml", "mu"])
+@pytest.mark.parametrize("L,dp", [(12, 25.0), (5, 50.0), (2, 25.0)])
+def test_lattice_profile_rows_match_oracle(oracle_tables, kind, L, dp):
+    """parcel_profile_with_lcl rows (PF:806-931) on the lattice: where the LCL row goes when the LCL coincides with a
+    level (saturated parcels), which levels are dropped below the lifted parcel, NaN-pressure levels."""
+    p, t, td = lattice_columns(700, L, 900 + L, dp)
+    opts = op.Options(op.MoistLapseLUT(oracle_tables), lcl_mode="converged")
+    fn = {"sb": op.surface_based_cape_cin, "ml": op.mixed_layer_cape_cin, "mu": op.most_unstable_cape_cin}[kind]
+    prof = fn(p, t, td, opts)[1]
+    res = hs.cape_cin(p, t, td, oracle_tables, kind=kind, profile=True)
+    n = prof["pressure"].shape[0]           # the oracle trims with dropna(how='all') like PF:1552/1637
+    for k in hs.PROFILE:
+        a, b = res["profile"][k][:n], prof[k]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), f"{k}: NaN pattern differs"
+        ok = ~np.isnan(b)
+        assert np.allclose(a[ok], b[ok], rtol=1e-11, atol=0), k
+        assert np.isnan(res["profile"][k][n:]).all()
